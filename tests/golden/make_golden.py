@@ -1,0 +1,76 @@
+"""Generate golden vectors by running the UNMODIFIED reference (imported from /root/reference) on
+seeded synthetic weights/inputs.  Run in the build container only (the GPU box has no reference):
+
+    python tests/golden/make_golden.py
+
+Outputs small .npz fixtures next to this file.  Noise is drawn by the reference itself after
+``torch.manual_seed(seed)`` (models.py:498-501); ``sovits_b200.synth.draw_noise`` replays the same
+draws for the oracle and the CUDA path.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("SOVITS_REF_DIR", "/root/reference")
+sys.path.insert(0, ROOT)
+for m in ("faiss", "librosa", "matplotlib", "matplotlib.pylab"):  # imported at module top, unused by infer
+    sys.modules[m] = types.ModuleType(m)
+sys.path.insert(0, REF)
+
+import models as ref_models  # noqa: E402
+import modules.modules as ref_modules  # noqa: E402
+import sovits_b200  # noqa: E402,F401
+from sovits_b200 import synth  # noqa: E402
+from sovits_b200.config import load_config  # noqa: E402
+
+
+def build_reference(cfg, sd):
+    import json
+    with open(sovits_b200.DEFAULT_CONFIG) as f:
+        model_kw = json.load(f)["model"]
+    net = ref_models.SynthesizerTrn(2048 // 2 + 1, 10240 // 512, **model_kw).eval()
+    own = net.state_dict()
+    missing = [k for k in sd if k not in own]
+    assert not missing, missing
+    for k, v in sd.items():
+        assert own[k].shape == v.shape, (k, own[k].shape, v.shape)
+    used = [k for k in own if not k.startswith(("enc_q.", "f0_decoder."))]
+    assert sorted(used) == sorted(sd.keys()), set(used) ^ set(sd.keys())
+    net.load_state_dict(sd, strict=False)
+    return net
+
+
+def main():
+    torch.set_num_threads(8)
+    cfg = load_config()
+    sd = synth.synth_state_dict(cfg)
+    net = build_reference(cfg, sd)
+    out = {}
+    for name, (B, T) in synth.GOLDEN_CASES.items():
+        c, f0, uv, sid = synth.golden_inputs(cfg, name)
+        taps = {}
+        hooks = []
+        hooks.append(net.flow.register_forward_hook(lambda m, i, o: taps.__setitem__("z", o.detach().clone())))
+        hooks.append(net.flow.register_forward_pre_hook(lambda m, i: taps.__setitem__("z_p", i[0].detach().clone())))
+        hooks.append(net.dec.m_source.register_forward_hook(lambda m, i, o: taps.__setitem__("har", o[0].detach().clone())))
+        with torch.no_grad():
+            o, f0_out = net.infer(c, f0=f0, uv=uv, g=sid, noice_scale=0.4)
+        for h in hooks:
+            h.remove()
+        print(name, o.shape, float(o.abs().max()), float(taps["z"].abs().max()))
+        np.savez_compressed(os.path.join(HERE, f"ref_infer_{name}.npz"),
+                            o=o.numpy(), z_p=taps["z_p"].numpy(), z=taps["z"].numpy(),
+                            har=taps["har"].transpose(1, 2).numpy(),
+                            B=B, T=T, seed=52468, noice_scale=0.4,
+                            f0=f0.numpy())
+    # module-level fixtures: one coupling layer + one ResBlock input/output are covered by z / o above.
+    print("done")
+
+
+if __name__ == "__main__":
+    main()
