@@ -1,0 +1,753 @@
+// C ABI of libsovits_b200.so: context, weight folding/packing, and the launch schedule of the
+// flow -> NSF source -> generator tail.  See include/sovits_b200.h for the contract.
+#include "../../include/sovits_b200.h"
+#include "kernels.h"
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace svb;
+
+#define SVB_VERSION "sovits_b200 0.1.0 (sm_100a)"
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct ConvW {            // folded fp32 weights of one Conv1d, packed [Cin][k][Cout]
+    float* w = nullptr;
+    float* b = nullptr;
+    int Cin = 0, Cout = 0, k = 0;
+    void* w_tc = nullptr;  // tensor-core image (fp16, swizzled), when built
+};
+
+struct FlowLayer {
+    ConvW pre, post;
+    float* cond_w_nat = nullptr;   // [2H*L][gin] natural layout for the GEMV
+    ConvW cond;                    // packed variant for time-varying g
+    std::vector<ConvW> in_layers, res_skip;
+    int in_c0 = 0, out_c0 = 0;     // which half feeds pre / receives post (Flip folded)
+};
+
+struct Stage {
+    float* up_w = nullptr;         // [s][Cin][2][Cout]
+    float* up_b = nullptr;
+    int Cin = 0, Cout = 0, s = 0, k = 0, p = 0;
+    float* noise_w = nullptr;      // [Cout][K]
+    float* noise_b = nullptr;
+    int noise_K = 0, noise_s = 0, noise_p = 0;
+    std::vector<ConvW> c1, c2;     // [branch*3 + d]
+};
+
+}  // namespace
+
+struct svb_ctx {
+    int device = 0;
+    bool loaded = false;
+    int precision = SVB_PREC_FP32;
+    svb_model_cfg cfg{};
+    std::vector<void*> allocs;
+    std::vector<FlowLayer> flow;
+    ConvW conv_pre;
+    float* dcond_w_nat = nullptr;  // dec.cond [U][gin]
+    float* dcond_b = nullptr;
+    ConvW dcond;                   // packed (time-varying g)
+    std::vector<Stage> stages;
+    float* post_w = nullptr;       // [C][7]
+    float post_b = 0.f;
+    int post_C = 0, post_K = 7;
+    float* lin_w = nullptr;
+    float lin_b = 0.f;
+    int hop = 1;
+    DevBuf ws;                     // library-owned workspace
+    DevBuf host_io;                // device staging for svb_infer_tail_host
+    bool debug = false;
+    std::map<std::string, DevBuf> dbg;
+    std::string err;
+};
+
+namespace {
+
+int fail(svb_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, SVB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
+    } while (0)
+
+struct HostT {
+    std::vector<float> v;
+    std::vector<int64_t> shape;
+};
+
+using TMap = std::unordered_map<std::string, const svb_tensor*>;
+
+int get_tensor(svb_ctx* ctx, const TMap& m, const std::string& name, std::vector<int64_t> want, HostT& out) {
+    auto it = m.find(name);
+    if (it == m.end()) return fail(ctx, SVB_ERR_MISSING_TENSOR, "missing tensor: " + name);
+    const svb_tensor* t = it->second;
+    int64_t n = 1;
+    out.shape.assign(t->shape, t->shape + t->ndim);
+    for (int i = 0; i < t->ndim; ++i) n *= t->shape[i];
+    int64_t wn = 1;
+    for (auto d : want) wn *= d;
+    if (n != wn || (int)want.size() != t->ndim) {
+        std::string s = "shape mismatch for " + name + ": got [";
+        for (int i = 0; i < t->ndim; ++i) s += std::to_string(t->shape[i]) + (i + 1 < t->ndim ? "," : "");
+        s += "] want [";
+        for (size_t i = 0; i < want.size(); ++i) s += std::to_string(want[i]) + (i + 1 < want.size() ? "," : "");
+        return fail(ctx, SVB_ERR_SHAPE, s + "]");
+    }
+    for (int i = 0; i < t->ndim; ++i)
+        if (t->shape[i] != want[i]) return fail(ctx, SVB_ERR_SHAPE, "shape mismatch for " + name);
+    out.v.resize(n);
+    if (t->dtype == 0) {
+        std::memcpy(out.v.data(), t->data, n * sizeof(float));
+    } else if (t->dtype == 1) {
+        const __half* h = static_cast<const __half*>(t->data);
+        for (int64_t i = 0; i < n; ++i) out.v[i] = __half2float(h[i]);
+    } else {
+        return fail(ctx, SVB_ERR_INVALID_ARG, "unsupported dtype for " + name);
+    }
+    return SVB_OK;
+}
+
+// torch.nn.utils.weight_norm(dim=0): w = g * v / ||v||, norm over all dims but 0 — for ConvTranspose1d dim 0
+// is Cin (vdecoder/hifigan/models.py:340-342).
+int folded(svb_ctx* ctx, const TMap& m, const std::string& prefix, std::vector<int64_t> shape, HostT& w) {
+    HostT g, v;
+    int rc = get_tensor(ctx, m, prefix + ".weight_v", shape, v);
+    if (rc) return rc;
+    rc = get_tensor(ctx, m, prefix + ".weight_g", {shape[0], 1, 1}, g);
+    if (rc) return rc;
+    int64_t rows = shape[0], cols = (int64_t)v.v.size() / rows;
+    w.v.resize(v.v.size());
+    w.shape = shape;
+    for (int64_t r = 0; r < rows; ++r) {
+        double ss = 0;
+        for (int64_t c = 0; c < cols; ++c) ss += (double)v.v[r * cols + c] * v.v[r * cols + c];
+        // match torch: norm computed in fp32 then g*v/norm in fp32
+        float nrm = (float)std::sqrt(ss);
+        float gg = g.v[r];
+        for (int64_t c = 0; c < cols; ++c) w.v[r * cols + c] = gg * v.v[r * cols + c] / nrm;
+    }
+    return SVB_OK;
+}
+
+int upload(svb_ctx* ctx, const void* src, size_t bytes, void** dst) {
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes ? bytes : 4));
+    ctx->allocs.push_back(p);
+    if (bytes) CU(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+    *dst = p;
+    return SVB_OK;
+}
+
+// w: [Cout][Cin][k] (natural Conv1d layout) -> packed [Cin][k][Cout]; optional channel reversals.
+int make_conv(svb_ctx* ctx, const std::vector<float>& w, const std::vector<float>& b, int Cout, int Cin, int k,
+              bool rev_in, bool rev_out, ConvW& out) {
+    std::vector<float> pk((size_t)Cin * k * Cout);
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int t = 0; t < k; ++t) {
+                int sco = rev_out ? Cout - 1 - co : co;
+                int sci = rev_in ? Cin - 1 - ci : ci;
+                pk[((size_t)ci * k + t) * Cout + co] = w[((size_t)sco * Cin + sci) * k + t];
+            }
+    std::vector<float> bb(Cout);
+    for (int co = 0; co < Cout; ++co) bb[co] = b[rev_out ? Cout - 1 - co : co];
+    out.Cin = Cin; out.Cout = Cout; out.k = k;
+    int rc = upload(ctx, pk.data(), pk.size() * sizeof(float), (void**)&out.w);
+    if (rc) return rc;
+    rc = upload(ctx, bb.data(), bb.size() * sizeof(float), (void**)&out.b);
+    if (rc) return rc;
+    if (Cin == Cout && (k == 3 || k == 7 || k == 11) && (Cin == 16 || Cin == 32 || Cin == 64 || Cin == 128 || Cin == 256)) {
+        size_t ib = tc_weight_image_bytes(Cin, k);
+        std::vector<uint8_t> img(ib);
+        tc_pack_weight_image(w.data(), Cin, k, img.data());
+        rc = upload(ctx, img.data(), ib, &out.w_tc);
+        if (rc) return rc;
+    }
+    return SVB_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WsPlan {
+    size_t total = 0;
+    size_t off_y, off_h, off_xin, off_acts, off_out, off_gcond, off_dgcond, off_phase;
+    size_t off_har, off_pre, off_X, off_A, off_Bb, off_T, off_O, off_z;
+};
+
+WsPlan plan_ws(const svb_model_cfg& c, int B, int T, int gT) {
+    WsPlan p;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    const size_t f = sizeof(float);
+    const int H = c.hidden_channels, C = c.inter_channels, L = c.flow_wn_layers;
+    size_t BT = (size_t)B * T;
+    p.off_z = take(BT * C * f);
+    p.off_h = take(BT * H * f);
+    p.off_xin = take(BT * 2 * H * f);
+    p.off_acts = take(BT * H * f);
+    p.off_out = take(BT * H * f);
+    p.off_gcond = take((size_t)B * 2 * H * L * (gT > 1 ? T : 1) * f);
+    p.off_dgcond = take((size_t)B * c.upsample_initial_channel * (gT > 1 ? T : 1) * f);
+    p.off_phase = take(BT * c.n_harmonics * sizeof(double));
+    long long hop = 1;
+    for (int i = 0; i < c.n_upsamples; ++i) hop *= c.upsample_rates[i];
+    p.off_har = take(BT * hop * f);
+    p.off_pre = take(BT * c.upsample_initial_channel * f);
+    size_t maxel = 0;
+    long long len = T;
+    for (int i = 0; i < c.n_upsamples; ++i) {
+        len *= c.upsample_rates[i];
+        size_t el = (size_t)(c.upsample_initial_channel >> (i + 1)) * (size_t)len;
+        if (el > maxel) maxel = el;
+    }
+    maxel *= B;
+    p.off_X = take(maxel * f);
+    p.off_A = take(maxel * f);
+    p.off_Bb = take(maxel * f);
+    p.off_T = take(maxel * f);
+    p.off_O = take(maxel * f);
+    p.total = o;
+    p.off_y = p.off_z;
+    return p;
+}
+
+int ensure_ws(svb_ctx* ctx, size_t need, void* user_ws, size_t user_bytes, char** base) {
+    if (user_ws) {
+        if (user_bytes < need) return fail(ctx, SVB_ERR_WORKSPACE, "caller workspace too small");
+        *base = static_cast<char*>(user_ws);
+        return SVB_OK;
+    }
+    if (ctx->ws.bytes < need) {
+        if (ctx->ws.p) CU(cudaFree(ctx->ws.p));
+        ctx->ws.p = nullptr; ctx->ws.bytes = 0;
+        CU(cudaMalloc(&ctx->ws.p, need));
+        ctx->ws.bytes = need;
+    }
+    *base = static_cast<char*>(ctx->ws.p);
+    return SVB_OK;
+}
+
+int dbg_keep(svb_ctx* ctx, const std::string& name, const float* src, size_t n, cudaStream_t st) {
+    if (!ctx->debug) return SVB_OK;
+    DevBuf& d = ctx->dbg[name];
+    if (d.bytes < n * sizeof(float)) {
+        if (d.p) CU(cudaFree(d.p));
+        CU(cudaMalloc(&d.p, n * sizeof(float)));
+        d.bytes = n * sizeof(float);
+    }
+    CU(cudaMemcpyAsync(d.p, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return SVB_OK;
+}
+
+int check_launch(svb_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SVB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return SVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- flow
+int run_flow(svb_ctx* ctx, const float* z_p, const float* g, int gT, const int32_t* lengths, float* y,
+             int B, int T, char* ws, const WsPlan& pl, cudaStream_t st) {
+    const svb_model_cfg& c = ctx->cfg;
+    const int H = c.hidden_channels, C = c.inter_channels, L = c.flow_wn_layers, half = C / 2;
+    float* h = reinterpret_cast<float*>(ws + pl.off_h);
+    float* xin = reinterpret_cast<float*>(ws + pl.off_xin);
+    float* acts = reinterpret_cast<float*>(ws + pl.off_acts);
+    float* out = reinterpret_cast<float*>(ws + pl.off_out);
+    float* gcond = reinterpret_cast<float*>(ws + pl.off_gcond);
+    if (y != z_p) CU(cudaMemcpyAsync(y, z_p, (size_t)B * C * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    for (int fl = c.n_flows - 1; fl >= 0; --fl) {
+        FlowLayer& F = ctx->flow[fl];
+        // h = pre(x0) * mask
+        ConvF32 a;
+        a.x = y; a.x_ctot = C; a.x_c0 = F.in_c0; a.Cin = half; a.Tin = T;
+        a.w = F.pre.w; a.bias = F.pre.b; a.Cout = H; a.k = 1;
+        a.y = h; a.y_ctot = H; a.Ty = T; a.n_out = T; a.lengths = lengths; a.B = B;
+        launch_conv_f32(a, st);
+        // conditioning: g -> [B, 2H*L, gT]
+        if (gT == 1) {
+            launch_gemv(F.cond_w_nat, F.cond.b, g, gcond, B, 2 * H * L, c.gin_channels, st);
+        } else {
+            ConvF32 cg;
+            cg.x = g; cg.x_ctot = c.gin_channels; cg.Cin = c.gin_channels; cg.Tin = T;
+            cg.w = F.cond.w; cg.bias = F.cond.b; cg.Cout = 2 * H * L; cg.k = 1;
+            cg.y = gcond; cg.y_ctot = 2 * H * L; cg.Ty = T; cg.n_out = T; cg.B = B;
+            launch_conv_f32(cg, st);
+        }
+        for (int i = 0; i < L; ++i) {
+            ConvF32 ci;
+            ci.x = h; ci.x_ctot = H; ci.Cin = H; ci.Tin = T;
+            ci.w = F.in_layers[i].w; ci.bias = F.in_layers[i].b; ci.Cout = 2 * H; ci.k = c.flow_kernel_size;
+            ci.pad_left = (c.flow_kernel_size - 1) / 2;
+            if (gT == 1) { ci.bias_b = gcond; ci.bias_b_stride = 2 * H * L; ci.bias_b_off = 2 * H * i; }
+            else { ci.bias_t = gcond; ci.bias_t_ctot = 2 * H * L; ci.bias_t_c0 = 2 * H * i; }
+            ci.y = xin; ci.y_ctot = 2 * H; ci.Ty = T; ci.n_out = T; ci.B = B;
+            launch_conv_f32(ci, st);
+            launch_gate(xin, acts, B, H, T, st);
+            const ConvW& R = F.res_skip[i];
+            if (i < L - 1) {
+                // residual half: h = (h + rs[:H]) * mask
+                ConvF32 r1;
+                r1.x = acts; r1.x_ctot = H; r1.Cin = H; r1.Tin = T;
+                r1.w = R.w; r1.bias = R.b; r1.Cout = H; r1.k = 1;
+                // packed layout is [Cin][1][2H]: restrict to the first H output columns via a strided view
+                // (handled by packing res/skip halves separately, see load)
+                r1.y = h; r1.y_ctot = H; r1.Ty = T; r1.n_out = T; r1.beta = 1.f; r1.lengths = lengths; r1.B = B;
+                launch_conv_f32(r1, st);
+                // skip half: out (+)= rs[H:]
+                ConvF32 r2 = r1;
+                r2.w = R.w + (size_t)H * H; r2.bias = R.b + H;
+                r2.y = out; r2.beta = (i > 0) ? 1.f : 0.f;
+                launch_conv_f32(r2, st);
+            } else {
+                ConvF32 r2;
+                r2.x = acts; r2.x_ctot = H; r2.Cin = H; r2.Tin = T;
+                r2.w = R.w; r2.bias = R.b; r2.Cout = H; r2.k = 1;
+                r2.y = out; r2.y_ctot = H; r2.Ty = T; r2.n_out = T; r2.beta = (i > 0) ? 1.f : 0.f;
+                r2.lengths = lengths; r2.B = B;
+                launch_conv_f32(r2, st);
+            }
+        }
+        // x1 = (x1 - post(out)*mask) * mask   (mean_only => logs = 0)
+        ConvF32 p;
+        p.x = out; p.x_ctot = H; p.Cin = H; p.Tin = T;
+        p.w = F.post.w; p.bias = F.post.b; p.Cout = half; p.k = 1;
+        p.y = y; p.y_ctot = C; p.y_c0 = F.out_c0; p.Ty = T; p.n_out = T;
+        p.alpha = -1.f; p.beta = 1.f; p.lengths = lengths; p.B = B;
+        launch_conv_f32(p, st);
+    }
+    return check_launch(ctx, "flow");
+}
+
+// ---------------------------------------------------------------------------------------------- generator
+int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const float* har, float* wav,
+                  int B, int T, char* ws, const WsPlan& pl, cudaStream_t st) {
+    const svb_model_cfg& c = ctx->cfg;
+    const int U = c.upsample_initial_channel;
+    float* dg = reinterpret_cast<float*>(ws + pl.off_dgcond);
+    float* pre = reinterpret_cast<float*>(ws + pl.off_pre);
+    float* X = reinterpret_cast<float*>(ws + pl.off_X);
+    float* A = reinterpret_cast<float*>(ws + pl.off_A);
+    float* Bb = reinterpret_cast<float*>(ws + pl.off_Bb);
+    float* Tm = reinterpret_cast<float*>(ws + pl.off_T);
+    float* O = reinterpret_cast<float*>(ws + pl.off_O);
+    const long long N = (long long)T * ctx->hop;
+    int rc;
+
+    // conv_pre(z) + cond(g)
+    ConvF32 cp;
+    cp.x = z; cp.x_ctot = c.inter_channels; cp.Cin = c.inter_channels; cp.Tin = T;
+    cp.w = ctx->conv_pre.w; cp.bias = ctx->conv_pre.b; cp.Cout = U; cp.k = ctx->conv_pre.k; cp.pad_left = (cp.k - 1) / 2;
+    cp.y = pre; cp.y_ctot = U; cp.Ty = T; cp.n_out = T; cp.B = B;
+    if (gT == 1) {
+        launch_gemv(ctx->dcond_w_nat, ctx->dcond_b, g, dg, B, U, c.gin_channels, st);
+        cp.bias_b = dg; cp.bias_b_stride = U; cp.bias_b_off = 0;
+    } else {
+        ConvF32 cg;
+        cg.x = g; cg.x_ctot = c.gin_channels; cg.Cin = c.gin_channels; cg.Tin = T;
+        cg.w = ctx->dcond.w; cg.bias = ctx->dcond.b; cg.Cout = U; cg.k = 1;
+        cg.y = dg; cg.y_ctot = U; cg.Ty = T; cg.n_out = T; cg.B = B;
+        launch_conv_f32(cg, st);
+        cp.bias_t = dg; cp.bias_t_ctot = U;
+    }
+    launch_conv_f32(cp, st);
+    if ((rc = dbg_keep(ctx, "conv_pre", pre, (size_t)B * U * T, st))) return rc;
+
+    const float* cur = pre;
+    int Lin = T;
+    const int nk = c.n_resblock_kernels;
+    for (int i = 0; i < c.n_upsamples; ++i) {
+        Stage& S = ctx->stages[i];
+        const int Lout = Lin * S.s;
+        // x = ups(lrelu(x, 0.1))  as s polyphase 2-tap convs
+        ConvF32 up;
+        up.x = cur; up.x_ctot = S.Cin; up.Cin = S.Cin; up.Tin = Lin;
+        up.w = S.up_w; up.bias = S.up_b; up.Cout = S.Cout; up.k = 2; up.dil = 1; up.pad_left = 1;
+        up.n_phase = S.s; up.w_phase_stride = (long long)S.Cin * 2 * S.Cout;
+        up.ostride = S.s; up.ooff = -S.p; up.n_out = Lin + 1;
+        up.in_act = 1; up.in_slope = 0.1f;
+        up.y = X; up.y_ctot = S.Cout; up.Ty = Lout; up.B = B;
+        launch_conv_f32(up, st);
+        launch_noise_conv_add(har, S.noise_w, S.noise_b, X, B, S.Cout, Lout, (int)N, S.noise_K, S.noise_s, S.noise_p, st);
+        if ((rc = dbg_keep(ctx, "ups" + std::to_string(i), X, (size_t)B * S.Cout * Lout, st))) return rc;
+        for (int j = 0; j < nk; ++j) {
+            const int k = c.resblock_kernel_sizes[j];
+            const float* src = X;
+            float* pp[2] = {A, Bb};
+            for (int d = 0; d < 3; ++d) {
+                const int dil = c.resblock_dilations[j][d];
+                const ConvW& W1 = S.c1[j * 3 + d];
+                const ConvW& W2 = S.c2[j * 3 + d];
+                const bool last = (d == 2);
+                float* dst = last ? O : pp[d & 1];
+                const float alpha = last ? 1.f / nk : 1.f;
+                const float beta = (last && j > 0) ? 1.f : 0.f;
+                bool done = false;
+                if (ctx->precision == SVB_PREC_TC && W1.w_tc && W2.w_tc) {
+                    PairTC pt;
+                    pt.x = src; pt.out = dst; pt.w1 = W1.w_tc; pt.w2 = W2.w_tc; pt.b1 = W1.b; pt.b2 = W2.b;
+                    pt.B = B; pt.C = S.Cout; pt.T = Lout; pt.k = k; pt.dil = dil; pt.alpha = alpha; pt.beta = beta;
+                    int trc = launch_pair_tc(pt, st);
+                    if (trc == 0) done = true;
+                    else if (trc != SVB_ERR_UNSUPPORTED) return fail(ctx, trc, "tensor-core pair kernel launch failed");
+                }
+                if (!done) {
+                    ConvF32 c1;
+                    c1.x = src; c1.x_ctot = S.Cout; c1.Cin = S.Cout; c1.Tin = Lout;
+                    c1.w = W1.w; c1.bias = W1.b; c1.Cout = S.Cout; c1.k = k; c1.dil = dil; c1.pad_left = dil * (k - 1) / 2;
+                    c1.in_act = 1; c1.in_slope = 0.1f;
+                    c1.y = Tm; c1.y_ctot = S.Cout; c1.Ty = Lout; c1.n_out = Lout; c1.B = B;
+                    launch_conv_f32(c1, st);
+                    ConvF32 c2;
+                    c2.x = Tm; c2.x_ctot = S.Cout; c2.Cin = S.Cout; c2.Tin = Lout;
+                    c2.w = W2.w; c2.bias = W2.b; c2.Cout = S.Cout; c2.k = k; c2.dil = 1; c2.pad_left = (k - 1) / 2;
+                    c2.in_act = 1; c2.in_slope = 0.1f;
+                    c2.res = src; c2.res_ctot = S.Cout;
+                    c2.y = dst; c2.y_ctot = S.Cout; c2.Ty = Lout; c2.n_out = Lout; c2.B = B;
+                    c2.alpha = alpha; c2.beta = beta;
+                    launch_conv_f32(c2, st);
+                }
+                src = dst;
+            }
+        }
+        if ((rc = dbg_keep(ctx, "stage" + std::to_string(i), O, (size_t)B * S.Cout * Lout, st))) return rc;
+        // O becomes the next stage's input; swap roles so the next stage does not overwrite it
+        float* tmp = O; O = Tm; Tm = tmp;   // next stage writes its output into the old T buffer
+        cur = tmp;
+        Lin = Lout;
+    }
+    launch_conv_post(cur, ctx->post_w, ctx->post_b, wav, B, ctx->post_C, Lin, ctx->post_K, 0.01f, st);
+    return check_launch(ctx, "generator");
+}
+
+}  // namespace
+
+// ================================================================================================ ABI
+extern "C" {
+
+const char* svb_version(void) { return SVB_VERSION; }
+
+const char* svb_strerror(int s) {
+    switch (s) {
+        case SVB_OK: return "ok";
+        case SVB_ERR_INVALID_ARG: return "invalid argument";
+        case SVB_ERR_CUDA: return "CUDA error";
+        case SVB_ERR_NOT_LOADED: return "weights not loaded";
+        case SVB_ERR_MISSING_TENSOR: return "missing tensor";
+        case SVB_ERR_SHAPE: return "tensor shape mismatch";
+        case SVB_ERR_UNSUPPORTED: return "unsupported configuration";
+        case SVB_ERR_WORKSPACE: return "workspace too small";
+        case SVB_ERR_ARCH: return "device is not sm_100";
+        default: return "unknown status";
+    }
+}
+
+const char* svb_last_error(const svb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t svb_launch_count(const svb_ctx*) { return launch_counter(); }
+
+int svb_create(int device, svb_ctx** out) {
+    if (!out) return SVB_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return SVB_ERR_CUDA;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return SVB_ERR_CUDA;
+    if (p.major != 10) return SVB_ERR_ARCH;   // sm_100a binary only: fail loudly elsewhere
+    if (cudaSetDevice(device) != cudaSuccess) return SVB_ERR_CUDA;
+    svb_ctx* c = new svb_ctx();
+    c->device = device;
+    *out = c;
+    return SVB_OK;
+}
+
+void svb_destroy(svb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (void* p : ctx->allocs) cudaFree(p);
+    if (ctx->ws.p) cudaFree(ctx->ws.p);
+    if (ctx->host_io.p) cudaFree(ctx->host_io.p);
+    for (auto& kv : ctx->dbg) if (kv.second.p) cudaFree(kv.second.p);
+    delete ctx;
+}
+
+int svb_set_precision(svb_ctx* ctx, int precision) {
+    if (!ctx || (precision != SVB_PREC_FP32 && precision != SVB_PREC_TC)) return SVB_ERR_INVALID_ARG;
+    ctx->precision = precision;
+    return SVB_OK;
+}
+int svb_get_precision(const svb_ctx* ctx) { return ctx ? ctx->precision : SVB_ERR_INVALID_ARG; }
+
+int svb_debug_enable(svb_ctx* ctx, int on) {
+    if (!ctx) return SVB_ERR_INVALID_ARG;
+    ctx->debug = on != 0;
+    return SVB_OK;
+}
+
+int svb_debug_fetch(svb_ctx* ctx, const char* what, float* dst, size_t n, void* stream) {
+    if (!ctx || !what || !dst) return SVB_ERR_INVALID_ARG;
+    auto it = ctx->dbg.find(what);
+    if (it == ctx->dbg.end()) return fail(ctx, SVB_ERR_INVALID_ARG, std::string("no debug tap named ") + what);
+    if (n * sizeof(float) > it->second.bytes) return fail(ctx, SVB_ERR_INVALID_ARG, "debug tap smaller than requested");
+    CU(cudaMemcpyAsync(dst, it->second.p, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SVB_OK;
+}
+
+int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, const svb_model_cfg* cfgp) {
+    if (!ctx || !tensors || !cfgp || n_tensors <= 0) return SVB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    const svb_model_cfg& c = *cfgp;
+    if (c.n_upsamples < 1 || c.n_upsamples > 8 || c.n_resblock_kernels != 3 || c.n_flows != 4 ||
+        (c.inter_channels & 1) || c.flow_wn_layers < 1 || (c.n_harmonics != 9 && c.n_harmonics != 1))
+        return fail(ctx, SVB_ERR_UNSUPPORTED, "unsupported model configuration");
+    for (int i = 0; i < c.n_upsamples; ++i)
+        if (c.upsample_kernel_sizes[i] != 2 * c.upsample_rates[i])
+            return fail(ctx, SVB_ERR_UNSUPPORTED, "upsample kernel size must be 2x the rate (polyphase 2-tap form)");
+    if ((c.upsample_initial_channel >> c.n_upsamples) < 1 || (c.hidden_channels % 8) || (c.inter_channels % 16))
+        return fail(ctx, SVB_ERR_UNSUPPORTED, "channel counts must be multiples of 8");
+    TMap m;
+    for (int i = 0; i < n_tensors; ++i)
+        if (tensors[i].name && tensors[i].data) m[tensors[i].name] = &tensors[i];
+    ctx->cfg = c;
+    ctx->hop = 1;
+    for (int i = 0; i < c.n_upsamples; ++i) ctx->hop *= c.upsample_rates[i];
+    const int H = c.hidden_channels, C = c.inter_channels, G = c.gin_channels, L = c.flow_wn_layers, half = C / 2;
+    int rc;
+    HostT w, b;
+
+    // ---- flow
+    ctx->flow.assign(c.n_flows, FlowLayer());
+    for (int fl = 0; fl < c.n_flows; ++fl) {
+        FlowLayer& F = ctx->flow[fl];
+        const std::string p = "flow.flows." + std::to_string(2 * fl) + ".";
+        const bool odd = (fl & 1) != 0;           // Flip folded into channel order
+        F.in_c0 = odd ? half : 0;
+        F.out_c0 = odd ? 0 : half;
+        if ((rc = get_tensor(ctx, m, p + "pre.weight", {H, half, 1}, w))) return rc;
+        if ((rc = get_tensor(ctx, m, p + "pre.bias", {H}, b))) return rc;
+        if ((rc = make_conv(ctx, w.v, b.v, H, half, 1, odd, false, F.pre))) return rc;
+        if ((rc = get_tensor(ctx, m, p + "post.weight", {half, H, 1}, w))) return rc;
+        if ((rc = get_tensor(ctx, m, p + "post.bias", {half}, b))) return rc;
+        if ((rc = make_conv(ctx, w.v, b.v, half, H, 1, false, odd, F.post))) return rc;
+        if ((rc = folded(ctx, m, p + "enc.cond_layer", {2 * H * L, G, 1}, w))) return rc;
+        if ((rc = get_tensor(ctx, m, p + "enc.cond_layer.bias", {2 * H * L}, b))) return rc;
+        if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&F.cond_w_nat))) return rc;
+        if ((rc = make_conv(ctx, w.v, b.v, 2 * H * L, G, 1, false, false, F.cond))) return rc;
+        F.in_layers.assign(L, ConvW());
+        F.res_skip.assign(L, ConvW());
+        for (int i = 0; i < L; ++i) {
+            const std::string q = p + "enc.in_layers." + std::to_string(i);
+            if ((rc = folded(ctx, m, q, {2 * H, H, c.flow_kernel_size}, w))) return rc;
+            if ((rc = get_tensor(ctx, m, q + ".bias", {2 * H}, b))) return rc;
+            if ((rc = make_conv(ctx, w.v, b.v, 2 * H, H, c.flow_kernel_size, false, false, F.in_layers[i]))) return rc;
+            const std::string r = p + "enc.res_skip_layers." + std::to_string(i);
+            const int co = (i < L - 1) ? 2 * H : H;
+            if ((rc = folded(ctx, m, r, {co, H, 1}, w))) return rc;
+            if ((rc = get_tensor(ctx, m, r + ".bias", {co}, b))) return rc;
+            if (co == 2 * H) {
+                // pack the residual half and the skip half as two consecutive [H][1][H] blocks
+                std::vector<float> pk((size_t)2 * H * H), bb(2 * H);
+                for (int hsel = 0; hsel < 2; ++hsel)
+                    for (int ci = 0; ci < H; ++ci)
+                        for (int o = 0; o < H; ++o)
+                            pk[(size_t)hsel * H * H + (size_t)ci * H + o] = w.v[(size_t)(hsel * H + o) * H + ci];
+                for (int o = 0; o < 2 * H; ++o) bb[o] = b.v[o];
+                ConvW& R = F.res_skip[i];
+                R.Cin = H; R.Cout = 2 * H; R.k = 1;
+                if ((rc = upload(ctx, pk.data(), pk.size() * sizeof(float), (void**)&R.w))) return rc;
+                if ((rc = upload(ctx, bb.data(), bb.size() * sizeof(float), (void**)&R.b))) return rc;
+            } else {
+                if ((rc = make_conv(ctx, w.v, b.v, H, H, 1, false, false, F.res_skip[i]))) return rc;
+            }
+        }
+    }
+
+    // ---- generator
+    const int U = c.upsample_initial_channel;
+    if ((rc = folded(ctx, m, "dec.conv_pre", {U, C, 7}, w))) return rc;
+    if ((rc = get_tensor(ctx, m, "dec.conv_pre.bias", {U}, b))) return rc;
+    if ((rc = make_conv(ctx, w.v, b.v, U, C, 7, false, false, ctx->conv_pre))) return rc;
+    if ((rc = get_tensor(ctx, m, "dec.cond.weight", {U, G, 1}, w))) return rc;
+    if ((rc = get_tensor(ctx, m, "dec.cond.bias", {U}, b))) return rc;
+    if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&ctx->dcond_w_nat))) return rc;
+    if ((rc = make_conv(ctx, w.v, b.v, U, G, 1, false, false, ctx->dcond))) return rc;
+    ctx->dcond_b = ctx->dcond.b;
+    ctx->stages.assign(c.n_upsamples, Stage());
+    for (int i = 0; i < c.n_upsamples; ++i) {
+        Stage& S = ctx->stages[i];
+        S.Cin = U >> i; S.Cout = U >> (i + 1); S.s = c.upsample_rates[i]; S.k = c.upsample_kernel_sizes[i];
+        S.p = (S.k - S.s + 1) / 2;
+        const std::string p = "dec.ups." + std::to_string(i);
+        if ((rc = folded(ctx, m, p, {S.Cin, S.Cout, S.k}, w))) return rc;    // ConvTranspose1d: [Cin][Cout][k]
+        if ((rc = get_tensor(ctx, m, p + ".bias", {S.Cout}, b))) return rc;
+        std::vector<float> pk((size_t)S.s * S.Cin * 2 * S.Cout);
+        for (int ph = 0; ph < S.s; ++ph)
+            for (int ci = 0; ci < S.Cin; ++ci)
+                for (int co = 0; co < S.Cout; ++co) {
+                    const size_t base = ((size_t)ph * S.Cin + ci) * 2 * S.Cout;
+                    pk[base + 0 * S.Cout + co] = w.v[((size_t)ci * S.Cout + co) * S.k + ph + S.s];  // tap 0 <-> x[i0-1]
+                    pk[base + 1 * S.Cout + co] = w.v[((size_t)ci * S.Cout + co) * S.k + ph];        // tap 1 <-> x[i0]
+                }
+        if ((rc = upload(ctx, pk.data(), pk.size() * sizeof(float), (void**)&S.up_w))) return rc;
+        if ((rc = upload(ctx, b.v.data(), b.v.size() * sizeof(float), (void**)&S.up_b))) return rc;
+        // noise conv
+        int stride = 1;
+        for (int q = i + 1; q < c.n_upsamples; ++q) stride *= c.upsample_rates[q];
+        const std::string np_ = "dec.noise_convs." + std::to_string(i);
+        if (i + 1 < c.n_upsamples) { S.noise_K = 2 * stride; S.noise_s = stride; S.noise_p = (stride + 1) / 2; }
+        else { S.noise_K = 1; S.noise_s = 1; S.noise_p = 0; }
+        if ((rc = get_tensor(ctx, m, np_ + ".weight", {S.Cout, 1, S.noise_K}, w))) return rc;
+        if ((rc = get_tensor(ctx, m, np_ + ".bias", {S.Cout}, b))) return rc;
+        if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&S.noise_w))) return rc;
+        if ((rc = upload(ctx, b.v.data(), b.v.size() * sizeof(float), (void**)&S.noise_b))) return rc;
+        S.c1.assign(9, ConvW());
+        S.c2.assign(9, ConvW());
+        for (int j = 0; j < 3; ++j) {
+            const int k = c.resblock_kernel_sizes[j];
+            const std::string r = "dec.resblocks." + std::to_string(i * 3 + j) + ".";
+            for (int d = 0; d < 3; ++d) {
+                if ((rc = folded(ctx, m, r + "convs1." + std::to_string(d), {S.Cout, S.Cout, k}, w))) return rc;
+                if ((rc = get_tensor(ctx, m, r + "convs1." + std::to_string(d) + ".bias", {S.Cout}, b))) return rc;
+                if ((rc = make_conv(ctx, w.v, b.v, S.Cout, S.Cout, k, false, false, S.c1[j * 3 + d]))) return rc;
+                if ((rc = folded(ctx, m, r + "convs2." + std::to_string(d), {S.Cout, S.Cout, k}, w))) return rc;
+                if ((rc = get_tensor(ctx, m, r + "convs2." + std::to_string(d) + ".bias", {S.Cout}, b))) return rc;
+                if ((rc = make_conv(ctx, w.v, b.v, S.Cout, S.Cout, k, false, false, S.c2[j * 3 + d]))) return rc;
+            }
+        }
+    }
+    ctx->post_C = U >> c.n_upsamples;
+    if ((rc = folded(ctx, m, "dec.conv_post", {1, ctx->post_C, 7}, w))) return rc;
+    if ((rc = get_tensor(ctx, m, "dec.conv_post.bias", {1}, b))) return rc;
+    ctx->post_b = b.v[0];
+    if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&ctx->post_w))) return rc;
+    if ((rc = get_tensor(ctx, m, "dec.m_source.l_linear.weight", {1, c.n_harmonics}, w))) return rc;
+    if ((rc = get_tensor(ctx, m, "dec.m_source.l_linear.bias", {1}, b))) return rc;
+    ctx->lin_b = b.v[0];
+    if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&ctx->lin_w))) return rc;
+    ctx->loaded = true;
+    return SVB_OK;
+}
+
+size_t svb_workspace_bytes(const svb_ctx* ctx, int B, int T) {
+    if (!ctx || !ctx->loaded || B < 1 || T < 1) return 0;
+    return plan_ws(ctx->cfg, B, T, T).total;   // sized for time-varying g (the larger case)
+}
+
+#define PRECHECK()                                                                     \
+    if (!ctx) return SVB_ERR_INVALID_ARG;                                              \
+    if (!ctx->loaded) return fail(ctx, SVB_ERR_NOT_LOADED, "svb_load_weights first");  \
+    if (B < 1 || T < 1) return fail(ctx, SVB_ERR_INVALID_ARG, "B and T must be >= 1"); \
+    CU(cudaSetDevice(ctx->device));
+
+int svb_flow_reverse(svb_ctx* ctx, const float* z_p, const float* g, int gT, const int32_t* lengths,
+                     float* z_out, int B, int T, void* ws, size_t ws_bytes, void* stream) {
+    PRECHECK();
+    if (!z_p || !g || !z_out || (gT != 1 && gT != T)) return fail(ctx, SVB_ERR_INVALID_ARG, "bad flow arguments");
+    WsPlan pl = plan_ws(ctx->cfg, B, T, gT);
+    char* base;
+    int rc = ensure_ws(ctx, pl.total, ws, ws_bytes, &base);
+    if (rc) return rc;
+    return run_flow(ctx, z_p, g, gT, lengths, z_out, B, T, base, pl, (cudaStream_t)stream);
+}
+
+int svb_nsf_source(svb_ctx* ctx, const float* f0, const float* rand_ini, const float* noise,
+                   float* har, int B, int T, void* stream) {
+    PRECHECK();
+    if (!f0 || !rand_ini || !har) return fail(ctx, SVB_ERR_INVALID_ARG, "bad source arguments");
+    WsPlan pl = plan_ws(ctx->cfg, B, T, 1);
+    char* base;
+    int rc = ensure_ws(ctx, pl.total, nullptr, 0, &base);
+    if (rc) return rc;
+    launch_nsf_source(f0, rand_ini, noise, ctx->lin_w, ctx->lin_b, reinterpret_cast<double*>(base + pl.off_phase), har,
+                      B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, (cudaStream_t)stream);
+    return check_launch(ctx, "nsf_source");
+}
+
+int svb_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const float* har,
+                  float* wav, int B, int T, void* ws, size_t ws_bytes, void* stream) {
+    PRECHECK();
+    if (!z || !g || !har || !wav || (gT != 1 && gT != T)) return fail(ctx, SVB_ERR_INVALID_ARG, "bad generator arguments");
+    WsPlan pl = plan_ws(ctx->cfg, B, T, gT);
+    char* base;
+    int rc = ensure_ws(ctx, pl.total, ws, ws_bytes, &base);
+    if (rc) return rc;
+    return run_generator(ctx, z, g, gT, har, wav, B, T, base, pl, (cudaStream_t)stream);
+}
+
+int svb_infer_tail(svb_ctx* ctx, const float* z_p, const float* g, int gT, const int32_t* lengths,
+                   const float* f0, const float* rand_ini, const float* noise,
+                   float* wav, int B, int T, void* ws, size_t ws_bytes, void* stream) {
+    PRECHECK();
+    if (!z_p || !g || !f0 || !rand_ini || !wav || (gT != 1 && gT != T)) return fail(ctx, SVB_ERR_INVALID_ARG, "bad tail arguments");
+    WsPlan pl = plan_ws(ctx->cfg, B, T, gT);
+    char* base;
+    int rc = ensure_ws(ctx, pl.total, ws, ws_bytes, &base);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* z = reinterpret_cast<float*>(base + pl.off_z);
+    float* har = reinterpret_cast<float*>(base + pl.off_har);
+    if ((rc = run_flow(ctx, z_p, g, gT, lengths, z, B, T, base, pl, st))) return rc;
+    if ((rc = dbg_keep(ctx, "z", z, (size_t)B * ctx->cfg.inter_channels * T, st))) return rc;
+    launch_nsf_source(f0, rand_ini, noise, ctx->lin_w, ctx->lin_b, reinterpret_cast<double*>(base + pl.off_phase), har,
+                      B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, st);
+    if ((rc = dbg_keep(ctx, "har", har, (size_t)B * T * ctx->hop, st))) return rc;
+    return run_generator(ctx, z, g, gT, har, wav, B, T, base, pl, st);
+}
+
+int svb_infer_tail_host(svb_ctx* ctx, const float* z_p, const float* g, int gT,
+                        const float* f0, const float* rand_ini, const float* noise,
+                        float* wav, int B, int T) {
+    PRECHECK();
+    if (!z_p || !g || !f0 || !rand_ini || !wav || (gT != 1 && gT != T)) return fail(ctx, SVB_ERR_INVALID_ARG, "bad tail arguments");
+    const svb_model_cfg& c = ctx->cfg;
+    const size_t N = (size_t)T * ctx->hop;
+    const size_t n_zp = (size_t)B * c.inter_channels * T, n_g = (size_t)B * c.gin_channels * gT, n_f0 = (size_t)B * T,
+                 n_ri = (size_t)B * c.n_harmonics, n_nz = noise ? (size_t)B * N * c.n_harmonics : 0, n_wav = (size_t)B * N;
+    const size_t need = (n_zp + n_g + n_f0 + n_ri + n_nz + n_wav + 64) * sizeof(float);
+    if (ctx->host_io.bytes < need) {
+        if (ctx->host_io.p) CU(cudaFree(ctx->host_io.p));
+        ctx->host_io.p = nullptr; ctx->host_io.bytes = 0;
+        CU(cudaMalloc(&ctx->host_io.p, need));
+        ctx->host_io.bytes = need;
+    }
+    float* d = static_cast<float*>(ctx->host_io.p);
+    float* d_zp = d; d += n_zp;
+    float* d_g = d; d += n_g;
+    float* d_f0 = d; d += n_f0;
+    float* d_ri = d; d += n_ri;
+    float* d_nz = d; d += n_nz;
+    float* d_wav = d;
+    cudaStream_t st = 0;
+    CU(cudaMemcpyAsync(d_zp, z_p, n_zp * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_g, g, n_g * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_f0, f0, n_f0 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_ri, rand_ini, n_ri * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (noise) CU(cudaMemcpyAsync(d_nz, noise, n_nz * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = svb_infer_tail(ctx, d_zp, d_g, gT, nullptr, d_f0, d_ri, noise ? d_nz : nullptr, d_wav, B, T, nullptr, 0, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(wav, d_wav, n_wav * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// Internal launch interface between the C-ABI host code (api.cu) and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace svb {
+
+// Generic 1-D convolution descriptor for the fp32 FFMA kernel (kernels_f32.cu).
+//   acc[b,co,t] = sum_{ci,tap} w[ci][tap][co] * act(x[b, x_c0+ci, t + tap*dil - pad_left])
+//   n = t*ostride + ooff  (polyphase transposed convs write with a stride)
+//   y[b, y_c0+co, n] = mask * maybe_tanh( alpha*(acc + bias[co] + bias_b[b,co] + res[b,res_c0+co,n]) + beta*y_old )
+struct ConvF32 {
+    const float* x = nullptr; int x_ctot = 0, x_c0 = 0, Cin = 0, Tin = 0;
+    const float* w = nullptr;           // [n_phase][Cin][k][Cout]
+    const float* bias = nullptr;        // [Cout] or null
+    const float* bias_b = nullptr;      // per-batch bias, bias_b[b*bias_b_stride + bias_b_off + co] or null
+    int bias_b_stride = 0, bias_b_off = 0;
+    const float* bias_t = nullptr;      // time-varying bias [B, bias_t_ctot, Ty] (speaker-mix g) or null
+    int bias_t_ctot = 0, bias_t_c0 = 0;
+    const float* res = nullptr; int res_ctot = 0, res_c0 = 0;
+    float* y = nullptr; int y_ctot = 0, y_c0 = 0, Ty = 0;
+    int Cout = 0, k = 1, dil = 1, pad_left = 0;
+    int n_out = 0, ostride = 1, ooff = 0;
+    int n_phase = 1; long long w_phase_stride = 0;   // phase p: w += p*w_phase_stride, ooff += p
+    int in_act = 0; float in_slope = 0.f;            // leaky-relu on the input
+    float alpha = 1.f, beta = 0.f;
+    int out_tanh = 0;
+    const int32_t* lengths = nullptr;                // mask n < lengths[b]
+    int B = 1;
+};
+
+void launch_conv_f32(const ConvF32& a, cudaStream_t st);
+
+// acts[b,c,t] = tanh(a[b,c,t]) * sigmoid(a[b,c+H,t])   (commons.py:129-136 after the conditioning add)
+void launch_gate(const float* a, float* acts, int B, int H, int T, cudaStream_t st);
+
+// out[b,co] = bias[co] + sum_ci W[co][ci] * g[b,ci]     (1x1 conv on a length-1 conditioning vector)
+void launch_gemv(const float* W, const float* bias, const float* g, float* out, int B, int Cout, int Cin, cudaStream_t st);
+
+// y[b,co,t] += bias[co] + sum_kk w[co][kk] * har[b, t*s - p + kk]   (vdecoder/hifigan/models.py:343-348,380-382)
+void launch_noise_conv_add(const float* har, const float* w, const float* bias, float* y,
+                           int B, int Cout, int Tout, int N, int K, int s, int p, cudaStream_t st);
+
+// wav[b,n] = tanh(bias + sum_{ci,k} w[ci][k] * lrelu(x[b,ci,n+k-pad], slope))   (conv_post, :390-392)
+void launch_conv_post(const float* x, const float* w, float bias, float* wav, int B, int C, int N, int K, float slope, cudaStream_t st);
+
+// NSF harmonic source (vdecoder/hifigan/models.py:250-271,307-320) in the closed form of SURVEY §9.7.
+void launch_nsf_source(const float* f0, const float* rand_ini, const float* noise, const float* lin_w, float lin_b,
+                       double* phase_ws /*[B,T,H]*/, float* har, int B, int T, int hop, int n_harm, float sr, cudaStream_t st);
+
+// ---- tensor-core path (kernels_tc.cu) --------------------------------------------------------------
+// One ResBlock "pair": y = x + conv2(lrelu(conv1(lrelu(x)) + b1)) + b2 with out = alpha*y + beta*out_old.
+struct PairTC {
+    const float* x = nullptr;      // [B,C,T] fp32 residual stream in
+    float* out = nullptr;          // [B,C,T]
+    const void* w1 = nullptr;      // packed fp16 tap images (see pack_tc_weights in api.cu)
+    const void* w2 = nullptr;
+    const float* b1 = nullptr; const float* b2 = nullptr;
+    int B = 1, C = 0, T = 0, k = 3, dil = 1;
+    float alpha = 1.f, beta = 0.f;
+};
+int launch_pair_tc(const PairTC& a, cudaStream_t st);   // returns 0 or a negative status
+size_t tc_weight_image_bytes(int C, int k);
+// host-side: build the swizzled fp16 image for one conv (w_folded is [Cout][Cin][k] fp32)
+void tc_pack_weight_image(const float* w_folded, int C, int k, void* dst_host);
+
+int64_t& launch_counter();
+
+}  // namespace svb

@@ -1,0 +1,350 @@
+// fp32 FFMA kernels for sm_100a: the strict-parity path (SVB_PREC_FP32) and the small bandwidth-bound
+// pieces shared with the tensor-core path (NSF source, noise convs, conv_post, gate, conditioning GEMV).
+//
+// Compiled WITHOUT fast-math: the NSF source reproduces the reference's fp32 `(f0*h/sr) % 1`
+// bit-for-bit (vdecoder/hifigan/models.py:144) and errors there are amplified by up to 4.4e5 samples.
+#include "kernels.h"
+#include <math.h>
+
+namespace svb {
+
+int64_t& launch_counter() { static int64_t c = 0; return c; }
+
+// =====================================================================================================
+// Generic 1-D convolution, fp32.  Block = 256 threads computes TCO output channels x TT time steps.
+//   threads: (cg = tid / TX) selects 8 output channels, (tx = tid % TX) selects 4 time steps tx + TX*j.
+//   Shared memory per Cin-chunk of CK channels: x tile [CK][TT+halo] (activation applied while loading)
+//   and weight tile [CK][k][TCO]; lanes read consecutive x (conflict-free), weights are warp-broadcast.
+// =====================================================================================================
+constexpr int CONV_THREADS = 256;
+constexpr int CONV_CK = 8;
+
+template <int TCO>
+__global__ void __launch_bounds__(CONV_THREADS) conv_f32_kernel(const ConvF32 a) {
+    constexpr int G = TCO / 8;                 // channel groups
+    constexpr int TX = CONV_THREADS / G;       // threads along time
+    constexpr int TT = 4 * TX;                 // time tile
+    extern __shared__ float smem[];
+    const int halo = (a.k - 1) * a.dil;
+    const int xs_pitch = TT + halo;
+    float* xs = smem;                                   // [CK][xs_pitch]
+    float* ws = smem + CONV_CK * xs_pitch;              // [CK][k][TCO]
+
+    const int tid = threadIdx.x;
+    const int cg = tid / TX, tx = tid % TX;
+    const int n_cot = (a.Cout + TCO - 1) / TCO;
+    const int phase = blockIdx.y / n_cot;
+    const int co0 = (blockIdx.y % n_cot) * TCO;
+    const int t0 = blockIdx.x * TT;
+    const int b = blockIdx.z;
+    const float* __restrict__ w = a.w + (long long)phase * a.w_phase_stride;
+    const float* __restrict__ xb = a.x + ((long long)b * a.x_ctot + a.x_c0) * (long long)a.Tin;
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int ci0 = 0; ci0 < a.Cin; ci0 += CONV_CK) {
+        // ---- stage x chunk
+        for (int idx = tid; idx < CONV_CK * xs_pitch; idx += CONV_THREADS) {
+            int c = idx / xs_pitch, j = idx - c * xs_pitch;
+            int ti = t0 + j - a.pad_left;
+            float v = 0.f;
+            if (ci0 + c < a.Cin && ti >= 0 && ti < a.Tin) {
+                v = __ldg(xb + (long long)(ci0 + c) * a.Tin + ti);
+                if (a.in_act) v = v > 0.f ? v : v * a.in_slope;
+            }
+            xs[idx] = v;
+        }
+        // ---- stage weight chunk
+        const int wn = CONV_CK * a.k * TCO;
+        for (int idx = tid; idx < wn; idx += CONV_THREADS) {
+            int co = idx % TCO;
+            int rest = idx / TCO;              // c*k + tap
+            int c = rest / a.k;
+            float v = 0.f;
+            if (ci0 + c < a.Cin && co0 + co < a.Cout)
+                v = __ldg(w + ((long long)(ci0 * a.k + rest)) * a.Cout + co0 + co);
+            ws[idx] = v;
+        }
+        __syncthreads();
+        for (int c = 0; c < CONV_CK; ++c) {
+            const float* xrow = xs + c * xs_pitch + tx;
+            const float* wrow = ws + (c * a.k) * TCO + cg * 8;
+            for (int tap = 0; tap < a.k; ++tap) {
+                float xv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xv[j] = xrow[TX * j + tap * a.dil];
+                const float4 w0 = *reinterpret_cast<const float4*>(wrow + tap * TCO);
+                const float4 w1 = *reinterpret_cast<const float4*>(wrow + tap * TCO + 4);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue
+    const int ooff = a.ooff + phase;
+    const int len = a.lengths ? a.lengths[b] : 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int co = co0 + cg * 8 + i;
+        if (co >= a.Cout) continue;
+        float bsum = a.bias ? __ldg(a.bias + co) : 0.f;
+        if (a.bias_b) bsum += __ldg(a.bias_b + (long long)b * a.bias_b_stride + a.bias_b_off + co);
+        float* yrow = a.y + ((long long)b * a.y_ctot + a.y_c0 + co) * (long long)a.Ty;
+        const float* rrow = a.res ? a.res + ((long long)b * a.res_ctot + a.res_c0 + co) * (long long)a.Ty : nullptr;
+        const float* btrow = a.bias_t ? a.bias_t + ((long long)b * a.bias_t_ctot + a.bias_t_c0 + co) * (long long)a.Ty : nullptr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int t = t0 + tx + TX * j;
+            if (t >= a.n_out) continue;
+            const long long n = (long long)t * a.ostride + ooff;
+            if (n < 0 || n >= a.Ty) continue;
+            float v = acc[i][j] + bsum;
+            if (btrow) v += __ldg(btrow + n);
+            if (rrow) v += __ldg(rrow + n);
+            v *= a.alpha;
+            if (a.beta != 0.f) v = fmaf(a.beta, yrow[n], v);
+            if (a.out_tanh) v = tanhf(v);
+            if (n >= len) v = 0.f;
+            yrow[n] = v;
+        }
+    }
+}
+
+template <int TCO>
+static void launch_conv_t(const ConvF32& a, cudaStream_t st) {
+    constexpr int G = TCO / 8, TX = CONV_THREADS / G, TT = 4 * TX;
+    const int halo = (a.k - 1) * a.dil;
+    size_t smem = sizeof(float) * (size_t)(CONV_CK * (TT + halo) + CONV_CK * a.k * TCO);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(conv_f32_kernel<TCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_set = true;
+    }
+    dim3 grid((a.n_out + TT - 1) / TT, ((a.Cout + TCO - 1) / TCO) * a.n_phase, a.B);
+    conv_f32_kernel<TCO><<<grid, CONV_THREADS, smem, st>>>(a);
+    launch_counter()++;
+}
+
+void launch_conv_f32(const ConvF32& a, cudaStream_t st) {
+    if (a.Cout >= 64) launch_conv_t<64>(a, st);
+    else if (a.Cout >= 32) launch_conv_t<32>(a, st);
+    else launch_conv_t<16>(a, st);
+}
+
+// =====================================================================================================
+// WN gate (modules/commons.py:129-136): acts = tanh(a[:, :H]) * sigmoid(a[:, H:])
+// =====================================================================================================
+__global__ void gate_kernel(const float* __restrict__ a, float* __restrict__ acts, int H, int T, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int t = (int)(i % T);
+    long long r = i / T;
+    int c = (int)(r % H);
+    long long b = r / H;
+    const float* base = a + (b * 2 * H) * (long long)T;
+    float ta = base[(long long)c * T + t];
+    float sa = base[(long long)(c + H) * T + t];
+    acts[i] = tanhf(ta) * (1.f / (1.f + expf(-sa)));
+}
+
+void launch_gate(const float* a, float* acts, int B, int H, int T, cudaStream_t st) {
+    long long total = (long long)B * H * T;
+    int threads = 256;
+    long long blocks = (total + threads - 1) / threads;
+    gate_kernel<<<(unsigned)blocks, threads, 0, st>>>(a, acts, H, T, total);
+    launch_counter()++;
+}
+
+// =====================================================================================================
+// Conditioning GEMV: out[b,co] = bias[co] + W[co,:] . g[b,:]   (one warp per output)
+// =====================================================================================================
+__global__ void gemv_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ g,
+                            float* __restrict__ out, int Cout, int Cin, int total) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= total) return;
+    int b = warp / Cout, co = warp % Cout;
+    const float* wr = W + (long long)co * Cin;
+    const float* gr = g + (long long)b * Cin;
+    float s = 0.f;
+    for (int i = lane; i < Cin; i += 32) s = fmaf(wr[i], gr[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[warp] = s + (bias ? bias[co] : 0.f);
+}
+
+void launch_gemv(const float* W, const float* bias, const float* g, float* out, int B, int Cout, int Cin, cudaStream_t st) {
+    int total = B * Cout;
+    int threads = 256;
+    int blocks = (total * 32 + threads - 1) / threads;
+    gemv_kernel<<<blocks, threads, 0, st>>>(W, bias, g, out, Cout, Cin, total);
+    launch_counter()++;
+}
+
+// =====================================================================================================
+// noise_convs[i]: strided analysis filter of the 1-channel excitation, accumulated into the stage input.
+// Block: 128 output steps x all channels.  The excitation window is staged as rows of `s` samples with
+// an odd pitch (s+1) so that lanes (consecutive t) hit distinct banks.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) noise_conv_add_kernel(const float* __restrict__ har, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ y,
+                                                             int Cout, int Tout, int N, int K, int s, int p) {
+    extern __shared__ float sm[];
+    const int TT = 128;
+    const int pitch = s + 1;
+    float* hs = sm;                          // [(TT+1)][pitch]  row r = har[(t0+r)*s - p .. +s)
+    float* wsm = sm + (TT + 1) * pitch;      // [Cout][K]
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * TT;
+    const float* hb = har + (long long)b * N;
+    const int rows = (K > 1) ? TT + 1 : TT;
+    for (int idx = threadIdx.x; idx < rows * s; idx += blockDim.x) {
+        int r = idx / s, c = idx - r * s;
+        long long n = (long long)(t0 + r) * s - p + c;
+        hs[r * pitch + c] = (n >= 0 && n < N) ? hb[n] : 0.f;
+    }
+    for (int idx = threadIdx.x; idx < Cout * K; idx += blockDim.x) wsm[idx] = w[idx];
+    __syncthreads();
+    const int tx = threadIdx.x % TT, cy = threadIdx.x / TT;
+    const int t = t0 + tx;
+    if (t >= Tout) return;
+    for (int co = cy; co < Cout; co += blockDim.x / TT) {
+        float accv = bias[co];
+        const float* wr = wsm + co * K;
+        for (int kk = 0; kk < K; ++kk) {
+            int r = tx + kk / s, c = kk % s;
+            accv = fmaf(wr[kk], hs[r * pitch + c], accv);
+        }
+        y[((long long)b * Cout + co) * Tout + t] += accv;
+    }
+}
+
+void launch_noise_conv_add(const float* har, const float* w, const float* bias, float* y,
+                           int B, int Cout, int Tout, int N, int K, int s, int p, cudaStream_t st) {
+    const int TT = 128;
+    size_t smem = sizeof(float) * ((size_t)(TT + 1) * (s + 1) + (size_t)Cout * K);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(noise_conv_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    dim3 grid((Tout + TT - 1) / TT, B);
+    noise_conv_add_kernel<<<grid, 256, smem, st>>>(har, w, bias, y, Cout, Tout, N, K, s, p);
+    launch_counter()++;
+}
+
+// =====================================================================================================
+// conv_post: leaky_relu(slope) -> Conv1d(C->1, K, pad (K-1)/2) -> tanh
+// =====================================================================================================
+__global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w, float bias,
+                                                        float* __restrict__ wav, int C, int N, int K, float slope) {
+    extern __shared__ float sm[];
+    const int TT = 256;
+    const int pad = (K - 1) / 2;
+    const int pitch = TT + K - 1;
+    float* xs = sm;               // [C][pitch]
+    float* wsm = sm + C * pitch;  // [C][K]
+    const int b = blockIdx.y, n0 = blockIdx.x * TT;
+    const float* xb = x + (long long)b * C * N;
+    for (int idx = threadIdx.x; idx < C * pitch; idx += blockDim.x) {
+        int c = idx / pitch, j = idx - c * pitch;
+        int n = n0 + j - pad;
+        float v = (n >= 0 && n < N) ? xb[(long long)c * N + n] : 0.f;
+        xs[idx] = v > 0.f ? v : v * slope;
+    }
+    for (int idx = threadIdx.x; idx < C * K; idx += blockDim.x) wsm[idx] = w[idx];
+    __syncthreads();
+    int n = n0 + threadIdx.x;
+    if (n >= N) return;
+    float acc = bias;
+    for (int c = 0; c < C; ++c)
+        for (int k = 0; k < K; ++k) acc = fmaf(wsm[c * K + k], xs[c * pitch + threadIdx.x + k], acc);
+    wav[(long long)b * N + n] = tanhf(acc);
+}
+
+void launch_conv_post(const float* x, const float* w, float bias, float* wav, int B, int C, int N, int K, float slope, cudaStream_t st) {
+    const int TT = 256;
+    size_t smem = sizeof(float) * ((size_t)C * (TT + K - 1) + (size_t)C * K);
+    dim3 grid((N + TT - 1) / TT, B);
+    conv_post_kernel<<<grid, 256, smem, st>>>(x, w, bias, wav, C, N, K, slope);
+    launch_counter()++;
+}
+
+// =====================================================================================================
+// NSF source.  f0 is constant inside a hop (nn.Upsample nearest, vdecoder/hifigan/models.py:330,369), so the
+// reference's doubly-wrapped cumsum over N samples (:160-166) collapses to
+//     phase[b, hop*F+k, h] = rand_ini[b,h] + sum_{f<F} hop*r[b,f,h] + (k+1)*r[b,F,h]   (mod 1)
+// with r = ((f0*(h+1))/sr) % 1 evaluated in fp32 exactly as :144 does, then promoted to fp64.
+// Only the T-long prefix sum is serial (kernel 1, fp64); kernel 2 is one thread per output sample.
+// =====================================================================================================
+__device__ __forceinline__ float rad_value(float f0, int h, float sr) {
+    float fn = __fmul_rn(f0, (float)(h + 1));
+    float q = __fdiv_rn(fn, sr);
+    return fmodf(q, 1.0f);
+}
+
+__global__ void nsf_phase_kernel(const float* __restrict__ f0, const float* __restrict__ rand_ini, double* __restrict__ phase,
+                                 int B, int T, int H, int hop, float sr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * H) return;
+    int b = i / H, h = i % H;
+    double acc = (h == 0) ? 0.0 : (double)rand_ini[b * H + h];
+    for (int t = 0; t < T; ++t) {
+        phase[((long long)b * T + t) * H + h] = acc;
+        double r = (double)rad_value(f0[(long long)b * T + t], h, sr);
+        acc += r * (double)hop;
+        acc -= floor(acc);
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(256) nsf_source_kernel(const float* __restrict__ f0, const float* __restrict__ noise,
+                                                         const double* __restrict__ phase, const float* __restrict__ lin_w, float lin_b,
+                                                         float* __restrict__ har, int T, int hop, float sr, long long N) {
+    const int b = blockIdx.y;
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int F = (int)(n / hop);
+    const int k = (int)(n - (long long)F * hop);
+    const float f = f0[(long long)b * T + F];
+    const float uv = f > 0.f ? 1.f : 0.f;
+    const float amp = uv * 0.003f + (1.f - uv) * (0.1f / 3.f);
+    const double* ph0 = phase + ((long long)b * T + F) * H;
+    const float* nz = noise ? noise + ((long long)b * N + n) * H : nullptr;
+    float acc = lin_b;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        double r = (double)rad_value(f, h, sr);
+        double ph = ph0[h] + (double)(k + 1) * r;
+        ph -= floor(ph);
+        float s = sinpif(2.0f * (float)ph) * 0.1f;
+        float v = s * uv + (nz ? amp * nz[h] : 0.f);
+        acc = fmaf(lin_w[h], v, acc);
+    }
+    har[(long long)b * N + n] = tanhf(acc);
+}
+
+void launch_nsf_source(const float* f0, const float* rand_ini, const float* noise, const float* lin_w, float lin_b,
+                       double* phase_ws, float* har, int B, int T, int hop, int n_harm, float sr, cudaStream_t st) {
+    int total = B * n_harm;
+    nsf_phase_kernel<<<(total + 63) / 64, 64, 0, st>>>(f0, rand_ini, phase_ws, B, T, n_harm, hop, sr);
+    launch_counter()++;
+    long long N = (long long)T * hop;
+    dim3 grid((unsigned)((N + 255) / 256), B);
+    if (n_harm == 9)
+        nsf_source_kernel<9><<<grid, 256, 0, st>>>(f0, noise, phase_ws, lin_w, lin_b, har, T, hop, sr, N);
+    else
+        nsf_source_kernel<1><<<grid, 256, 0, st>>>(f0, noise, phase_ws, lin_w, lin_b, har, T, hop, sr, N);
+    launch_counter()++;
+}
+
+}  // namespace svb

@@ -141,7 +141,7 @@ def synth_state_dict(cfg: ModelCfg, seed: int = 20260922, dtype=torch.float32) -
             if ".res_skip_layers." in key or ".in_layers." in key or "cond_layer" in key:
                 gain = 1.0
             if ".resblocks." in key:
-                gain = 0.7                          # keep the 9-deep residual chains O(1)
+                gain = 1.0                          # residual branches carry as much energy as the skip path
             v = randn(shape, gain / math.sqrt(fan))
             sd[key] = v
             # weight_norm: norm over all dims but 0 (also for ConvTranspose1d)
