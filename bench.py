@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py — 44.1 kHz output samples/s of the so-vits-svc waveform-generation hot path on B200.
+
+A step = one ``SynthesizerTrn.infer`` over a batch of synthetic utterances (BASELINE config 2 by default:
+8 x 862 frames = 8 x 10 s; ContentVec-768 features, f0, uv, speaker id; seeded random-init weights).
+  value : whole-job samples/s with inputs resident in HBM when the timed region starts
+  e2e   : same through the public API with pinned HOST inputs (H2D inside the timed region) and the
+          waveform read back to the host every step
+  roofline     : dominant kernel (tcgen05 ResBlock pair), CUDA-event device time inside this script
+  cpu_baseline : the oracle port of the reference path on the host cores (bounded sample)
+``--impl reference`` times that CPU port as the reference arm (the reference is pure Python/PyTorch; there is
+no compiled reference to build, and /root/reference does not exist on the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "44.1 kHz audio samples/sec"
+UNIT = "samples/s"
+FLOP_PER_SAMPLE_DEC = 1269530.0      # generator FLOPs per output sample
+WORKLOAD = "config2: configs/config.json NSF-HiFiGAN 44.1 kHz, ContentVec768 synthetic feats, batch 8 x 10 s (862 frames)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("SVB_BENCH_PRECISION", "tc"), choices=["tc", "fp32"])
+    ap.add_argument("--batch", type=int, default=8, help="utterances per GPU")
+    ap.add_argument("--frames", type=int, default=862)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_rate(cfg, sd, T, runs, warmup, threads):
+    """Oracle port of the reference infer on the host cores, one 10 s utterance (B=1) per step."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import svc_oracle as O
+    from sovits_b200 import synth
+    torch.set_num_threads(threads)
+    c, f0, uv, sid = synth.synth_inputs(cfg, 1, T)
+    noise = synth.draw_noise(1, T, cfg)
+    times = []
+    for i in range(warmup + runs):
+        t0 = time.perf_counter()
+        O.infer(sd, cfg, c, f0, uv, sid, noise, noice_scale=0.4)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    N = T * cfg.hop
+    return N / (sum(times) / len(times)), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    import sovits_b200  # noqa: F401
+    from sovits_b200 import synth
+    from sovits_b200.config import load_config
+    cfg = load_config()
+    sd = synth.synth_state_dict(cfg)
+    cores = os.cpu_count() or 1
+    rate, times = cpu_oracle_rate(cfg, sd, args.frames, args.steps, max(1, min(args.warmup, 1)), cores)
+    ms = 1000.0 * sum(times) / len(times)
+    sample = f"each step = 1 utterance x {args.frames} frames (1/{args.batch} of the batch) on {cores} host threads"
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": args.batch * args.gpus, "frames": args.frames},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    import sovits_b200
+    from sovits_b200 import models, synth
+    from sovits_b200 import dist as sdist
+    from sovits_b200.config import load_config
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    cfg = load_config()
+    B, T = args.batch, args.frames
+    N = T * cfg.hop
+    # ---- weights: rank 0 makes them, one NCCL broadcast (the path's only collective)
+    if world > 1:
+        shapes = synth.param_shapes(cfg)
+        sd = synth.synth_state_dict(cfg) if rank == 0 else None
+        sd = sdist.broadcast_state_dict(sd, shapes, src=0, device=dev)
+    else:
+        sd = synth.synth_state_dict(cfg)
+    with open(sovits_b200.DEFAULT_CONFIG) as f:
+        kw = json.load(f)["model"]
+    net = models.SynthesizerTrn(1025, 20, **kw).eval()
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    net.set_precision(args.precision)
+
+    # ---- inputs: the global batch, sharded by contiguous blocks
+    c, f0, uv, sid = synth.synth_inputs(cfg, B * world, T)
+    lo, hi = sdist.shard_range(B * world, rank, world)
+    host = [t[lo:hi].contiguous().pin_memory() for t in (c, f0, uv, sid)]
+    devin = [t.to(dev) for t in host]
+    out_host = torch.empty((B, 1, N), dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    d2h = out_host.numel() * out_host.element_size()
+
+    def step_dev():
+        return net.infer(devin[0], devin[1], devin[2], g=devin[3], noice_scale=0.4)[0]
+
+    def step_e2e():
+        ins = [t.to(dev, non_blocking=True) for t in host]
+        o = net.infer(ins[0], ins[1], ins[2], g=ins[3], noice_scale=0.4)[0]
+        out_host.copy_(o, non_blocking=True)
+        return o
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    step_e2e()
+    eng = net._b200_engine
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = eng.launch_count
+    ms_dev = timed(step_dev, args.steps)
+    launches = (eng.launch_count - l0)
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- roofline of the dominant kernel: CUDA events around every launch of it, on the launching stream
+    roof, secondary = None, []
+    eng.profile_enable(True)
+    for _ in range(min(args.steps, 3)):
+        step_dev()
+    torch.cuda.synchronize()
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        with open(pk_path) as f:
+            peaks = json.load(f)
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json, sustained bf16==fp16 rate)" if peaks else "fallback"
+    name = "pair_tc" if args.precision == "tc" else "pair_f32"
+    pr = eng.profile_read(name)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(name)
+        except Exception:
+            traffic = None
+    if pr and pr["ms"] > 0:
+        ach = pr["flops"] / (pr["ms"] * 1e-3) / 1e12
+        roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                "traffic": traffic, "launches": pr["count"], "avg_launch_ms": pr["ms"] / pr["count"], "peak_source": peak_src,
+                "hbm_gbs_algorithmic": pr["bytes"] / (pr["ms"] * 1e-3) / 1e9}
+    ps = eng.profile_read("nsf_source")
+    if ps and ps["ms"] > 0:
+        a = ps["bytes"] / (ps["ms"] * 1e-3) / 1e9
+        secondary.append({"kernel": "nsf_source", "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak})
+    for nm in ("flow", "generator"):
+        pp = eng.profile_read(nm)
+        if pp:
+            secondary.append({"kernel": nm, "ms_per_step": pp["ms"] / max(1, pp["count"])})
+    eng.profile_enable(False)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, times = cpu_oracle_rate(cfg, {k: v.cpu() for k, v in sd.items()}, T, runs=2, warmup=1, threads=cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"oracle port of SynthesizerTrn.infer, 1 utterance x {T} frames, 1 warm-up + 2 timed runs ({sum(times):.1f} s)"}
+
+    if rank == 0:
+        total_samples = float(B * world * N)
+        value = total_samples * args.steps / (ms_dev * 1e-3)
+        e2e_v = total_samples * args.steps / (ms_e2e * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16 operands / f32 accumulate (tcgen05)" if args.precision == "tc" else "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": B * world, "frames": T, "samples_per_item": N,
+                           "parallelism": f"dp{world}", "precision": args.precision,
+                           "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
+                           "rtf": value / 44100.0},
+                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_secondary": secondary,
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

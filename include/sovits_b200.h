@@ -134,6 +134,11 @@ SVB_API int64_t svb_launch_count(const svb_ctx* ctx);
  * svb_generator/svb_infer_tail call into dst (device, fp32, n floats); test hook. */
 SVB_API int svb_debug_enable(svb_ctx* ctx, int on);
 SVB_API int svb_debug_fetch(svb_ctx* ctx, const char* what, float* dst, size_t n, void* stream);
+/* CUDA-event timers on the launching stream, per kernel family ("pair_tc","pair_f32","flow","nsf_source",
+ * "generator"): enable, run, then read the summed device time, launch count and algorithmic FLOPs/bytes
+ * (bench.py's roofline).  Re-enabling clears the counters. */
+SVB_API int svb_profile_enable(svb_ctx* ctx, int on);
+SVB_API int svb_profile_read(svb_ctx* ctx, const char* name, double* total_ms, int64_t* count, double* flops, double* bytes);
 SVB_API const char* svb_version(void);
 
 #ifdef __cplusplus

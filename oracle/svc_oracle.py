@@ -75,7 +75,7 @@ def rel_attention(sd, p, x, attn_mask, n_heads, window, dtype):
     qs = q / math.sqrt(dk)
     scores = qs @ k.transpose(-2, -1)                                  # [B,h,L,L]
     ek, ev = W("emb_rel_k")[0], W("emb_rel_v")[0]                       # [2w+1, dk]
-    idx = torch.arange(L)
+    idx = torch.arange(L, device=x.device)
     rel = idx[None, :] - idx[:, None]                                   # j - i
     band = rel.abs() <= window
     ridx = (rel + window).clamp(0, 2 * window)
@@ -86,7 +86,7 @@ def rel_attention(sd, p, x, attn_mask, n_heads, window, dtype):
     pa = F.softmax(scores, dim=-1)
     out = pa @ v
     # relative values: w[b,h,i,r] = p[b,h,i,i+r-window]
-    rw = torch.zeros(B, n_heads, L, 2 * window + 1, dtype=dtype)
+    rw = torch.zeros(B, n_heads, L, 2 * window + 1, dtype=dtype, device=x.device)
     for r in range(2 * window + 1):
         off = r - window
         d = torch.diagonal(pa, offset=off, dim1=2, dim2=3)              # p[i, i+off]
@@ -170,7 +170,7 @@ def nsf_source(sd, f0, rand_ini, har_noise, cfg, dtype):
     sr = float(cfg.sampling_rate)
     upp = cfg.hop
     f0u = torch.repeat_interleave(f0.to(dtype), upp, dim=1)[:, :, None]            # [B,N,1]
-    harm = torch.arange(1, cfg.n_harmonics + 1, dtype=dtype)[None, None, :]
+    harm = torch.arange(1, cfg.n_harmonics + 1, dtype=dtype, device=f0.device)[None, None, :]
     fn = f0u * harm
     rad = (fn / sr) % 1
     ri = rand_ini.to(dtype).clone()
@@ -265,7 +265,7 @@ def generator(sd, z, g, har, cfg, dtype, taps: Optional[dict] = None):
 def prologue(sd, c, f0, uv, sid, cfg, dtype, vol=None):
     """models.py:503-520: mask (all ones), g = emb_g(sid)^T, x = pre(c)*mask + emb_uv(uv)^T (+vol)."""
     B, _, T = c.shape
-    x_mask = torch.ones(B, 1, T, dtype=dtype)
+    x_mask = torch.ones(B, 1, T, dtype=dtype, device=c.device)
     if sid.dim() == 1:
         sid = sid.unsqueeze(0)
     g = sd["emb_g.weight"].to(dtype)[sid].transpose(1, 2)            # [B,gin,1]
@@ -293,7 +293,7 @@ def infer(sd, cfg, c, f0, uv, sid, noise, noice_scale=0.35, dtype=torch.float32,
 def tail(sd, cfg, z_p, g, f0, noise, dtype=torch.float32, taps: Optional[dict] = None):
     """The three CUDA kernels' scope only: flow(reverse) -> NSF source -> generator."""
     B, _, T = z_p.shape
-    x_mask = torch.ones(B, 1, T, dtype=dtype)
+    x_mask = torch.ones(B, 1, T, dtype=dtype, device=z_p.device)
     z = flow_reverse(sd, z_p.to(dtype), x_mask, g.to(dtype), cfg, dtype)
     har = nsf_source(sd, f0, noise["rand_ini"], noise["har_noise"], cfg, dtype)
     if taps is not None:

@@ -74,6 +74,9 @@ struct svb_ctx {
     DevBuf host_io;                // device staging for svb_infer_tail_host
     bool debug = false;
     std::map<std::string, DevBuf> dbg;
+    bool profile = false;
+    struct ProfEntry { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; double flops = 0, bytes = 0; };
+    std::map<std::string, ProfEntry> prof;
     std::string err;
 };
 
@@ -260,6 +263,21 @@ int dbg_keep(svb_ctx* ctx, const std::string& name, const float* src, size_t n, 
     return SVB_OK;
 }
 
+// CUDA-event timers on the launching stream (svb_profile_enable); read back by svb_profile_read.
+struct ProfScope {
+    svb_ctx* c; cudaStream_t st; cudaEvent_t e1 = nullptr; svb_ctx::ProfEntry* ent = nullptr;
+    ProfScope(svb_ctx* c_, const char* name, cudaStream_t st_, double flops, double bytes) : c(c_), st(st_) {
+        if (!c->profile) return;
+        ent = &c->prof[name];
+        cudaEvent_t e0;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        ent->ev.push_back({e0, e1});
+        ent->flops += flops; ent->bytes += bytes;
+    }
+    ~ProfScope() { if (ent) cudaEventRecord(e1, st); }
+};
+
 int check_launch(svb_ctx* ctx, const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, SVB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -404,6 +422,9 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
                 const float alpha = last ? 1.f / nk : 1.f;
                 const float beta = (last && j > 0) ? 1.f : 0.f;
                 bool done = false;
+                const double pair_flops = 2.0 * 2.0 * S.Cout * (double)S.Cout * k * (double)Lout * B;
+                const double pair_bytes = 3.0 * S.Cout * (double)Lout * B * sizeof(float);   // read x (tile + residual) + write out
+                ProfScope ps(ctx, (ctx->precision == SVB_PREC_TC && W1.w_tc) ? "pair_tc" : "pair_f32", st, pair_flops, pair_bytes);
                 if (ctx->precision == SVB_PREC_TC && W1.w_tc && W2.w_tc) {
                     PairTC pt;
                     pt.x = src; pt.out = dst; pt.w1 = W1.w_tc; pt.w2 = W2.w_tc; pt.b1 = W1.b; pt.b2 = W2.b;
@@ -501,6 +522,33 @@ int svb_get_precision(const svb_ctx* ctx) { return ctx ? ctx->precision : SVB_ER
 int svb_debug_enable(svb_ctx* ctx, int on) {
     if (!ctx) return SVB_ERR_INVALID_ARG;
     ctx->debug = on != 0;
+    return SVB_OK;
+}
+
+int svb_profile_enable(svb_ctx* ctx, int on) {
+    if (!ctx) return SVB_ERR_INVALID_ARG;
+    for (auto& kv : ctx->prof)
+        for (auto& e : kv.second.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    ctx->prof.clear();
+    ctx->profile = on != 0;
+    return SVB_OK;
+}
+
+int svb_profile_read(svb_ctx* ctx, const char* name, double* total_ms, int64_t* count, double* flops, double* bytes) {
+    if (!ctx || !name) return SVB_ERR_INVALID_ARG;
+    auto it = ctx->prof.find(name);
+    if (it == ctx->prof.end()) return fail(ctx, SVB_ERR_INVALID_ARG, std::string("no profile entry named ") + name);
+    double ms = 0;
+    for (auto& e : it->second.ev) {
+        CU(cudaEventSynchronize(e.second));
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, e.first, e.second));
+        ms += t;
+    }
+    if (total_ms) *total_ms = ms;
+    if (count) *count = (int64_t)it->second.ev.size();
+    if (flops) *flops = it->second.flops;
+    if (bytes) *bytes = it->second.bytes;
     return SVB_OK;
 }
 
@@ -706,11 +754,19 @@ int svb_infer_tail(svb_ctx* ctx, const float* z_p, const float* g, int gT, const
     cudaStream_t st = (cudaStream_t)stream;
     float* z = reinterpret_cast<float*>(base + pl.off_z);
     float* har = reinterpret_cast<float*>(base + pl.off_har);
-    if ((rc = run_flow(ctx, z_p, g, gT, lengths, z, B, T, base, pl, st))) return rc;
+    {
+        ProfScope ps(ctx, "flow", st, 0, 0);
+        if ((rc = run_flow(ctx, z_p, g, gT, lengths, z, B, T, base, pl, st))) return rc;
+    }
     if ((rc = dbg_keep(ctx, "z", z, (size_t)B * ctx->cfg.inter_channels * T, st))) return rc;
-    launch_nsf_source(f0, rand_ini, noise, ctx->lin_w, ctx->lin_b, reinterpret_cast<double*>(base + pl.off_phase), har,
-                      B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, st);
+    {
+        const double N = (double)T * ctx->hop;
+        ProfScope ps(ctx, "nsf_source", st, 0, (double)B * (T * 4.0 + N * 4.0 + (noise ? N * 4.0 * ctx->cfg.n_harmonics : 0.0)));
+        launch_nsf_source(f0, rand_ini, noise, ctx->lin_w, ctx->lin_b, reinterpret_cast<double*>(base + pl.off_phase), har,
+                          B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, st);
+    }
     if ((rc = dbg_keep(ctx, "har", har, (size_t)B * T * ctx->hop, st))) return rc;
+    ProfScope ps(ctx, "generator", st, 0, 0);
     return run_generator(ctx, z, g, gT, har, wav, B, T, base, pl, st);
 }
 

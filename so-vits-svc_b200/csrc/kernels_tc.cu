@@ -1,8 +1,365 @@
-// placeholder — replaced below
+// tcgen05 tensor-core kernels (sm_100a): the HiFiGAN ResBlock "pair"
+//     out = alpha * ( x + conv2(lrelu(conv1(lrelu(x)) + b1)) + b2 ) + beta * out_old
+// (vdecoder/hifigan/models.py:60-67, one iteration of the loop; 92.5 % of the path's FLOPs).
+//
+// Mapping onto the 5th-gen tensor cores: a k-tap dilated Conv1d is k shifted channel-mixing GEMMs.
+//   M = 128 time steps (TMEM lanes), N = C_out (TMEM columns), K = C_in per tap.
+//   A = activations, staged in shared memory as [time][channel] fp16 rows (K-major, hardware swizzle);
+//       a tap shift of s samples is a ROW offset of the A descriptor, so one staged tile feeds all taps.
+//   B = folded weights per tap [C_out][C_in] fp16, pre-swizzled on the host and streamed from L2 with
+//       1-D bulk TMA copies through an mbarrier ring.
+//   D = fp32 accumulators in TMEM; epilogue warps read them with tcgen05.ld (thread == time step),
+//       apply bias + LeakyReLU, convert to fp16 and write the second conv's A tile in place.
+// The residual stream stays fp32 in HBM/L2; only MMA operands are fp16 (11-bit significand, the same
+// as the TF32 operands of the reference's cuDNN path).
+//
+// Warp roles (320 threads): warps 0-7 stage x / run epilogues (warp w owns TMEM lanes 32*(w%4)..+31 and
+// half (w/4) of the channels), warp 8 allocates TMEM and issues MMAs (one elected lane), warp 9 streams
+// weights.
 #include "kernels.h"
+#include "tc_common.cuh"
 #include "../../include/sovits_b200.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
 namespace svb {
-size_t tc_weight_image_bytes(int C, int k) { return (size_t)C * C * k * 2; }
-void tc_pack_weight_image(const float*, int, int, void*) {}
-int launch_pair_tc(const PairTC&, cudaStream_t) { return SVB_ERR_UNSUPPORTED; }
+
+using namespace tc;
+
+namespace {
+
+constexpr int TC_THREADS = 320;
+constexpr int NWORK = 256;           // worker threads (8 warps)
+constexpr int NSTAGE = 2;
+constexpr int MAX_HALO = 56;         // >= max (k-1)*dil = 50, multiple of 8
+
+template <int C>
+struct TCGeom {
+    static constexpr int CPP = C < 64 ? C : 64;         // channels per K-panel
+    static constexpr int NP = C / CPP;                  // K-panels
+    static constexpr int RB = CPP * 2;                  // operand row bytes: 128 / 64 / 32
+    static constexpr int KSTEPS = CPP / 16;             // MMAs (K=16) per panel row
+    static constexpr int SUB = C * RB;                  // bytes of one (tap, panel) weight block: C_out rows
+    static constexpr int SPC_RAW = 32768 / SUB;         // sub-blocks per ring chunk (<= 32 KB)
+    static constexpr int SPC = SPC_RAW < 1 ? 1 : (SPC_RAW > 11 * NP ? 11 * NP : SPC_RAW);
+    static constexpr int STAGE_BYTES = ((SPC * SUB + 1023) / 1024) * 1024;
+};
+
+struct PairParams {
+    const float* x; float* out;
+    const uint8_t* w1; const uint8_t* w2;
+    const float* b1; const float* b2;
+    int T, k, dil;
+    float alpha, beta;
+    int bo_mode;     // 0: descriptor base_offset = 0;  1: base_offset = (start_address >> 7) & 7
+};
+
+template <int C, int MB>
+constexpr size_t pair_smem_bytes() {
+    using G = TCGeom<C>;
+    return 1024 /*align slack*/ + (size_t)G::NP * (128 * MB + MAX_HALO) * G::RB + (size_t)NSTAGE * G::STAGE_BYTES + 256;
 }
+
+template <int C, int MB>
+__global__ void __launch_bounds__(TC_THREADS, 1) pair_tc_kernel(const PairParams p) {
+    using G = TCGeom<C>;
+    constexpr int R1 = 128 * MB;
+    constexpr int AROWS = R1 + MAX_HALO;
+    constexpr int APANEL = AROWS * G::RB;
+    constexpr int TMEM_COLS = (MB * C) < 32 ? 32 : (MB * C);
+    static_assert(TMEM_COLS == 32 || TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw);
+    const uint32_t a_base = base;                                   // A tile (A1, then A2 in place)
+    const uint32_t ring_base = base + G::NP * APANEL;               // weight ring
+    const uint32_t bar_base = ring_base + NSTAGE * G::STAGE_BYTES;  // barriers
+    const uint32_t bar_full = bar_base;                             // [NSTAGE]
+    const uint32_t bar_empty = bar_base + 8 * NSTAGE;               // [NSTAGE]
+    const uint32_t bar_a = bar_base + 16 * NSTAGE;                  // A tile ready (256 arrivals), 2 phases
+    const uint32_t bar_acc = bar_a + 8;                             // accumulators ready, 2 phases
+    const uint32_t tmem_slot = bar_acc + 8;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - base));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int k = p.k, dil = p.dil;
+    const int TOUT = R1 - (k - 1);
+    const int t0 = blockIdx.x * TOUT;
+    const int h2 = (k - 1) / 2, h1 = dil * (k - 1) / 2;
+    const int tA0 = t0 - h2 - h1;          // time of A1 row 0
+    const int tM0 = t0 - h2;               // time of mid (conv1 output / A2) row 0
+    const int RA1 = R1 + (k - 1) * dil;    // rows of A1 the MMAs touch
+    const float* __restrict__ xb = p.x + (size_t)b * C * p.T;
+    float* __restrict__ ob = p.out + (size_t)b * C * p.T;
+
+    // ---------------------------------------------------------------- setup
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_a, NWORK);
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 8) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 9) {
+        // ------------------------------------------------------------ weight producer
+        if (lane == 0) {
+            const int total_sb = k * G::NP;
+            int chunk = 0;
+            for (int conv = 0; conv < 2; ++conv) {
+                const uint8_t* wsrc = conv ? p.w2 : p.w1;
+                for (int sb0 = 0; sb0 < total_sb; sb0 += G::SPC, ++chunk) {
+                    const int s = chunk % NSTAGE;
+                    if (chunk >= NSTAGE) mbar_wait(bar_empty + 8 * s, ((chunk / NSTAGE) - 1) & 1);
+                    const int nsb = (total_sb - sb0) < G::SPC ? (total_sb - sb0) : G::SPC;
+                    const uint32_t bytes = (uint32_t)nsb * G::SUB;
+                    mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+                    bulk_g2s(ring_base + s * G::STAGE_BYTES, wsrc + (size_t)sb0 * G::SUB, bytes, bar_full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(128, C);
+            const int total_sb = k * G::NP;
+            int chunk = 0;
+            for (int conv = 0; conv < 2; ++conv) {
+                mbar_wait(bar_a, conv);
+                tc_fence_after();
+                const int cd = conv ? 1 : dil;
+                for (int sb = 0; sb < total_sb; ++sb) {
+                    const int s = chunk % NSTAGE;
+                    const int within = sb % G::SPC;
+                    if (within == 0) {
+                        mbar_wait(bar_full + 8 * s, (chunk / NSTAGE) & 1);
+                        tc_fence_after();
+                    }
+                    const int tap = sb / G::NP, pn = sb % G::NP;
+                    const uint32_t bsub = ring_base + s * G::STAGE_BYTES + within * G::SUB;
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb) {
+                        const uint32_t arow = a_base + pn * APANEL + (uint32_t)(mb * 128 + tap * cd) * G::RB;
+                        const uint32_t bo = p.bo_mode ? ((arow >> 7) & 7u) : 0u;
+#pragma unroll
+                        for (int ks = 0; ks < G::KSTEPS; ++ks) {
+                            const uint64_t ad = make_smem_desc(arow + ks * 32, G::RB, bo);
+                            const uint64_t bd = make_smem_desc(bsub + ks * 32, G::RB, 0);
+                            umma_f16(tmem_base + mb * C, ad, bd, idesc, (sb > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    }
+                    if (within == G::SPC - 1 || sb == total_sb - 1) {
+                        umma_commit(bar_empty + 8 * s);   // frees the ring stage once these MMAs retire
+                        ++chunk;
+                    }
+                }
+                umma_commit(bar_acc);                      // accumulators of this conv are complete
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ workers (warps 0-7)
+        // (1) stage A1 = lrelu(x) tile as fp16 [time][channel], zero outside [0,T)
+        for (int r = tid; r < RA1; r += NWORK) {
+            const int t = tA0 + r;
+            const bool valid = (t >= 0) && (t < p.T);
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += 16) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = valid ? __ldg(xb + (size_t)(c0 + j) * p.T + t) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
+                const int pn = c0 / G::CPP;
+                const int ch0 = (c0 % G::CPP) / 8;
+                uint8_t* prow = sm + pn * APANEL;
+                uint4 q0 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                uint4 q1 = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+                *reinterpret_cast<uint4*>(prow + swz_offset(r, ch0, G::RB)) = q0;
+                *reinterpret_cast<uint4*>(prow + swz_offset(r, ch0 + 1, G::RB)) = q1;
+            }
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_a);
+
+        const int q = warp & 3, hsel = warp >> 2;
+        const int rib = 32 * q + lane;                 // row inside a 128-row block == TMEM lane
+        constexpr int CH = C / 2;                      // channels handled by this warp-half
+        constexpr int CG = CH < 16 ? CH : 16;          // columns per tcgen05.ld
+        const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
+
+        // (2) epilogue 1: mid = conv1 + b1 -> lrelu -> fp16 -> A2 (in place), zero outside [0,T)
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int mb = 0; mb < MB; ++mb) {
+            const int row = mb * 128 + rib;
+            const int tm = tM0 + row;
+            const bool valid = (tm >= 0) && (tm < p.T);
+#pragma unroll 1
+            for (int cc = 0; cc < CH; cc += CG) {
+                const int c0 = hsel * CH + cc;
+                float v[16];
+                if (CG == 16) {
+                    uint32_t r[16];
+                    tmem_ld16(tlane + mb * C + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                } else {
+                    uint32_t r[8];
+                    tmem_ld8(tlane + mb * C + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < CG; ++j) {
+                    float y = v[j] + __ldg(p.b1 + c0 + j);
+                    y = y > 0.f ? y : 0.1f * y;
+                    v[j] = valid ? y : 0.f;
+                }
+                const int pn = c0 / G::CPP;
+                const int ch0 = (c0 % G::CPP) / 8;
+                uint8_t* prow = sm + pn * APANEL;
+                uint4 q0 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                *reinterpret_cast<uint4*>(prow + swz_offset(row, ch0, G::RB)) = q0;
+                if (CG == 16) {
+                    uint4 q1 = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+                    *reinterpret_cast<uint4*>(prow + swz_offset(row, ch0 + 1, G::RB)) = q1;
+                }
+            }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(bar_a);
+
+        // (3) epilogue 2: out = alpha*(conv2 + b2 + x) + beta*out_old
+        mbar_wait(bar_acc, 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int mb = 0; mb < MB; ++mb) {
+            const int o = mb * 128 + rib;
+            const int t = t0 + o;
+            const bool valid = (o < TOUT) && (t < p.T);
+#pragma unroll 1
+            for (int cc = 0; cc < CH; cc += CG) {
+                const int c0 = hsel * CH + cc;
+                float v[16];
+                if (CG == 16) {
+                    uint32_t r[16];
+                    tmem_ld16(tlane + mb * C + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                } else {
+                    uint32_t r[8];
+                    tmem_ld8(tlane + mb * C + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+                }
+                if (valid) {
+                    float xr[16];
+#pragma unroll
+                    for (int j = 0; j < CG; ++j) xr[j] = __ldg(xb + (size_t)(c0 + j) * p.T + t);
+                    if (p.beta != 0.f) {
+#pragma unroll
+                        for (int j = 0; j < CG; ++j) {
+                            float* dst = ob + (size_t)(c0 + j) * p.T + t;
+                            *dst = fmaf(p.beta, *dst, p.alpha * (v[j] + __ldg(p.b2 + c0 + j) + xr[j]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CG; ++j)
+                            ob[(size_t)(c0 + j) * p.T + t] = p.alpha * (v[j] + __ldg(p.b2 + c0 + j) + xr[j]);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+
+    // ---------------------------------------------------------------- teardown
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+int env_int(const char* name, int dflt) {
+    const char* s = std::getenv(name);
+    return s ? std::atoi(s) : dflt;
+}
+
+template <int C, int MB>
+int launch_pair_t(const PairTC& a, cudaStream_t st) {
+    constexpr size_t smem = pair_smem_bytes<C, MB>();
+    static_assert(smem <= 227 * 1024, "pair kernel shared memory exceeds 227 KB");
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(pair_tc_kernel<C, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return SVB_ERR_CUDA;
+        attr_set = true;
+    }
+    static const int bo_mode = env_int("SVB_TC_BASE_OFFSET", 0);
+    PairParams p;
+    p.x = a.x; p.out = a.out;
+    p.w1 = static_cast<const uint8_t*>(a.w1); p.w2 = static_cast<const uint8_t*>(a.w2);
+    p.b1 = a.b1; p.b2 = a.b2; p.T = a.T; p.k = a.k; p.dil = a.dil; p.alpha = a.alpha; p.beta = a.beta;
+    p.bo_mode = bo_mode;
+    const int TOUT = 128 * MB - (a.k - 1);
+    dim3 grid((a.T + TOUT - 1) / TOUT, a.B);
+    pair_tc_kernel<C, MB><<<grid, TC_THREADS, smem, st>>>(p);
+    launch_counter()++;
+    return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;
+}
+
+}  // namespace
+
+size_t tc_weight_image_bytes(int C, int k) { return (size_t)C * C * k * 2; }
+
+// w_folded: [Cout][Cin][k] fp32  ->  image [tap][panel][Cout row][swizzled Cin halves]
+void tc_pack_weight_image(const float* w, int C, int k, void* dst_host) {
+    const int CPP = C < 64 ? C : 64, NP = C / CPP, RB = CPP * 2, SUB = C * RB;
+    uint8_t* dst = static_cast<uint8_t*>(dst_host);
+    for (int tap = 0; tap < k; ++tap)
+        for (int pn = 0; pn < NP; ++pn) {
+            uint8_t* blk = dst + (size_t)(tap * NP + pn) * SUB;
+            for (int n = 0; n < C; ++n)
+                for (int cc = 0; cc < CPP; ++cc) {
+                    const int ci = pn * CPP + cc;
+                    const float v = w[((size_t)n * C + ci) * k + tap];
+                    const __half h = __float2half_rn(v);
+                    const uint32_t off = tc::swz_offset((uint32_t)n, (uint32_t)(cc / 8), (uint32_t)RB) + (cc % 8) * 2;
+                    std::memcpy(blk + off, &h, 2);
+                }
+        }
+}
+
+int launch_pair_tc(const PairTC& a, cudaStream_t st) {
+    if (!(a.k == 3 || a.k == 7 || a.k == 11) || (a.k - 1) * a.dil > 50) return SVB_ERR_UNSUPPORTED;
+    static const int mb128 = env_int("SVB_TC_MB128", 4);
+    switch (a.C) {
+        case 16: return launch_pair_t<16, 16>(a, st);
+        case 32: return launch_pair_t<32, 8>(a, st);
+        case 64: return launch_pair_t<64, 4>(a, st);
+        case 128: return mb128 == 2 ? launch_pair_t<128, 2>(a, st) : launch_pair_t<128, 4>(a, st);
+        case 256: return launch_pair_t<256, 2>(a, st);
+        default: return SVB_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace svb

@@ -110,6 +110,17 @@ class TailEngine:
         L.check(self.lib, self._ctx, rc, "svb_debug_fetch")
         return out
 
+    def profile_enable(self, on: bool = True) -> None:
+        L.check(self.lib, self._ctx, self.lib.svb_profile_enable(self._ctx, int(on)), "svb_profile_enable")
+
+    def profile_read(self, name: str):
+        """-> dict(ms, count, flops, bytes) summed over the launches since profile_enable(True), or None."""
+        ms, cnt, fl, by = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+        rc = self.lib.svb_profile_read(self._ctx, name.encode(), C.byref(ms), C.byref(cnt), C.byref(fl), C.byref(by))
+        if rc != 0:
+            return None
+        return {"ms": ms.value, "count": cnt.value, "flops": fl.value, "bytes": by.value}
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.svb_launch_count(self._ctx))

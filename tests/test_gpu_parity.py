@@ -1,0 +1,228 @@
+"""GPU tier (B200): the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the same
+seeded inputs, against the committed reference fixtures, and — at BASELINE's full size — through
+size-independent properties.  Tolerances (waveform in (-1,1), activations O(1..10)):
+  * fp32 path  vs oracle/reference fixture:  L-inf <= 1e-4   (T1)
+  * tensor-core path (fp16 operands, fp32 accumulate) vs the same: L-inf <= TC_TOL, the band of the
+    reference's own TF32-vs-fp32 self-disagreement (T2/T3); measured values are printed.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import svc_oracle as O
+from sovits_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+TC_TOL = 2e-2
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+DEV = torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def eng(cfg, sd):
+    from sovits_b200.engine import TailEngine
+    e = TailEngine(cfg, DEV, "fp32")
+    e.load_state_dict(sd)
+    yield e
+    e.close()
+
+
+def _case(cfg, sd, B, T, seed=1234, zero_f0=False):
+    c, f0, uv, sid = synth.synth_inputs(cfg, B, T, seed)
+    if zero_f0:
+        f0 = torch.zeros_like(f0)
+    noise = synth.draw_noise(B, T, cfg)
+    g = sd["emb_g.weight"][sid].transpose(1, 2).contiguous()
+    gen = torch.Generator().manual_seed(seed + 1)
+    z_p = torch.randn((B, cfg.inter_channels, T), generator=gen) * 1.4
+    return z_p, g, f0, noise
+
+
+@pytest.mark.parametrize("B,T", [(2, 24), (1, 33), (3, 130)])
+def test_nsf_source_matches_oracle(cfg, sd, eng, B, T):
+    _, _, f0, noise = _case(cfg, sd, B, T)
+    f0[:, 3:7] = 0.0
+    ref = O.nsf_source_closed_form(sd, f0, noise["rand_ini"], noise["har_noise"], cfg)[:, 0]
+    got = eng.nsf_source(f0.to(DEV), noise["rand_ini"].to(DEV), noise["har_noise"].to(DEV)).cpu().double()
+    assert float((got - ref).abs().max()) < 5e-6
+    lit = O.nsf_source(sd, f0, noise["rand_ini"], noise["har_noise"], cfg, torch.float32)[:, 0]
+    assert float((got - lit.double()).abs().max()) < 1e-4      # vs the reference's own fp32 double-cumsum
+    got0 = eng.nsf_source(f0.to(DEV), noise["rand_ini"].to(DEV), None).cpu().double()
+    ref0 = O.nsf_source_closed_form(sd, f0, noise["rand_ini"], torch.zeros_like(noise["har_noise"]), cfg)[:, 0]
+    assert float((got0 - ref0).abs().max()) < 5e-6
+
+
+def test_nsf_source_ten_seconds_and_unvoiced(cfg, sd, eng):
+    B, T = 2, 862
+    _, _, f0, noise = _case(cfg, sd, B, T)
+    ref = O.nsf_source_closed_form(sd, f0, noise["rand_ini"], noise["har_noise"], cfg)[:, 0]
+    got = eng.nsf_source(f0.to(DEV), noise["rand_ini"].to(DEV), noise["har_noise"].to(DEV)).cpu().double()
+    assert float((got - ref).abs().max()) < 5e-6
+    f00 = torch.zeros_like(f0)
+    got = eng.nsf_source(f00.to(DEV), noise["rand_ini"].to(DEV), noise["har_noise"].to(DEV)).cpu().double()
+    ref = O.nsf_source_closed_form(sd, f00, noise["rand_ini"], noise["har_noise"], cfg)[:, 0]
+    assert torch.isfinite(got).all() and float((got - ref).abs().max()) < 5e-6
+
+
+@pytest.mark.parametrize("B,T", [(2, 24), (1, 33), (2, 200)])
+def test_flow_reverse_matches_oracle(cfg, sd, eng, B, T):
+    z_p, g, _, _ = _case(cfg, sd, B, T)
+    ref = O.flow_reverse(sd, z_p, torch.ones(B, 1, T), g, cfg, torch.float32)
+    got = eng.flow_reverse(z_p.to(DEV), g.to(DEV)).cpu()
+    assert float((got - ref).abs().max()) < FP32_TOL
+
+
+def test_flow_reverse_ragged_lengths_and_time_varying_g(cfg, sd, eng):
+    B, T = 3, 40
+    z_p, g, _, _ = _case(cfg, sd, B, T)
+    lengths = torch.tensor([40, 17, 1])
+    mask = (torch.arange(T)[None, :] < lengths[:, None]).float()[:, None, :]
+    z_p = z_p * mask
+    ref = O.flow_reverse(sd, z_p, mask, g, cfg, torch.float32)
+    got = eng.flow_reverse(z_p.to(DEV), g.to(DEV), lengths.to(DEV)).cpu()
+    assert float((got - ref).abs().max()) < FP32_TOL
+    gt = g.expand(B, cfg.gin_channels, T).clone() + 0.1 * torch.randn(B, cfg.gin_channels, T)   # speaker-mix style g
+    ref = O.flow_reverse(sd, z_p, mask, gt, cfg, torch.float32)
+    got = eng.flow_reverse(z_p.to(DEV), gt.to(DEV), lengths.to(DEV)).cpu()
+    assert float((got - ref).abs().max()) < FP32_TOL
+
+
+@pytest.mark.parametrize("B,T", [(2, 24), (1, 33)])
+def test_generator_fp32_stagewise(cfg, sd, eng, B, T):
+    z_p, g, f0, noise = _case(cfg, sd, B, T)
+    taps = {}
+    ref = O.tail(sd, cfg, z_p, g, f0, noise, torch.float32, taps)
+    eng.set_precision("fp32")
+    eng.debug_enable(True)
+    got = eng.infer_tail(z_p.to(DEV), g.to(DEV), f0.to(DEV), noise["rand_ini"].to(DEV), noise["har_noise"].to(DEV)).cpu()
+    for name in ["z", "conv_pre"] + [f"{k}{i}" for i in range(5) for k in ("ups", "stage")]:
+        t = taps[name]
+        d = eng.debug_fetch(name, tuple(t.shape)).cpu()
+        err = float((d - t).abs().max())
+        assert err < FP32_TOL * max(1.0, float(t.abs().max())), (name, err)
+    eng.debug_enable(False)
+    assert float((got - ref).abs().max()) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", list(synth.GOLDEN_CASES))
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_tail_matches_reference_fixture(cfg, sd, eng, name, precision):
+    """flow + source + generator on the reference's own z_p, against the reference's own waveform."""
+    gold = np.load(os.path.join(GOLD, f"ref_infer_{name}.npz"))
+    B, T = synth.GOLDEN_CASES[name]
+    c, f0, uv, sid = synth.golden_inputs(cfg, name)
+    noise = synth.draw_noise(B, T, cfg, seed=int(gold["seed"]))
+    g = sd["emb_g.weight"][sid].transpose(1, 2).contiguous()
+    eng.set_precision(precision)
+    got = eng.infer_tail(torch.from_numpy(gold["z_p"]).to(DEV), g.to(DEV), f0.to(DEV), noise["rand_ini"].to(DEV),
+                         noise["har_noise"].to(DEV)).cpu()
+    eng.set_precision("fp32")
+    err = float((got - torch.from_numpy(gold["o"])).abs().max())
+    print(f"[parity] {name} {precision}: L-inf vs reference waveform = {err:.3e}")
+    assert err < (FP32_TOL if precision == "fp32" else TC_TOL)
+
+
+def test_tc_stagewise_against_oracle(cfg, sd, eng):
+    """Every (C, k, dilation) of the tensor-core pair kernel, boundary tiles included (T*hop is not a
+    multiple of any tile size)."""
+    B, T = 2, 37
+    z_p, g, f0, noise = _case(cfg, sd, B, T)
+    taps = {}
+    ref = O.tail(sd, cfg, z_p, g, f0, noise, torch.float32, taps)
+    eng.set_precision("tc")
+    eng.debug_enable(True)
+    got = eng.infer_tail(z_p.to(DEV), g.to(DEV), f0.to(DEV), noise["rand_ini"].to(DEV), noise["har_noise"].to(DEV)).cpu()
+    worst = {}
+    for i in range(5):
+        t = taps[f"stage{i}"]
+        d = eng.debug_fetch(f"stage{i}", tuple(t.shape)).cpu()
+        worst[i] = float((d - t).abs().max()) / float(t.abs().max())
+    eng.debug_enable(False)
+    eng.set_precision("fp32")
+    print("[parity] tc stage-wise relative L-inf:", {k: f"{v:.2e}" for k, v in worst.items()})
+    for i, v in worst.items():
+        assert v < 1e-2, (i, v)
+    assert float((got - ref).abs().max()) < TC_TOL
+
+
+def test_full_infer_against_oracle_with_replayed_rng(cfg, sd):
+    """SynthesizerTrn.infer end to end on the GPU; the oracle gets the very noise tensors torch's CUDA generator
+    produced (same seed, same order: SURVEY §9.9)."""
+    import json
+    import sovits_b200
+    from sovits_b200 import models
+    with open(sovits_b200.DEFAULT_CONFIG) as f:
+        kw = json.load(f)["model"]
+    net = models.SynthesizerTrn(1025, 20, **kw).eval()
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    B, T = 2, 31
+    c, f0, uv, sid = synth.synth_inputs(cfg, B, T)
+    N = T * cfg.hop
+    torch.manual_seed(52468)
+    noise = {"z_noise": torch.randn(B, cfg.inter_channels, T, device=DEV).cpu(),
+             "rand_ini": torch.rand(B, cfg.n_harmonics, device=DEV).cpu(),
+             "har_noise": torch.randn(B, N, cfg.n_harmonics, device=DEV).cpu()}
+    ref, _ = O.infer(sd, cfg, c, f0, uv, sid, noise, noice_scale=0.4)
+    for precision, tol in (("fp32", 2e-4), ("tc", TC_TOL)):
+        net.set_precision(precision)
+        o, f0_out = net.infer(c.to(DEV), f0.to(DEV), uv.to(DEV), g=sid.to(DEV), noice_scale=0.4)
+        assert o.shape == (B, 1, N) and torch.equal(f0_out.cpu(), f0)
+        err = float((o.cpu() - ref).abs().max())
+        print(f"[parity] full infer {precision}: L-inf = {err:.3e}")
+        assert err < tol
+        o2, _ = net.infer(c.to(DEV), f0.to(DEV), uv.to(DEV), g=sid.to(DEV), noice_scale=0.4)
+        assert torch.equal(o, o2)                       # same seed -> bit-identical (reference behaviour)
+
+
+def test_full_size_properties(cfg, sd, eng):
+    """BASELINE config 2 size (8 x 862 frames): batch independence (item i of a batch == item i alone, given its
+    own noise slice), finiteness, tc-vs-fp32 agreement, host-buffer entry point."""
+    B, T = 8, 862
+    z_p, g, f0, noise = _case(cfg, sd, B, T)
+    dv = lambda t: t.to(DEV)
+    outs = {}
+    for precision in ("fp32", "tc"):
+        eng.set_precision(precision)
+        full = eng.infer_tail(dv(z_p), dv(g), dv(f0), dv(noise["rand_ini"]), dv(noise["har_noise"]))
+        assert torch.isfinite(full).all() and float(full.abs().max()) <= 1.0
+        i = 5
+        one = eng.infer_tail(dv(z_p[i:i + 1]), dv(g[i:i + 1]), dv(f0[i:i + 1]), dv(noise["rand_ini"][i:i + 1]),
+                             dv(noise["har_noise"][i:i + 1]))
+        assert torch.equal(one[0], full[i]), precision
+        outs[precision] = full
+    eng.set_precision("fp32")
+    err = float((outs["tc"] - outs["fp32"]).abs().max())
+    print(f"[parity] full size tc vs fp32 L-inf = {err:.3e}")
+    assert err < TC_TOL
+    i = 2
+    host = eng.infer_tail_host(z_p[i:i + 1], g[i:i + 1], f0[i:i + 1], noise["rand_ini"][i:i + 1], noise["har_noise"][i:i + 1])
+    assert torch.equal(host[0], outs["fp32"][i].cpu())
+
+
+def test_error_paths(cfg, sd):
+    from sovits_b200 import lib as L
+    lib = L.load_library()
+    ctx = C.c_void_p()
+    assert lib.svb_create(0, C.byref(ctx)) == 0
+    buf = torch.zeros(16, device=DEV)
+    rc = lib.svb_nsf_source(ctx, buf.data_ptr(), buf.data_ptr(), None, buf.data_ptr(), 1, 1, None)
+    assert rc == -3 and b"svb_load_weights" in lib.svb_last_error(ctx)          # SVB_ERR_NOT_LOADED
+    assert lib.svb_create(99, C.byref(C.c_void_p())) != 0
+    lib.svb_destroy(ctx)
+    from sovits_b200.engine import TailEngine
+    e = TailEngine(cfg, DEV, "fp32")
+    bad = {k: v for k, v in sd.items() if k != "dec.ups.2.weight_g"}
+    with pytest.raises(L.SvbError, match="dec.ups.2.weight_g"):
+        e.load_state_dict(bad)
+    e.load_state_dict(sd)
+    z = torch.zeros(1, cfg.inter_channels, 8, device=DEV)
+    g_bad = torch.zeros(1, cfg.gin_channels, 3, device=DEV)
+    with pytest.raises(L.SvbError):
+        e.flow_reverse(z, g_bad)
+    e.close()

@@ -1,0 +1,119 @@
+"""CPU tier: host-side mirror of the reference surface, C-ABI export check, no-GPU behaviour."""
+import ctypes
+import json
+import os
+import re
+import sys
+import types
+
+import pytest
+import torch
+
+import sovits_b200
+from sovits_b200 import lib as L
+from sovits_b200 import models, synth
+from sovits_b200.frontend import f0_to_coarse
+import svc_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _model_kwargs():
+    with open(sovits_b200.DEFAULT_CONFIG) as f:
+        return json.load(f)["model"]
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads (no compute call) and exports every function include/sovits_b200.h declares."""
+    header = open(os.path.join(ROOT, "include", "sovits_b200.h")).read()
+    declared = set(re.findall(r"SVB_API\s+[\w\s\*]+?\b(svb_\w+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    lib = L.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.svb_version()
+    assert lib.svb_strerror(-6) == b"unsupported configuration"
+
+
+def test_state_dict_layout_matches_reference_keys(cfg, sd):
+    net = models.SynthesizerTrn(1025, 20, **_model_kwargs())
+    own = net.state_dict()
+    assert set(own) == set(sd)
+    for k, v in sd.items():
+        assert tuple(own[k].shape) == tuple(v.shape), k
+    # a reference checkpoint also carries enc_q.* / f0_decoder.*: they must be tolerated
+    extra = dict(sd)
+    extra["enc_q.pre.weight"] = torch.zeros(192, 1025, 1)
+    net.load_state_dict(extra)
+    assert torch.equal(net.state_dict()["dec.ups.0.weight_v"], sd["dec.ups.0.weight_v"])
+
+
+def test_frontend_matches_oracle_prefix(cfg, sd):
+    net = models.SynthesizerTrn(1025, 20, **_model_kwargs()).eval()
+    net.load_state_dict(sd)
+    c, f0, uv, sid = synth.golden_inputs(cfg, "b2_t24")
+    noise = synth.draw_noise(2, 24, cfg)
+    with torch.no_grad():
+        x_mask = torch.ones(2, 1, 24)
+        x = net.pre(c) * x_mask + net.emb_uv(uv.long()).transpose(1, 2)
+        for flag in (True, False):
+            z_p, _, _, _ = net.enc_p(x, x_mask, f0_to_coarse(f0), noice_scale=0.4, z_noise=noise["z_noise"], all_ones_mask=flag)
+            xo, xm, _ = O.prologue(sd, c, f0, uv, sid, cfg, torch.float32)
+            zo, _, _ = O.text_encoder(sd, xo, xm, O.f0_to_coarse(f0), noise["z_noise"], 0.4, cfg, torch.float32)
+            assert torch.allclose(z_p, zo, atol=1e-5)
+
+
+def test_infer_fails_loudly_without_cuda(cfg, sd):
+    net = models.SynthesizerTrn(1025, 20, **_model_kwargs()).eval()
+    net.load_state_dict(sd)
+    c, f0, uv, sid = synth.golden_inputs(cfg, "b1_t33")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net.infer(c, f0, uv, g=sid)
+
+
+def test_unsupported_configs_are_rejected():
+    kw = _model_kwargs()
+    kw["use_depthwise_conv"] = True
+    with pytest.raises(NotImplementedError):
+        models.SynthesizerTrn(1025, 20, **kw)
+    kw = _model_kwargs()
+    kw["vocoder_name"] = "nsf-snake-hifigan"
+    with pytest.raises(NotImplementedError):
+        models.SynthesizerTrn(1025, 20, **kw)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("SOVITS_REF_DIR", "/root/reference")),
+                    reason="reference tree not present (GPU box)")
+def test_patch_reference_keeps_surface(cfg, sd):
+    """The zero-edit integration: subclass of the reference's own SynthesizerTrn."""
+    ref = os.environ.get("SOVITS_REF_DIR", "/root/reference")
+    for m in ("faiss", "librosa", "matplotlib", "matplotlib.pylab"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.path.insert(0, ref)
+    try:
+        import models as ref_models
+        cls = models.patch_reference(ref_models)
+        assert ref_models.SynthesizerTrn is cls
+        net = cls(1025, 20, **_model_kwargs()).eval()
+        missing = net.load_state_dict(sd, strict=False)
+        assert all(k.startswith(("enc_q.", "f0_decoder.")) for k in missing.missing_keys)
+        c, f0, uv, sid = synth.golden_inputs(cfg, "b1_t33")
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            net.infer(c, f0, uv, g=sid)
+        # with the tail stubbed by the oracle the patched prefix must reproduce the reference fixture
+        import numpy as np
+        gold = np.load(os.path.join(ROOT, "tests", "golden", "ref_infer_b1_t33.npz"))
+        seen = {}
+
+        def fake_tail(self, z_p, c_mask, g, f0_):
+            seen["z_p"] = z_p.clone()
+            return torch.zeros(z_p.shape[0], 1, z_p.shape[2] * 512)
+        cls._run_tail = fake_tail
+        net.infer(c, f0, uv, g=sid, noice_scale=0.4)
+        assert torch.allclose(seen["z_p"], torch.from_numpy(gold["z_p"]), atol=1e-6)
+    finally:
+        sys.path.remove(ref)
+        for m in ("models", "utils", "modules", "vdecoder"):
+            for k in [k for k in sys.modules if k == m or k.startswith(m + ".")]:
+                del sys.modules[k]

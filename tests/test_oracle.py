@@ -1,0 +1,115 @@
+"""CPU tier: the oracle against the committed reference fixtures (tests/golden/make_golden.py ran the
+unmodified reference in the build container), plus oracle self-consistency."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import svc_oracle as O
+from sovits_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    return np.load(os.path.join(GOLD, f"ref_infer_{name}.npz"))
+
+
+@pytest.mark.parametrize("name", list(synth.GOLDEN_CASES))
+def test_oracle_matches_reference_fixture(cfg, sd, name):
+    g = _load(name)
+    B, T = synth.GOLDEN_CASES[name]
+    c, f0, uv, sid = synth.golden_inputs(cfg, name)
+    noise = synth.draw_noise(B, T, cfg, seed=int(g["seed"]))
+    taps = {}
+    o, _ = O.infer(sd, cfg, c, f0, uv, sid, noise, noice_scale=float(g["noice_scale"]), taps=taps)
+    # fp32 restatement vs fp32 reference: identical op order up to the rel-pos band sums
+    assert torch.allclose(taps["z_p"], torch.from_numpy(g["z_p"]), atol=2e-5)
+    assert torch.allclose(taps["z"], torch.from_numpy(g["z"]), atol=5e-5)
+    assert torch.allclose(taps["har"], torch.from_numpy(g["har"]), atol=1e-6)
+    assert float((o - torch.from_numpy(g["o"])).abs().max()) < 2e-5   # waveform in (-1,1)
+
+
+def test_oracle_fp64_close_to_fp32_reference(cfg, sd):
+    g = _load("b1_t33")
+    c, f0, uv, sid = synth.golden_inputs(cfg, "b1_t33")
+    noise = synth.draw_noise(1, 33, cfg)
+    o64, _ = O.infer(sd, cfg, c, f0, uv, sid, noise, noice_scale=0.4, dtype=torch.float64)
+    assert float((o64 - torch.from_numpy(g["o"]).double()).abs().max()) < 5e-5
+
+
+@pytest.mark.parametrize("name", list(synth.GOLDEN_CASES))
+def test_closed_form_source_matches_reference(cfg, sd, name):
+    """the per-hop closed form (what the CUDA kernel implements) vs the reference's cumsum."""
+    g = _load(name)
+    B, T = synth.GOLDEN_CASES[name]
+    _, f0, _, _ = synth.golden_inputs(cfg, name)
+    noise = synth.draw_noise(B, T, cfg)
+    har = O.nsf_source_closed_form(sd, f0, noise["rand_ini"], noise["har_noise"], cfg)
+    assert float((har - torch.from_numpy(g["har"]).double()).abs().max()) < 2e-5
+
+
+def test_closed_form_source_long_clip(cfg, sd):
+    """At 10 s (862 hops): the closed form (fp32 `r` like the reference, fp64 phase) stays within 1e-4 of both
+    the reference's fp32 double-cumsum and its fp64 evaluation (measured 7e-6 / 1.3e-5)."""
+    T = 862
+    _, f0, _, _ = synth.synth_inputs(cfg, 1, T)
+    noise = synth.draw_noise(1, T, cfg)
+    lit = O.nsf_source(sd, f0, noise["rand_ini"], noise["har_noise"], cfg, torch.float32)
+    cf = O.nsf_source_closed_form(sd, f0, noise["rand_ini"], noise["har_noise"], cfg)
+    lit64 = O.nsf_source(sd, f0, noise["rand_ini"], noise["har_noise"], cfg, torch.float64)
+    assert float((cf - lit64).abs().max()) < 1e-4          # differs only by evaluating r in fp32 (as the reference does)
+    assert float((cf - lit.double()).abs().max()) < 1e-4   # fp32 reference scan error at 441k samples
+
+
+def test_flow_without_flip_equals_reference_order(cfg, sd):
+    """the Flip-free formulation the library packs weights for."""
+    torch.manual_seed(0)
+    B, T, C = 2, 17, cfg.inter_channels
+    half = C // 2
+    z = torch.randn(B, C, T)
+    g = torch.randn(B, cfg.gin_channels, 1)
+    mask = torch.ones(B, 1, T)
+    ref = O.flow_reverse(sd, z, mask, g, cfg, torch.float32)
+    y = z.clone()
+    import torch.nn.functional as F
+    for fl in reversed(range(4)):
+        p = f"flow.flows.{2 * fl}."
+        odd = fl % 2 == 1
+        pw, pb = sd[p + "pre.weight"], sd[p + "pre.bias"]
+        qw, qb = sd[p + "post.weight"], sd[p + "post.bias"]
+        if odd:
+            x0 = y[:, half:]
+            pw = torch.flip(pw, [1])
+            qw, qb = torch.flip(qw, [0]), torch.flip(qb, [0])
+        else:
+            x0 = y[:, :half]
+        h = F.conv1d(x0, pw, pb) * mask
+        h = O.wn_forward(sd, p + "enc.", h, mask, g, cfg, torch.float32)
+        m = F.conv1d(h, qw, qb) * mask
+        if odd:
+            y = torch.cat([y[:, :half] - m, y[:, half:]], 1)
+        else:
+            y = torch.cat([y[:, :half], y[:, half:] - m], 1)
+    assert torch.allclose(y, ref, atol=1e-5)
+
+
+def test_polyphase_transposed_conv(cfg, sd):
+    """ConvTranspose1d(k=2s) == s interleaved 2-tap convs, the form the kernels use."""
+    import torch.nn.functional as F
+    for i, (s, k) in enumerate(zip(cfg.upsample_rates, cfg.upsample_kernel_sizes)):
+        w = O.wn_weight(sd, f"dec.ups.{i}", torch.float64)           # [Cin,Cout,k]
+        b = sd[f"dec.ups.{i}.bias"].double()
+        L = 11
+        x = torch.randn(1, w.shape[0], L, dtype=torch.float64)
+        p = (k - s + 1) // 2
+        ref = F.conv_transpose1d(x, w, b, stride=s, padding=p)
+        out = torch.zeros_like(ref)
+        xp = F.pad(x, (1, 1))                                         # x[-1] = x[L] = 0
+        for ph in range(s):
+            for i0 in range(L + 1):
+                n = i0 * s + ph - p
+                if 0 <= n < L * s:
+                    out[0, :, n] = b + w[:, :, ph].t() @ xp[0, :, i0 + 1] + w[:, :, ph + s].t() @ xp[0, :, i0]
+        assert torch.allclose(out, ref, atol=1e-10)
