@@ -134,6 +134,11 @@ SVB_API int64_t svb_launch_count(const svb_ctx* ctx);
  * svb_generator/svb_infer_tail call into dst (device, fp32, n floats); test hook. */
 SVB_API int svb_debug_enable(svb_ctx* ctx, int on);
 SVB_API int svb_debug_fetch(svb_ctx* ctx, const char* what, float* dst, size_t n, void* stream);
+/* Test / microbenchmark hook: one ResBlock pair (stage, branch j, dilation index d) of the loaded generator on
+ * caller device buffers x,out [B,C,L] (scratch [B,C,L] for the fp32 form).  variant >= 0 selects a tensor-core
+ * tile variant, variant == -2 the two fp32 FFMA convolutions. */
+SVB_API int svb_debug_pair(svb_ctx* ctx, int stage, int j, int d, const float* x, float* out, float* scratch,
+                           int B, int L, int variant, float alpha, float beta, void* stream);
 /* CUDA-event timers on the launching stream, per kernel family ("pair_tc","pair_f32","flow","nsf_source",
  * "generator"): enable, run, then read the summed device time, launch count and algorithmic FLOPs/bytes
  * (bench.py's roofline).  Re-enabling clears the counters. */

@@ -32,7 +32,17 @@ struct ConvW {            // folded fp32 weights of one Conv1d, packed [Cin][k][
     void* w_tc = nullptr;  // tensor-core image (fp16, swizzled), when built
 };
 
+struct ConvNW {           // tensor-core image of one layer for convn_tc_kernel
+    void* img = nullptr;
+    float* bias = nullptr;   // per column, column order
+    int cinp = 0, cin_real = 0, N_total = 0, NC = 0, k = 1, pad_left = 0;
+};
+
 struct FlowLayer {
+    ConvNW pre_tc, post_tc;
+    std::vector<ConvNW> in_tc, rs_tc;
+    float* cond_w_perm = nullptr;  // cond_layer rows permuted to the gate kernel's column order
+    float* cond_b_perm = nullptr;
     ConvW pre, post;
     float* cond_w_nat = nullptr;   // [2H*L][gin] natural layout for the GEMV
     ConvW cond;                    // packed variant for time-varying g
@@ -48,6 +58,7 @@ struct Stage {
     float* noise_b = nullptr;
     int noise_K = 0, noise_s = 0, noise_p = 0;
     std::vector<ConvW> c1, c2;     // [branch*3 + d]
+    ConvNW up_tc;
 };
 
 }  // namespace
@@ -60,6 +71,8 @@ struct svb_ctx {
     std::vector<void*> allocs;
     std::vector<FlowLayer> flow;
     ConvW conv_pre;
+    ConvNW conv_pre_tc;
+    bool flow_tc_ok = false, gen_tc_ok = false;
     float* dcond_w_nat = nullptr;  // dec.cond [U][gin]
     float* dcond_b = nullptr;
     ConvW dcond;                   // packed (time-varying g)
@@ -190,6 +203,19 @@ int make_conv(svb_ctx* ctx, const std::vector<float>& w, const std::vector<float
     return SVB_OK;
 }
 
+int make_convn(svb_ctx* ctx, int cinp, int cin_real, int N_total, int NC, int k, int pad_left,
+               const std::function<float(int, int, int)>& wcol, const std::function<float(int)>& bcol, ConvNW& out) {
+    out.cinp = cinp; out.cin_real = cin_real; out.N_total = N_total; out.NC = NC; out.k = k; out.pad_left = pad_left;
+    const size_t ib = convn_weight_image_bytes(cinp, N_total, NC, k);
+    std::vector<uint8_t> img(ib);
+    convn_pack_weight_image(cinp, N_total, NC, k, [&](int col, int ci, int tap) { return ci < cin_real ? wcol(col, ci, tap) : 0.f; }, img.data());
+    int rc = upload(ctx, img.data(), ib, &out.img);
+    if (rc) return rc;
+    std::vector<float> bc(N_total);
+    for (int c = 0; c < N_total; ++c) bc[c] = bcol(c);
+    return upload(ctx, bc.data(), bc.size() * sizeof(float), (void**)&out.bias);
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsPlan {
@@ -295,7 +321,50 @@ int run_flow(svb_ctx* ctx, const float* z_p, const float* g, int gT, const int32
     float* out = reinterpret_cast<float*>(ws + pl.off_out);
     float* gcond = reinterpret_cast<float*>(ws + pl.off_gcond);
     if (y != z_p) CU(cudaMemcpyAsync(y, z_p, (size_t)B * C * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    for (int fl = c.n_flows - 1; fl >= 0; --fl) {
+    const bool use_tc = ctx->precision == SVB_PREC_TC && ctx->flow_tc_ok && gT == 1;
+    for (int fl = c.n_flows - 1; use_tc && fl >= 0; --fl) {
+        FlowLayer& F = ctx->flow[fl];
+        int trc;
+        auto base_args = [&](const ConvNW& W, const float* x, int x_ctot, int x_c0) {
+            ConvNTC a;
+            a.x = x; a.x_ctot = x_ctot; a.x_c0 = x_c0; a.cin_real = W.cin_real; a.cinp = W.cinp; a.Tin = T;
+            a.w = W.img; a.bias = W.bias; a.k = W.k; a.dil = 1; a.pad_left = W.pad_left;
+            a.n_rows = T; a.N_total = W.N_total; a.NC = W.NC; a.chunks_per_cta = 1; a.Ty = T; a.lengths = lengths; a.B = B;
+            return a;
+        };
+        {   // h = pre(x0) * mask
+            ConvNTC a = base_args(F.pre_tc, y, C, F.in_c0);
+            a.seg[0].y = h; a.seg[0].y_ctot = H; a.seg[0].col0 = 0; a.seg[0].col1 = H; a.seg[0].masked = 1;
+            if ((trc = launch_convn_tc(a, st))) return fail(ctx, trc, "convn launch failed (flow pre)");
+        }
+        launch_gemv(F.cond_w_perm, F.cond_b_perm, g, gcond, B, 2 * H * L, c.gin_channels, st);
+        for (int i = 0; i < L; ++i) {
+            {   // acts = tanh(.)*sigmoid(.) of in_layers[i](h) + cond
+                ConvNTC a = base_args(F.in_tc[i], h, H, 0);
+                a.mode = 2; a.bias_b = gcond; a.bias_b_stride = 2 * H * L; a.bias_b_off = 2 * H * i;
+                a.seg[0].y = acts; a.seg[0].y_ctot = H;
+                if ((trc = launch_convn_tc(a, st))) return fail(ctx, trc, "convn launch failed (flow in_layer)");
+            }
+            {   // res/skip
+                ConvNTC a = base_args(F.rs_tc[i], acts, H, 0);
+                if (i < L - 1) {
+                    a.n_seg = 2;
+                    a.seg[0].y = h; a.seg[0].y_ctot = H; a.seg[0].col0 = 0; a.seg[0].col1 = H; a.seg[0].beta = 1.f; a.seg[0].masked = 1;
+                    a.seg[1].y = out; a.seg[1].y_ctot = H; a.seg[1].col0 = H; a.seg[1].col1 = 2 * H; a.seg[1].beta = (i > 0) ? 1.f : 0.f; a.seg[1].masked = 1;
+                } else {
+                    a.seg[0].y = out; a.seg[0].y_ctot = H; a.seg[0].col0 = 0; a.seg[0].col1 = H; a.seg[0].beta = (i > 0) ? 1.f : 0.f; a.seg[0].masked = 1;
+                }
+                if ((trc = launch_convn_tc(a, st))) return fail(ctx, trc, "convn launch failed (flow res_skip)");
+            }
+        }
+        {   // x1 = (x1 - post(out)) * mask
+            ConvNTC a = base_args(F.post_tc, out, H, 0);
+            a.seg[0].y = y; a.seg[0].y_ctot = C; a.seg[0].y_c0 = F.out_c0; a.seg[0].col0 = 0; a.seg[0].col1 = half;
+            a.seg[0].alpha = -1.f; a.seg[0].beta = 1.f; a.seg[0].masked = 1;
+            if ((trc = launch_convn_tc(a, st))) return fail(ctx, trc, "convn launch failed (flow post)");
+        }
+    }
+    for (int fl = c.n_flows - 1; !use_tc && fl >= 0; --fl) {
         FlowLayer& F = ctx->flow[fl];
         // h = pre(x0) * mask
         ConvF32 a;
@@ -389,7 +458,19 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         launch_conv_f32(cg, st);
         cp.bias_t = dg; cp.bias_t_ctot = U;
     }
-    launch_conv_f32(cp, st);
+    const bool gen_tc = ctx->precision == SVB_PREC_TC && ctx->gen_tc_ok && gT == 1;
+    if (gen_tc) {
+        const ConvNW& W = ctx->conv_pre_tc;
+        ConvNTC a;
+        a.x = z; a.x_ctot = c.inter_channels; a.cin_real = W.cin_real; a.cinp = W.cinp; a.Tin = T;
+        a.w = W.img; a.bias = W.bias; a.bias_b = dg; a.bias_b_stride = U; a.bias_b_off = 0;
+        a.k = W.k; a.pad_left = W.pad_left; a.n_rows = T; a.N_total = W.N_total; a.NC = W.NC; a.chunks_per_cta = 1; a.Ty = T; a.B = B;
+        a.seg[0].y = pre; a.seg[0].y_ctot = U; a.seg[0].col0 = 0; a.seg[0].col1 = U;
+        int trc = launch_convn_tc(a, st);
+        if (trc) return fail(ctx, trc, "convn launch failed (conv_pre)");
+    } else {
+        launch_conv_f32(cp, st);
+    }
     if ((rc = dbg_keep(ctx, "conv_pre", pre, (size_t)B * U * T, st))) return rc;
 
     const float* cur = pre;
@@ -406,7 +487,19 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         up.ostride = S.s; up.ooff = -S.p; up.n_out = Lin + 1;
         up.in_act = 1; up.in_slope = 0.1f;
         up.y = X; up.y_ctot = S.Cout; up.Ty = Lout; up.B = B;
-        launch_conv_f32(up, st);
+        if (gen_tc) {
+            const ConvNW& W = S.up_tc;
+            ConvNTC a;
+            a.x = cur; a.x_ctot = S.Cin; a.cin_real = S.Cin; a.cinp = W.cinp; a.Tin = Lin; a.in_act = 1; a.in_slope = 0.1f;
+            a.w = W.img; a.bias = W.bias; a.k = 2; a.pad_left = 1; a.n_rows = Lin + 1; a.N_total = W.N_total; a.NC = W.NC;
+            a.chunks_per_cta = (W.N_total + W.NC - 1) / W.NC;
+            a.mode = 1; a.s = S.s; a.p = S.p; a.Ty = Lout; a.B = B;
+            a.seg[0].y = X; a.seg[0].y_ctot = S.Cout;
+            int trc = launch_convn_tc(a, st);
+            if (trc) return fail(ctx, trc, "convn launch failed (ups)");
+        } else {
+            launch_conv_f32(up, st);
+        }
         launch_noise_conv_add(har, S.noise_w, S.noise_b, X, B, S.Cout, Lout, (int)N, S.noise_K, S.noise_s, S.noise_p, st);
         if ((rc = dbg_keep(ctx, "ups" + std::to_string(i), X, (size_t)B * S.Cout * Lout, st))) return rc;
         for (int j = 0; j < nk; ++j) {
@@ -525,6 +618,44 @@ int svb_debug_enable(svb_ctx* ctx, int on) {
     return SVB_OK;
 }
 
+// One ResBlock pair (stage, branch j, dilation index d) of the loaded generator on caller buffers [B,C,L]:
+// variant >= 0 -> tensor-core tile variant, variant == -2 -> the two fp32 FFMA convs.  Microbenchmark / unit-test hook.
+int svb_debug_pair(svb_ctx* ctx, int stage, int j, int d, const float* x, float* out, float* scratch, int B, int L, int variant,
+                   float alpha, float beta, void* stream) {
+    if (!ctx || !ctx->loaded) return SVB_ERR_NOT_LOADED;
+    if (stage < 0 || stage >= ctx->cfg.n_upsamples || j < 0 || j >= 3 || d < 0 || d >= 3 || !x || !out) return SVB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Stage& S = ctx->stages[stage];
+    const int k = ctx->cfg.resblock_kernel_sizes[j], dil = ctx->cfg.resblock_dilations[j][d];
+    const ConvW& W1 = S.c1[j * 3 + d];
+    const ConvW& W2 = S.c2[j * 3 + d];
+    if (variant >= 0) {
+        PairTC pt;
+        pt.x = x; pt.out = out; pt.w1 = W1.w_tc; pt.w2 = W2.w_tc; pt.b1 = W1.b; pt.b2 = W2.b;
+        pt.B = B; pt.C = S.Cout; pt.T = L; pt.k = k; pt.dil = dil; pt.alpha = alpha; pt.beta = beta; pt.variant = variant;
+        int rc = launch_pair_tc(pt, st);
+        if (rc) return fail(ctx, rc, "pair kernel launch failed");
+        return check_launch(ctx, "debug_pair");
+    }
+    if (!scratch) return SVB_ERR_INVALID_ARG;
+    ConvF32 c1;
+    c1.x = x; c1.x_ctot = S.Cout; c1.Cin = S.Cout; c1.Tin = L;
+    c1.w = W1.w; c1.bias = W1.b; c1.Cout = S.Cout; c1.k = k; c1.dil = dil; c1.pad_left = dil * (k - 1) / 2;
+    c1.in_act = 1; c1.in_slope = 0.1f;
+    c1.y = scratch; c1.y_ctot = S.Cout; c1.Ty = L; c1.n_out = L; c1.B = B;
+    launch_conv_f32(c1, st);
+    ConvF32 c2;
+    c2.x = scratch; c2.x_ctot = S.Cout; c2.Cin = S.Cout; c2.Tin = L;
+    c2.w = W2.w; c2.bias = W2.b; c2.Cout = S.Cout; c2.k = k; c2.dil = 1; c2.pad_left = (k - 1) / 2;
+    c2.in_act = 1; c2.in_slope = 0.1f;
+    c2.res = x; c2.res_ctot = S.Cout;
+    c2.y = out; c2.y_ctot = S.Cout; c2.Ty = L; c2.n_out = L; c2.B = B;
+    c2.alpha = alpha; c2.beta = beta;
+    launch_conv_f32(c2, st);
+    return check_launch(ctx, "debug_pair");
+}
+
 int svb_profile_enable(svb_ctx* ctx, int on) {
     if (!ctx) return SVB_ERR_INVALID_ARG;
     for (auto& kv : ctx->prof)
@@ -594,13 +725,42 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
         if ((rc = get_tensor(ctx, m, p + "pre.weight", {H, half, 1}, w))) return rc;
         if ((rc = get_tensor(ctx, m, p + "pre.bias", {H}, b))) return rc;
         if ((rc = make_conv(ctx, w.v, b.v, H, half, 1, odd, false, F.pre))) return rc;
+        const bool flow_tc = (H == 192) && (half <= H) && (half % 32 == 0) && (c.flow_kernel_size - 1 <= 8);
+        ctx->flow_tc_ok = flow_tc;
+        if (flow_tc) {
+            const std::vector<float> wv = w.v, bv = b.v;
+            if ((rc = make_convn(ctx, H, half, H, H, 1, 0,
+                                 [&](int col, int ci, int) { return wv[(size_t)col * half + (odd ? half - 1 - ci : ci)]; },
+                                 [&](int col) { return bv[col]; }, F.pre_tc))) return rc;
+        }
         if ((rc = get_tensor(ctx, m, p + "post.weight", {half, H, 1}, w))) return rc;
         if ((rc = get_tensor(ctx, m, p + "post.bias", {half}, b))) return rc;
         if ((rc = make_conv(ctx, w.v, b.v, half, H, 1, false, odd, F.post))) return rc;
+        if (flow_tc) {
+            const std::vector<float> wv = w.v, bv = b.v;
+            if ((rc = make_convn(ctx, H, H, half, half, 1, 0,
+                                 [&](int col, int ci, int) { return wv[(size_t)(odd ? half - 1 - col : col) * H + ci]; },
+                                 [&](int col) { return bv[odd ? half - 1 - col : col]; }, F.post_tc))) return rc;
+        }
         if ((rc = folded(ctx, m, p + "enc.cond_layer", {2 * H * L, G, 1}, w))) return rc;
         if ((rc = get_tensor(ctx, m, p + "enc.cond_layer.bias", {2 * H * L}, b))) return rc;
         if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&F.cond_w_nat))) return rc;
         if ((rc = make_conv(ctx, w.v, b.v, 2 * H * L, G, 1, false, false, F.cond))) return rc;
+        // gate kernel column order: chunk c (of H columns) = [tanh channels c*H/2.. | sigmoid channels c*H/2..]
+        auto gate_row = [H](int col) { const int cc = col / H, j = col % H, hh = H / 2; return j < hh ? cc * hh + j : H + cc * hh + (j - hh); };
+        if (flow_tc) {
+            std::vector<float> wp(w.v.size()), bp(b.v.size());
+            for (int i = 0; i < L; ++i)
+                for (int col = 0; col < 2 * H; ++col) {
+                    const int src = 2 * H * i + gate_row(col), dst = 2 * H * i + col;
+                    std::memcpy(&wp[(size_t)dst * G], &w.v[(size_t)src * G], sizeof(float) * G);
+                    bp[dst] = b.v[src];
+                }
+            if ((rc = upload(ctx, wp.data(), wp.size() * sizeof(float), (void**)&F.cond_w_perm))) return rc;
+            if ((rc = upload(ctx, bp.data(), bp.size() * sizeof(float), (void**)&F.cond_b_perm))) return rc;
+            F.in_tc.assign(L, ConvNW());
+            F.rs_tc.assign(L, ConvNW());
+        }
         F.in_layers.assign(L, ConvW());
         F.res_skip.assign(L, ConvW());
         for (int i = 0; i < L; ++i) {
@@ -608,10 +768,22 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
             if ((rc = folded(ctx, m, q, {2 * H, H, c.flow_kernel_size}, w))) return rc;
             if ((rc = get_tensor(ctx, m, q + ".bias", {2 * H}, b))) return rc;
             if ((rc = make_conv(ctx, w.v, b.v, 2 * H, H, c.flow_kernel_size, false, false, F.in_layers[i]))) return rc;
+            if (flow_tc) {
+                const int kk = c.flow_kernel_size;
+                const std::vector<float> wv = w.v, bv = b.v;
+                if ((rc = make_convn(ctx, H, H, 2 * H, H, kk, (kk - 1) / 2,
+                                     [&](int col, int ci, int tap) { return wv[((size_t)gate_row(col) * H + ci) * kk + tap]; },
+                                     [&](int col) { return bv[gate_row(col)]; }, F.in_tc[i]))) return rc;
+            }
             const std::string r = p + "enc.res_skip_layers." + std::to_string(i);
             const int co = (i < L - 1) ? 2 * H : H;
             if ((rc = folded(ctx, m, r, {co, H, 1}, w))) return rc;
             if ((rc = get_tensor(ctx, m, r + ".bias", {co}, b))) return rc;
+            if (flow_tc) {
+                const std::vector<float> wv = w.v, bv = b.v;
+                if ((rc = make_convn(ctx, H, H, co, H, 1, 0, [&](int col, int ci, int) { return wv[(size_t)col * H + ci]; },
+                                     [&](int col) { return bv[col]; }, F.rs_tc[i]))) return rc;
+            }
             if (co == 2 * H) {
                 // pack the residual half and the skip half as two consecutive [H][1][H] blocks
                 std::vector<float> pk((size_t)2 * H * H), bb(2 * H);
@@ -635,6 +807,16 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
     if ((rc = folded(ctx, m, "dec.conv_pre", {U, C, 7}, w))) return rc;
     if ((rc = get_tensor(ctx, m, "dec.conv_pre.bias", {U}, b))) return rc;
     if ((rc = make_conv(ctx, w.v, b.v, U, C, 7, false, false, ctx->conv_pre))) return rc;
+    ctx->gen_tc_ok = (C == 192 || C == 128 || C == 256) && (U % 256 == 0);
+    for (int i = 0; i < c.n_upsamples; ++i) {
+        const int ci_ = U >> i, n_ = (U >> (i + 1)) * c.upsample_rates[i];
+        if (!(ci_ == 512 || ci_ == 256 || ci_ == 128 || ci_ == 64 || ci_ == 32) || (n_ % 32)) ctx->gen_tc_ok = false;
+    }
+    if (ctx->gen_tc_ok) {
+        const std::vector<float> wv = w.v, bv = b.v;
+        if ((rc = make_convn(ctx, C, C, U, 256 / convn_mb(C), 7, 3, [&](int col, int ci, int tap) { return wv[((size_t)col * C + ci) * 7 + tap]; },
+                             [&](int col) { return bv[col]; }, ctx->conv_pre_tc))) return rc;
+    }
     if ((rc = get_tensor(ctx, m, "dec.cond.weight", {U, G, 1}, w))) return rc;
     if ((rc = get_tensor(ctx, m, "dec.cond.bias", {U}, b))) return rc;
     if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&ctx->dcond_w_nat))) return rc;
@@ -658,6 +840,17 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
                 }
         if ((rc = upload(ctx, pk.data(), pk.size() * sizeof(float), (void**)&S.up_w))) return rc;
         if ((rc = upload(ctx, b.v.data(), b.v.size() * sizeof(float), (void**)&S.up_b))) return rc;
+        if (ctx->gen_tc_ok) {
+            // polyphase GEMM columns: col = co*s + phase; tap 0 multiplies x[i-1] (kernel index phase+s), tap 1 x[i] (index phase)
+            const std::vector<float> wv = w.v, bv = b.v;
+            const int s_ = S.s, Co = S.Cout, kk = S.k;
+            const int ntot = Co * s_;
+            int nc = 256 / convn_mb(S.Cin);
+            if (nc > ntot) nc = ntot;
+            if ((rc = make_convn(ctx, S.Cin, S.Cin, ntot, nc, 2, 1,
+                                 [&](int col, int ci, int tap) { const int co = col / s_, ph = col % s_; return wv[((size_t)ci * Co + co) * kk + (tap == 0 ? ph + s_ : ph)]; },
+                                 [&](int col) { return bv[col / s_]; }, S.up_tc))) return rc;
+        }
         // noise conv
         int stride = 1;
         for (int q = i + 1; q < c.n_upsamples; ++q) stride *= c.upsample_rates[q];

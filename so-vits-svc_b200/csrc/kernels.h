@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <functional>
 
 namespace svb {
 
@@ -58,11 +59,41 @@ struct PairTC {
     const float* b1 = nullptr; const float* b2 = nullptr;
     int B = 1, C = 0, T = 0, k = 3, dil = 1;
     float alpha = 1.f, beta = 0.f;
+    int variant = -1;              // -1: library default (env SVB_TC_VARIANT), else explicit tile variant
 };
 int launch_pair_tc(const PairTC& a, cudaStream_t st);   // returns 0 or a negative status
 size_t tc_weight_image_bytes(int C, int k);
 // host-side: build the swizzled fp16 image for one conv (w_folded is [Cout][Cin][k] fp32)
 void tc_pack_weight_image(const float* w_folded, int C, int k, void* dst_host);
+
+// ---- generic tensor-core convolution-as-GEMM (kernels_convn.cu): conv_pre, polyphase ups, flow WN layers ----------
+struct ConvNSeg {                 // destination of a column range [col0, col1)
+    float* y = nullptr; int y_ctot = 0, y_c0 = 0;
+    int col0 = 0, col1 = 0;
+    float alpha = 1.f, beta = 0.f;
+    const float* res = nullptr; int res_ctot = 0, res_c0 = 0;
+    int masked = 0;
+};
+struct ConvNTC {
+    const float* x = nullptr; int x_ctot = 0, x_c0 = 0, cin_real = 0, Tin = 0;
+    int cinp = 0;                  // padded Cin (template selector): 32,64,128,192,256,512
+    int in_act = 0; float in_slope = 0.f;
+    const void* w = nullptr;       // fp16 image [chunk][tap][panel][NC rows][swizzled]
+    const float* bias = nullptr;   // per column (column order), nullable
+    const float* bias_b = nullptr; int bias_b_stride = 0, bias_b_off = 0;   // per-batch column bias
+    int k = 1, dil = 1, pad_left = 0;
+    int n_rows = 0;                // output rows (time steps of the GEMM's M dimension)
+    int N_total = 0, NC = 0, chunks_per_cta = 1;
+    int mode = 0;                  // 0 plain (column == channel), 1 polyphase (column = co*s + phase), 2 tanh*sigmoid gate
+    int s = 1, p = 0, Ty = 0;      // polyphase stride / padding; Ty = length of the output time axis
+    ConvNSeg seg[2]; int n_seg = 1;
+    const int32_t* lengths = nullptr;
+    int B = 1;
+};
+int launch_convn_tc(const ConvNTC& a, cudaStream_t st);
+int convn_mb(int cinp);
+size_t convn_weight_image_bytes(int cinp, int N_total, int NC, int k);
+void convn_pack_weight_image(int cinp, int N_total, int NC, int k, const std::function<float(int, int, int)>& wcol, void* dst_host);
 
 int64_t& launch_counter();
 

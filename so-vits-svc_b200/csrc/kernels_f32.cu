@@ -195,49 +195,59 @@ void launch_gemv(const float* W, const float* bias, const float* g, float* out, 
 // Block: 128 output steps x all channels.  The excitation window is staged as rows of `s` samples with
 // an odd pitch (s+1) so that lanes (consecutive t) hit distinct banks.
 // =====================================================================================================
+// Block: 64 output steps x 32 channels (256 threads = 64 t x 4 groups of 8 channels).  The excitation window is
+// staged as rows of `s` samples with an odd pitch (s+1) so lanes (consecutive t) hit distinct banks; the weight
+// slice is staged transposed [kk][co] so each thread reads its 8 channels as two warp-broadcast float4.
 __global__ void __launch_bounds__(256) noise_conv_add_kernel(const float* __restrict__ har, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ y,
                                                              int Cout, int Tout, int N, int K, int s, int p) {
     extern __shared__ float sm[];
-    const int TT = 128;
+    constexpr int TT = 64, TC = 32;
     const int pitch = s + 1;
-    float* hs = sm;                          // [(TT+1)][pitch]  row r = har[(t0+r)*s - p .. +s)
-    float* wsm = sm + (TT + 1) * pitch;      // [Cout][K]
-    const int b = blockIdx.y;
-    const int t0 = blockIdx.x * TT;
-    const float* hb = har + (long long)b * N;
     const int rows = (K > 1) ? TT + 1 : TT;
+    float* hs = sm;                                   // [rows][pitch]  row r = har[(t0+r)*s - p .. +s)
+    float* wsm = sm + (((TT + 1) * pitch + 3) & ~3);  // [K][TC]
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * TT;
+    const int co0 = blockIdx.y * TC;
+    const float* hb = har + (long long)b * N;
     for (int idx = threadIdx.x; idx < rows * s; idx += blockDim.x) {
         int r = idx / s, c = idx - r * s;
         long long n = (long long)(t0 + r) * s - p + c;
         hs[r * pitch + c] = (n >= 0 && n < N) ? hb[n] : 0.f;
     }
-    for (int idx = threadIdx.x; idx < Cout * K; idx += blockDim.x) wsm[idx] = w[idx];
+    for (int idx = threadIdx.x; idx < K * TC; idx += blockDim.x) {
+        int co = idx / K, kk = idx - co * K;            // coalesced read of w[co][kk]
+        wsm[kk * TC + co] = (co0 + co < Cout) ? w[(long long)(co0 + co) * K + kk] : 0.f;
+    }
     __syncthreads();
-    const int tx = threadIdx.x % TT, cy = threadIdx.x / TT;
+    const int tx = threadIdx.x % TT, cg = threadIdx.x / TT;
     const int t = t0 + tx;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = (co0 + cg * 8 + i < Cout) ? bias[co0 + cg * 8 + i] : 0.f;
+    int r = tx, c = 0;
+    for (int kk = 0; kk < K; ++kk) {
+        const float h = hs[r * pitch + c];
+        const float4 w0 = *reinterpret_cast<const float4*>(wsm + kk * TC + cg * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(wsm + kk * TC + cg * 8 + 4);
+        acc[0] = fmaf(w0.x, h, acc[0]); acc[1] = fmaf(w0.y, h, acc[1]); acc[2] = fmaf(w0.z, h, acc[2]); acc[3] = fmaf(w0.w, h, acc[3]);
+        acc[4] = fmaf(w1.x, h, acc[4]); acc[5] = fmaf(w1.y, h, acc[5]); acc[6] = fmaf(w1.z, h, acc[6]); acc[7] = fmaf(w1.w, h, acc[7]);
+        if (++c == s) { c = 0; ++r; }
+    }
     if (t >= Tout) return;
-    for (int co = cy; co < Cout; co += blockDim.x / TT) {
-        float accv = bias[co];
-        const float* wr = wsm + co * K;
-        for (int kk = 0; kk < K; ++kk) {
-            int r = tx + kk / s, c = kk % s;
-            accv = fmaf(wr[kk], hs[r * pitch + c], accv);
-        }
-        y[((long long)b * Cout + co) * Tout + t] += accv;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int co = co0 + cg * 8 + i;
+        if (co < Cout) y[((long long)b * Cout + co) * Tout + t] += acc[i];
     }
 }
 
 void launch_noise_conv_add(const float* har, const float* w, const float* bias, float* y,
                            int B, int Cout, int Tout, int N, int K, int s, int p, cudaStream_t st) {
-    const int TT = 128;
-    size_t smem = sizeof(float) * ((size_t)(TT + 1) * (s + 1) + (size_t)Cout * K);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(noise_conv_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
-    dim3 grid((Tout + TT - 1) / TT, B);
+    constexpr int TT = 64, TC = 32;
+    size_t smem = sizeof(float) * ((size_t)(((TT + 1) * (s + 1) + 3) & ~3) + (size_t)K * TC);
+    dim3 grid((Tout + TT - 1) / TT, (Cout + TC - 1) / TC, B);
     noise_conv_add_kernel<<<grid, 256, smem, st>>>(har, w, bias, y, Cout, Tout, N, K, s, p);
     launch_counter()++;
 }
@@ -292,16 +302,27 @@ __device__ __forceinline__ float rad_value(float f0, int h, float sr) {
     return fmodf(q, 1.0f);
 }
 
+// one warp per (batch, harmonic): lanes own contiguous chunks of frames, fp64 exclusive scan across lanes
 __global__ void nsf_phase_kernel(const float* __restrict__ f0, const float* __restrict__ rand_ini, double* __restrict__ phase,
                                  int B, int T, int H, int hop, float sr) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * H) return;
-    int b = i / H, h = i % H;
-    double acc = (h == 0) ? 0.0 : (double)rand_ini[b * H + h];
-    for (int t = 0; t < T; ++t) {
+    const int i = blockIdx.x;                 // b*H + h
+    const int lane = threadIdx.x;
+    const int b = i / H, h = i % H;
+    const int ch = (T + 31) / 32;
+    const int t_lo = lane * ch, t_hi = min(T, t_lo + ch);
+    double local = 0.0;
+    for (int t = t_lo; t < t_hi; ++t) local += (double)rad_value(f0[(long long)b * T + t], h, sr) * (double)hop;
+    double incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    double acc = (incl - local) + ((h == 0) ? 0.0 : (double)rand_ini[b * H + h]);
+    acc -= floor(acc);
+    for (int t = t_lo; t < t_hi; ++t) {
         phase[((long long)b * T + t) * H + h] = acc;
-        double r = (double)rad_value(f0[(long long)b * T + t], h, sr);
-        acc += r * (double)hop;
+        acc += (double)rad_value(f0[(long long)b * T + t], h, sr) * (double)hop;
         acc -= floor(acc);
     }
 }
@@ -335,8 +356,7 @@ __global__ void __launch_bounds__(256) nsf_source_kernel(const float* __restrict
 
 void launch_nsf_source(const float* f0, const float* rand_ini, const float* noise, const float* lin_w, float lin_b,
                        double* phase_ws, float* har, int B, int T, int hop, int n_harm, float sr, cudaStream_t st) {
-    int total = B * n_harm;
-    nsf_phase_kernel<<<(total + 63) / 64, 64, 0, st>>>(f0, rand_ini, phase_ws, B, T, n_harm, hop, sr);
+    nsf_phase_kernel<<<B * n_harm, 32, 0, st>>>(f0, rand_ini, phase_ws, B, T, n_harm, hop, sr);
     launch_counter()++;
     long long N = (long long)T * hop;
     dim3 grid((unsigned)((N + 255) / 256), B);

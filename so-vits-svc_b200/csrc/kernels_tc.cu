@@ -35,14 +35,14 @@ constexpr int NWORK = 256;           // worker threads (8 warps)
 constexpr int NSTAGE = 2;
 constexpr int MAX_HALO = 56;         // >= max (k-1)*dil = 50, multiple of 8
 
-template <int C>
+template <int C, int STAGE_KB = 32>
 struct TCGeom {
     static constexpr int CPP = C < 64 ? C : 64;         // channels per K-panel
     static constexpr int NP = C / CPP;                  // K-panels
     static constexpr int RB = CPP * 2;                  // operand row bytes: 128 / 64 / 32
     static constexpr int KSTEPS = CPP / 16;             // MMAs (K=16) per panel row
     static constexpr int SUB = C * RB;                  // bytes of one (tap, panel) weight block: C_out rows
-    static constexpr int SPC_RAW = 32768 / SUB;         // sub-blocks per ring chunk (<= 32 KB)
+    static constexpr int SPC_RAW = STAGE_KB * 1024 / SUB;   // sub-blocks per ring chunk
     static constexpr int SPC = SPC_RAW < 1 ? 1 : (SPC_RAW > 11 * NP ? 11 * NP : SPC_RAW);
     static constexpr int STAGE_BYTES = ((SPC * SUB + 1023) / 1024) * 1024;
 };
@@ -53,18 +53,17 @@ struct PairParams {
     const float* b1; const float* b2;
     int T, k, dil;
     float alpha, beta;
-    int bo_mode;     // 0: descriptor base_offset = 0;  1: base_offset = (start_address >> 7) & 7
 };
 
-template <int C, int MB>
+template <int C, int MB, int STAGE_KB>
 constexpr size_t pair_smem_bytes() {
-    using G = TCGeom<C>;
+    using G = TCGeom<C, STAGE_KB>;
     return 1024 /*align slack*/ + (size_t)G::NP * (128 * MB + MAX_HALO) * G::RB + (size_t)NSTAGE * G::STAGE_BYTES + 256;
 }
 
-template <int C, int MB>
-__global__ void __launch_bounds__(TC_THREADS, 1) pair_tc_kernel(const PairParams p) {
-    using G = TCGeom<C>;
+template <int C, int MB, int STAGE_KB, int MINB>
+__global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairParams p) {
+    using G = TCGeom<C, STAGE_KB>;
     constexpr int R1 = 128 * MB;
     constexpr int AROWS = R1 + MAX_HALO;
     constexpr int APANEL = AROWS * G::RB;
@@ -149,15 +148,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pair_tc_kernel(const PairParams
                     }
                     const int tap = sb / G::NP, pn = sb % G::NP;
                     const uint32_t bsub = ring_base + s * G::STAGE_BYTES + within * G::SUB;
+                    // descriptors differ only in the 14-bit start-address field: build the constant part once
+                    const uint32_t a0 = a_base + pn * APANEL + (uint32_t)(tap * cd) * G::RB;
+                    const uint64_t a_d0 = make_smem_desc(a0, G::RB, 0);
+                    const uint64_t b_d0 = make_smem_desc(bsub, G::RB, 0);
+                    const uint32_t acc0 = (sb > 0) ? 1u : 0u;
 #pragma unroll
                     for (int mb = 0; mb < MB; ++mb) {
-                        const uint32_t arow = a_base + pn * APANEL + (uint32_t)(mb * 128 + tap * cd) * G::RB;
-                        const uint32_t bo = p.bo_mode ? ((arow >> 7) & 7u) : 0u;
 #pragma unroll
                         for (int ks = 0; ks < G::KSTEPS; ++ks) {
-                            const uint64_t ad = make_smem_desc(arow + ks * 32, G::RB, bo);
-                            const uint64_t bd = make_smem_desc(bsub + ks * 32, G::RB, 0);
-                            umma_f16(tmem_base + mb * C, ad, bd, idesc, (sb > 0 || ks > 0) ? 1u : 0u);
+                            const uint64_t ad = a_d0 + (uint64_t)(((uint32_t)(mb * 128) * G::RB + ks * 32) >> 4);
+                            const uint64_t bd = b_d0 + (uint64_t)((ks * 32) >> 4);
+                            umma_f16(tmem_base + mb * C, ad, bd, idesc, (ks > 0) ? 1u : acc0);
                         }
                     }
                     if (within == G::SPC - 1 || sb == total_sb - 1) {
@@ -271,15 +273,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pair_tc_kernel(const PairParams
                     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
                 }
                 if (valid) {
-                    float xr[16];
+                    float xr[16], oo[16];
 #pragma unroll
                     for (int j = 0; j < CG; ++j) xr[j] = __ldg(xb + (size_t)(c0 + j) * p.T + t);
                     if (p.beta != 0.f) {
 #pragma unroll
-                        for (int j = 0; j < CG; ++j) {
-                            float* dst = ob + (size_t)(c0 + j) * p.T + t;
-                            *dst = fmaf(p.beta, *dst, p.alpha * (v[j] + __ldg(p.b2 + c0 + j) + xr[j]));
-                        }
+                        for (int j = 0; j < CG; ++j) oo[j] = ob[(size_t)(c0 + j) * p.T + t];
+#pragma unroll
+                        for (int j = 0; j < CG; ++j)
+                            ob[(size_t)(c0 + j) * p.T + t] = fmaf(p.beta, oo[j], p.alpha * (v[j] + __ldg(p.b2 + c0 + j) + xr[j]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < CG; ++j)
@@ -304,25 +306,23 @@ int env_int(const char* name, int dflt) {
     return s ? std::atoi(s) : dflt;
 }
 
-template <int C, int MB>
+template <int C, int MB, int STAGE_KB, int MINB>
 int launch_pair_t(const PairTC& a, cudaStream_t st) {
-    constexpr size_t smem = pair_smem_bytes<C, MB>();
-    static_assert(smem <= 227 * 1024, "pair kernel shared memory exceeds 227 KB");
+    constexpr size_t smem = pair_smem_bytes<C, MB, STAGE_KB>();
+    static_assert(smem * MINB + 1024 * MINB <= 228 * 1024, "pair kernel shared memory exceeds the SM budget");
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(pair_tc_kernel<C, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(pair_tc_kernel<C, MB, STAGE_KB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return SVB_ERR_CUDA;
         attr_set = true;
     }
-    static const int bo_mode = env_int("SVB_TC_BASE_OFFSET", 0);
     PairParams p;
     p.x = a.x; p.out = a.out;
     p.w1 = static_cast<const uint8_t*>(a.w1); p.w2 = static_cast<const uint8_t*>(a.w2);
     p.b1 = a.b1; p.b2 = a.b2; p.T = a.T; p.k = a.k; p.dil = a.dil; p.alpha = a.alpha; p.beta = a.beta;
-    p.bo_mode = bo_mode;
     const int TOUT = 128 * MB - (a.k - 1);
     dim3 grid((a.T + TOUT - 1) / TOUT, a.B);
-    pair_tc_kernel<C, MB><<<grid, TC_THREADS, smem, st>>>(p);
+    pair_tc_kernel<C, MB, STAGE_KB, MINB><<<grid, TC_THREADS, smem, st>>>(p);
     launch_counter()++;
     return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;
 }
@@ -349,15 +349,30 @@ void tc_pack_weight_image(const float* w, int C, int k, void* dst_host) {
         }
 }
 
+// Tile variants.  variant 0: one CTA per SM with the largest tile (weights amortised over 128*MB rows);
+// variant 1: two CTAs per SM (<= 113 KB smem, <= 256 TMEM columns, <= 102 registers each) so that one CTA's
+// load / epilogue phases overlap the other's MMA phases.  C=256 needs all 512 TMEM columns and stays 1 CTA/SM.
 int launch_pair_tc(const PairTC& a, cudaStream_t st) {
     if (!(a.k == 3 || a.k == 7 || a.k == 11) || (a.k - 1) * a.dil > 50) return SVB_ERR_UNSUPPORTED;
-    static const int mb128 = env_int("SVB_TC_MB128", 4);
+    static const int env_variant = env_int("SVB_TC_VARIANT", -1);
+    int variant = a.variant >= 0 ? a.variant : env_variant;
+    if (variant < 0) variant = (a.C <= 64) ? 1 : 0;     // measured on B200 (profiles/r01/bench_pair_sweep.log): 2 CTAs/SM wins for C <= 64
+    if (variant == 1) {
+        switch (a.C) {
+            case 16: return launch_pair_t<16, 16, 8, 2>(a, st);
+            case 32: return launch_pair_t<32, 8, 22, 2>(a, st);
+            case 64: return launch_pair_t<64, 4, 16, 2>(a, st);
+            case 128: return launch_pair_t<128, 2, 16, 2>(a, st);
+            case 256: return launch_pair_t<256, 2, 32, 1>(a, st);
+            default: return SVB_ERR_UNSUPPORTED;
+        }
+    }
     switch (a.C) {
-        case 16: return launch_pair_t<16, 16>(a, st);
-        case 32: return launch_pair_t<32, 8>(a, st);
-        case 64: return launch_pair_t<64, 4>(a, st);
-        case 128: return mb128 == 2 ? launch_pair_t<128, 2>(a, st) : launch_pair_t<128, 4>(a, st);
-        case 256: return launch_pair_t<256, 2>(a, st);
+        case 16: return launch_pair_t<16, 16, 32, 1>(a, st);
+        case 32: return launch_pair_t<32, 8, 32, 1>(a, st);
+        case 64: return launch_pair_t<64, 4, 32, 1>(a, st);
+        case 128: return launch_pair_t<128, 4, 32, 1>(a, st);
+        case 256: return launch_pair_t<256, 2, 32, 1>(a, st);
         default: return SVB_ERR_UNSUPPORTED;
     }
 }

@@ -110,6 +110,20 @@ class TailEngine:
         L.check(self.lib, self._ctx, rc, "svb_debug_fetch")
         return out
 
+    def debug_pair(self, stage: int, j: int, d: int, x: torch.Tensor, variant: int, out: Optional[torch.Tensor] = None,
+                   alpha: float = 1.0, beta: float = 0.0) -> torch.Tensor:
+        """One ResBlock pair on x [B,C,L]; variant >= 0: tensor-core tile variant, -2: fp32 FFMA convs."""
+        x = self._f32(x, "x")
+        B, Cc, Ln = x.shape
+        if out is None:
+            out = torch.empty_like(x)
+        scratch = torch.empty_like(x) if variant < 0 else None
+        rc = self.lib.svb_debug_pair(self._ctx, stage, j, d, x.data_ptr(), out.data_ptr(),
+                                     scratch.data_ptr() if scratch is not None else None, B, Ln, variant,
+                                     alpha, beta, self._stream())
+        L.check(self.lib, self._ctx, rc, "svb_debug_pair")
+        return out
+
     def profile_enable(self, on: bool = True) -> None:
         L.check(self.lib, self._ctx, self.lib.svb_profile_enable(self._ctx, int(on)), "svb_profile_enable")
 

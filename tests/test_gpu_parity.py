@@ -92,6 +92,22 @@ def test_flow_reverse_ragged_lengths_and_time_varying_g(cfg, sd, eng):
     assert float((got - ref).abs().max()) < FP32_TOL
 
 
+@pytest.mark.parametrize("B,T", [(2, 24), (1, 33), (2, 200)])
+def test_flow_reverse_tensor_core(cfg, sd, eng, B, T):
+    """The flow on the tcgen05 conv-as-GEMM kernel (gate fused) incl. ragged lengths; z has |max| ~ 15."""
+    z_p, g, _, _ = _case(cfg, sd, B, T)
+    lengths = torch.tensor([T, max(1, T // 3), 1][:B])
+    mask = (torch.arange(T)[None, :] < lengths[:, None]).float()[:, None, :]
+    z_p = z_p * mask
+    ref = O.flow_reverse(sd, z_p, mask, g, cfg, torch.float32)
+    eng.set_precision("tc")
+    got = eng.flow_reverse(z_p.to(DEV), g.to(DEV), lengths.to(DEV)).cpu()
+    eng.set_precision("fp32")
+    err = float((got - ref).abs().max())
+    print(f"[parity] flow tc B={B} T={T}: L-inf = {err:.3e} (|z|max {float(ref.abs().max()):.1f})")
+    assert err < 2e-2
+
+
 @pytest.mark.parametrize("B,T", [(2, 24), (1, 33)])
 def test_generator_fp32_stagewise(cfg, sd, eng, B, T):
     z_p, g, f0, noise = _case(cfg, sd, B, T)
@@ -138,6 +154,12 @@ def test_tc_stagewise_against_oracle(cfg, sd, eng):
     eng.debug_enable(True)
     got = eng.infer_tail(z_p.to(DEV), g.to(DEV), f0.to(DEV), noise["rand_ini"].to(DEV), noise["har_noise"].to(DEV)).cpu()
     worst = {}
+    for name in ["z", "conv_pre"] + [f"ups{i}" for i in range(5)]:
+        t = taps[name]
+        d = eng.debug_fetch(name, tuple(t.shape)).cpu()
+        rel = float((d - t).abs().max()) / float(t.abs().max())
+        print(f"[parity] tc {name}: relative L-inf {rel:.2e}")
+        assert rel < 1e-2, (name, rel)
     for i in range(5):
         t = taps[f"stage{i}"]
         d = eng.debug_fetch(f"stage{i}", tuple(t.shape)).cpu()
