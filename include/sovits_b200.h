@@ -139,6 +139,9 @@ SVB_API int svb_debug_fetch(svb_ctx* ctx, const char* what, float* dst, size_t n
  * tile variant, variant == -2 the two fp32 FFMA convolutions. */
 SVB_API int svb_debug_pair(svb_ctx* ctx, int stage, int j, int d, const float* x, float* out, float* scratch,
                            int B, int L, int variant, float alpha, float beta, void* stream);
+/* Same for one whole ResBlock branch j (three pairs) through the fused tensor-core kernel (stages with C <= 64). */
+SVB_API int svb_debug_resblock(svb_ctx* ctx, int stage, int j, const float* x, float* out, int B, int L, int variant,
+                               float alpha, float beta, void* stream);
 /* CUDA-event timers on the launching stream, per kernel family ("pair_tc","pair_f32","flow","nsf_source",
  * "generator"): enable, run, then read the summed device time, launch count and algorithmic FLOPs/bytes
  * (bench.py's roofline).  Re-enabling clears the counters. */

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -502,8 +503,25 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         }
         launch_noise_conv_add(har, S.noise_w, S.noise_b, X, B, S.Cout, Lout, (int)N, S.noise_K, S.noise_s, S.noise_p, st);
         if ((rc = dbg_keep(ctx, "ups" + std::to_string(i), X, (size_t)B * S.Cout * Lout, st))) return rc;
+        static const int fuse_rb = [] { const char* e = std::getenv("SVB_FUSE_RESBLOCK"); return e ? std::atoi(e) : 1; }();
         for (int j = 0; j < nk; ++j) {
             const int k = c.resblock_kernel_sizes[j];
+            if (ctx->precision == SVB_PREC_TC && fuse_rb && S.Cout <= 64 && S.c1[j * 3].w_tc) {
+                // narrow stages: the whole ResBlock in one kernel (residual stream in TMEM)
+                ResblockTC rb;
+                rb.x = X; rb.out = O; rb.B = B; rb.C = S.Cout; rb.T = Lout; rb.k = k;
+                for (int d = 0; d < 3; ++d) {
+                    rb.dil[d] = c.resblock_dilations[j][d];
+                    rb.w[2 * d] = S.c1[j * 3 + d].w_tc; rb.w[2 * d + 1] = S.c2[j * 3 + d].w_tc;
+                    rb.bias[2 * d] = S.c1[j * 3 + d].b; rb.bias[2 * d + 1] = S.c2[j * 3 + d].b;
+                }
+                rb.alpha = 1.f / nk; rb.beta = (j > 0) ? 1.f : 0.f;
+                const double rflops = 3 * 2.0 * 2.0 * S.Cout * (double)S.Cout * k * (double)Lout * B;
+                ProfScope ps(ctx, "resblock_tc", st, rflops, 2.0 * S.Cout * (double)Lout * B * sizeof(float));
+                int trc = launch_resblock_tc(rb, st);
+                if (trc == 0) continue;
+                if (trc != SVB_ERR_UNSUPPORTED) return fail(ctx, trc, "fused ResBlock kernel launch failed");
+            }
             const float* src = X;
             float* pp[2] = {A, Bb};
             for (int d = 0; d < 3; ++d) {
@@ -654,6 +672,26 @@ int svb_debug_pair(svb_ctx* ctx, int stage, int j, int d, const float* x, float*
     c2.alpha = alpha; c2.beta = beta;
     launch_conv_f32(c2, st);
     return check_launch(ctx, "debug_pair");
+}
+
+// One whole ResBlock branch j of a stage through the fused tensor-core kernel (variant >= 0).
+int svb_debug_resblock(svb_ctx* ctx, int stage, int j, const float* x, float* out, int B, int L, int variant,
+                       float alpha, float beta, void* stream) {
+    if (!ctx || !ctx->loaded) return SVB_ERR_NOT_LOADED;
+    if (stage < 0 || stage >= ctx->cfg.n_upsamples || j < 0 || j >= 3 || !x || !out) return SVB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    Stage& S = ctx->stages[stage];
+    ResblockTC rb;
+    rb.x = x; rb.out = out; rb.B = B; rb.C = S.Cout; rb.T = L; rb.k = ctx->cfg.resblock_kernel_sizes[j];
+    for (int d = 0; d < 3; ++d) {
+        rb.dil[d] = ctx->cfg.resblock_dilations[j][d];
+        rb.w[2 * d] = S.c1[j * 3 + d].w_tc; rb.w[2 * d + 1] = S.c2[j * 3 + d].w_tc;
+        rb.bias[2 * d] = S.c1[j * 3 + d].b; rb.bias[2 * d + 1] = S.c2[j * 3 + d].b;
+    }
+    rb.alpha = alpha; rb.beta = beta; rb.variant = variant;
+    int rc = launch_resblock_tc(rb, (cudaStream_t)stream);
+    if (rc) return fail(ctx, rc, "fused ResBlock kernel launch failed");
+    return check_launch(ctx, "debug_resblock");
 }
 
 int svb_profile_enable(svb_ctx* ctx, int on) {

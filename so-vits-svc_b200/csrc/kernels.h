@@ -66,6 +66,18 @@ size_t tc_weight_image_bytes(int C, int k);
 // host-side: build the swizzled fp16 image for one conv (w_folded is [Cout][Cin][k] fp32)
 void tc_pack_weight_image(const float* w_folded, int C, int k, void* dst_host);
 
+// ---- fused ResBlock1 (three pairs, one branch) for C <= 64 (kernels_resblock.cu) -------------------------------------
+struct ResblockTC {
+    const float* x = nullptr; float* out = nullptr;     // [B,C,T]
+    const void* w[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // c1[d0], c2[d0], c1[d1], c2[d1], c1[d2], c2[d2]
+    const float* bias[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int B = 1, C = 0, T = 0, k = 3;
+    int dil[3] = {1, 3, 5};
+    float alpha = 1.f, beta = 0.f;
+    int variant = -1;
+};
+int launch_resblock_tc(const ResblockTC& a, cudaStream_t st);
+
 // ---- generic tensor-core convolution-as-GEMM (kernels_convn.cu): conv_pre, polyphase ups, flow WN layers ----------
 struct ConvNSeg {                 // destination of a column range [col0, col1)
     float* y = nullptr; int y_ctot = 0, y_c0 = 0;

@@ -1,0 +1,341 @@
+// Fused HiFiGAN ResBlock1 on tcgen05 (sm_100a) for the narrow stages (C <= 64), vdecoder/hifigan/models.py:60-67:
+//     for d in (d0, d1, d2):  x = x + c2_d( lrelu( c1_d( lrelu(x) ) + b1 ) ) + b2        (c1_d dilation d, c2_d dilation 1)
+//     out = alpha * x + beta * out_old                                                     (the xs / num_kernels sum, :383-389)
+// One CTA owns a tile of 128*MB time steps for the WHOLE block: the fp32 residual stream x lives in TMEM
+// (tcgen05.st / tcgen05.ld) next to the fp32 accumulators, the fp16 MMA operand tile lives in shared memory and is
+// rewritten in place by the epilogues, so HBM sees one read of x and one write of out per element instead of the
+// nine read/read/write passes of the pair-by-pair schedule.  Rows near the tile edge become invalid as the six
+// convolutions eat their receptive field (halo = sum_d (d+1)(k-1)/2 per side: 12 / 36 / 60 for k = 3 / 7 / 11);
+// tiles overlap by 2*halo and only the interior is written.
+//
+// Same warp roles and operand conventions as pair_tc_kernel (kernels_tc.cu): row r of the tile <-> time tt0 + r for
+// every buffer, a tap offset is a row offset of the A descriptor (the tile is padded by PAD rows of zeros on both
+// sides so negative offsets stay inside the buffer).
+#include "kernels.h"
+#include "tc_common.cuh"
+#include "../../include/sovits_b200.h"
+
+#include <cstdlib>
+
+namespace svb {
+
+using namespace tc;
+
+namespace {
+
+constexpr int RBK_THREADS = 320;
+constexpr int RBK_NWORK = 256;
+constexpr int RBK_PAD = 32;          // >= max |tap offset| = 5*5 = 25
+
+struct ResblockParams {
+    const float* x; float* out;
+    const uint8_t* w[6];             // c1[d0], c2[d0], c1[d1], c2[d1], c1[d2], c2[d2] tensor-core images
+    const float* bias[6];
+    int T, k, halo;
+    int dil[3];
+    float alpha, beta;
+};
+
+template <int C, int STAGE_KB>
+struct RBGeom {
+    static constexpr int RB = C * 2;                 // operand row bytes (C <= 64: one K-panel)
+    static constexpr int KSTEPS = C / 16;
+    static constexpr int SUB = C * RB;               // one tap's weight block
+    static constexpr int SPC_RAW = STAGE_KB * 1024 / SUB;
+    static constexpr int SPC = SPC_RAW < 1 ? 1 : (SPC_RAW > 11 ? 11 : SPC_RAW);
+    static constexpr int STAGE_BYTES = ((SPC * SUB + 1023) / 1024) * 1024;
+};
+
+template <int C, int MB, int STAGE_KB>
+constexpr size_t resblock_smem_bytes() {
+    using G = RBGeom<C, STAGE_KB>;
+    return 1024 + (size_t)(128 * MB + 2 * RBK_PAD) * G::RB + 2 * (size_t)G::STAGE_BYTES + 256;
+}
+
+template <int C, int MB, int STAGE_KB, int MINB>
+__global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const ResblockParams p) {
+    using G = RBGeom<C, STAGE_KB>;
+    constexpr int R1 = 128 * MB;
+    constexpr int AROWS = R1 + 2 * RBK_PAD;
+    constexpr int TMEM_COLS = 2 * MB * C;
+    constexpr int ACC0 = MB * C;                      // accumulator column base (residual at 0)
+    static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
+    static_assert(C == 16 || C == 32 || C == 64, "fused ResBlock kernel serves C <= 64");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw);
+    const uint32_t a_base = base;
+    const uint32_t ring_base = base + AROWS * G::RB;
+    const uint32_t bar_base = ring_base + 2 * G::STAGE_BYTES;
+    const uint32_t bar_full = bar_base, bar_empty = bar_base + 16, bar_a = bar_base + 32, bar_acc = bar_base + 40;
+    const uint32_t tmem_slot = bar_base + 48;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - base));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int k = p.k;
+    const int TOUT = R1 - 2 * p.halo;
+    const int tt0 = blockIdx.x * TOUT - p.halo;       // time of tile row 0
+    const float* __restrict__ xb = p.x + (size_t)b * C * p.T;
+    float* __restrict__ ob = p.out + (size_t)b * C * p.T;
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_a, RBK_NWORK);
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 8) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 9) {
+        // ------------------------------------------------------------ weight producer: six convolutions back to back
+        if (lane == 0) {
+            int chunk = 0;
+            for (int q = 0; q < 6; ++q) {
+                const uint8_t* wsrc = p.w[q];
+                for (int sb0 = 0; sb0 < k; sb0 += G::SPC, ++chunk) {
+                    const int s = chunk & 1;
+                    if (chunk >= 2) mbar_wait(bar_empty + 8 * s, ((chunk >> 1) - 1) & 1);
+                    const int nsb = (k - sb0) < G::SPC ? (k - sb0) : G::SPC;
+                    const uint32_t bytes = (uint32_t)nsb * G::SUB;
+                    mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+                    bulk_g2s(ring_base + s * G::STAGE_BYTES, wsrc + (size_t)sb0 * G::SUB, bytes, bar_full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(128, C);
+            const int h = (k - 1) / 2;
+            int chunk = 0;
+            for (int q = 0; q < 6; ++q) {
+                mbar_wait(bar_a, q & 1);
+                tc_fence_after();
+                const int cd = (q & 1) ? 1 : p.dil[q >> 1];
+                for (int tap = 0; tap < k; ++tap) {
+                    const int s = chunk & 1;
+                    const int within = tap % G::SPC;
+                    if (within == 0) { mbar_wait(bar_full + 8 * s, (chunk >> 1) & 1); tc_fence_after(); }
+                    const uint32_t a0 = a_base + (uint32_t)(RBK_PAD + (tap - h) * cd) * G::RB;
+                    const uint64_t a_d0 = make_smem_desc(a0, G::RB, 0);
+                    const uint64_t b_d0 = make_smem_desc(ring_base + s * G::STAGE_BYTES + within * G::SUB, G::RB, 0);
+                    const uint32_t acc0 = (tap > 0) ? 1u : 0u;
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll
+                        for (int ks = 0; ks < G::KSTEPS; ++ks) {
+                            const uint64_t ad = a_d0 + (uint64_t)(((uint32_t)(mb * 128) * G::RB + ks * 32) >> 4);
+                            const uint64_t bd = b_d0 + (uint64_t)((ks * 32) >> 4);
+                            umma_f16(tmem_base + ACC0 + mb * C, ad, bd, idesc, (ks > 0) ? 1u : acc0);
+                        }
+                    }
+                    if (within == G::SPC - 1 || tap == k - 1) { umma_commit(bar_empty + 8 * s); ++chunk; }
+                }
+                umma_commit(bar_acc);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ workers
+        const int q4 = warp & 3, hsel = warp >> 2;
+        const int rib = 32 * q4 + lane;
+        constexpr int CH = C / 2;                      // channels per warp-half
+        constexpr int CG = CH < 16 ? CH : 16;          // columns per tcgen05.ld/st
+        const uint32_t tlane = tmem_base + ((uint32_t)(32 * q4) << 16);
+
+        // zero the PAD rows above and below the tile (never written again)
+        for (int i = tid; i < 2 * RBK_PAD * (G::RB / 16); i += RBK_NWORK) {
+            const int rr = i / (G::RB / 16), ch = i % (G::RB / 16);
+            const int row = rr < RBK_PAD ? rr : (R1 + rr);
+            *reinterpret_cast<uint4*>(sm + swz_offset(row, ch, G::RB)) = make_uint4(0, 0, 0, 0);
+        }
+        // (0) load x: fp32 -> TMEM residual, lrelu -> fp16 operand tile
+#pragma unroll 1
+        for (int mb = 0; mb < MB; ++mb) {
+            const int row = mb * 128 + rib;
+            const int t = tt0 + row;
+            const bool valid = (t >= 0) && (t < p.T);
+#pragma unroll 1
+            for (int cc = 0; cc < CH; cc += CG) {
+                const int c0 = hsel * CH + cc;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < CG; ++j) v[j] = valid ? __ldg(xb + (size_t)(c0 + j) * p.T + t) : 0.f;
+                if (CG == 16) {
+                    uint32_t r[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(v[j]);
+                    tmem_st16(tlane + mb * C + c0, r);
+                } else {
+                    uint32_t r[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(v[j]);
+                    tmem_st8(tlane + mb * C + c0, r);
+                }
+#pragma unroll
+                for (int j = 0; j < CG; ++j) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
+                const int ch0 = c0 / 8;
+                *reinterpret_cast<uint4*>(sm + swz_offset(row + RBK_PAD, ch0, G::RB)) =
+                    make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                if (CG == 16)
+                    *reinterpret_cast<uint4*>(sm + swz_offset(row + RBK_PAD, ch0 + 1, G::RB)) =
+                        make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+            }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(bar_a);
+
+#pragma unroll 1
+        for (int q = 0; q < 6; ++q) {
+            mbar_wait(bar_acc, q & 1);
+            tc_fence_after();
+            const float* __restrict__ bias = p.bias[q];
+            const bool second = (q & 1) != 0;
+            const bool last = (q == 5);
+#pragma unroll 1
+            for (int mb = 0; mb < MB; ++mb) {
+                const int row = mb * 128 + rib;
+                const int t = tt0 + row;
+                const bool valid = (t >= 0) && (t < p.T);
+#pragma unroll 1
+                for (int cc = 0; cc < CH; cc += CG) {
+                    const int c0 = hsel * CH + cc;
+                    float v[16], xr[16];
+                    if (CG == 16) {
+                        uint32_t r[16], rr[16];
+                        tmem_ld16(tlane + ACC0 + mb * C + c0, r);
+                        if (second) tmem_ld16(tlane + mb * C + c0, rr);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(r[j]); xr[j] = second ? __uint_as_float(rr[j]) : 0.f; }
+                    } else {
+                        uint32_t r[8], rr[8];
+                        tmem_ld8(tlane + ACC0 + mb * C + c0, r);
+                        if (second) tmem_ld8(tlane + mb * C + c0, rr);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { v[j] = __uint_as_float(r[j]); xr[j] = second ? __uint_as_float(rr[j]) : 0.f; }
+                    }
+#pragma unroll
+                    for (int j = 0; j < CG; ++j) v[j] = v[j] + __ldg(bias + c0 + j) + xr[j];     // conv2: new residual value
+                    if (last) {
+                        const bool wr = valid && (row >= p.halo) && (row < R1 - p.halo);
+                        if (wr) {
+                            if (p.beta != 0.f) {
+                                float oo[16];
+#pragma unroll
+                                for (int j = 0; j < CG; ++j) oo[j] = ob[(size_t)(c0 + j) * p.T + t];
+#pragma unroll
+                                for (int j = 0; j < CG; ++j) ob[(size_t)(c0 + j) * p.T + t] = fmaf(p.beta, oo[j], p.alpha * v[j]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < CG; ++j) ob[(size_t)(c0 + j) * p.T + t] = p.alpha * v[j];
+                            }
+                        }
+                        continue;
+                    }
+                    if (second) {                                   // keep the fp32 residual stream in TMEM
+                        if (CG == 16) {
+                            uint32_t r[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(v[j]);
+                            tmem_st16(tlane + mb * C + c0, r);
+                        } else {
+                            uint32_t r[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(v[j]);
+                            tmem_st8(tlane + mb * C + c0, r);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < CG; ++j) {
+                        const float y = v[j] > 0.f ? v[j] : 0.1f * v[j];
+                        v[j] = valid ? y : 0.f;                     // zero padding of the next convolution outside [0,T)
+                    }
+                    const int ch0 = c0 / 8;
+                    *reinterpret_cast<uint4*>(sm + swz_offset(row + RBK_PAD, ch0, G::RB)) =
+                        make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                    if (CG == 16)
+                        *reinterpret_cast<uint4*>(sm + swz_offset(row + RBK_PAD, ch0 + 1, G::RB)) =
+                            make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+                }
+            }
+            if (!last) {
+                if (second) tmem_st_wait();
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(bar_a);
+            }
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+int rb_env_int(const char* name, int dflt) {
+    const char* s = std::getenv(name);
+    return s ? std::atoi(s) : dflt;
+}
+
+template <int C, int MB, int STAGE_KB, int MINB>
+int launch_resblock_t(const ResblockTC& a, cudaStream_t st) {
+    constexpr size_t smem = resblock_smem_bytes<C, MB, STAGE_KB>();
+    static_assert((smem + 1024) * MINB <= 228 * 1024, "fused ResBlock kernel shared memory exceeds the SM budget");
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(resblock_tc_kernel<C, MB, STAGE_KB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return SVB_ERR_CUDA;
+        attr_set = true;
+    }
+    ResblockParams p;
+    p.x = a.x; p.out = a.out;
+    for (int q = 0; q < 6; ++q) { p.w[q] = static_cast<const uint8_t*>(a.w[q]); p.bias[q] = a.bias[q]; }
+    p.T = a.T; p.k = a.k; p.alpha = a.alpha; p.beta = a.beta;
+    int halo = 0;
+    for (int d = 0; d < 3; ++d) { p.dil[d] = a.dil[d]; halo += (a.dil[d] + 1) * (a.k - 1) / 2; }
+    p.halo = halo;
+    const int TOUT = 128 * MB - 2 * halo;
+    if (TOUT < 64) return SVB_ERR_UNSUPPORTED;
+    dim3 grid((a.T + TOUT - 1) / TOUT, a.B);
+    resblock_tc_kernel<C, MB, STAGE_KB, MINB><<<grid, RBK_THREADS, smem, st>>>(p);
+    launch_counter()++;
+    return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;
+}
+
+}  // namespace
+
+// variant 0: one CTA/SM with all 512 TMEM columns (largest tile); variant 1: two CTAs/SM with 256 columns each.
+int launch_resblock_tc(const ResblockTC& a, cudaStream_t st) {
+    if (!(a.k == 3 || a.k == 7 || a.k == 11)) return SVB_ERR_UNSUPPORTED;
+    for (int d = 0; d < 3; ++d)
+        if (a.dil[d] * (a.k - 1) / 2 > RBK_PAD - 1 || a.dil[d] < 1) return SVB_ERR_UNSUPPORTED;
+    static const int env_variant = rb_env_int("SVB_RB_VARIANT", -1);
+    int variant = a.variant >= 0 ? a.variant : env_variant;
+    if (variant < 0) variant = 0;
+    if (variant == 1) {
+        switch (a.C) {
+            case 16: return launch_resblock_t<16, 8, 8, 2>(a, st);
+            case 32: return launch_resblock_t<32, 4, 22, 2>(a, st);
+            case 64: return launch_resblock_t<64, 4, 32, 1>(a, st);     // 2 CTAs/SM would leave 256-2*120 = 16 useful rows
+            default: return SVB_ERR_UNSUPPORTED;
+        }
+    }
+    switch (a.C) {
+        case 16: return launch_resblock_t<16, 16, 8, 1>(a, st);
+        case 32: return launch_resblock_t<32, 8, 32, 1>(a, st);
+        case 64: return launch_resblock_t<64, 4, 32, 1>(a, st);
+        default: return SVB_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace svb

@@ -124,6 +124,18 @@ class TailEngine:
         L.check(self.lib, self._ctx, rc, "svb_debug_pair")
         return out
 
+    def debug_resblock(self, stage: int, j: int, x: torch.Tensor, variant: int, out: Optional[torch.Tensor] = None,
+                       alpha: float = 1.0, beta: float = 0.0) -> torch.Tensor:
+        """One whole ResBlock branch (3 pairs) on x [B,C,L] through the fused tensor-core kernel."""
+        x = self._f32(x, "x")
+        B, Cc, Ln = x.shape
+        if out is None:
+            out = torch.empty_like(x)
+        rc = self.lib.svb_debug_resblock(self._ctx, stage, j, x.data_ptr(), out.data_ptr(), B, Ln, variant, alpha, beta,
+                                         self._stream())
+        L.check(self.lib, self._ctx, rc, "svb_debug_resblock")
+        return out
+
     def profile_enable(self, on: bool = True) -> None:
         L.check(self.lib, self._ctx, self.lib.svb_profile_enable(self._ctx, int(on)), "svb_profile_enable")
 

@@ -64,6 +64,8 @@ SIGNATURES = {
     "svb_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "svb_debug_pair": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]),
+    "svb_debug_resblock": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_float, C.c_float, C.c_void_p]),
     "svb_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "svb_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]),

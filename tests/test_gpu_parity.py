@@ -172,6 +172,28 @@ def test_tc_stagewise_against_oracle(cfg, sd, eng):
     assert float((got - ref).abs().max()) < TC_TOL
 
 
+@pytest.mark.parametrize("stage", [2, 3, 4])
+def test_fused_resblock_matches_pair_chain(cfg, sd, eng, stage):
+    """The fused ResBlock kernel (residual stream in TMEM, halo recompute) against three fp32 FFMA pairs, for every
+    branch and both tile variants; L is not a multiple of any tile size and alpha/beta accumulate like the generator."""
+    C = cfg.stage_channels[stage]
+    B, Ln = 2, 5000 + 37 * stage
+    g = torch.Generator().manual_seed(7 + stage)
+    x = (torch.randn((B, C, Ln), generator=g) * 1.3).to(DEV)
+    old = (torch.randn((B, C, Ln), generator=g)).to(DEV)
+    for j in range(3):
+        ref = x
+        for d in range(3):
+            ref = eng.debug_pair(stage, j, d, ref, -2)
+        want = ref / 3.0 + old
+        for variant in (0, 1):
+            out = old.clone()
+            eng.debug_resblock(stage, j, x, variant, out=out, alpha=1.0 / 3.0, beta=1.0)
+            rel = float((out - want).abs().max()) / float(want.abs().max())
+            print(f"[parity] fused resblock stage{stage} C={C} k={cfg.resblock_kernel_sizes[j]} v{variant}: rel L-inf {rel:.2e}")
+            assert rel < 1e-2, (stage, j, variant, rel)
+
+
 def test_full_infer_against_oracle_with_replayed_rng(cfg, sd):
     """SynthesizerTrn.infer end to end on the GPU; the oracle gets the very noise tensors torch's CUDA generator
     produced (same seed, same order: SURVEY §9.9)."""

@@ -67,10 +67,28 @@ def main():
                     rows.append(row)
                     print(f"stage{i} C={C:3d} k={k:2d} d={dil} v={v}: {ms:7.3f} ms  {tf:7.1f} TF/s ({tf / peak:5.1%})  "
                           f"{row['gbs_algorithmic']:6.0f} GB/s  linf {err:.2e}", flush=True)
+        if C <= 64:
+            for j, k in enumerate(cfg.resblock_kernel_sizes):
+                for v in variants:
+                    out = eng.debug_resblock(i, j, x, v)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(a.iters):
+                        eng.debug_resblock(i, j, x, v, out=out)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / a.iters
+                    flops = 3 * 2 * 2 * C * C * k * L * a.batch
+                    tf = flops / (ms * 1e-3) / 1e12
+                    rows.append({"stage": i, "C": C, "L": L, "k": k, "fused": True, "variant": v, "ms": ms, "tflops": tf,
+                                 "frac_of_peak": tf / peak, "gbs_algorithmic": 2 * C * L * a.batch * 4 / (ms * 1e-3) / 1e9})
+                    print(f"stage{i} C={C:3d} k={k:2d} FUSED-RESBLOCK v={v}: {ms:7.3f} ms  {tf:7.1f} TF/s ({tf / peak:5.1%})", flush=True)
         del x
     tot = {}
     for r in rows:
-        tot[r["variant"]] = tot.get(r["variant"], 0.0) + r["ms"]
+        key = ("fused" if r.get("fused") else "pair", r["variant"])
+        tot[str(key)] = tot.get(str(key), 0.0) + r["ms"]
     print("sum of pair ms per step by variant:", tot)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump({"rows": rows, "total_ms": tot, "peak_tflops": peak}, open(os.path.join(ROOT, "gpurun_out", "bench_pair.json"), "w"), indent=1)
