@@ -504,9 +504,10 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         launch_noise_conv_add(har, S.noise_w, S.noise_b, X, B, S.Cout, Lout, (int)N, S.noise_K, S.noise_s, S.noise_p, st);
         if ((rc = dbg_keep(ctx, "ups" + std::to_string(i), X, (size_t)B * S.Cout * Lout, st))) return rc;
         static const int fuse_rb = [] { const char* e = std::getenv("SVB_FUSE_RESBLOCK"); return e ? std::atoi(e) : 1; }();
+        static const int fuse_maxc = [] { const char* e = std::getenv("SVB_FUSE_MAXC"); return e ? std::atoi(e) : 32; }();
         for (int j = 0; j < nk; ++j) {
             const int k = c.resblock_kernel_sizes[j];
-            if (ctx->precision == SVB_PREC_TC && fuse_rb && S.Cout <= 64 && S.c1[j * 3].w_tc) {
+            if (ctx->precision == SVB_PREC_TC && fuse_rb && S.Cout <= fuse_maxc && S.c1[j * 3].w_tc) {
                 // narrow stages: the whole ResBlock in one kernel (residual stream in TMEM)
                 ResblockTC rb;
                 rb.x = X; rb.out = O; rb.B = B; rb.C = S.Cout; rb.T = Lout; rb.k = k;

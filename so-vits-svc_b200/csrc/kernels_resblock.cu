@@ -49,7 +49,7 @@ struct RBGeom {
 template <int C, int MB, int STAGE_KB>
 constexpr size_t resblock_smem_bytes() {
     using G = RBGeom<C, STAGE_KB>;
-    return 1024 + (size_t)(128 * MB + 2 * RBK_PAD) * G::RB + 2 * (size_t)G::STAGE_BYTES + 256;
+    return 1024 + (size_t)(128 * MB + 2 * RBK_PAD) * G::RB + 2 * (size_t)G::STAGE_BYTES + 256 + 6 * C * 4;
 }
 
 template <int C, int MB, int STAGE_KB, int MINB>
@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
     const uint32_t bar_full = bar_base, bar_empty = bar_base + 16, bar_a = bar_base + 32, bar_acc = bar_base + 40;
     const uint32_t tmem_slot = bar_base + 48;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - base));
+    float* sbias = reinterpret_cast<float*>(sm + (bar_base + 256 - base));     // [6][C]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
         fence_barrier_init();
     }
     if (warp == 8) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+    for (int i = tid; i < 6 * C; i += RBK_THREADS) sbias[i] = __ldg(p.bias[i / C] + (i % C));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -156,36 +158,28 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
             *reinterpret_cast<uint4*>(sm + swz_offset(row, ch, G::RB)) = make_uint4(0, 0, 0, 0);
         }
         // (0) load x: fp32 -> TMEM residual, lrelu -> fp16 operand tile
+        const int cbase = hsel * CH;
 #pragma unroll 1
         for (int mb = 0; mb < MB; ++mb) {
             const int row = mb * 128 + rib;
             const int t = tt0 + row;
             const bool valid = (t >= 0) && (t < p.T);
-#pragma unroll 1
+            const float* __restrict__ xt = xb + (valid ? t : 0);
+            uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
+            const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
+#pragma unroll
             for (int cc = 0; cc < CH; cc += CG) {
-                const int c0 = hsel * CH + cc;
+                const int c0 = cbase + cc;
+                uint32_t r[16];
                 float v[16];
 #pragma unroll
-                for (int j = 0; j < CG; ++j) v[j] = valid ? __ldg(xb + (size_t)(c0 + j) * p.T + t) : 0.f;
-                if (CG == 16) {
-                    uint32_t r[16];
+                for (int j = 0; j < CG; ++j) { v[j] = valid ? __ldg(xt + (size_t)(c0 + j) * p.T) : 0.f; r[j] = __float_as_uint(v[j]); }
+                if (CG == 16) tmem_st16(tlane + mb * C + c0, r);
+                else tmem_st8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r));
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(v[j]);
-                    tmem_st16(tlane + mb * C + c0, r);
-                } else {
-                    uint32_t r[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(v[j]);
-                    tmem_st8(tlane + mb * C + c0, r);
-                }
-#pragma unroll
-                for (int j = 0; j < CG; ++j) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
-                const int ch0 = c0 / 8;
-                *reinterpret_cast<uint4*>(sm + swz_offset(row + RBK_PAD, ch0, G::RB)) =
-                    make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-                if (CG == 16)
-                    *reinterpret_cast<uint4*>(sm + swz_offset(row + RBK_PAD, ch0 + 1, G::RB)) =
-                        make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+                for (int j = 0; j < CG; ++j) v[j] = lrelu01(v[j]);
+                store_chunk8(prow, phase, c0 / 8, v, 0xffffffffu);
+                if (CG == 16) store_chunk8(prow, phase, c0 / 8 + 1, v + 8, 0xffffffffu);
             }
         }
         tmem_st_wait();
@@ -197,82 +191,115 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
         for (int q = 0; q < 6; ++q) {
             mbar_wait(bar_acc, q & 1);
             tc_fence_after();
-            const float* __restrict__ bias = p.bias[q];
-            const bool second = (q & 1) != 0;
-            const bool last = (q == 5);
+            const float* __restrict__ bq_ = sbias + q * C;
+            if ((q & 1) == 0) {
+                // ---- first conv of a pair: mid = lrelu(acc + b1) -> operand tile
 #pragma unroll 1
-            for (int mb = 0; mb < MB; ++mb) {
-                const int row = mb * 128 + rib;
-                const int t = tt0 + row;
-                const bool valid = (t >= 0) && (t < p.T);
-#pragma unroll 1
-                for (int cc = 0; cc < CH; cc += CG) {
-                    const int c0 = hsel * CH + cc;
-                    float v[16], xr[16];
-                    if (CG == 16) {
-                        uint32_t r[16], rr[16];
-                        tmem_ld16(tlane + ACC0 + mb * C + c0, r);
-                        if (second) tmem_ld16(tlane + mb * C + c0, rr);
+                for (int mb = 0; mb < MB; ++mb) {
+                    const int row = mb * 128 + rib;
+                    const int t = tt0 + row;
+                    const uint32_t keep = ((t >= 0) && (t < p.T)) ? 0xffffffffu : 0u;
+                    uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
+                    const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
+#pragma unroll
+                    for (int cc = 0; cc < CH; cc += CG) {
+                        const int c0 = cbase + cc;
+                        uint32_t r[16];
+                        if (CG == 16) tmem_ld16(tlane + ACC0 + mb * C + c0, r);
+                        else tmem_ld8(tlane + ACC0 + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r));
                         tmem_ld_wait();
+                        float v[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(r[j]); xr[j] = second ? __uint_as_float(rr[j]) : 0.f; }
-                    } else {
-                        uint32_t r[8], rr[8];
-                        tmem_ld8(tlane + ACC0 + mb * C + c0, r);
-                        if (second) tmem_ld8(tlane + mb * C + c0, rr);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { v[j] = __uint_as_float(r[j]); xr[j] = second ? __uint_as_float(rr[j]) : 0.f; }
-                    }
-#pragma unroll
-                    for (int j = 0; j < CG; ++j) v[j] = v[j] + __ldg(bias + c0 + j) + xr[j];     // conv2: new residual value
-                    if (last) {
-                        const bool wr = valid && (row >= p.halo) && (row < R1 - p.halo);
-                        if (wr) {
-                            if (p.beta != 0.f) {
-                                float oo[16];
-#pragma unroll
-                                for (int j = 0; j < CG; ++j) oo[j] = ob[(size_t)(c0 + j) * p.T + t];
-#pragma unroll
-                                for (int j = 0; j < CG; ++j) ob[(size_t)(c0 + j) * p.T + t] = fmaf(p.beta, oo[j], p.alpha * v[j]);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < CG; ++j) ob[(size_t)(c0 + j) * p.T + t] = p.alpha * v[j];
-                            }
+                        for (int j4 = 0; j4 < CG; j4 += 4) {
+                            const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
+                            v[j4 + 0] = lrelu01(__uint_as_float(r[j4 + 0]) + bb.x);
+                            v[j4 + 1] = lrelu01(__uint_as_float(r[j4 + 1]) + bb.y);
+                            v[j4 + 2] = lrelu01(__uint_as_float(r[j4 + 2]) + bb.z);
+                            v[j4 + 3] = lrelu01(__uint_as_float(r[j4 + 3]) + bb.w);
                         }
-                        continue;
+                        store_chunk8(prow, phase, c0 / 8, v, keep);
+                        if (CG == 16) store_chunk8(prow, phase, c0 / 8 + 1, v + 8, keep);
                     }
-                    if (second) {                                   // keep the fp32 residual stream in TMEM
-                        if (CG == 16) {
-                            uint32_t r[16];
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(v[j]);
-                            tmem_st16(tlane + mb * C + c0, r);
-                        } else {
-                            uint32_t r[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(v[j]);
-                            tmem_st8(tlane + mb * C + c0, r);
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < CG; ++j) {
-                        const float y = v[j] > 0.f ? v[j] : 0.1f * v[j];
-                        v[j] = valid ? y : 0.f;                     // zero padding of the next convolution outside [0,T)
-                    }
-                    const int ch0 = c0 / 8;
-                    *reinterpret_cast<uint4*>(sm + swz_offset(row + RBK_PAD, ch0, G::RB)) =
-                        make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-                    if (CG == 16)
-                        *reinterpret_cast<uint4*>(sm + swz_offset(row + RBK_PAD, ch0 + 1, G::RB)) =
-                            make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
                 }
-            }
-            if (!last) {
-                if (second) tmem_st_wait();
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(bar_a);
+            } else if (q < 5) {
+                // ---- second conv of pair 0/1: x <- x + acc + b2 (TMEM), operand tile <- lrelu(x)
+#pragma unroll 1
+                for (int mb = 0; mb < MB; ++mb) {
+                    const int row = mb * 128 + rib;
+                    const int t = tt0 + row;
+                    const uint32_t keep = ((t >= 0) && (t < p.T)) ? 0xffffffffu : 0u;
+                    uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
+                    const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
+#pragma unroll
+                    for (int cc = 0; cc < CH; cc += CG) {
+                        const int c0 = cbase + cc;
+                        uint32_t r[16], xr[16];
+                        if (CG == 16) { tmem_ld16(tlane + ACC0 + mb * C + c0, r); tmem_ld16(tlane + mb * C + c0, xr); }
+                        else { tmem_ld8(tlane + ACC0 + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r)); tmem_ld8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(xr)); }
+                        tmem_ld_wait();
+                        float v[16];
+#pragma unroll
+                        for (int j4 = 0; j4 < CG; j4 += 4) {
+                            const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
+                            v[j4 + 0] = __uint_as_float(r[j4 + 0]) + bb.x + __uint_as_float(xr[j4 + 0]);
+                            v[j4 + 1] = __uint_as_float(r[j4 + 1]) + bb.y + __uint_as_float(xr[j4 + 1]);
+                            v[j4 + 2] = __uint_as_float(r[j4 + 2]) + bb.z + __uint_as_float(xr[j4 + 2]);
+                            v[j4 + 3] = __uint_as_float(r[j4 + 3]) + bb.w + __uint_as_float(xr[j4 + 3]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < CG; ++j) xr[j] = __float_as_uint(v[j]);
+                        if (CG == 16) tmem_st16(tlane + mb * C + c0, xr);
+                        else tmem_st8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(xr));
+#pragma unroll
+                        for (int j = 0; j < CG; ++j) v[j] = lrelu01(v[j]);
+                        store_chunk8(prow, phase, c0 / 8, v, keep);
+                        if (CG == 16) store_chunk8(prow, phase, c0 / 8 + 1, v + 8, keep);
+                    }
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(bar_a);
+            } else {
+                // ---- last conv: out = alpha*(x + acc + b2) + beta*out_old for the interior rows
+                const bool has_beta = p.beta != 0.f;
+#pragma unroll 1
+                for (int mb = 0; mb < MB; ++mb) {
+                    const int row = mb * 128 + rib;
+                    const int t = tt0 + row;
+                    const bool wr = (t < p.T) && (row >= p.halo) && (row < R1 - p.halo);
+                    float* __restrict__ ot = ob + (wr ? t : 0);
+#pragma unroll
+                    for (int cc = 0; cc < CH; cc += CG) {
+                        const int c0 = cbase + cc;
+                        uint32_t r[16], xr[16];
+                        float oo[16];
+                        if (CG == 16) { tmem_ld16(tlane + ACC0 + mb * C + c0, r); tmem_ld16(tlane + mb * C + c0, xr); }
+                        else { tmem_ld8(tlane + ACC0 + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r)); tmem_ld8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(xr)); }
+                        if (wr && has_beta) {
+#pragma unroll
+                            for (int j = 0; j < CG; ++j) oo[j] = ot[(size_t)(c0 + j) * p.T];
+                        }
+                        tmem_ld_wait();
+                        if (wr) {
+#pragma unroll
+                            for (int j4 = 0; j4 < CG; j4 += 4) {
+                                const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
+                                const float b4[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int j = j4 + e;
+                                    float y = p.alpha * (__uint_as_float(r[j]) + b4[e] + __uint_as_float(xr[j]));
+                                    if (has_beta) y = fmaf(p.beta, oo[j], y);
+                                    ot[(size_t)(c0 + j) * p.T] = y;
+                                }
+                            }
+                        }
+                    }
+                }
             }
         }
         tc_fence_before();
@@ -321,7 +348,7 @@ int launch_resblock_tc(const ResblockTC& a, cudaStream_t st) {
         if (a.dil[d] * (a.k - 1) / 2 > RBK_PAD - 1 || a.dil[d] < 1) return SVB_ERR_UNSUPPORTED;
     static const int env_variant = rb_env_int("SVB_RB_VARIANT", -1);
     int variant = a.variant >= 0 ? a.variant : env_variant;
-    if (variant < 0) variant = 0;
+    if (variant < 0) variant = 1;     // measured: two CTAs/SM win for C <= 32 (profiles/r01/bench_pair_sweep_fused.log)
     if (variant == 1) {
         switch (a.C) {
             case 16: return launch_resblock_t<16, 8, 8, 2>(a, st);

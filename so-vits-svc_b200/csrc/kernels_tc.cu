@@ -58,7 +58,7 @@ struct PairParams {
 template <int C, int MB, int STAGE_KB>
 constexpr size_t pair_smem_bytes() {
     using G = TCGeom<C, STAGE_KB>;
-    return 1024 /*align slack*/ + (size_t)G::NP * (128 * MB + MAX_HALO) * G::RB + (size_t)NSTAGE * G::STAGE_BYTES + 256;
+    return 1024 /*align slack*/ + (size_t)G::NP * (128 * MB + MAX_HALO) * G::RB + (size_t)NSTAGE * G::STAGE_BYTES + 256 + 2 * C * 4;
 }
 
 template <int C, int MB, int STAGE_KB, int MINB>
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
     const uint32_t bar_acc = bar_a + 8;                             // accumulators ready, 2 phases
     const uint32_t tmem_slot = bar_acc + 8;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - base));
+    float* sbias = reinterpret_cast<float*>(sm + (bar_base + 256 - base));     // [2][C]: b1 | b2
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
+    for (int i = tid; i < 2 * C; i += TC_THREADS) sbias[i] = i < C ? __ldg(p.b1 + i) : __ldg(p.b2 + i - C);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -176,20 +178,18 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
         for (int r = tid; r < RA1; r += NWORK) {
             const int t = tA0 + r;
             const bool valid = (t >= 0) && (t < p.T);
-#pragma unroll 1
+            const float* __restrict__ xt = xb + (valid ? t : 0);
+            const uint32_t phase = swz_phase(r, G::RB);
+#pragma unroll
             for (int c0 = 0; c0 < C; c0 += 16) {
                 float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = valid ? __ldg(xb + (size_t)(c0 + j) * p.T + t) : 0.f;
+                for (int j = 0; j < 16; ++j) v[j] = valid ? __ldg(xt + (size_t)(c0 + j) * p.T) : 0.f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
-                const int pn = c0 / G::CPP;
-                const int ch0 = (c0 % G::CPP) / 8;
-                uint8_t* prow = sm + pn * APANEL;
-                uint4 q0 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-                uint4 q1 = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
-                *reinterpret_cast<uint4*>(prow + swz_offset(r, ch0, G::RB)) = q0;
-                *reinterpret_cast<uint4*>(prow + swz_offset(r, ch0 + 1, G::RB)) = q1;
+                for (int j = 0; j < 16; ++j) v[j] = lrelu01(v[j]);
+                uint8_t* prow = sm + (c0 / G::CPP) * APANEL + r * G::RB;
+                store_chunk8(prow, phase, (c0 % G::CPP) / 8, v, 0xffffffffu);
+                store_chunk8(prow, phase, (c0 % G::CPP) / 8 + 1, v + 8, 0xffffffffu);
             }
         }
         fence_proxy_async();
@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
         constexpr int CH = C / 2;                      // channels handled by this warp-half
         constexpr int CG = CH < 16 ? CH : 16;          // columns per tcgen05.ld
         const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
+        const int cbase = hsel * CH;
 
         // (2) epilogue 1: mid = conv1 + b1 -> lrelu -> fp16 -> A2 (in place), zero outside [0,T)
         mbar_wait(bar_acc, 0);
@@ -208,38 +209,33 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
         for (int mb = 0; mb < MB; ++mb) {
             const int row = mb * 128 + rib;
             const int tm = tM0 + row;
-            const bool valid = (tm >= 0) && (tm < p.T);
-#pragma unroll 1
-            for (int cc = 0; cc < CH; cc += CG) {
-                const int c0 = hsel * CH + cc;
-                float v[16];
-                if (CG == 16) {
-                    uint32_t r[16];
-                    tmem_ld16(tlane + mb * C + c0, r);
-                    tmem_ld_wait();
+            const uint32_t keep = ((tm >= 0) && (tm < p.T)) ? 0xffffffffu : 0u;
+            const uint32_t phase = swz_phase(row, G::RB);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-                } else {
-                    uint32_t r[8];
-                    tmem_ld8(tlane + mb * C + c0, r);
-                    tmem_ld_wait();
+            for (int cc = 0; cc < CH; cc += 2 * CG) {          // two column groups per TMEM round trip
+                uint32_t r0[16], r1[16];
+                const int c0 = cbase + cc, c1 = c0 + CG;
+                const bool two = (cc + CG) < CH;
+                if (CG == 16) { tmem_ld16(tlane + mb * C + c0, r0); if (two) tmem_ld16(tlane + mb * C + c1, r1); }
+                else tmem_ld8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r0));
+                tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
-                }
+                for (int g = 0; g < 2; ++g) {
+                    if (g == 1 && !two) break;
+                    const int cg0 = g ? c1 : c0;
+                    const uint32_t* rr = g ? r1 : r0;
+                    float v[16];
 #pragma unroll
-                for (int j = 0; j < CG; ++j) {
-                    float y = v[j] + __ldg(p.b1 + c0 + j);
-                    y = y > 0.f ? y : 0.1f * y;
-                    v[j] = valid ? y : 0.f;
-                }
-                const int pn = c0 / G::CPP;
-                const int ch0 = (c0 % G::CPP) / 8;
-                uint8_t* prow = sm + pn * APANEL;
-                uint4 q0 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-                *reinterpret_cast<uint4*>(prow + swz_offset(row, ch0, G::RB)) = q0;
-                if (CG == 16) {
-                    uint4 q1 = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
-                    *reinterpret_cast<uint4*>(prow + swz_offset(row, ch0 + 1, G::RB)) = q1;
+                    for (int j4 = 0; j4 < CG; j4 += 4) {
+                        const float4 bq = *reinterpret_cast<const float4*>(sbias + cg0 + j4);
+                        v[j4 + 0] = lrelu01(__uint_as_float(rr[j4 + 0]) + bq.x);
+                        v[j4 + 1] = lrelu01(__uint_as_float(rr[j4 + 1]) + bq.y);
+                        v[j4 + 2] = lrelu01(__uint_as_float(rr[j4 + 2]) + bq.z);
+                        v[j4 + 3] = lrelu01(__uint_as_float(rr[j4 + 3]) + bq.w);
+                    }
+                    uint8_t* prow = sm + (cg0 / G::CPP) * APANEL + row * G::RB;
+                    store_chunk8(prow, phase, (cg0 % G::CPP) / 8, v, keep);
+                    if (CG == 16) store_chunk8(prow, phase, (cg0 % G::CPP) / 8 + 1, v + 8, keep);
                 }
             }
         }
@@ -250,42 +246,42 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
         // (3) epilogue 2: out = alpha*(conv2 + b2 + x) + beta*out_old
         mbar_wait(bar_acc, 1);
         tc_fence_after();
+        const bool has_beta = p.beta != 0.f;
 #pragma unroll 1
         for (int mb = 0; mb < MB; ++mb) {
             const int o = mb * 128 + rib;
             const int t = t0 + o;
             const bool valid = (o < TOUT) && (t < p.T);
-#pragma unroll 1
+            const float* __restrict__ xt = xb + (valid ? t : 0);
+            float* __restrict__ ot = ob + (valid ? t : 0);
+#pragma unroll
             for (int cc = 0; cc < CH; cc += CG) {
-                const int c0 = hsel * CH + cc;
-                float v[16];
-                if (CG == 16) {
-                    uint32_t r[16];
-                    tmem_ld16(tlane + mb * C + c0, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-                } else {
-                    uint32_t r[8];
-                    tmem_ld8(tlane + mb * C + c0, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
-                }
+                const int c0 = cbase + cc;
+                uint32_t r[16];
+                float xr[16], oo[16];
+                if (CG == 16) tmem_ld16(tlane + mb * C + c0, r);
+                else tmem_ld8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r));
                 if (valid) {
-                    float xr[16], oo[16];
 #pragma unroll
-                    for (int j = 0; j < CG; ++j) xr[j] = __ldg(xb + (size_t)(c0 + j) * p.T + t);
-                    if (p.beta != 0.f) {
+                    for (int j = 0; j < CG; ++j) xr[j] = __ldg(xt + (size_t)(c0 + j) * p.T);
+                    if (has_beta) {
 #pragma unroll
-                        for (int j = 0; j < CG; ++j) oo[j] = ob[(size_t)(c0 + j) * p.T + t];
+                        for (int j = 0; j < CG; ++j) oo[j] = ot[(size_t)(c0 + j) * p.T];
+                    }
+                }
+                tmem_ld_wait();
+                if (valid) {
 #pragma unroll
-                        for (int j = 0; j < CG; ++j)
-                            ob[(size_t)(c0 + j) * p.T + t] = fmaf(p.beta, oo[j], p.alpha * (v[j] + __ldg(p.b2 + c0 + j) + xr[j]));
-                    } else {
+                    for (int j4 = 0; j4 < CG; j4 += 4) {
+                        const float4 bq = *reinterpret_cast<const float4*>(sbias + C + c0 + j4);
+                        const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
-                        for (int j = 0; j < CG; ++j)
-                            ob[(size_t)(c0 + j) * p.T + t] = p.alpha * (v[j] + __ldg(p.b2 + c0 + j) + xr[j]);
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = j4 + e;
+                            float y = p.alpha * (__uint_as_float(r[j]) + bb[e] + xr[j]);
+                            if (has_beta) y = fmaf(p.beta, oo[j], y);
+                            ot[(size_t)(c0 + j) * p.T] = y;
+                        }
                     }
                 }
             }
@@ -356,7 +352,7 @@ int launch_pair_tc(const PairTC& a, cudaStream_t st) {
     if (!(a.k == 3 || a.k == 7 || a.k == 11) || (a.k - 1) * a.dil > 50) return SVB_ERR_UNSUPPORTED;
     static const int env_variant = env_int("SVB_TC_VARIANT", -1);
     int variant = a.variant >= 0 ? a.variant : env_variant;
-    if (variant < 0) variant = (a.C <= 64) ? 1 : 0;     // measured on B200 (profiles/r01/bench_pair_sweep.log): 2 CTAs/SM wins for C <= 64
+    if (variant < 0) variant = 1;     // measured on B200 (profiles/r01/bench_pair_sweep_epi.log): two CTAs/SM win for every C that allows it
     if (variant == 1) {
         switch (a.C) {
             case 16: return launch_pair_t<16, 16, 8, 2>(a, st);

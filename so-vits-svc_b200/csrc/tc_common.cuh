@@ -137,6 +137,17 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ float lrelu01(float v) { return fmaxf(v, 0.1f * v); }   // LeakyReLU(0.1): max(v, 0.1 v)
+
+// Write 8 fp16 values (one 16-byte chunk `chunk` of a swizzled operand row) given the row's base pointer
+// (operand base + row*row_bytes) and the row's swizzle phase ((row*row_bytes) >> 7) & mask.  `keep` is all-ones or 0.
+__device__ __forceinline__ void store_chunk8(uint8_t* row_ptr, uint32_t phase, int chunk, const float* v, uint32_t keep) {
+    uint4 q = make_uint4(pack_h2(v[0], v[1]) & keep, pack_h2(v[2], v[3]) & keep, pack_h2(v[4], v[5]) & keep, pack_h2(v[6], v[7]) & keep);
+    *reinterpret_cast<uint4*>(row_ptr + ((((uint32_t)chunk) ^ phase) << 4)) = q;
+}
+__device__ __forceinline__ uint32_t swz_phase(uint32_t row, uint32_t row_bytes) {
+    return ((row * row_bytes) >> 7) & (row_bytes / 16u - 1u);
+}
 
 }  // namespace tc
 }  // namespace svb
