@@ -37,6 +37,7 @@ struct ConvNW {           // tensor-core image of one layer for convn_tc_kernel
     void* img = nullptr;
     float* bias = nullptr;   // per column, column order
     int cinp = 0, cin_real = 0, N_total = 0, NC = 0, k = 1, pad_left = 0;
+    int noise = 0, noise_stride = 0, noise_w0 = 0;   // fused noise conv (polyphase ups of the narrow stages)
 };
 
 struct FlowLayer {
@@ -205,11 +206,13 @@ int make_conv(svb_ctx* ctx, const std::vector<float>& w, const std::vector<float
 }
 
 int make_convn(svb_ctx* ctx, int cinp, int cin_real, int N_total, int NC, int k, int pad_left,
-               const std::function<float(int, int, int)>& wcol, const std::function<float(int)>& bcol, ConvNW& out) {
+               const std::function<float(int, int, int)>& wcol, const std::function<float(int)>& bcol, ConvNW& out,
+               const std::function<float(int, int)>* ncol = nullptr) {
     out.cinp = cinp; out.cin_real = cin_real; out.N_total = N_total; out.NC = NC; out.k = k; out.pad_left = pad_left;
-    const size_t ib = convn_weight_image_bytes(cinp, N_total, NC, k);
+    out.noise = ncol ? 1 : 0;
+    const size_t ib = convn_weight_image_bytes(cinp, N_total, NC, k, out.noise);
     std::vector<uint8_t> img(ib);
-    convn_pack_weight_image(cinp, N_total, NC, k, [&](int col, int ci, int tap) { return ci < cin_real ? wcol(col, ci, tap) : 0.f; }, img.data());
+    convn_pack_weight_image(cinp, N_total, NC, k, [&](int col, int ci, int tap) { return ci < cin_real ? wcol(col, ci, tap) : 0.f; }, ncol, img.data());
     int rc = upload(ctx, img.data(), ib, &out.img);
     if (rc) return rc;
     std::vector<float> bc(N_total);
@@ -496,12 +499,14 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
             a.chunks_per_cta = (W.N_total + W.NC - 1) / W.NC;
             a.mode = 1; a.s = S.s; a.p = S.p; a.Ty = Lout; a.B = B;
             a.seg[0].y = X; a.seg[0].y_ctot = S.Cout;
+            if (W.noise) { a.har = har; a.har_N = (int)N; a.noise_stride = W.noise_stride; a.noise_w0 = W.noise_w0; }
             int trc = launch_convn_tc(a, st);
             if (trc) return fail(ctx, trc, "convn launch failed (ups)");
         } else {
             launch_conv_f32(up, st);
         }
-        launch_noise_conv_add(har, S.noise_w, S.noise_b, X, B, S.Cout, Lout, (int)N, S.noise_K, S.noise_s, S.noise_p, st);
+        if (!(gen_tc && S.up_tc.noise))
+            launch_noise_conv_add(har, S.noise_w, S.noise_b, X, B, S.Cout, Lout, (int)N, S.noise_K, S.noise_s, S.noise_p, st);
         if ((rc = dbg_keep(ctx, "ups" + std::to_string(i), X, (size_t)B * S.Cout * Lout, st))) return rc;
         static const int fuse_rb = [] { const char* e = std::getenv("SVB_FUSE_RESBLOCK"); return e ? std::atoi(e) : 1; }();
         static const int fuse_maxc = [] { const char* e = std::getenv("SVB_FUSE_MAXC"); return e ? std::atoi(e) : 32; }();
@@ -879,17 +884,7 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
                 }
         if ((rc = upload(ctx, pk.data(), pk.size() * sizeof(float), (void**)&S.up_w))) return rc;
         if ((rc = upload(ctx, b.v.data(), b.v.size() * sizeof(float), (void**)&S.up_b))) return rc;
-        if (ctx->gen_tc_ok) {
-            // polyphase GEMM columns: col = co*s + phase; tap 0 multiplies x[i-1] (kernel index phase+s), tap 1 x[i] (index phase)
-            const std::vector<float> wv = w.v, bv = b.v;
-            const int s_ = S.s, Co = S.Cout, kk = S.k;
-            const int ntot = Co * s_;
-            int nc = 256 / convn_mb(S.Cin);
-            if (nc > ntot) nc = ntot;
-            if ((rc = make_convn(ctx, S.Cin, S.Cin, ntot, nc, 2, 1,
-                                 [&](int col, int ci, int tap) { const int co = col / s_, ph = col % s_; return wv[((size_t)ci * Co + co) * kk + (tap == 0 ? ph + s_ : ph)]; },
-                                 [&](int col) { return bv[col / s_]; }, S.up_tc))) return rc;
-        }
+        const std::vector<float> upw_host = w.v, upb_host = b.v;
         // noise conv
         int stride = 1;
         for (int q = i + 1; q < c.n_upsamples; ++q) stride *= c.upsample_rates[q];
@@ -900,6 +895,28 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
         if ((rc = get_tensor(ctx, m, np_ + ".bias", {S.Cout}, b))) return rc;
         if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&S.noise_w))) return rc;
         if ((rc = upload(ctx, b.v.data(), b.v.size() * sizeof(float), (void**)&S.noise_b))) return rc;
+        if (ctx->gen_tc_ok) {
+            // polyphase GEMM columns: col = co*s + phase; tap 0 multiplies x[i-1] (kernel index phase+s), tap 1 x[i] (index phase).
+            // Narrow stages also absorb noise_convs[i]: window u = phase*s' + kk of har[i*s*s' - p*s' - p_n + u] (<= 16 wide).
+            const std::vector<float> nwv = w.v, nbv = b.v;
+            const int s_ = S.s, Co = S.Cout, kk = S.k;
+            const int ntot = Co * s_;
+            int nc = 256 / convn_mb(S.Cin);
+            if (nc > ntot) nc = ntot;
+            const int sp = S.noise_s, Kn = S.noise_K, pn_ = S.noise_p;
+            const bool fuse_noise = ((s_ - 1) * sp + Kn <= 16) && (S.Cin <= 128);
+            std::function<float(int, int)> ncol = [&](int col, int u) {
+                const int co = col / s_, ph = col % s_;
+                const int q = u - ph * sp;
+                return (q >= 0 && q < Kn) ? nwv[(size_t)co * Kn + q] : 0.f;
+            };
+            if ((rc = make_convn(ctx, S.Cin, S.Cin, ntot, nc, 2, 1,
+                                 [&](int col, int ci, int tap) { const int co = col / s_, ph = col % s_; return upw_host[((size_t)ci * Co + co) * kk + (tap == 0 ? ph + s_ : ph)]; },
+                                 [&](int col) { return upb_host[col / s_] + (fuse_noise ? nbv[col / s_] : 0.f); }, S.up_tc,
+                                 fuse_noise ? &ncol : nullptr))) return rc;
+            S.up_tc.noise_stride = s_ * sp;
+            S.up_tc.noise_w0 = -S.p * sp - pn_;
+        }
         S.c1.assign(9, ConvW());
         S.c2.assign(9, ConvW());
         for (int j = 0; j < 3; ++j) {

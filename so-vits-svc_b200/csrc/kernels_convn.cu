@@ -5,8 +5,13 @@
 //
 // Structure: the activation tile A = act(x)[rows][Cin] (fp16, K-major, hardware swizzle) is staged ONCE per CTA and
 // stays resident; the output columns (N_total = C_out, or C_out*s for the polyphase form) are processed in chunks
-// of NC <= 256/MB columns with DOUBLE-BUFFERED TMEM accumulators, so the epilogue of chunk j overlaps the MMAs of
-// chunk j+1.  Weights stream through a 2-stage mbarrier ring of 1-D bulk TMA copies, like the pair kernel.
+// of NC columns with (when a CTA owns several chunks) DOUBLE-BUFFERED TMEM accumulators, so the epilogue of chunk j
+// overlaps the MMAs of chunk j+1.  Weights stream through a 2-stage mbarrier ring of 1-D bulk TMA copies.
+//
+// Polyphase mode can also absorb the stage's noise_convs[i] (vdecoder/hifigan/models.py:343-348,380-382): for the
+// narrow stages the excitation window of an output row is <= 16 samples, so it is staged as one extra 16-wide K panel
+// (fp16, 32-byte swizzled rows) and the strided analysis filter becomes ONE more MMA per chunk against a banded
+// (Toeplitz-expanded) weight block - no separate read-modify-write pass over the stage tensor.
 #include "kernels.h"
 #include "tc_common.cuh"
 #include "../../include/sovits_b200.h"
@@ -21,9 +26,8 @@ namespace {
 
 constexpr int CN_THREADS = 320;
 constexpr int CN_NWORK = 256;
-constexpr int CN_NSTAGE = 2;
-constexpr int CN_STAGE_BYTES = 32768;
-constexpr int CN_BUFCOLS = 256;      // TMEM columns per accumulator buffer (2 buffers = 512)
+constexpr int CN_HALO = 8;            // >= max (k-1)*dil over the layers served here (k7 -> 6), multiple of 8
+constexpr int CN_NOISE_RB = 32;       // noise panel: 16 fp16 per row
 
 template <int CINP>
 struct CNGeom {
@@ -33,35 +37,35 @@ struct CNGeom {
     static constexpr int KSTEPS = CPP / 16;
 };
 
-template <int CINP, int MB>
-constexpr size_t convn_smem_bytes(int halo_rows_max) {
-    return 1024 + (size_t)CNGeom<CINP>::NP * (128 * MB + halo_rows_max) * CNGeom<CINP>::RB + (size_t)CN_NSTAGE * CN_STAGE_BYTES + 256;
-}
+struct ConvNDev {                     // launch-time geometry (host computed)
+    int stage_bytes, tmem_cols, bufcols, blkcols, nbuf;
+    int noise;                        // 1: noise panel present
+    uint32_t off_noise, off_ring, off_bar, off_bias;   // byte offsets from the 1024-aligned smem base
+};
 
-constexpr int CN_HALO = 8;   // >= max (k-1)*dil over the layers served here (k7 d1 -> 6), multiple of 8
-
-template <int CINP, int MB>
-__global__ void __launch_bounds__(CN_THREADS, 1) convn_tc_kernel(const ConvNTC a) {
+template <int CINP, int MB, int MINB>
+__global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNTC a, const ConvNDev d) {
     using G = CNGeom<CINP>;
     constexpr int R1 = 128 * MB;
     constexpr int AROWS = R1 + CN_HALO;
     constexpr int APANEL = AROWS * G::RB;
-    constexpr int BLKCOLS = CN_BUFCOLS / MB;            // TMEM column stride between the MB row-blocks of a buffer
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw);
     const uint32_t a_base = base;
-    const uint32_t ring_base = base + G::NP * APANEL;
-    const uint32_t bar_base = ring_base + CN_NSTAGE * CN_STAGE_BYTES;
+    const uint32_t n_base = base + d.off_noise;
+    const uint32_t ring_base = base + d.off_ring;
+    const uint32_t bar_base = base + d.off_bar;
     const uint32_t bar_full = bar_base;                  // [2]
     const uint32_t bar_empty = bar_base + 16;            // [2]
     const uint32_t bar_a = bar_base + 32;                // A tile staged (256 arrivals)
-    const uint32_t bar_tfull = bar_base + 40;            // [2] accumulator buffer complete (1 arrival: commit)
+    const uint32_t bar_tfull = bar_base + 40;            // [2] accumulator buffer complete
     const uint32_t bar_tempty = bar_base + 56;           // [2] accumulator buffer drained (256 arrivals)
     const uint32_t tmem_slot = bar_base + 72;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - base));
+    float* sbias = reinterpret_cast<float*>(sm + d.off_bias);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
@@ -71,8 +75,10 @@ __global__ void __launch_bounds__(CN_THREADS, 1) convn_tc_kernel(const ConvNTC a
     const int c_lo = blockIdx.z * a.chunks_per_cta;
     const int c_hi = min(n_chunks, c_lo + a.chunks_per_cta);
     const int SUB = NC * G::RB;                           // bytes of one (tap, panel) weight block
-    const int SPC = max(1, CN_STAGE_BYTES / SUB);         // sub-blocks per ring chunk
-    const int sb_per_chunk = a.k * G::NP;
+    const int SUBN = NC * CN_NOISE_RB;                    // bytes of the noise weight block
+    const int n_reg = a.k * G::NP;                        // regular sub-blocks per chunk
+    const int n_sb = n_reg + (d.noise ? 1 : 0);
+    const size_t chunk_bytes = (size_t)n_reg * SUB + (d.noise ? SUBN : 0);
     const int RA = R1 + (a.k - 1) * a.dil;                // A rows touched
 
     if (tid == 0) {
@@ -83,7 +89,13 @@ __global__ void __launch_bounds__(CN_THREADS, 1) convn_tc_kernel(const ConvNTC a
         mbar_init(bar_a, CN_NWORK);
         fence_barrier_init();
     }
-    if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    if (warp == 8) { tmem_alloc(tmem_slot, d.tmem_cols); tmem_relinquish(); }
+    // per-column bias (+ per-utterance conditioning bias) of this CTA's chunks -> shared memory
+    for (int col = c_lo * NC + tid; col < min(c_hi * NC, a.N_total); col += CN_THREADS) {
+        float v = a.bias ? __ldg(a.bias + col) : 0.f;
+        if (a.bias_b) v += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + a.bias_b_off + col);
+        sbias[col - c_lo * NC] = v;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -94,14 +106,21 @@ __global__ void __launch_bounds__(CN_THREADS, 1) convn_tc_kernel(const ConvNTC a
         if (lane == 0) {
             int ring = 0;
             for (int c = c_lo; c < c_hi; ++c) {
-                const uint8_t* wsrc = static_cast<const uint8_t*>(a.w) + (size_t)c * sb_per_chunk * SUB;
-                for (int sb0 = 0; sb0 < sb_per_chunk; sb0 += SPC, ++ring) {
+                const uint8_t* wsrc = static_cast<const uint8_t*>(a.w) + (size_t)c * chunk_bytes;
+                int idx = 0;
+                uint32_t off = 0;
+                while (idx < n_sb) {
+                    uint32_t bytes = 0;
+                    while (idx < n_sb) {
+                        const uint32_t sbb = idx < n_reg ? SUB : SUBN;
+                        if (bytes && bytes + sbb > (uint32_t)d.stage_bytes) break;
+                        bytes += sbb; ++idx;
+                    }
                     const int s = ring & 1;
                     if (ring >= 2) mbar_wait(bar_empty + 8 * s, ((ring >> 1) - 1) & 1);
-                    const int nsb = min(SPC, sb_per_chunk - sb0);
-                    const uint32_t bytes = (uint32_t)nsb * SUB;
                     mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
-                    bulk_g2s(ring_base + s * CN_STAGE_BYTES, wsrc + (size_t)sb0 * SUB, bytes, bar_full + 8 * s);
+                    bulk_g2s(ring_base + s * d.stage_bytes, wsrc + off, bytes, bar_full + 8 * s);
+                    off += bytes; ++ring;
                 }
             }
         }
@@ -113,28 +132,51 @@ __global__ void __launch_bounds__(CN_THREADS, 1) convn_tc_kernel(const ConvNTC a
             tc_fence_after();
             int ring = 0;
             for (int c = c_lo; c < c_hi; ++c) {
-                const int u = c - c_lo, buf = u & 1;
-                if (u >= 2) { mbar_wait(bar_tempty + 8 * buf, ((u >> 1) - 1) & 1); tc_fence_after(); }
-                const uint32_t dcol = tmem_base + buf * CN_BUFCOLS;
-                for (int sb = 0; sb < sb_per_chunk; ++sb) {
+                const int u = c - c_lo, buf = (d.nbuf > 1) ? (u & 1) : 0;
+                if (u >= d.nbuf) { mbar_wait(bar_tempty + 8 * buf, ((u / d.nbuf) - 1) & 1); tc_fence_after(); }
+                const uint32_t dcol = tmem_base + buf * d.bufcols;
+                int idx = 0;
+                while (idx < n_sb) {
+                    // same greedy grouping as the producer
+                    const int g0 = idx;
+                    uint32_t bytes = 0;
+                    while (idx < n_sb) {
+                        const uint32_t sbb = idx < n_reg ? SUB : SUBN;
+                        if (bytes && bytes + sbb > (uint32_t)d.stage_bytes) break;
+                        bytes += sbb; ++idx;
+                    }
                     const int s = ring & 1;
-                    const int within = sb % SPC;
-                    if (within == 0) { mbar_wait(bar_full + 8 * s, (ring >> 1) & 1); tc_fence_after(); }
-                    const int tap = sb / G::NP, pn = sb % G::NP;
-                    const uint32_t a0 = a_base + pn * APANEL + (uint32_t)(tap * a.dil) * G::RB;
-                    const uint64_t a_d0 = make_smem_desc(a0, G::RB, 0);
-                    const uint64_t b_d0 = make_smem_desc(ring_base + s * CN_STAGE_BYTES + within * SUB, G::RB, 0);
-                    const uint32_t acc0 = (sb > 0) ? 1u : 0u;
+                    mbar_wait(bar_full + 8 * s, (ring >> 1) & 1);
+                    tc_fence_after();
+                    uint32_t boff = 0;
+                    for (int sb = g0; sb < idx; ++sb) {
+                        const uint32_t bsub = ring_base + s * d.stage_bytes + boff;
+                        const uint32_t acc0 = (sb > 0) ? 1u : 0u;
+                        if (sb < n_reg) {
+                            const int tap = sb / G::NP, pn = sb % G::NP;
+                            const uint64_t a_d0 = make_smem_desc(a_base + pn * APANEL + (uint32_t)(tap * a.dil) * G::RB, G::RB, 0);
+                            const uint64_t b_d0 = make_smem_desc(bsub, G::RB, 0);
 #pragma unroll
-                    for (int mb = 0; mb < MB; ++mb) {
+                            for (int mb = 0; mb < MB; ++mb) {
 #pragma unroll
-                        for (int ks = 0; ks < G::KSTEPS; ++ks) {
-                            const uint64_t ad = a_d0 + (uint64_t)(((uint32_t)(mb * 128) * G::RB + ks * 32) >> 4);
-                            const uint64_t bd = b_d0 + (uint64_t)((ks * 32) >> 4);
-                            umma_f16(dcol + mb * BLKCOLS, ad, bd, idesc, (ks > 0) ? 1u : acc0);
+                                for (int ks = 0; ks < G::KSTEPS; ++ks) {
+                                    const uint64_t ad = a_d0 + (uint64_t)(((uint32_t)(mb * 128) * G::RB + ks * 32) >> 4);
+                                    const uint64_t bd = b_d0 + (uint64_t)((ks * 32) >> 4);
+                                    umma_f16(dcol + mb * d.blkcols, ad, bd, idesc, (ks > 0) ? 1u : acc0);
+                                }
+                            }
+                            boff += SUB;
+                        } else {
+                            const uint64_t a_d0 = make_smem_desc(n_base, CN_NOISE_RB, 0);
+                            const uint64_t b_d0 = make_smem_desc(bsub, CN_NOISE_RB, 0);
+#pragma unroll
+                            for (int mb = 0; mb < MB; ++mb)
+                                umma_f16(dcol + mb * d.blkcols, a_d0 + (uint64_t)(((uint32_t)(mb * 128) * CN_NOISE_RB) >> 4), b_d0, idesc, acc0);
+                            boff += SUBN;
                         }
                     }
-                    if (within == SPC - 1 || sb == sb_per_chunk - 1) { umma_commit(bar_empty + 8 * s); ++ring; }
+                    umma_commit(bar_empty + 8 * s);
+                    ++ring;
                 }
                 umma_commit(bar_tfull + 8 * buf);
             }
@@ -147,21 +189,37 @@ __global__ void __launch_bounds__(CN_THREADS, 1) convn_tc_kernel(const ConvNTC a
             for (int r = tid; r < RA; r += CN_NWORK) {
                 const int ti = i0 - a.pad_left + r;
                 const bool rv = (ti >= 0) && (ti < a.Tin);
-#pragma unroll 1
+                const float* __restrict__ xt = xb + (rv ? ti : 0);
+                const uint32_t phase = swz_phase(r, G::RB);
+#pragma unroll 2
                 for (int c0 = 0; c0 < CINP; c0 += 16) {
                     float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = (rv && (c0 + j) < a.cin_real) ? __ldg(xb + (size_t)(c0 + j) * a.Tin + ti) : 0.f;
+                    for (int j = 0; j < 16; ++j) v[j] = (rv && (c0 + j) < a.cin_real) ? __ldg(xt + (size_t)(c0 + j) * a.Tin) : 0.f;
                     if (a.in_act) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : a.in_slope * v[j];
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], a.in_slope * v[j]);
                     }
-                    const int pn = c0 / G::CPP, ch0 = (c0 % G::CPP) / 8;
-                    uint8_t* prow = sm + pn * APANEL;
-                    *reinterpret_cast<uint4*>(prow + swz_offset(r, ch0, G::RB)) =
-                        make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-                    *reinterpret_cast<uint4*>(prow + swz_offset(r, ch0 + 1, G::RB)) =
-                        make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+                    uint8_t* prow = sm + (c0 / G::CPP) * APANEL + r * G::RB;
+                    store_chunk8(prow, phase, (c0 % G::CPP) / 8, v, 0xffffffffu);
+                    store_chunk8(prow, phase, (c0 % G::CPP) / 8 + 1, v + 8, 0xffffffffu);
+                }
+            }
+            if (d.noise) {
+                // excitation window of output row i: har[i*noise_stride + noise_w0 + u], u in [0,16)
+                const float* __restrict__ hb = a.har + (size_t)b * a.har_N;
+                for (int r = tid; r < R1; r += CN_NWORK) {
+                    const long long h0 = (long long)(i0 + r) * a.noise_stride + a.noise_w0;
+                    float v[16];
+#pragma unroll
+                    for (int uu = 0; uu < 16; ++uu) {
+                        const long long hi = h0 + uu;
+                        v[uu] = (hi >= 0 && hi < a.har_N) ? __ldg(hb + hi) : 0.f;
+                    }
+                    uint8_t* prow = sm + d.off_noise + r * CN_NOISE_RB;
+                    const uint32_t phase = swz_phase(r, CN_NOISE_RB);
+                    store_chunk8(prow, phase, 0, v, 0xffffffffu);
+                    store_chunk8(prow, phase, 1, v + 8, 0xffffffffu);
                 }
             }
             fence_proxy_async();
@@ -173,95 +231,116 @@ __global__ void __launch_bounds__(CN_THREADS, 1) convn_tc_kernel(const ConvNTC a
         const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
         const int len = a.lengths ? a.lengths[b] : 0x7fffffff;
         for (int c = c_lo; c < c_hi; ++c) {
-            const int u = c - c_lo, buf = u & 1;
-            mbar_wait(bar_tfull + 8 * buf, (u >> 1) & 1);
+            const int u = c - c_lo, buf = (d.nbuf > 1) ? (u & 1) : 0;
+            mbar_wait(bar_tfull + 8 * buf, (u / d.nbuf) & 1);
             tc_fence_after();
             const int col_base = c * NC;
             const int ncols = min(NC, a.N_total - col_base);
+            const float* __restrict__ cb_ = sbias + (col_base - c_lo * NC);
 #pragma unroll 1
             for (int mb = 0; mb < MB; ++mb) {
                 const int i = i0 + mb * 128 + rib;                 // output row
-                const uint32_t tcol = tlane + buf * CN_BUFCOLS + mb * BLKCOLS;
+                const bool rowok = i < a.n_rows;
+                const uint32_t tcol = tlane + buf * d.bufcols + mb * d.blkcols;
                 if (a.mode == 2) {
                     // ---- gate: cols [0,NC/2) = tanh pre-activations, [NC/2,NC) = sigmoid pre-activations of the same channels
                     const int hc = NC / 2;
                     const int j_lo = hsel * (hc / 2), j_hi = (hsel + 1) * (hc / 2);
+                    float* __restrict__ yb = a.seg[0].y + ((size_t)b * a.seg[0].y_ctot + a.seg[0].y_c0 + c * hc) * (size_t)a.Ty + (rowok ? i : 0);
+#pragma unroll 1
                     for (int j0 = j_lo; j0 < j_hi; j0 += 16) {
                         uint32_t ra[16], rb[16];
                         tmem_ld16(tcol + j0, ra);
                         tmem_ld16(tcol + hc + j0, rb);
                         tmem_ld_wait();
-                        if (i < a.n_rows) {
+                        if (rowok) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
-                                const int ca = col_base + j0 + j, cb = col_base + hc + j0 + j;
-                                float ta = __uint_as_float(ra[j]) + __ldg(a.bias + ca);
-                                float sa = __uint_as_float(rb[j]) + __ldg(a.bias + cb);
-                                if (a.bias_b) {
-                                    ta += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + a.bias_b_off + ca);
-                                    sa += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + a.bias_b_off + cb);
-                                }
-                                const float g = tanhf(ta) * (1.f / (1.f + expf(-sa)));
-                                const int ch = c * hc + j0 + j;
-                                a.seg[0].y[((size_t)b * a.seg[0].y_ctot + a.seg[0].y_c0 + ch) * (size_t)a.Ty + i] = g;
+                                const float ta = __uint_as_float(ra[j]) + cb_[j0 + j];
+                                const float sa = __uint_as_float(rb[j]) + cb_[hc + j0 + j];
+                                yb[(size_t)(j0 + j) * a.Ty] = tanhf(ta) * (1.f / (1.f + expf(-sa)));
                             }
                         }
                     }
-                } else {
-                    const int w_lo = hsel * (ncols / 2), w_hi = (hsel + 1) * (ncols / 2);   // ncols is a multiple of 32
+                } else if (a.mode == 1) {
+                    // ---- polyphase: column = co*s + phase; output index n = i*s + phase - p (s is 2 or 8)
+                    const ConvNSeg& sg = a.seg[0];
+                    const int w_lo = hsel * (ncols / 2), w_hi = (hsel + 1) * (ncols / 2);
+                    const long long n0 = (long long)i * a.s - a.p;             // output index of phase 0
+                    const bool inner = rowok && n0 >= 0 && n0 + a.s <= a.Ty;
+#pragma unroll 1
                     for (int j0 = w_lo; j0 < w_hi; j0 += 16) {
                         uint32_t r[16];
                         tmem_ld16(tcol + j0, r);
                         tmem_ld_wait();
-                        const int col0 = col_base + j0;
+                        if (!rowok) continue;
                         float v[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            v[j] = __uint_as_float(r[j]) + (a.bias ? __ldg(a.bias + col0 + j) : 0.f);
-                            if (a.bias_b) v[j] += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + a.bias_b_off + col0 + j);
+                        for (int j4 = 0; j4 < 16; j4 += 4) {
+                            const float4 bq = *reinterpret_cast<const float4*>(cb_ + j0 + j4);
+                            v[j4 + 0] = sg.alpha * (__uint_as_float(r[j4 + 0]) + bq.x);
+                            v[j4 + 1] = sg.alpha * (__uint_as_float(r[j4 + 1]) + bq.y);
+                            v[j4 + 2] = sg.alpha * (__uint_as_float(r[j4 + 2]) + bq.z);
+                            v[j4 + 3] = sg.alpha * (__uint_as_float(r[j4 + 3]) + bq.w);
                         }
-                        if (a.mode == 1) {
-                            // ---- polyphase: column = co*s + phase; output index n = i*s + phase - p
-                            const ConvNSeg& sg = a.seg[0];
-                            if (i < a.n_rows) {
+                        const int col0 = col_base + j0;
+                        if (a.s == 8) {
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const int col = col0 + j;
-                                    const int co = col / a.s, ph = col - co * a.s;
-                                    const long long n = (long long)i * a.s + ph - a.p;
-                                    if (n >= 0 && n < a.Ty) {
-                                        float* dst = sg.y + ((size_t)b * sg.y_ctot + sg.y_c0 + co) * (size_t)a.Ty + n;
-                                        float o = sg.alpha * v[j];
-                                        if (sg.beta != 0.f) o = fmaf(sg.beta, *dst, o);
-                                        *dst = o;
+                            for (int e = 0; e < 2; ++e) {
+                                float* dst = sg.y + ((size_t)b * sg.y_ctot + sg.y_c0 + (col0 >> 3) + e) * (size_t)a.Ty + n0;
+                                if (inner && sg.beta == 0.f) {
+                                    *reinterpret_cast<float4*>(dst) = make_float4(v[8 * e], v[8 * e + 1], v[8 * e + 2], v[8 * e + 3]);
+                                    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[8 * e + 4], v[8 * e + 5], v[8 * e + 6], v[8 * e + 7]);
+                                } else {
+#pragma unroll
+                                    for (int ph = 0; ph < 8; ++ph) {
+                                        const long long n = n0 + ph;
+                                        if (n >= 0 && n < a.Ty) dst[ph] = (sg.beta != 0.f) ? fmaf(sg.beta, dst[ph], v[8 * e + ph]) : v[8 * e + ph];
                                     }
                                 }
                             }
-                        } else {
-                            // ---- plain: one column per output channel; up to two destination segments
-                            const ConvNSeg& sg = (a.n_seg > 1 && col0 >= a.seg[1].col0) ? a.seg[1] : a.seg[0];
-                            if (i < a.n_rows) {
-                                float rr[16], oo[16];
-                                const size_t rowoff = (size_t)i;
-                                if (sg.res) {
+                        } else {   // s == 2
 #pragma unroll
-                                    for (int j = 0; j < 16; ++j)
-                                        rr[j] = __ldg(sg.res + ((size_t)b * sg.res_ctot + sg.res_c0 + (col0 + j - sg.col0)) * (size_t)a.Ty + rowoff);
-                                }
-                                if (sg.beta != 0.f) {
+                            for (int e = 0; e < 8; ++e) {
+                                float* dst = sg.y + ((size_t)b * sg.y_ctot + sg.y_c0 + (col0 >> 1) + e) * (size_t)a.Ty + n0;
 #pragma unroll
-                                    for (int j = 0; j < 16; ++j)
-                                        oo[j] = sg.y[((size_t)b * sg.y_ctot + sg.y_c0 + (col0 + j - sg.col0)) * (size_t)a.Ty + rowoff];
+                                for (int ph = 0; ph < 2; ++ph) {
+                                    const long long n = n0 + ph;
+                                    if (inner || (n >= 0 && n < a.Ty)) dst[ph] = (sg.beta != 0.f) ? fmaf(sg.beta, dst[ph], v[2 * e + ph]) : v[2 * e + ph];
                                 }
+                            }
+                        }
+                    }
+                } else {
+                    // ---- plain: one column per output channel; up to two destination segments
+                    const int w_lo = hsel * (ncols / 2), w_hi = (hsel + 1) * (ncols / 2);   // ncols is a multiple of 32
+#pragma unroll 1
+                    for (int j0 = w_lo; j0 < w_hi; j0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(tcol + j0, r);
+                        const int col0 = col_base + j0;
+                        const ConvNSeg& sg = (a.n_seg > 1 && col0 >= a.seg[1].col0) ? a.seg[1] : a.seg[0];
+                        float rr[16], oo[16];
+                        float* __restrict__ yb = sg.y + ((size_t)b * sg.y_ctot + sg.y_c0 + (col0 - sg.col0)) * (size_t)a.Ty + (rowok ? i : 0);
+                        if (rowok && sg.res) {
+                            const float* __restrict__ rb_ = sg.res + ((size_t)b * sg.res_ctot + sg.res_c0 + (col0 - sg.col0)) * (size_t)a.Ty + i;
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    float o = v[j];
-                                    if (sg.res) o += rr[j];
-                                    o *= sg.alpha;
-                                    if (sg.beta != 0.f) o = fmaf(sg.beta, oo[j], o);
-                                    if (sg.masked && i >= len) o = 0.f;
-                                    sg.y[((size_t)b * sg.y_ctot + sg.y_c0 + (col0 + j - sg.col0)) * (size_t)a.Ty + rowoff] = o;
-                                }
+                            for (int j = 0; j < 16; ++j) rr[j] = __ldg(rb_ + (size_t)j * a.Ty);
+                        }
+                        if (rowok && sg.beta != 0.f) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) oo[j] = yb[(size_t)j * a.Ty];
+                        }
+                        tmem_ld_wait();
+                        if (rowok) {
+                            const bool dead = sg.masked && i >= len;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float o = __uint_as_float(r[j]) + cb_[j0 + j];
+                                if (sg.res) o += rr[j];
+                                o *= sg.alpha;
+                                if (sg.beta != 0.f) o = fmaf(sg.beta, oo[j], o);
+                                yb[(size_t)j * a.Ty] = dead ? 0.f : o;
                             }
                         }
                     }
@@ -273,22 +352,48 @@ __global__ void __launch_bounds__(CN_THREADS, 1) convn_tc_kernel(const ConvNTC a
     }
 
     __syncthreads();
-    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, d.tmem_cols); }
 }
 
-template <int CINP, int MB>
+int pow2ceil(int v) { int p = 32; while (p < v) p <<= 1; return p; }
+
+template <int CINP, int MB, int MINB>
 int launch_convn_t(const ConvNTC& a, cudaStream_t st) {
-    constexpr size_t smem = convn_smem_bytes<CINP, MB>(CN_HALO);
-    static_assert(smem <= 227 * 1024, "convn kernel shared memory exceeds 227 KB");
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(convn_tc_kernel<CINP, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return SVB_ERR_CUDA;
-        attr_set = true;
-    }
+    using G = CNGeom<CINP>;
     const int n_chunks = (a.N_total + a.NC - 1) / a.NC;
-    dim3 grid((a.n_rows + 128 * MB - 1) / (128 * MB), a.B, (n_chunks + a.chunks_per_cta - 1) / a.chunks_per_cta);
-    convn_tc_kernel<CINP, MB><<<grid, CN_THREADS, smem, st>>>(a);
+    const int cpc = a.chunks_per_cta < 1 ? 1 : a.chunks_per_cta;
+    ConvNDev d;
+    d.noise = a.har ? 1 : 0;
+    d.nbuf = cpc > 1 ? 2 : 1;
+    d.blkcols = pow2ceil(a.NC);
+    d.bufcols = MB * d.blkcols;
+    d.tmem_cols = pow2ceil(d.nbuf * d.bufcols);
+    if (d.tmem_cols > 512) return SVB_ERR_UNSUPPORTED;
+    const int SUB = a.NC * G::RB;
+    int stage = SUB > 16384 ? 32768 : 16384;
+    if (SUB > stage) return SVB_ERR_UNSUPPORTED;
+    d.stage_bytes = stage;
+    uint32_t off = (uint32_t)G::NP * (128 * MB + CN_HALO) * G::RB;
+    off = (off + 1023u) & ~1023u;
+    d.off_noise = off;
+    if (d.noise) off += 128 * MB * CN_NOISE_RB;
+    off = (off + 1023u) & ~1023u;
+    d.off_ring = off;
+    off += 2 * stage;
+    d.off_bar = off;
+    off += 256;
+    d.off_bias = off;
+    off += (uint32_t)cpc * a.NC * 4;
+    const size_t smem = 1024 + off;
+    if (smem > 227 * 1024) return SVB_ERR_UNSUPPORTED;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        if (cudaFuncSetAttribute(convn_tc_kernel<CINP, MB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return SVB_ERR_CUDA;
+        attr_smem = smem;
+    }
+    dim3 grid((a.n_rows + 128 * MB - 1) / (128 * MB), a.B, (n_chunks + cpc - 1) / cpc);
+    convn_tc_kernel<CINP, MB, MINB><<<grid, CN_THREADS, smem, st>>>(a, d);
     launch_counter()++;
     return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;
 }
@@ -299,29 +404,38 @@ int convn_mb(int cinp) { return cinp >= 512 ? 1 : (cinp == 192 ? 1 : 2); }
 
 int launch_convn_tc(const ConvNTC& a, cudaStream_t st) {
     if ((a.k - 1) * a.dil > CN_HALO || a.NC % 32 || a.NC > 256 / convn_mb(a.cinp) || a.N_total % 32) return SVB_ERR_UNSUPPORTED;
+    if (a.mode == 1 && !(a.s == 2 || a.s == 8)) return SVB_ERR_UNSUPPORTED;
     switch (a.cinp) {
-        case 512: return launch_convn_t<512, 1>(a, st);
-        case 256: return launch_convn_t<256, 2>(a, st);
-        case 192: return launch_convn_t<192, 1>(a, st);
-        case 128: return launch_convn_t<128, 2>(a, st);
-        case 64: return launch_convn_t<64, 2>(a, st);
-        case 32: return launch_convn_t<32, 2>(a, st);
+        case 512: return launch_convn_t<512, 1, 1>(a, st);
+        case 256: return launch_convn_t<256, 2, 1>(a, st);
+        case 192: return launch_convn_t<192, 1, 1>(a, st);
+        case 128: return launch_convn_t<128, 2, 2>(a, st);
+        case 64: return launch_convn_t<64, 2, 2>(a, st);
+        case 32: return launch_convn_t<32, 2, 2>(a, st);
         default: return SVB_ERR_UNSUPPORTED;
     }
 }
 
-size_t convn_weight_image_bytes(int cinp, int N_total, int NC, int k) { return (size_t)((N_total + NC - 1) / NC) * NC * cinp * k * 2; }
+size_t convn_weight_image_bytes(int cinp, int N_total, int NC, int k, int noise) {
+    const int CPP = cinp < 64 ? cinp : 64, RB = CPP * 2;
+    (void)RB;
+    return (size_t)((N_total + NC - 1) / NC) * ((size_t)NC * cinp * k * 2 + (noise ? (size_t)NC * CN_NOISE_RB : 0));
+}
 
-// wcol(col, ci, tap) -> folded weight value; image layout [chunk][tap][panel][NC rows][swizzled Cin halves]
-void convn_pack_weight_image(int cinp, int N_total, int NC, int k, const std::function<float(int, int, int)>& wcol, void* dst_host) {
+// wcol(col, ci, tap) -> folded weight value; ncol(col, u) -> banded noise weight (u in [0,16)) or null.
+// Image layout per chunk: [tap][panel][NC rows][swizzled Cin halves] then (optionally) [NC rows][16 halves, 32-byte rows].
+void convn_pack_weight_image(int cinp, int N_total, int NC, int k, const std::function<float(int, int, int)>& wcol,
+                             const std::function<float(int, int)>* ncol, void* dst_host) {
     const int CPP = cinp < 64 ? cinp : 64, NP = cinp / CPP, RB = CPP * 2;
     const int n_chunks = (N_total + NC - 1) / NC;
     uint8_t* dst = static_cast<uint8_t*>(dst_host);
     const size_t SUB = (size_t)NC * RB;
-    for (int c = 0; c < n_chunks; ++c)
+    const size_t chunk_bytes = (size_t)k * NP * SUB + (ncol ? (size_t)NC * CN_NOISE_RB : 0);
+    for (int c = 0; c < n_chunks; ++c) {
+        uint8_t* cbase = dst + (size_t)c * chunk_bytes;
         for (int tap = 0; tap < k; ++tap)
             for (int pn = 0; pn < NP; ++pn) {
-                uint8_t* blk = dst + ((size_t)(c * k + tap) * NP + pn) * SUB;
+                uint8_t* blk = cbase + ((size_t)tap * NP + pn) * SUB;
                 for (int n = 0; n < NC; ++n)
                     for (int cc = 0; cc < CPP; ++cc) {
                         const int col = c * NC + n;
@@ -331,6 +445,18 @@ void convn_pack_weight_image(int cinp, int N_total, int NC, int k, const std::fu
                         std::memcpy(blk + off, &h, 2);
                     }
             }
+        if (ncol) {
+            uint8_t* blk = cbase + (size_t)k * NP * SUB;
+            for (int n = 0; n < NC; ++n)
+                for (int uu = 0; uu < 16; ++uu) {
+                    const int col = c * NC + n;
+                    const float v = col < N_total ? (*ncol)(col, uu) : 0.f;
+                    const __half h = __float2half_rn(v);
+                    const uint32_t off = tc::swz_offset((uint32_t)n, (uint32_t)(uu / 8), (uint32_t)CN_NOISE_RB) + (uu % 8) * 2;
+                    std::memcpy(blk + off, &h, 2);
+                }
+        }
+    }
 }
 
 }  // namespace svb

@@ -45,9 +45,30 @@ class ChannelNorm(nn.Module):
         return F.layer_norm(x.transpose(1, 2), (self.channels,), self.gamma, self.beta, self.eps).transpose(1, 2)
 
 
+class _TF32Like:
+    """The reference's 1x1 convolutions run through cuDNN, whose CUDA default is TF32.  The same mixes are
+    plain GEMMs here; let them follow torch's *convolution* precision switch so that `cudnn.conv.fp32_precision='ieee'`
+    still gives a strict-fp32 prefix."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        want = False
+        if torch.cuda.is_available():
+            try:
+                want = torch.backends.cudnn.conv.fp32_precision == "tf32"
+            except Exception:
+                want = bool(torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = want
+        return self
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
+
+
 class WindowedRelAttention(nn.Module):
     """Multi-head self-attention with shared windowed relative-position keys/values
-    (modules/attentions.py:161-239, heads_share=True, window_size=4)."""
+    (modules/attentions.py:161-239, heads_share=True, window_size=4).  Works on time-major [B,T,C] activations."""
 
     def __init__(self, channels: int, n_heads: int, window: int = 4):
         super().__init__()
@@ -59,39 +80,48 @@ class WindowedRelAttention(nn.Module):
         self.conv_o = nn.Conv1d(channels, channels, 1)
         self.emb_rel_k = nn.Parameter(torch.randn(1, 2 * window + 1, self.dk) * self.dk ** -0.5)
         self.emb_rel_v = nn.Parameter(torch.randn(1, 2 * window + 1, self.dk) * self.dk ** -0.5)
+        self._band_cache = {}
+
+    def _band(self, L: int, device):
+        """Flat indices i*L + j of the 2w+1 band entries of each row i and their validity (0 <= j < L)."""
+        key = (L, str(device))
+        hit = self._band_cache.get(key)
+        if hit is None:
+            i = torch.arange(L, device=device)[:, None]
+            j = i + torch.arange(-self.window, self.window + 1, device=device)[None, :]
+            valid = (j >= 0) & (j < L)
+            idx = (i * L + j.clamp(0, L - 1)).reshape(1, 1, L * (2 * self.window + 1))
+            hit = (idx, valid.reshape(1, 1, L, 2 * self.window + 1))
+            self._band_cache = {key: hit}
+        return hit
 
     def forward(self, x, attn_mask=None):
-        B, D, L = x.shape
+        """x: [B,T,C] -> [B,T,C]."""
+        B, L, D = x.shape
         h, dk, w = self.n_heads, self.dk, self.window
-        q = self.conv_q(x).view(B, h, dk, L).transpose(2, 3) / math.sqrt(dk)
-        k = self.conv_k(x).view(B, h, dk, L).transpose(2, 3)
-        v = self.conv_v(x).view(B, h, dk, L).transpose(2, 3)
-        scores = q @ k.transpose(-2, -1)                               # [B,h,L,L]
-        rel_k = q @ self.emb_rel_k[0].t()                              # [B,h,L,2w+1]
-        for r in range(2 * w + 1):
-            off = r - w
-            if abs(off) >= L:
-                continue
-            i0, i1 = max(0, -off), min(L, L - off)
-            scores.diagonal(off, -2, -1).add_(rel_k[:, :, i0:i1, r])
+        wqkv = torch.cat([self.conv_q.weight[:, :, 0], self.conv_k.weight[:, :, 0], self.conv_v.weight[:, :, 0]], 0)
+        bqkv = torch.cat([self.conv_q.bias, self.conv_k.bias, self.conv_v.bias], 0)
+        qkv = F.linear(x, wqkv, bqkv).view(B, L, 3, h, dk).permute(2, 0, 3, 1, 4)      # [3,B,h,L,dk]
+        q = qkv[0] * (1.0 / math.sqrt(dk))
+        k, v = qkv[1], qkv[2]
+        scores = q @ k.transpose(-2, -1)                                                  # [B,h,L,L]
+        idx, valid = self._band(L, x.device)
+        nb = 2 * w + 1
+        rel_k = (q @ self.emb_rel_k[0].t()) * valid                                       # [B,h,L,2w+1]
+        scores.view(B, h, L * L).scatter_add_(2, idx.expand(B, h, L * nb), rel_k.reshape(B, h, L * nb))
         if attn_mask is not None:
             scores = scores.masked_fill(attn_mask == 0, -1e4)
         p = F.softmax(scores, dim=-1)
         out = p @ v
-        rel_w = p.new_zeros(B, h, L, 2 * w + 1)
-        for r in range(2 * w + 1):
-            off = r - w
-            if abs(off) >= L:
-                continue
-            i0, i1 = max(0, -off), min(L, L - off)
-            rel_w[:, :, i0:i1, r] = p.diagonal(off, -2, -1)
+        rel_w = p.view(B, h, L * L).gather(2, idx.expand(B, h, L * nb)).view(B, h, L, nb) * valid
         out = out + rel_w @ self.emb_rel_v[0]
-        out = out.transpose(2, 3).reshape(B, D, L)
-        return self.conv_o(out)
+        out = out.transpose(1, 2).reshape(B, L, D)
+        return F.linear(out, self.conv_o.weight[:, :, 0], self.conv_o.bias)
 
 
 class ConvFFN(nn.Module):
-    """modules/attentions.py:317-363 with same padding and ReLU."""
+    """modules/attentions.py:317-363 with same padding and ReLU; the k-tap convs are run as one GEMM over the
+    concatenation of the k shifted time-major views."""
 
     def __init__(self, channels: int, filter_channels: int, kernel_size: int):
         super().__init__()
@@ -99,32 +129,58 @@ class ConvFFN(nn.Module):
         self.conv_1 = nn.Conv1d(channels, filter_channels, kernel_size)
         self.conv_2 = nn.Conv1d(filter_channels, channels, kernel_size)
 
-    def _pad(self, x):
+    def _conv(self, x, conv):
         k = self.kernel_size
-        return x if k == 1 else F.pad(x, ((k - 1) // 2, k // 2))
+        if k == 1:
+            return F.linear(x, conv.weight[:, :, 0], conv.bias)
+        L = x.shape[1]
+        xp = F.pad(x, (0, 0, (k - 1) // 2, k // 2))
+        cols = torch.cat([xp[:, t:t + L] for t in range(k)], dim=-1)                     # [B,T,k*C], tap-major
+        wmat = conv.weight.permute(0, 2, 1).reshape(conv.weight.shape[0], -1)             # [F, k*C]
+        return F.linear(cols, wmat, conv.bias)
 
-    def forward(self, x, x_mask):
-        x = torch.relu(self.conv_1(self._pad(x * x_mask)))
-        return self.conv_2(self._pad(x * x_mask)) * x_mask
+    def forward(self, x, x_mask=None):
+        """x: [B,T,C]; x_mask: [B,T,1] or None (all ones)."""
+        if x_mask is not None:
+            x = x * x_mask
+        y = torch.relu(self._conv(x, self.conv_1))
+        if x_mask is not None:
+            y = y * x_mask
+        y = self._conv(y, self.conv_2)
+        return y if x_mask is None else y * x_mask
+
+
+class ChannelNormT(ChannelNorm):
+    """Same parameters as ChannelNorm, applied to time-major [B,T,C] (no transposes)."""
+
+    def forward(self, x):
+        return F.layer_norm(x, (self.channels,), self.gamma, self.beta, self.eps)
 
 
 class RelEncoder(nn.Module):
-    """modules/attentions.py:73-107 (dropout omitted: inference only)."""
+    """modules/attentions.py:73-107 (dropout omitted: inference only).  Internally time-major."""
 
     def __init__(self, hidden, filter_channels, n_heads, n_layers, kernel_size, window=4):
         super().__init__()
         self.attn_layers = nn.ModuleList(WindowedRelAttention(hidden, n_heads, window) for _ in range(n_layers))
-        self.norm_layers_1 = nn.ModuleList(ChannelNorm(hidden) for _ in range(n_layers))
+        self.norm_layers_1 = nn.ModuleList(ChannelNormT(hidden) for _ in range(n_layers))
         self.ffn_layers = nn.ModuleList(ConvFFN(hidden, filter_channels, kernel_size) for _ in range(n_layers))
-        self.norm_layers_2 = nn.ModuleList(ChannelNorm(hidden) for _ in range(n_layers))
+        self.norm_layers_2 = nn.ModuleList(ChannelNormT(hidden) for _ in range(n_layers))
 
     def forward(self, x, x_mask, all_ones_mask: bool = False):
+        """x: [B,C,T], x_mask: [B,1,T] -> [B,C,T]."""
+        mt = None if all_ones_mask else x_mask.transpose(1, 2)                            # [B,T,1]
         attn_mask = None if all_ones_mask else x_mask.unsqueeze(2) * x_mask.unsqueeze(-1)
-        x = x * x_mask
-        for attn, n1, ffn, n2 in zip(self.attn_layers, self.norm_layers_1, self.ffn_layers, self.norm_layers_2):
-            x = n1(x + attn(x, attn_mask))
-            x = n2(x + ffn(x, x_mask))
-        return x * x_mask
+        x = x.transpose(1, 2).contiguous()
+        if mt is not None:
+            x = x * mt
+        with _TF32Like():
+            for attn, n1, ffn, n2 in zip(self.attn_layers, self.norm_layers_1, self.ffn_layers, self.norm_layers_2):
+                x = n1(x + attn(x, attn_mask))
+                x = n2(x + ffn(x, mt))
+        if mt is not None:
+            x = x * mt
+        return x.transpose(1, 2)
 
 
 class PriorEncoder(nn.Module):
