@@ -80,6 +80,7 @@ typedef struct svb_model_cfg {
     int32_t resblock_dilations[4][3];
     int32_t sampling_rate;           /* 44100 */
     int32_t n_harmonics;             /* 9 (harmonic_num 8 + fundamental)                    */
+    int32_t snake;                   /* 1: vdecoder/hifiganwithsnake (SnakeAlias activations), 0: LeakyReLU */
 } svb_model_cfg;
 
 /* replaces: Svc.load_model's `.to(dev)` of the model (inference/infer_tool.py:189-200) */

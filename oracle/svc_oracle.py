@@ -214,9 +214,33 @@ def nsf_source_closed_form(sd, f0, rand_ini, har_noise, cfg):
 
 
 # ----------------------------------------------------------------------------- generator
-def resblock1(sd, p, x, k, dils, dtype):
-    """vdecoder/hifigan/models.py:60-67."""
+def snake_alias(sd, p, x, dtype):
+    """vdecoder/hifiganwithsnake/alias/act.py:109-129: 2x kaiser-sinc upsample (resample.py:35-54) -> SnakeBeta with
+    log-scale alpha/beta (act.py:81-92) -> 2x low-pass downsample (filter.py:93-109), replicate padding."""
+    C = x.shape[1]
+    f = sd[p + "upsample.filter"].to(dtype).expand(C, -1, -1)
+    xp = F.pad(x, (5, 5), mode="replicate")
+    u = 2 * F.conv_transpose1d(xp, f, stride=2, groups=C)[..., 15:-15]
+    alpha = torch.exp(sd[p + "act.alpha"].to(dtype))[None, :, None]
+    beta = torch.exp(sd[p + "act.beta"].to(dtype))[None, :, None]
+    sn = u + (1.0 / (beta + 0.000000001)) * torch.sin(u * alpha) ** 2
+    sp = F.pad(sn, (5, 6), mode="replicate")
+    fd = sd[p + "downsample.lowpass.filter"].to(dtype).expand(C, -1, -1)
+    return F.conv1d(sp, fd, stride=2, groups=C)
+
+
+def resblock1(sd, p, x, k, dils, dtype, snake=False):
+    """vdecoder/hifigan/models.py:60-67 (hifiganwithsnake/models.py:66-74 when snake)."""
     for j, d in enumerate(dils):
+        if snake:
+            xt = snake_alias(sd, p + f"activations.{2 * j}.", x, dtype)
+            xt = F.conv1d(xt, wn_weight(sd, p + f"convs1.{j}", dtype), sd[p + f"convs1.{j}.bias"].to(dtype),
+                          dilation=d, padding=d * (k - 1) // 2)
+            xt = snake_alias(sd, p + f"activations.{2 * j + 1}.", xt, dtype)
+            xt = F.conv1d(xt, wn_weight(sd, p + f"convs2.{j}", dtype), sd[p + f"convs2.{j}.bias"].to(dtype),
+                          padding=(k - 1) // 2)
+            x = xt + x
+            continue
         xt = F.leaky_relu(x, LRELU_SLOPE)
         xt = F.conv1d(xt, wn_weight(sd, p + f"convs1.{j}", dtype), sd[p + f"convs1.{j}.bias"].to(dtype),
                       dilation=d, padding=d * (k - 1) // 2)
@@ -234,8 +258,9 @@ def generator(sd, z, g, har, cfg, dtype, taps: Optional[dict] = None):
     if taps is not None:
         taps["conv_pre"] = x
     nk = len(cfg.resblock_kernel_sizes)
+    snake = getattr(cfg, "snake", False)
     for i, (u, k) in enumerate(zip(cfg.upsample_rates, cfg.upsample_kernel_sizes)):
-        x = F.leaky_relu(x, LRELU_SLOPE)
+        x = snake_alias(sd, f"dec.snakes.{i}.", x, dtype) if snake else F.leaky_relu(x, LRELU_SLOPE)
         x = F.conv_transpose1d(x, wn_weight(sd, f"dec.ups.{i}", dtype), sd[f"dec.ups.{i}.bias"].to(dtype),
                                stride=u, padding=(k - u + 1) // 2)
         nw = sd[f"dec.noise_convs.{i}.weight"].to(dtype)
@@ -250,12 +275,12 @@ def generator(sd, z, g, har, cfg, dtype, taps: Optional[dict] = None):
         acc = None
         for j in range(nk):
             r = resblock1(sd, f"dec.resblocks.{i * nk + j}.", x, cfg.resblock_kernel_sizes[j],
-                          cfg.resblock_dilation_sizes[j], dtype)
+                          cfg.resblock_dilation_sizes[j], dtype, snake)
             acc = r if acc is None else acc + r
         x = acc / nk
         if taps is not None:
             taps[f"stage{i}"] = x
-    x = F.leaky_relu(x)  # default slope 0.01 (:390)
+    x = snake_alias(sd, "dec.snake_post.", x, dtype) if snake else F.leaky_relu(x)  # default slope 0.01 (:390)
     x = F.conv1d(x, wn_weight(sd, "dec.conv_post", dtype), sd["dec.conv_post.bias"].to(dtype), padding=3)
     return torch.tanh(x)
 

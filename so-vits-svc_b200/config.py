@@ -56,6 +56,11 @@ class ModelCfg:
         return p
 
     @property
+    def snake(self) -> bool:
+        """vdecoder/hifiganwithsnake: every LeakyReLU replaced by anti-aliased SnakeBeta (models.py:426-431)."""
+        return self.vocoder_name == "nsf-snake-hifigan"
+
+    @property
     def stage_channels(self) -> List[int]:
         return [self.upsample_initial_channel // (2 ** (i + 1)) for i in range(len(self.upsample_rates))]
 
@@ -67,8 +72,8 @@ class ModelCfg:
             raise NotImplementedError("use_transformer_flow is outside the hot path (SURVEY §8)")
         if self.resblock != "1":
             raise NotImplementedError("only ResBlock1 generators are implemented")
-        if self.vocoder_name not in ("nsf-hifigan",):
-            raise NotImplementedError(f"vocoder {self.vocoder_name!r} not implemented in the CUDA tail yet")
+        if self.vocoder_name not in ("nsf-hifigan", "nsf-snake-hifigan"):
+            raise NotImplementedError(f"vocoder {self.vocoder_name!r} not implemented in the CUDA tail")
         if len(self.resblock_kernel_sizes) != 3:
             raise NotImplementedError("generator expects three ResBlock branches")
 

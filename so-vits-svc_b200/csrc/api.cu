@@ -52,7 +52,15 @@ struct FlowLayer {
     int in_c0 = 0, out_c0 = 0;     // which half feeds pre / receives post (Flip folded)
 };
 
+struct SnakeP {           // SnakeAlias parameters of one activation: e^alpha and 1/(e^beta + 1e-9) per channel
+    float* ealpha = nullptr;
+    float* inv_beta = nullptr;
+    int C = 0;
+};
+
 struct Stage {
+    SnakeP snake_in;               // dec.snakes[i] (before ups[i])
+    std::vector<SnakeP> acts;      // dec.resblocks[3i+j].activations[a] at [j*6 + a]
     float* up_w = nullptr;         // [s][Cin][2][Cout]
     float* up_b = nullptr;
     int Cin = 0, Cout = 0, s = 0, k = 0, p = 0;
@@ -79,6 +87,8 @@ struct svb_ctx {
     float* dcond_b = nullptr;
     ConvW dcond;                   // packed (time-varying g)
     std::vector<Stage> stages;
+    SnakeP snake_post;
+    float* snake_filt = nullptr;   // the fixed 12-tap kaiser-sinc filter
     float* post_w = nullptr;       // [C][7]
     float post_b = 0.f;
     int post_C = 0, post_K = 7;
@@ -225,7 +235,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct WsPlan {
     size_t total = 0;
     size_t off_y, off_h, off_xin, off_acts, off_out, off_gcond, off_dgcond, off_phase;
-    size_t off_har, off_pre, off_X, off_A, off_Bb, off_T, off_O, off_z;
+    size_t off_har, off_pre, off_X, off_A, off_Bb, off_T, off_O, off_z, off_S;
 };
 
 WsPlan plan_ws(const svb_model_cfg& c, int B, int T, int gT) {
@@ -260,6 +270,7 @@ WsPlan plan_ws(const svb_model_cfg& c, int B, int T, int gT) {
     p.off_Bb = take(maxel * f);
     p.off_T = take(maxel * f);
     p.off_O = take(maxel * f);
+    p.off_S = c.snake ? take(maxel * f) : 0;
     p.total = o;
     p.off_y = p.off_z;
     return p;
@@ -462,7 +473,11 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         launch_conv_f32(cg, st);
         cp.bias_t = dg; cp.bias_t_ctot = U;
     }
-    const bool gen_tc = ctx->precision == SVB_PREC_TC && ctx->gen_tc_ok && gT == 1;
+    // The SnakeAlias variant is a time-domain filter around every activation, not an elementwise op: it runs as its own
+    // kernel in front of the fp32 FFMA convolutions (the tensor-core kernels fuse LeakyReLU and are not used for it).
+    const bool snake = c.snake != 0;
+    float* Sb = snake ? reinterpret_cast<float*>(ws + pl.off_S) : nullptr;
+    const bool gen_tc = ctx->precision == SVB_PREC_TC && ctx->gen_tc_ok && gT == 1 && !snake;
     if (gen_tc) {
         const ConvNW& W = ctx->conv_pre_tc;
         ConvNTC a;
@@ -484,12 +499,13 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         Stage& S = ctx->stages[i];
         const int Lout = Lin * S.s;
         // x = ups(lrelu(x, 0.1))  as s polyphase 2-tap convs
+        if (snake) launch_snake_alias(cur, Sb, S.snake_in.ealpha, S.snake_in.inv_beta, ctx->snake_filt, B, S.Cin, Lin, st);
         ConvF32 up;
-        up.x = cur; up.x_ctot = S.Cin; up.Cin = S.Cin; up.Tin = Lin;
+        up.x = snake ? Sb : cur; up.x_ctot = S.Cin; up.Cin = S.Cin; up.Tin = Lin;
         up.w = S.up_w; up.bias = S.up_b; up.Cout = S.Cout; up.k = 2; up.dil = 1; up.pad_left = 1;
         up.n_phase = S.s; up.w_phase_stride = (long long)S.Cin * 2 * S.Cout;
         up.ostride = S.s; up.ooff = -S.p; up.n_out = Lin + 1;
-        up.in_act = 1; up.in_slope = 0.1f;
+        up.in_act = snake ? 0 : 1; up.in_slope = 0.1f;
         up.y = X; up.y_ctot = S.Cout; up.Ty = Lout; up.B = B;
         if (gen_tc) {
             const ConvNW& W = S.up_tc;
@@ -512,7 +528,7 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         static const int fuse_maxc = [] { const char* e = std::getenv("SVB_FUSE_MAXC"); return e ? std::atoi(e) : 32; }();
         for (int j = 0; j < nk; ++j) {
             const int k = c.resblock_kernel_sizes[j];
-            if (ctx->precision == SVB_PREC_TC && fuse_rb && S.Cout <= fuse_maxc && S.c1[j * 3].w_tc) {
+            if (ctx->precision == SVB_PREC_TC && !snake && fuse_rb && S.Cout <= fuse_maxc && S.c1[j * 3].w_tc) {
                 // narrow stages: the whole ResBlock in one kernel (residual stream in TMEM)
                 ResblockTC rb;
                 rb.x = X; rb.out = O; rb.B = B; rb.C = S.Cout; rb.T = Lout; rb.k = k;
@@ -541,8 +557,8 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
                 bool done = false;
                 const double pair_flops = 2.0 * 2.0 * S.Cout * (double)S.Cout * k * (double)Lout * B;
                 const double pair_bytes = 3.0 * S.Cout * (double)Lout * B * sizeof(float);   // read x (tile + residual) + write out
-                ProfScope ps(ctx, (ctx->precision == SVB_PREC_TC && W1.w_tc) ? "pair_tc" : "pair_f32", st, pair_flops, pair_bytes);
-                if (ctx->precision == SVB_PREC_TC && W1.w_tc && W2.w_tc) {
+                ProfScope ps(ctx, (ctx->precision == SVB_PREC_TC && W1.w_tc && !snake) ? "pair_tc" : "pair_f32", st, pair_flops, pair_bytes);
+                if (ctx->precision == SVB_PREC_TC && !snake && W1.w_tc && W2.w_tc) {
                     PairTC pt;
                     pt.x = src; pt.out = dst; pt.w1 = W1.w_tc; pt.w2 = W2.w_tc; pt.b1 = W1.b; pt.b2 = W2.b;
                     pt.B = B; pt.C = S.Cout; pt.T = Lout; pt.k = k; pt.dil = dil; pt.alpha = alpha; pt.beta = beta;
@@ -551,16 +567,18 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
                     else if (trc != SVB_ERR_UNSUPPORTED) return fail(ctx, trc, "tensor-core pair kernel launch failed");
                 }
                 if (!done) {
+                    if (snake) { const SnakeP& a1 = S.acts[j * 6 + 2 * d]; launch_snake_alias(src, Sb, a1.ealpha, a1.inv_beta, ctx->snake_filt, B, S.Cout, Lout, st); }
                     ConvF32 c1;
-                    c1.x = src; c1.x_ctot = S.Cout; c1.Cin = S.Cout; c1.Tin = Lout;
+                    c1.x = snake ? Sb : src; c1.x_ctot = S.Cout; c1.Cin = S.Cout; c1.Tin = Lout;
                     c1.w = W1.w; c1.bias = W1.b; c1.Cout = S.Cout; c1.k = k; c1.dil = dil; c1.pad_left = dil * (k - 1) / 2;
-                    c1.in_act = 1; c1.in_slope = 0.1f;
+                    c1.in_act = snake ? 0 : 1; c1.in_slope = 0.1f;
                     c1.y = Tm; c1.y_ctot = S.Cout; c1.Ty = Lout; c1.n_out = Lout; c1.B = B;
                     launch_conv_f32(c1, st);
+                    if (snake) { const SnakeP& a2 = S.acts[j * 6 + 2 * d + 1]; launch_snake_alias(Tm, Sb, a2.ealpha, a2.inv_beta, ctx->snake_filt, B, S.Cout, Lout, st); }
                     ConvF32 c2;
-                    c2.x = Tm; c2.x_ctot = S.Cout; c2.Cin = S.Cout; c2.Tin = Lout;
+                    c2.x = snake ? Sb : Tm; c2.x_ctot = S.Cout; c2.Cin = S.Cout; c2.Tin = Lout;
                     c2.w = W2.w; c2.bias = W2.b; c2.Cout = S.Cout; c2.k = k; c2.dil = 1; c2.pad_left = (k - 1) / 2;
-                    c2.in_act = 1; c2.in_slope = 0.1f;
+                    c2.in_act = snake ? 0 : 1; c2.in_slope = 0.1f;
                     c2.res = src; c2.res_ctot = S.Cout;
                     c2.y = dst; c2.y_ctot = S.Cout; c2.Ty = Lout; c2.n_out = Lout; c2.B = B;
                     c2.alpha = alpha; c2.beta = beta;
@@ -575,7 +593,12 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         cur = tmp;
         Lin = Lout;
     }
-    launch_conv_post(cur, ctx->post_w, ctx->post_b, wav, B, ctx->post_C, Lin, ctx->post_K, 0.01f, st);
+    if (snake) {
+        launch_snake_alias(cur, Sb, ctx->snake_post.ealpha, ctx->snake_post.inv_beta, ctx->snake_filt, B, ctx->post_C, Lin, st);
+        launch_conv_post(Sb, ctx->post_w, ctx->post_b, wav, B, ctx->post_C, Lin, ctx->post_K, 1.0f, st);   // slope 1 = no activation
+    } else {
+        launch_conv_post(cur, ctx->post_w, ctx->post_b, wav, B, ctx->post_C, Lin, ctx->post_K, 0.01f, st);
+    }
     return check_launch(ctx, "generator");
 }
 
@@ -931,6 +954,30 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
                 if ((rc = make_conv(ctx, w.v, b.v, S.Cout, S.Cout, k, false, false, S.c2[j * 3 + d]))) return rc;
             }
         }
+    }
+    if (c.snake) {
+        auto load_snake = [&](const std::string& prefix, int Cc, SnakeP& out) -> int {
+            HostT al, be;
+            int r2;
+            if ((r2 = get_tensor(ctx, m, prefix + "act.alpha", {Cc}, al))) return r2;
+            if ((r2 = get_tensor(ctx, m, prefix + "act.beta", {Cc}, be))) return r2;
+            std::vector<float> ea(Cc), ib(Cc);
+            for (int q = 0; q < Cc; ++q) { ea[q] = std::exp(al.v[q]); ib[q] = 1.0f / (std::exp(be.v[q]) + 0.000000001f); }
+            out.C = Cc;
+            if ((r2 = upload(ctx, ea.data(), Cc * sizeof(float), (void**)&out.ealpha))) return r2;
+            return upload(ctx, ib.data(), Cc * sizeof(float), (void**)&out.inv_beta);
+        };
+        for (int i = 0; i < c.n_upsamples; ++i) {
+            Stage& S = ctx->stages[i];
+            if ((rc = load_snake("dec.snakes." + std::to_string(i) + ".", S.Cin, S.snake_in))) return rc;
+            S.acts.assign(18, SnakeP());
+            for (int j = 0; j < 3; ++j)
+                for (int a2 = 0; a2 < 6; ++a2)
+                    if ((rc = load_snake("dec.resblocks." + std::to_string(i * 3 + j) + ".activations." + std::to_string(a2) + ".", S.Cout, S.acts[j * 6 + a2]))) return rc;
+        }
+        if ((rc = load_snake("dec.snake_post.", U >> c.n_upsamples, ctx->snake_post))) return rc;
+        if ((rc = get_tensor(ctx, m, "dec.snake_post.upsample.filter", {1, 1, 12}, w))) return rc;
+        if ((rc = upload(ctx, w.v.data(), 12 * sizeof(float), (void**)&ctx->snake_filt))) return rc;
     }
     ctx->post_C = U >> c.n_upsamples;
     if ((rc = folded(ctx, m, "dec.conv_post", {1, ctx->post_C, 7}, w))) return rc;

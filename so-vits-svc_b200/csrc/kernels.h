@@ -42,6 +42,10 @@ void launch_gemv(const float* W, const float* bias, const float* g, float* out, 
 void launch_noise_conv_add(const float* har, const float* w, const float* bias, float* y,
                            int B, int Cout, int Tout, int N, int K, int s, int p, cudaStream_t st);
 
+// y = SnakeAlias(x) per channel (vdecoder/hifiganwithsnake/alias/act.py:109-129); ealpha = e^alpha, inv_beta = 1/(e^beta+1e-9)
+void launch_snake_alias(const float* x, float* y, const float* ealpha, const float* inv_beta, const float* filt,
+                        int B, int C, int L, cudaStream_t st);
+
 // wav[b,n] = tanh(bias + sum_{ci,k} w[ci][k] * lrelu(x[b,ci,n+k-pad], slope))   (conv_post, :390-392)
 void launch_conv_post(const float* x, const float* w, float bias, float* wav, int B, int C, int N, int K, float slope, cudaStream_t st);
 

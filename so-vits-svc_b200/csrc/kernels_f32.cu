@@ -253,6 +253,61 @@ void launch_noise_conv_add(const float* har, const float* w, const float* bias, 
 }
 
 // =====================================================================================================
+// SnakeAlias (vdecoder/hifiganwithsnake/alias/act.py:109-129), one (batch, channel, 256-step tile) per
+// block:  u = 2x kaiser-sinc upsample of replicate-padded x;  s = u + sin^2(u*e^alpha)/(e^beta + 1e-9);
+//         y = 12-tap low-pass of replicate-padded s, decimated by 2.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) snake_alias_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                          const float* __restrict__ ealpha, const float* __restrict__ inv_beta,
+                                                          const float* __restrict__ filt, int C, int L) {
+    __shared__ float xs[272];
+    __shared__ float ss[528];
+    __shared__ float f[12];
+    const int c = blockIdx.y, b = blockIdx.z;
+    const int t0 = blockIdx.x * 256;
+    const float* xr = x + ((long long)b * C + c) * L;
+    if (threadIdx.x < 12) f[threadIdx.x] = filt[threadIdx.x];
+    for (int j = threadIdx.x; j < 266; j += 256) {
+        int ti = min(max(t0 - 5 + j, 0), L - 1);
+        xs[j] = xr[ti];
+    }
+    __syncthreads();
+    const float ea = ealpha[c], ib = inv_beta[c];
+    for (int idx = threadIdx.x; idx < 522; idx += 256) {
+        const int m = min(max(2 * t0 - 5 + idx, 0), 2 * L - 1);
+        // u[m] = 2 * sum_i xp[i] * f[m + 15 - 2i],  xp[i] = x[clamp(i - 5)],  0 <= m + 15 - 2i <= 11
+        const int i_lo = (m + 5) >> 1;            // ceil((m + 4) / 2)
+        float u = 0.f;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const int i = i_lo + q;
+            const int tap = m + 15 - 2 * i;
+            if (tap >= 0 && tap <= 11) {
+                const int xi = min(max(i - 5, 0), L - 1) - (t0 - 5);
+                u = fmaf(xs[min(max(xi, 0), 265)], f[tap], u);
+            }
+        }
+        u *= 2.f;
+        const float sn = sinf(u * ea);
+        ss[idx] = u + ib * sn * sn;
+    }
+    __syncthreads();
+    const int t = t0 + threadIdx.x;
+    if (t >= L) return;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) acc = fmaf(f[j], ss[2 * threadIdx.x + j], acc);
+    y[((long long)b * C + c) * L + t] = acc;
+}
+
+void launch_snake_alias(const float* x, float* y, const float* ealpha, const float* inv_beta, const float* filt,
+                        int B, int C, int L, cudaStream_t st) {
+    dim3 grid((L + 255) / 256, C, B);
+    snake_alias_kernel<<<grid, 256, 0, st>>>(x, y, ealpha, inv_beta, filt, C, L);
+    launch_counter()++;
+}
+
+// =====================================================================================================
 // conv_post: leaky_relu(slope) -> Conv1d(C->1, K, pad (K-1)/2) -> tanh
 // =====================================================================================================
 __global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w, float bias,

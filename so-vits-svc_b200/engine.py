@@ -38,6 +38,7 @@ def _cfg_struct(cfg: ModelCfg) -> L.svb_model_cfg:
             s.resblock_dilations[j][d] = dil
     s.sampling_rate = cfg.sampling_rate
     s.n_harmonics = cfg.n_harmonics
+    s.snake = 1 if cfg.snake else 0
     return s
 
 

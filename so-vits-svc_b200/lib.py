@@ -36,7 +36,7 @@ class svb_model_cfg(C.Structure):
         ("upsample_rates", C.c_int32 * 8), ("upsample_kernel_sizes", C.c_int32 * 8),
         ("n_resblock_kernels", C.c_int32), ("resblock_kernel_sizes", C.c_int32 * 4),
         ("resblock_dilations", (C.c_int32 * 3) * 4),
-        ("sampling_rate", C.c_int32), ("n_harmonics", C.c_int32),
+        ("sampling_rate", C.c_int32), ("n_harmonics", C.c_int32), ("snake", C.c_int32),
     ]
 
 

@@ -107,6 +107,20 @@ def param_shapes(cfg: ModelCfg) -> "OrderedDict[str, tuple]":
                     s[r + f"{grp}.{d}.bias"] = (ch,)
                     s[r + f"{grp}.{d}.weight_g"] = (ch, 1, 1)
                     s[r + f"{grp}.{d}.weight_v"] = (ch, ch, k)
+    if cfg.snake:
+        # vdecoder/hifiganwithsnake/models.py:364-374,61-64: SnakeAlias before every ups / conv / conv_post
+        def snake_keys(prefix, chn):
+            s[prefix + "act.alpha"] = (chn,)
+            s[prefix + "act.beta"] = (chn,)
+            s[prefix + "upsample.filter"] = (1, 1, 12)
+            s[prefix + "downsample.lowpass.filter"] = (1, 1, 12)
+        for i in range(n_up):
+            snake_keys(f"dec.snakes.{i}.", U // (2 ** i))
+            chn = U // (2 ** (i + 1))
+            for j in range(len(cfg.resblock_kernel_sizes)):
+                for a in range(2 * len(cfg.resblock_dilation_sizes[j])):
+                    snake_keys(f"dec.resblocks.{i * len(cfg.resblock_kernel_sizes) + j}.activations.{a}.", chn)
+        snake_keys("dec.snake_post.", U // (2 ** n_up))
     ch = U // (2 ** n_up)
     s["dec.conv_post.bias"] = (1,)
     s["dec.conv_post.weight_g"] = (1, 1, 1)
@@ -114,6 +128,19 @@ def param_shapes(cfg: ModelCfg) -> "OrderedDict[str, tuple]":
     s["dec.cond.weight"] = (U, G, 1)
     s["dec.cond.bias"] = (U,)
     return s
+
+
+def kaiser_sinc_filter12() -> torch.Tensor:
+    """The fixed 12-tap anti-aliasing filter of SnakeAlias (cutoff 0.25, half-width 0.3, Kaiser window;
+    vdecoder/hifiganwithsnake/alias/filter.py:29-58), normalised to unit sum."""
+    ks, cutoff, half_width = 12, 0.25, 0.3
+    half = ks // 2
+    A = 2.285 * (half - 1) * math.pi * (4 * half_width) + 7.95
+    beta = 0.1102 * (A - 8.7) if A > 50 else (0.5842 * (A - 21) ** 0.4 + 0.07886 * (A - 21) if A >= 21 else 0.0)
+    win = torch.kaiser_window(ks, beta=beta, periodic=False)
+    t = torch.arange(-half, half, dtype=torch.float32) + 0.5
+    f = 2 * cutoff * win * torch.sinc(2 * cutoff * t)
+    return f / f.sum()
 
 
 def synth_state_dict(cfg: ModelCfg, seed: int = 20260922, dtype=torch.float32) -> Dict[str, torch.Tensor]:
@@ -141,12 +168,20 @@ def synth_state_dict(cfg: ModelCfg, seed: int = 20260922, dtype=torch.float32) -
             if ".res_skip_layers." in key or ".in_layers." in key or "cond_layer" in key:
                 gain = 1.0
             if ".resblocks." in key:
-                gain = 1.0                          # residual branches carry as much energy as the skip path
+                gain = 0.45 if cfg.snake else 1.0   # residual branches comparable to the skip path (snake passes more energy than lrelu)
+            if cfg.snake and (".ups." in key or "conv_pre" in key):
+                gain = 0.7
             v = randn(shape, gain / math.sqrt(fan))
             sd[key] = v
             # weight_norm: norm over all dims but 0 (also for ConvTranspose1d)
             nrm = v.reshape(shape[0], -1).norm(dim=1).reshape(shape[0], 1, 1)
             sd[key.replace("weight_v", "weight_g")] = nrm * rand((shape[0], 1, 1), 0.5, 1.5)
+        elif leaf == "filter":
+            sd[key] = kaiser_sinc_filter12().reshape(shape)
+        elif leaf == "alpha" and ".act." in key:
+            sd[key] = randn(shape, 0.3)              # log-scale frequency of SnakeBeta
+        elif leaf == "beta" and ".act." in key:
+            sd[key] = randn(shape, 0.3) + 1.0        # log-scale magnitude (1/beta ~ 0.37)
         elif leaf in ("gamma",):
             sd[key] = rand(shape, 0.8, 1.2)
         elif leaf in ("beta", "bias"):
@@ -198,11 +233,12 @@ def draw_noise(B: int, T: int, cfg: ModelCfg, seed: int = 52468, device="cpu"):
 
 
 GOLDEN_CASES = {"b2_t24": (2, 24), "b1_t33": (1, 33)}
+SNAKE_GOLDEN_CASES = {"snake_b1_t20": (1, 20)}        # vocoder_name = "nsf-snake-hifigan" (BASELINE config 4)
 
 
 def golden_inputs(cfg: ModelCfg, name: str):
     """Inputs of the committed reference fixtures (tests/golden/make_golden.py)."""
-    B, T = GOLDEN_CASES[name]
+    B, T = GOLDEN_CASES[name] if name in GOLDEN_CASES else SNAKE_GOLDEN_CASES[name]
     c, f0, uv, sid = synth_inputs(cfg, B, T)
     if name == "b1_t33":            # odd T, an unvoiced span with voiced<->unvoiced edges inside a clip
         f0[:, 5:12] = 0.0

@@ -33,6 +33,7 @@ def build_reference(cfg, sd):
     import json
     with open(sovits_b200.DEFAULT_CONFIG) as f:
         model_kw = json.load(f)["model"]
+    model_kw["vocoder_name"] = cfg.vocoder_name
     net = ref_models.SynthesizerTrn(2048 // 2 + 1, 10240 // 512, **model_kw).eval()
     own = net.state_dict()
     missing = [k for k in sd if k not in own]
@@ -68,7 +69,21 @@ def main():
                             har=taps["har"].transpose(1, 2).numpy(),
                             B=B, T=T, seed=52468, noice_scale=0.4,
                             f0=f0.numpy())
-    # module-level fixtures: one coupling layer + one ResBlock input/output are covered by z / o above.
+    # Snake-activation generator (vdecoder/hifiganwithsnake, BASELINE config 4)
+    cfg_s = load_config()
+    cfg_s.vocoder_name = "nsf-snake-hifigan"
+    sd_s = synth.synth_state_dict(cfg_s)
+    net_s = build_reference(cfg_s, sd_s)
+    for name, (B, T) in synth.SNAKE_GOLDEN_CASES.items():
+        c, f0, uv, sid = synth.golden_inputs(cfg_s, name)
+        taps = {}
+        hk = net_s.flow.register_forward_pre_hook(lambda m, i: taps.__setitem__("z_p", i[0].detach().clone()))
+        with torch.no_grad():
+            o, _ = net_s.infer(c, f0=f0, uv=uv, g=sid, noice_scale=0.4)
+        hk.remove()
+        print(name, o.shape, float(o.abs().max()))
+        np.savez_compressed(os.path.join(HERE, f"ref_infer_{name}.npz"), o=o.numpy(), z_p=taps["z_p"].numpy(),
+                            B=B, T=T, seed=52468, noice_scale=0.4, f0=f0.numpy())
     print("done")
 
 

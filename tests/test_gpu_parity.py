@@ -254,6 +254,33 @@ def test_full_size_properties(cfg, sd, eng):
     assert torch.equal(host[0], outs["fp32"][i].cpu())
 
 
+def test_snake_variant_matches_reference_fixture():
+    """BASELINE config 4 (vdecoder/hifiganwithsnake): SnakeAlias kernel + fp32 FFMA convolutions vs the reference's own
+    waveform; `precision="tc"` must give the same result (the Snake path does not use the LeakyReLU-fused TC kernels)."""
+    from sovits_b200.config import load_config
+    from sovits_b200.engine import TailEngine
+    cfg_s = load_config()
+    cfg_s.vocoder_name = "nsf-snake-hifigan"
+    sd_s = synth.synth_state_dict(cfg_s)
+    e = TailEngine(cfg_s, DEV, "fp32")
+    e.load_state_dict(sd_s)
+    for name, (B, T) in synth.SNAKE_GOLDEN_CASES.items():
+        gold = np.load(os.path.join(GOLD, f"ref_infer_{name}.npz"))
+        c, f0, uv, sid = synth.golden_inputs(cfg_s, name)
+        noise = synth.draw_noise(B, T, cfg_s)
+        g = sd_s["emb_g.weight"][sid].transpose(1, 2).contiguous()
+        outs = []
+        for precision in ("fp32", "tc"):
+            e.set_precision(precision)
+            got = e.infer_tail(torch.from_numpy(gold["z_p"]).to(DEV), g.to(DEV), f0.to(DEV), noise["rand_ini"].to(DEV),
+                               noise["har_noise"].to(DEV)).cpu()
+            err = float((got - torch.from_numpy(gold["o"])).abs().max())
+            print(f"[parity] snake {name} {precision}: L-inf vs reference waveform = {err:.3e}")
+            assert err < (FP32_TOL if precision == "fp32" else TC_TOL)
+            outs.append(got)
+    e.close()
+
+
 def test_error_paths(cfg, sd):
     from sovits_b200 import lib as L
     lib = L.load_library()

@@ -78,9 +78,22 @@ def test_unsupported_configs_are_rejected():
     with pytest.raises(NotImplementedError):
         models.SynthesizerTrn(1025, 20, **kw)
     kw = _model_kwargs()
-    kw["vocoder_name"] = "nsf-snake-hifigan"
+    kw["use_transformer_flow"] = True
     with pytest.raises(NotImplementedError):
         models.SynthesizerTrn(1025, 20, **kw)
+
+
+def test_snake_variant_state_dict_layout(cfg):
+    """vocoder_name='nsf-snake-hifigan' (BASELINE config 4) adds the SnakeAlias keys of hifiganwithsnake/models.py."""
+    from sovits_b200.config import load_config
+    cfg_s = load_config()
+    cfg_s.vocoder_name = "nsf-snake-hifigan"
+    kw = _model_kwargs()
+    kw["vocoder_name"] = "nsf-snake-hifigan"
+    net = models.SynthesizerTrn(1025, 20, **kw)
+    sd_s = synth.synth_state_dict(cfg_s)
+    assert set(net.state_dict()) == set(sd_s)
+    assert "dec.resblocks.7.activations.5.act.beta" in sd_s and "dec.snake_post.downsample.lowpass.filter" in sd_s
 
 
 @pytest.mark.skipif(not os.path.isdir(os.environ.get("SOVITS_REF_DIR", "/root/reference")),

@@ -31,6 +31,20 @@ def test_oracle_matches_reference_fixture(cfg, sd, name):
     assert float((o - torch.from_numpy(g["o"])).abs().max()) < 2e-5   # waveform in (-1,1)
 
 
+def test_snake_oracle_matches_reference_fixture():
+    """vdecoder/hifiganwithsnake (SnakeAlias activations): oracle vs the reference run stored by make_golden.py."""
+    from sovits_b200.config import load_config
+    cfg_s = load_config()
+    cfg_s.vocoder_name = "nsf-snake-hifigan"
+    sd_s = synth.synth_state_dict(cfg_s)
+    for name, (B, T) in synth.SNAKE_GOLDEN_CASES.items():
+        g = _load(name)
+        c, f0, uv, sid = synth.golden_inputs(cfg_s, name)
+        noise = synth.draw_noise(B, T, cfg_s)
+        o, _ = O.infer(sd_s, cfg_s, c, f0, uv, sid, noise, noice_scale=0.4)
+        assert float((o - torch.from_numpy(g["o"])).abs().max()) < 2e-5
+
+
 def test_oracle_fp64_close_to_fp32_reference(cfg, sd):
     g = _load("b1_t33")
     c, f0, uv, sid = synth.golden_inputs(cfg, "b1_t33")
