@@ -217,12 +217,12 @@ int make_conv(svb_ctx* ctx, const std::vector<float>& w, const std::vector<float
 
 int make_convn(svb_ctx* ctx, int cinp, int cin_real, int N_total, int NC, int k, int pad_left,
                const std::function<float(int, int, int)>& wcol, const std::function<float(int)>& bcol, ConvNW& out,
-               const std::function<float(int, int)>* ncol = nullptr) {
+               const std::function<float(int, int)>* ncol = nullptr, int noise_kind = 1) {
     out.cinp = cinp; out.cin_real = cin_real; out.N_total = N_total; out.NC = NC; out.k = k; out.pad_left = pad_left;
-    out.noise = ncol ? 1 : 0;
+    out.noise = ncol ? noise_kind : 0;
     const size_t ib = convn_weight_image_bytes(cinp, N_total, NC, k, out.noise);
     std::vector<uint8_t> img(ib);
-    convn_pack_weight_image(cinp, N_total, NC, k, [&](int col, int ci, int tap) { return ci < cin_real ? wcol(col, ci, tap) : 0.f; }, ncol, img.data());
+    convn_pack_weight_image(cinp, N_total, NC, k, [&](int col, int ci, int tap) { return ci < cin_real ? wcol(col, ci, tap) : 0.f; }, ncol, out.noise, img.data());
     int rc = upload(ctx, img.data(), ib, &out.img);
     if (rc) return rc;
     std::vector<float> bc(N_total);
@@ -515,7 +515,7 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
             a.chunks_per_cta = (W.N_total + W.NC - 1) / W.NC;
             a.mode = 1; a.s = S.s; a.p = S.p; a.Ty = Lout; a.B = B;
             a.seg[0].y = X; a.seg[0].y_ctot = S.Cout;
-            if (W.noise) { a.har = har; a.har_N = (int)N; a.noise_stride = W.noise_stride; a.noise_w0 = W.noise_w0; }
+            if (W.noise) { a.har = har; a.har_N = (int)N; a.noise_stride = W.noise_stride; a.noise_w0 = W.noise_w0; a.noise_wide = (W.noise == 2); }
             int trc = launch_convn_tc(a, st);
             if (trc) return fail(ctx, trc, "convn launch failed (ups)");
         } else {
@@ -927,7 +927,9 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
             int nc = 256 / convn_mb(S.Cin);
             if (nc > ntot) nc = ntot;
             const int sp = S.noise_s, Kn = S.noise_K, pn_ = S.noise_p;
-            const bool fuse_noise = ((s_ - 1) * sp + Kn <= 16) && (S.Cin <= 128);
+            const int nwin = (s_ - 1) * sp + Kn;                   // excitation window of one output row
+            const int noise_kind = nwin <= 16 ? 1 : (nwin <= 80 ? 2 : 0);
+            const bool fuse_noise = noise_kind != 0 && S.Cin <= 256;
             std::function<float(int, int)> ncol = [&](int col, int u) {
                 const int co = col / s_, ph = col % s_;
                 const int q = u - ph * sp;
@@ -936,7 +938,7 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
             if ((rc = make_convn(ctx, S.Cin, S.Cin, ntot, nc, 2, 1,
                                  [&](int col, int ci, int tap) { const int co = col / s_, ph = col % s_; return upw_host[((size_t)ci * Co + co) * kk + (tap == 0 ? ph + s_ : ph)]; },
                                  [&](int col) { return upb_host[col / s_] + (fuse_noise ? nbv[col / s_] : 0.f); }, S.up_tc,
-                                 fuse_noise ? &ncol : nullptr))) return rc;
+                                 fuse_noise ? &ncol : nullptr, noise_kind))) return rc;
             S.up_tc.noise_stride = s_ * sp;
             S.up_tc.noise_w0 = -S.p * sp - pn_;
         }

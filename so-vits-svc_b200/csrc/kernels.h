@@ -107,12 +107,13 @@ struct ConvNTC {
     int B = 1;
     // optional fused noise conv (polyphase mode): excitation window har[b, i*noise_stride + noise_w0 + u], u in [0,16)
     const float* har = nullptr; int har_N = 0; int noise_stride = 0, noise_w0 = 0;
+    int noise_wide = 0;            // 1: window of up to 80 samples (64-sample + 16-sample panels) instead of 16
 };
 int launch_convn_tc(const ConvNTC& a, cudaStream_t st);
 int convn_mb(int cinp);
 size_t convn_weight_image_bytes(int cinp, int N_total, int NC, int k, int noise);
 void convn_pack_weight_image(int cinp, int N_total, int NC, int k, const std::function<float(int, int, int)>& wcol,
-                             const std::function<float(int, int)>* ncol, void* dst_host);
+                             const std::function<float(int, int)>* ncol, int noise, void* dst_host);
 
 int64_t& launch_counter();
 

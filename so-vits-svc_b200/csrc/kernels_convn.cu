@@ -39,8 +39,9 @@ struct CNGeom {
 
 struct ConvNDev {                     // launch-time geometry (host computed)
     int stage_bytes, tmem_cols, bufcols, blkcols, nbuf;
-    int noise;                        // 1: noise panel present
-    uint32_t off_noise, off_ring, off_bar, off_bias;   // byte offsets from the 1024-aligned smem base
+    int noise_np;                     // noise panels (0, 1 or 2)
+    int noise_rb[2];                  // their row bytes (128 -> 64 samples, 32 -> 16 samples)
+    uint32_t off_noise[2], off_ring, off_bar, off_bias;   // byte offsets from the 1024-aligned smem base
 };
 
 template <int CINP, int MB, int MINB>
@@ -55,7 +56,6 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw);
     const uint32_t a_base = base;
-    const uint32_t n_base = base + d.off_noise;
     const uint32_t ring_base = base + d.off_ring;
     const uint32_t bar_base = base + d.off_bar;
     const uint32_t bar_full = bar_base;                  // [2]
@@ -75,10 +75,11 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
     const int c_lo = blockIdx.z * a.chunks_per_cta;
     const int c_hi = min(n_chunks, c_lo + a.chunks_per_cta);
     const int SUB = NC * G::RB;                           // bytes of one (tap, panel) weight block
-    const int SUBN = NC * CN_NOISE_RB;                    // bytes of the noise weight block
     const int n_reg = a.k * G::NP;                        // regular sub-blocks per chunk
-    const int n_sb = n_reg + (d.noise ? 1 : 0);
-    const size_t chunk_bytes = (size_t)n_reg * SUB + (d.noise ? SUBN : 0);
+    const int n_sb = n_reg + d.noise_np;
+    const int SUBN0 = NC * d.noise_rb[0], SUBN1 = NC * d.noise_rb[1];   // bytes of the noise weight blocks
+    const size_t chunk_bytes = (size_t)n_reg * SUB + (d.noise_np > 0 ? SUBN0 : 0) + (d.noise_np > 1 ? SUBN1 : 0);
+    auto sb_bytes = [&](int idx) -> uint32_t { return idx < n_reg ? (uint32_t)SUB : (idx == n_reg ? (uint32_t)SUBN0 : (uint32_t)SUBN1); };
     const int RA = R1 + (a.k - 1) * a.dil;                // A rows touched
 
     if (tid == 0) {
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                 while (idx < n_sb) {
                     uint32_t bytes = 0;
                     while (idx < n_sb) {
-                        const uint32_t sbb = idx < n_reg ? SUB : SUBN;
+                        const uint32_t sbb = sb_bytes(idx);
                         if (bytes && bytes + sbb > (uint32_t)d.stage_bytes) break;
                         bytes += sbb; ++idx;
                     }
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                     const int g0 = idx;
                     uint32_t bytes = 0;
                     while (idx < n_sb) {
-                        const uint32_t sbb = idx < n_reg ? SUB : SUBN;
+                        const uint32_t sbb = sb_bytes(idx);
                         if (bytes && bytes + sbb > (uint32_t)d.stage_bytes) break;
                         bytes += sbb; ++idx;
                     }
@@ -167,12 +168,15 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                             }
                             boff += SUB;
                         } else {
-                            const uint64_t a_d0 = make_smem_desc(n_base, CN_NOISE_RB, 0);
-                            const uint64_t b_d0 = make_smem_desc(bsub, CN_NOISE_RB, 0);
-#pragma unroll
+                            const int pnn = sb - n_reg;
+                            const uint32_t rbn = (uint32_t)d.noise_rb[pnn];
+                            const uint64_t a_d0 = make_smem_desc(base + d.off_noise[pnn], rbn, 0);
+                            const uint64_t b_d0 = make_smem_desc(bsub, rbn, 0);
                             for (int mb = 0; mb < MB; ++mb)
-                                umma_f16(dcol + mb * d.blkcols, a_d0 + (uint64_t)(((uint32_t)(mb * 128) * CN_NOISE_RB) >> 4), b_d0, idesc, acc0);
-                            boff += SUBN;
+                                for (uint32_t ks = 0; ks < rbn / 32u; ++ks)
+                                    umma_f16(dcol + mb * d.blkcols, a_d0 + (uint64_t)(((uint32_t)(mb * 128) * rbn + ks * 32u) >> 4),
+                                             b_d0 + (uint64_t)((ks * 32u) >> 4), idesc, (ks > 0) ? 1u : acc0);
+                            boff += sb_bytes(sb);
                         }
                     }
                     umma_commit(bar_empty + 8 * s);
@@ -205,21 +209,29 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                     store_chunk8(prow, phase, (c0 % G::CPP) / 8 + 1, v + 8, 0xffffffffu);
                 }
             }
-            if (d.noise) {
-                // excitation window of output row i: har[i*noise_stride + noise_w0 + u], u in [0,16)
+            if (d.noise_np) {
+                // excitation window of output row i: har[i*noise_stride + noise_w0 + u]; panel 0 holds u in [0, rb0/2),
+                // panel 1 the next rb1/2 samples
                 const float* __restrict__ hb = a.har + (size_t)b * a.har_N;
-                for (int r = tid; r < R1; r += CN_NWORK) {
-                    const long long h0 = (long long)(i0 + r) * a.noise_stride + a.noise_w0;
-                    float v[16];
+                int u0 = 0;
+                for (int pnn = 0; pnn < d.noise_np; ++pnn) {
+                    const int rbn = d.noise_rb[pnn];
+                    const int groups = rbn / 32;                       // 16-sample groups per row
+                    for (int it = tid; it < R1 * groups; it += CN_NWORK) {
+                        const int r = it / groups, gq = it % groups;
+                        const long long h0 = (long long)(i0 + r) * a.noise_stride + a.noise_w0 + u0 + 16 * gq;
+                        float v[16];
 #pragma unroll
-                    for (int uu = 0; uu < 16; ++uu) {
-                        const long long hi = h0 + uu;
-                        v[uu] = (hi >= 0 && hi < a.har_N) ? __ldg(hb + hi) : 0.f;
+                        for (int uu = 0; uu < 16; ++uu) {
+                            const long long hi = h0 + uu;
+                            v[uu] = (hi >= 0 && hi < a.har_N) ? __ldg(hb + hi) : 0.f;
+                        }
+                        uint8_t* prow = sm + d.off_noise[pnn] + r * rbn;
+                        const uint32_t phase = swz_phase(r, rbn);
+                        store_chunk8(prow, phase, 2 * gq, v, 0xffffffffu);
+                        store_chunk8(prow, phase, 2 * gq + 1, v + 8, 0xffffffffu);
                     }
-                    uint8_t* prow = sm + d.off_noise + r * CN_NOISE_RB;
-                    const uint32_t phase = swz_phase(r, CN_NOISE_RB);
-                    store_chunk8(prow, phase, 0, v, 0xffffffffu);
-                    store_chunk8(prow, phase, 1, v + 8, 0xffffffffu);
+                    u0 += rbn / 2;
                 }
             }
             fence_proxy_async();
@@ -363,7 +375,9 @@ int launch_convn_t(const ConvNTC& a, cudaStream_t st) {
     const int n_chunks = (a.N_total + a.NC - 1) / a.NC;
     const int cpc = a.chunks_per_cta < 1 ? 1 : a.chunks_per_cta;
     ConvNDev d;
-    d.noise = a.har ? 1 : 0;
+    d.noise_np = a.har ? (a.noise_wide ? 2 : 1) : 0;
+    d.noise_rb[0] = a.noise_wide ? 128 : CN_NOISE_RB;
+    d.noise_rb[1] = CN_NOISE_RB;
     d.nbuf = cpc > 1 ? 2 : 1;
     d.blkcols = pow2ceil(a.NC);
     d.bufcols = MB * d.blkcols;
@@ -375,9 +389,11 @@ int launch_convn_t(const ConvNTC& a, cudaStream_t st) {
     d.stage_bytes = stage;
     uint32_t off = (uint32_t)G::NP * (128 * MB + CN_HALO) * G::RB;
     off = (off + 1023u) & ~1023u;
-    d.off_noise = off;
-    if (d.noise) off += 128 * MB * CN_NOISE_RB;
-    off = (off + 1023u) & ~1023u;
+    for (int pnn = 0; pnn < 2; ++pnn) {
+        d.off_noise[pnn] = off;
+        if (pnn < d.noise_np) off += 128 * MB * d.noise_rb[pnn];
+        off = (off + 1023u) & ~1023u;
+    }
     d.off_ring = off;
     off += 2 * stage;
     d.off_bar = off;
@@ -416,21 +432,23 @@ int launch_convn_tc(const ConvNTC& a, cudaStream_t st) {
     }
 }
 
+// noise: 0 none, 1 one 16-sample panel, 2 a 64-sample + a 16-sample panel (window <= 80)
 size_t convn_weight_image_bytes(int cinp, int N_total, int NC, int k, int noise) {
-    const int CPP = cinp < 64 ? cinp : 64, RB = CPP * 2;
-    (void)RB;
-    return (size_t)((N_total + NC - 1) / NC) * ((size_t)NC * cinp * k * 2 + (noise ? (size_t)NC * CN_NOISE_RB : 0));
+    const size_t nb = noise == 0 ? 0 : (noise == 1 ? (size_t)NC * CN_NOISE_RB : (size_t)NC * (128 + CN_NOISE_RB));
+    return (size_t)((N_total + NC - 1) / NC) * ((size_t)NC * cinp * k * 2 + nb);
 }
 
 // wcol(col, ci, tap) -> folded weight value; ncol(col, u) -> banded noise weight (u in [0,16)) or null.
 // Image layout per chunk: [tap][panel][NC rows][swizzled Cin halves] then (optionally) [NC rows][16 halves, 32-byte rows].
 void convn_pack_weight_image(int cinp, int N_total, int NC, int k, const std::function<float(int, int, int)>& wcol,
-                             const std::function<float(int, int)>* ncol, void* dst_host) {
+                             const std::function<float(int, int)>* ncol, int noise, void* dst_host) {
     const int CPP = cinp < 64 ? cinp : 64, NP = cinp / CPP, RB = CPP * 2;
     const int n_chunks = (N_total + NC - 1) / NC;
     uint8_t* dst = static_cast<uint8_t*>(dst_host);
     const size_t SUB = (size_t)NC * RB;
-    const size_t chunk_bytes = (size_t)k * NP * SUB + (ncol ? (size_t)NC * CN_NOISE_RB : 0);
+    const int nrb[2] = {noise == 2 ? 128 : CN_NOISE_RB, CN_NOISE_RB};
+    const int nnp = ncol ? (noise == 2 ? 2 : 1) : 0;
+    const size_t chunk_bytes = (size_t)k * NP * SUB + (nnp > 0 ? (size_t)NC * nrb[0] : 0) + (nnp > 1 ? (size_t)NC * nrb[1] : 0);
     for (int c = 0; c < n_chunks; ++c) {
         uint8_t* cbase = dst + (size_t)c * chunk_bytes;
         for (int tap = 0; tap < k; ++tap)
@@ -445,16 +463,20 @@ void convn_pack_weight_image(int cinp, int N_total, int NC, int k, const std::fu
                         std::memcpy(blk + off, &h, 2);
                     }
             }
-        if (ncol) {
-            uint8_t* blk = cbase + (size_t)k * NP * SUB;
+        uint8_t* blk = cbase + (size_t)k * NP * SUB;
+        int u0 = 0;
+        for (int pnn = 0; pnn < nnp; ++pnn) {
+            const int rbn = nrb[pnn], width = rbn / 2;
             for (int n = 0; n < NC; ++n)
-                for (int uu = 0; uu < 16; ++uu) {
+                for (int uu = 0; uu < width; ++uu) {
                     const int col = c * NC + n;
-                    const float v = col < N_total ? (*ncol)(col, uu) : 0.f;
+                    const float v = col < N_total ? (*ncol)(col, u0 + uu) : 0.f;
                     const __half h = __float2half_rn(v);
-                    const uint32_t off = tc::swz_offset((uint32_t)n, (uint32_t)(uu / 8), (uint32_t)CN_NOISE_RB) + (uu % 8) * 2;
+                    const uint32_t off = tc::swz_offset((uint32_t)n, (uint32_t)(uu / 8), (uint32_t)rbn) + (uu % 8) * 2;
                     std::memcpy(blk + off, &h, 2);
                 }
+            blk += (size_t)NC * rbn;
+            u0 += width;
         }
     }
 }
