@@ -235,7 +235,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct WsPlan {
     size_t total = 0;
     size_t off_y, off_h, off_xin, off_acts, off_out, off_gcond, off_dgcond, off_phase;
-    size_t off_har, off_pre, off_X, off_A, off_Bb, off_T, off_O, off_z, off_S;
+    size_t off_har, off_pre, off_X, off_A, off_Bb, off_T, off_O, off_z, off_S, off_A16, off_B16;
 };
 
 WsPlan plan_ws(const svb_model_cfg& c, int B, int T, int gT) {
@@ -271,6 +271,8 @@ WsPlan plan_ws(const svb_model_cfg& c, int B, int T, int gT) {
     p.off_T = take(maxel * f);
     p.off_O = take(maxel * f);
     p.off_S = c.snake ? take(maxel * f) : 0;
+    p.off_A16 = take(maxel * 2);      // fp16 [B][T][C] copies of lrelu(residual stream) for the TMA-fed pair kernels
+    p.off_B16 = take(maxel * 2);
     p.total = o;
     p.off_y = p.off_z;
     return p;
@@ -525,6 +527,8 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
             launch_noise_conv_add(har, S.noise_w, S.noise_b, X, B, S.Cout, Lout, (int)N, S.noise_K, S.noise_s, S.noise_p, st);
         if ((rc = dbg_keep(ctx, "ups" + std::to_string(i), X, (size_t)B * S.Cout * Lout, st))) return rc;
         static const int fuse_rb = [] { const char* e = std::getenv("SVB_FUSE_RESBLOCK"); return e ? std::atoi(e) : 1; }();
+        static const int use_tma = [] { const char* e = std::getenv("SVB_TC_TMA"); return e ? std::atoi(e) : 1; }();
+        void* a16[2] = {ws + pl.off_A16, ws + pl.off_B16};
         static const int fuse_maxc = [] { const char* e = std::getenv("SVB_FUSE_MAXC"); return e ? std::atoi(e) : 32; }();
         for (int j = 0; j < nk; ++j) {
             const int k = c.resblock_kernel_sizes[j];
@@ -562,6 +566,11 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
                     PairTC pt;
                     pt.x = src; pt.out = dst; pt.w1 = W1.w_tc; pt.w2 = W2.w_tc; pt.b1 = W1.b; pt.b2 = W2.b;
                     pt.B = B; pt.C = S.Cout; pt.T = Lout; pt.k = k; pt.dil = dil; pt.alpha = alpha; pt.beta = beta;
+                    if (use_tma && pair_tc_supports_tma(S.Cout, -1)) {
+                        // pair d writes lrelu(out) as fp16 [B][T][C]; pair d+1 loads its operand tile from it with TMA
+                        if (d > 0) pt.a16_in = a16[(d - 1) & 1];
+                        if (!last) pt.a16_out = a16[d & 1];
+                    }
                     int trc = launch_pair_tc(pt, st);
                     if (trc == 0) done = true;
                     else if (trc != SVB_ERR_UNSUPPORTED) return fail(ctx, trc, "tensor-core pair kernel launch failed");

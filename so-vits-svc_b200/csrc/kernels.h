@@ -64,7 +64,10 @@ struct PairTC {
     int B = 1, C = 0, T = 0, k = 3, dil = 1;
     float alpha = 1.f, beta = 0.f;
     int variant = -1;              // -1: library default (env SVB_TC_VARIANT), else explicit tile variant
+    const void* a16_in = nullptr;  // optional fp16 [B][T][C] copy of lrelu(x): the A tile is then loaded by TMA (tensor map)
+    void* a16_out = nullptr;       // optional fp16 [B][T][C] copy of lrelu(out) for the next pair
 };
+bool pair_tc_supports_tma(int C, int variant);
 int launch_pair_tc(const PairTC& a, cudaStream_t st);   // returns 0 or a negative status
 size_t tc_weight_image_bytes(int C, int k);
 // host-side: build the swizzled fp16 image for one conv (w_folded is [Cout][Cin][k] fp32)

@@ -18,6 +18,7 @@
 // weights.
 #include "kernels.h"
 #include "tc_common.cuh"
+#include <cuda.h>
 #include "../../include/sovits_b200.h"
 
 #include <cstdlib>
@@ -33,7 +34,9 @@ namespace {
 constexpr int TC_THREADS = 320;
 constexpr int NWORK = 256;           // worker threads (8 warps)
 constexpr int NSTAGE = 2;
-constexpr int MAX_HALO = 56;         // >= max (k-1)*dil = 50, multiple of 8
+constexpr int MAX_HALO = 64;         // upper bound of the per-variant halo rows (>= max (k-1)*dil = 50)
+constexpr int TMA_NBOX = 3;          // the A tile arrives as 3 row-boxes (box rows must be <= 256 and a multiple of 8)
+template <int MB> struct TileRows { static constexpr int HALO = (MB == 4) ? 64 : 56; static constexpr int AROWS = 128 * MB + HALO; };
 
 template <int C, int STAGE_KB = 32>
 struct TCGeom {
@@ -53,19 +56,20 @@ struct PairParams {
     const float* b1; const float* b2;
     int T, k, dil;
     float alpha, beta;
+    __half* a16_out;     // optional second output: fp16 lrelu(out) in [B][T][C] (the next pair's TMA-loadable operand)
 };
 
 template <int C, int MB, int STAGE_KB>
 constexpr size_t pair_smem_bytes() {
     using G = TCGeom<C, STAGE_KB>;
-    return 1024 /*align slack*/ + (size_t)G::NP * (128 * MB + MAX_HALO) * G::RB + (size_t)NSTAGE * G::STAGE_BYTES + 256 + 2 * C * 4;
+    return 1024 /*align slack*/ + (size_t)G::NP * TileRows<MB>::AROWS * G::RB + (size_t)NSTAGE * G::STAGE_BYTES + 256 + 2 * C * 4;
 }
 
-template <int C, int MB, int STAGE_KB, int MINB>
-__global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairParams p) {
+template <int C, int MB, int STAGE_KB, int MINB, bool TMA_IN>
+__global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmap) {
     using G = TCGeom<C, STAGE_KB>;
     constexpr int R1 = 128 * MB;
-    constexpr int AROWS = R1 + MAX_HALO;
+    constexpr int AROWS = TileRows<MB>::AROWS;
     constexpr int APANEL = AROWS * G::RB;
     constexpr int TMEM_COLS = (MB * C) < 32 ? 32 : (MB * C);
     static_assert(TMEM_COLS == 32 || TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
@@ -81,7 +85,8 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
     const uint32_t bar_empty = bar_base + 8 * NSTAGE;               // [NSTAGE]
     const uint32_t bar_a = bar_base + 16 * NSTAGE;                  // A tile ready (256 arrivals), 2 phases
     const uint32_t bar_acc = bar_a + 8;                             // accumulators ready, 2 phases
-    const uint32_t tmem_slot = bar_acc + 8;
+    const uint32_t bar_tma = bar_acc + 8;                           // A1 tile landed (TMA transaction bytes)
+    const uint32_t tmem_slot = bar_acc + 16;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - base));
     float* sbias = reinterpret_cast<float*>(sm + (bar_base + 256 - base));     // [2][C]: b1 | b2
 
@@ -102,6 +107,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_a, NWORK);
         mbar_init(bar_acc, 1);
+        mbar_init(bar_tma, 1);
         fence_barrier_init();
     }
     if (warp == 8) {
@@ -115,8 +121,18 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 9) {
-        // ------------------------------------------------------------ weight producer
+        // ------------------------------------------------------------ weight producer (and A-tile TMA issuer)
         if (lane == 0) {
+            if (TMA_IN) {
+                // the previous pair already wrote lrelu(x) as fp16 [B][T][C]: the tensor map delivers it swizzled, rows
+                // outside [0,T) zero-filled, straight into the A-operand layout - no thread touches the data
+                constexpr int BOX = AROWS / TMA_NBOX;
+                tma_prefetch_desc(&tmap);
+                mbar_arrive_expect_tx(bar_tma, (uint32_t)(G::NP * AROWS * G::RB));
+                for (int pn = 0; pn < G::NP; ++pn)
+                    for (int bx = 0; bx < TMA_NBOX; ++bx)
+                        tma_load_3d(a_base + pn * APANEL + bx * BOX * G::RB, &tmap, pn * G::CPP, tA0 + bx * BOX, b, bar_tma);
+            }
             const int total_sb = k * G::NP;
             int chunk = 0;
             for (int conv = 0; conv < 2; ++conv) {
@@ -138,7 +154,8 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
             const int total_sb = k * G::NP;
             int chunk = 0;
             for (int conv = 0; conv < 2; ++conv) {
-                mbar_wait(bar_a, conv);
+                if (TMA_IN) { if (conv == 0) mbar_wait(bar_tma, 0); else mbar_wait(bar_a, 0); }
+                else mbar_wait(bar_a, conv);
                 tc_fence_after();
                 const int cd = conv ? 1 : dil;
                 for (int sb = 0; sb < total_sb; ++sb) {
@@ -174,8 +191,8 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
         }
     } else {
         // ------------------------------------------------------------ workers (warps 0-7)
-        // (1) stage A1 = lrelu(x) tile as fp16 [time][channel], zero outside [0,T)
-        for (int r = tid; r < RA1; r += NWORK) {
+        // (1) stage A1 = lrelu(x) tile as fp16 [time][channel], zero outside [0,T)  (skipped when the tile comes by TMA)
+        for (int r = tid; !TMA_IN && r < RA1; r += NWORK) {
             const int t = tA0 + r;
             const bool valid = (t >= 0) && (t < p.T);
             const float* __restrict__ xt = xb + (valid ? t : 0);
@@ -192,8 +209,10 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
                 store_chunk8(prow, phase, (c0 % G::CPP) / 8 + 1, v + 8, 0xffffffffu);
             }
         }
-        fence_proxy_async();
-        mbar_arrive(bar_a);
+        if (!TMA_IN) {
+            fence_proxy_async();
+            mbar_arrive(bar_a);
+        }
 
         const int q = warp & 3, hsel = warp >> 2;
         const int rib = 32 * q + lane;                 // row inside a 128-row block == TMEM lane
@@ -281,7 +300,13 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
                             float y = p.alpha * (__uint_as_float(r[j]) + bb[e] + xr[j]);
                             if (has_beta) y = fmaf(p.beta, oo[j], y);
                             ot[(size_t)(c0 + j) * p.T] = y;
+                            xr[j] = lrelu01(y);
                         }
+                    }
+                    if (p.a16_out) {
+                        uint4* dst = reinterpret_cast<uint4*>(p.a16_out + ((size_t)b * p.T + t) * C + c0);
+                        dst[0] = make_uint4(pack_h2(xr[0], xr[1]), pack_h2(xr[2], xr[3]), pack_h2(xr[4], xr[5]), pack_h2(xr[6], xr[7]));
+                        if (CG == 16) dst[1] = make_uint4(pack_h2(xr[8], xr[9]), pack_h2(xr[10], xr[11]), pack_h2(xr[12], xr[13]), pack_h2(xr[14], xr[15]));
                     }
                 }
             }
@@ -302,28 +327,75 @@ int env_int(const char* name, int dflt) {
     return s ? std::atoi(s) : dflt;
 }
 
-template <int C, int MB, int STAGE_KB, int MINB>
-int launch_pair_t(const PairTC& a, cudaStream_t st) {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// fp16 activation copy [B][T][C] viewed as a rank-3 tensor (C innermost); box = one 64-channel panel x box_rows time steps
+int make_a16_tmap(CUtensorMap* out, const void* base, int B, int T, int C, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return SVB_ERR_CUDA;
+    const int cpp = C < 64 ? C : 64;
+    cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t gstr[2] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2};
+    cuuint32_t box[3] = {(cuuint32_t)cpp, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle sw = cpp * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (cpp * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : SVB_ERR_CUDA;
+}
+
+template <int C, int MB, int STAGE_KB, int MINB, bool TMA_IN>
+int launch_pair_t2(const PairTC& a, cudaStream_t st) {
     constexpr size_t smem = pair_smem_bytes<C, MB, STAGE_KB>();
     static_assert(smem * MINB + 1024 * MINB <= 228 * 1024, "pair kernel shared memory exceeds the SM budget");
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(pair_tc_kernel<C, MB, STAGE_KB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(pair_tc_kernel<C, MB, STAGE_KB, MINB, TMA_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return SVB_ERR_CUDA;
         attr_set = true;
+    }
+    alignas(64) CUtensorMap tmap;
+    std::memset(&tmap, 0, sizeof(tmap));
+    if (TMA_IN) {
+        if (make_a16_tmap(&tmap, a.a16_in, a.B, a.T, C, TileRows<MB>::AROWS / TMA_NBOX) != 0) return SVB_ERR_CUDA;
     }
     PairParams p;
     p.x = a.x; p.out = a.out;
     p.w1 = static_cast<const uint8_t*>(a.w1); p.w2 = static_cast<const uint8_t*>(a.w2);
     p.b1 = a.b1; p.b2 = a.b2; p.T = a.T; p.k = a.k; p.dil = a.dil; p.alpha = a.alpha; p.beta = a.beta;
+    p.a16_out = static_cast<__half*>(a.a16_out);
     const int TOUT = 128 * MB - (a.k - 1);
     dim3 grid((a.T + TOUT - 1) / TOUT, a.B);
-    pair_tc_kernel<C, MB, STAGE_KB, MINB><<<grid, TC_THREADS, smem, st>>>(p);
+    pair_tc_kernel<C, MB, STAGE_KB, MINB, TMA_IN><<<grid, TC_THREADS, smem, st>>>(p, tmap);
     launch_counter()++;
     return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;
 }
 
+template <int C, int MB, int STAGE_KB, int MINB>
+int launch_pair_t(const PairTC& a, cudaStream_t st) {
+    // the TMA-fed variant exists for the tiles whose row count splits into three 8-row-aligned boxes (MB = 2, 4) and C >= 64
+    if constexpr ((MB == 2 || MB == 4) && C >= 64) {
+        if (a.a16_in) return launch_pair_t2<C, MB, STAGE_KB, MINB, true>(a, st);
+    } else {
+        if (a.a16_in) return SVB_ERR_UNSUPPORTED;
+    }
+    return launch_pair_t2<C, MB, STAGE_KB, MINB, false>(a, st);
+}
+
 }  // namespace
+
+bool pair_tc_supports_tma(int C, int variant) { (void)variant; return C >= 64; }   // every tile variant for C >= 64 has MB in {2,4}
 
 size_t tc_weight_image_bytes(int C, int k) { return (size_t)C * C * k * 2; }
 

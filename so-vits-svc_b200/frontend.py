@@ -134,9 +134,19 @@ class ConvFFN(nn.Module):
         if k == 1:
             return F.linear(x, conv.weight[:, :, 0], conv.bias)
         L = x.shape[1]
+        cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        if cin > cout:
+            # wide -> narrow: one GEMM against the k tap matrices stacked along the OUTPUT, then shift-and-add the k
+            # narrow slices (avoids materialising the k-times wider im2col tensor)
+            wst = conv.weight.permute(2, 0, 1).reshape(k * cout, cin)                     # [k*Cout, Cin], tap-major
+            ya = F.pad(F.linear(x, wst), (0, 0, (k - 1) // 2, k // 2))                    # [B, L+k-1, k*Cout]
+            y = ya[:, 0:L, 0:cout]
+            for t in range(1, k):
+                y = y + ya[:, t:t + L, t * cout:(t + 1) * cout]
+            return y + conv.bias
         xp = F.pad(x, (0, 0, (k - 1) // 2, k // 2))
         cols = torch.cat([xp[:, t:t + L] for t in range(k)], dim=-1)                     # [B,T,k*C], tap-major
-        wmat = conv.weight.permute(0, 2, 1).reshape(conv.weight.shape[0], -1)             # [F, k*C]
+        wmat = conv.weight.permute(0, 2, 1).reshape(cout, -1)                             # [F, k*C]
         return F.linear(cols, wmat, conv.bias)
 
     def forward(self, x, x_mask=None):
