@@ -81,6 +81,8 @@ typedef struct svb_model_cfg {
     int32_t sampling_rate;           /* 44100 */
     int32_t n_harmonics;             /* 9 (harmonic_num 8 + fundamental)                    */
     int32_t snake;                   /* 1: vdecoder/hifiganwithsnake (SnakeAlias activations), 0: LeakyReLU */
+    int32_t num_mels;                /* > 0: the mel-conditioned vocoder vdecoder/nsf_hifigan (no flow, no speaker
+                                        conditioning; conv_pre takes num_mels channels; keys without the "dec." prefix) */
 } svb_model_cfg;
 
 /* replaces: Svc.load_model's `.to(dev)` of the model (inference/infer_tool.py:189-200) */
@@ -93,6 +95,9 @@ SVB_API int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tens
 
 SVB_API int svb_set_precision(svb_ctx* ctx, int precision /* svb_precision */);
 SVB_API int svb_get_precision(const svb_ctx* ctx);
+/* Kernel-schedule switches (all numerically equivalent paths): "tma" (0/1: pair kernels load their operand tile from an
+ * fp16 [B][T][C] copy through a TMA tensor map), "fuse_resblock" (0/1), "fuse_maxc" (largest C using the fused ResBlock). */
+SVB_API int svb_set_option(svb_ctx* ctx, const char* name, int value);
 
 /* Device scratch needed by svb_infer_tail for a [B,*,T] call.  Pass ws = NULL to let the library
  * keep its own grow-only workspace. */
@@ -114,6 +119,12 @@ SVB_API int svb_nsf_source(svb_ctx* ctx, const float* f0, const float* rand_ini,
  * z: [B,inter,T] (already masked); har: [B,N]; wav: [B,N]. */
 SVB_API int svb_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const float* har,
                   float* wav, int B, int T, void* ws, size_t ws_bytes, void* stream);
+
+/* replaces: vdecoder.nsf_hifigan.models.Generator.forward(mel, f0) (vdecoder/nsf_hifigan/models.py:259-278; callers
+ * modules/enhancer.py:106, diffusion/vocoder.py:81-84).  mel: [B,num_mels,T]; f0: [B,T]; wav: [B,N].  Needs a context
+ * loaded with svb_model_cfg.num_mels > 0. */
+SVB_API int svb_vocoder(svb_ctx* ctx, const float* mel, const float* f0, const float* rand_ini, const float* noise,
+                        float* wav, int B, int T, void* ws, size_t ws_bytes, void* stream);
 
 /* replaces: `z = self.flow(z_p, c_mask, g=g, reverse=True); o = self.dec(z * c_mask, g=g, f0=f0)`
  * (models.py:530-531): the three calls above back-to-back on one stream. */

@@ -324,3 +324,44 @@ def tail(sd, cfg, z_p, g, f0, noise, dtype=torch.float32, taps: Optional[dict] =
     if taps is not None:
         taps.update({"z": z, "har": har})
     return generator(sd, z, g.to(dtype), har, cfg, dtype, taps)
+
+
+# ----------------------------------------------------------------------------- mel-conditioned vocoder
+def vocoder_source(sd, f0, rand_ini, har_noise, cfg, dtype=torch.float32):
+    """vdecoder/nsf_hifigan/models.py:138-178 (SineGen: frame-rate rad_values, fp64 cumsum, linear-interpolated wrap
+    detection, fp64 sample-rate cumsum) + :215-218 (SourceModuleHnNSF).  Returns [B,1,N]."""
+    upp = cfg.hop
+    f0 = f0.to(dtype).unsqueeze(-1)
+    fn = f0 * torch.arange(1, cfg.n_harmonics + 1, device=f0.device).reshape(1, 1, -1)
+    rad = (fn / cfg.sampling_rate) % 1
+    ri = rand_ini.to(dtype).clone()
+    ri[:, 0] = 0
+    rad[:, 0, :] = rad[:, 0, :] + ri
+    tmp = torch.cumsum(rad.double(), 1).to(dtype)
+    tmp = tmp * upp
+    tmp = F.interpolate(tmp.transpose(2, 1), scale_factor=upp, mode="linear", align_corners=True).transpose(2, 1)
+    rad_up = F.interpolate(rad.transpose(2, 1), scale_factor=upp, mode="nearest").transpose(2, 1)
+    tmp = tmp % 1
+    wrap = (tmp[:, 1:, :] - tmp[:, :-1, :]) < 0
+    shift = torch.zeros_like(rad_up)
+    shift[:, 1:, :] = wrap * -1.0
+    sines = torch.sin(torch.cumsum(rad_up.double() + shift.double(), dim=1) * 2 * math.pi).to(dtype) * 0.1
+    uv = (f0 > 0).to(dtype)
+    uv = F.interpolate(uv.transpose(2, 1), scale_factor=upp, mode="nearest").transpose(2, 1)
+    amp = uv * 0.003 + (1 - uv) * 0.1 / 3
+    sw = sines * uv + amp * har_noise.to(dtype)
+    merged = torch.tanh(F.linear(sw, sd["m_source.l_linear.weight"].to(dtype), sd["m_source.l_linear.bias"].to(dtype)))
+    return merged.transpose(1, 2)
+
+
+@torch.no_grad()
+def vocoder(sd, cfg, mel, f0, rand_ini, har_noise, dtype=torch.float32):
+    """vdecoder/nsf_hifigan/models.py:259-278: har = m_source(f0); conv_pre(mel); 5 x (lrelu, ups, + noise_conv, 3 ResBlocks
+    averaged); lrelu; conv_post; tanh.  Paddings (k-u)//2 and stride//2 coincide with the SVC decoder's for even k-u / stride."""
+    har = vocoder_source(sd, f0, rand_ini, har_noise, cfg, dtype)
+    sd2 = {"dec." + k: v for k, v in sd.items()}
+    U = cfg.upsample_initial_channel
+    sd2["dec.cond.weight"] = torch.zeros(U, 1, 1)
+    sd2["dec.cond.bias"] = torch.zeros(U)
+    g = torch.zeros(mel.shape[0], 1, 1, dtype=dtype, device=mel.device)
+    return generator(sd2, mel.to(dtype), g, har, cfg, dtype)

@@ -47,6 +47,7 @@ class ModelCfg:
     flow_wn_layers: int = 4
     enc_window: int = 4          # attentions.py:74 default window_size
     n_harmonics: int = 9         # hifigan/models.py:332 harmonic_num=8 -> dim 9
+    num_mels: int = 0            # > 0: mel-conditioned vocoder vdecoder/nsf_hifigan (no flow / speaker conditioning)
 
     @property
     def hop(self) -> int:

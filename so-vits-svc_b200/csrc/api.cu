@@ -99,6 +99,9 @@ struct svb_ctx {
     DevBuf host_io;                // device staging for svb_infer_tail_host
     bool debug = false;
     std::map<std::string, DevBuf> dbg;
+    int opt_tma = 0;            // TMA-fed pair kernels (fp16 operand copies): measured neutral on B200, off by default
+    int opt_fuse_rb = 1;        // fused ResBlock kernel for narrow stages
+    int opt_fuse_maxc = 32;     // ... up to this channel count
     bool profile = false;
     struct ProfEntry { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; double flops = 0, bytes = 0; };
     std::map<std::string, ProfEntry> prof;
@@ -460,11 +463,15 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
     int rc;
 
     // conv_pre(z) + cond(g)
+    const bool melv = c.num_mels > 0;
+    const int Cpre = melv ? c.num_mels : c.inter_channels;
     ConvF32 cp;
-    cp.x = z; cp.x_ctot = c.inter_channels; cp.Cin = c.inter_channels; cp.Tin = T;
+    cp.x = z; cp.x_ctot = Cpre; cp.Cin = Cpre; cp.Tin = T;
     cp.w = ctx->conv_pre.w; cp.bias = ctx->conv_pre.b; cp.Cout = U; cp.k = ctx->conv_pre.k; cp.pad_left = (cp.k - 1) / 2;
     cp.y = pre; cp.y_ctot = U; cp.Ty = T; cp.n_out = T; cp.B = B;
-    if (gT == 1) {
+    if (melv) {
+        // vdecoder/nsf_hifigan: no speaker conditioning
+    } else if (gT == 1) {
         launch_gemv(ctx->dcond_w_nat, ctx->dcond_b, g, dg, B, U, c.gin_channels, st);
         cp.bias_b = dg; cp.bias_b_stride = U; cp.bias_b_off = 0;
     } else {
@@ -479,12 +486,13 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
     // kernel in front of the fp32 FFMA convolutions (the tensor-core kernels fuse LeakyReLU and are not used for it).
     const bool snake = c.snake != 0;
     float* Sb = snake ? reinterpret_cast<float*>(ws + pl.off_S) : nullptr;
-    const bool gen_tc = ctx->precision == SVB_PREC_TC && ctx->gen_tc_ok && gT == 1 && !snake;
+    const bool gen_tc = ctx->precision == SVB_PREC_TC && ctx->gen_tc_ok && (gT == 1 || melv) && !snake;
     if (gen_tc) {
         const ConvNW& W = ctx->conv_pre_tc;
         ConvNTC a;
-        a.x = z; a.x_ctot = c.inter_channels; a.cin_real = W.cin_real; a.cinp = W.cinp; a.Tin = T;
-        a.w = W.img; a.bias = W.bias; a.bias_b = dg; a.bias_b_stride = U; a.bias_b_off = 0;
+        a.x = z; a.x_ctot = Cpre; a.cin_real = W.cin_real; a.cinp = W.cinp; a.Tin = T;
+        a.w = W.img; a.bias = W.bias;
+        if (!melv) { a.bias_b = dg; a.bias_b_stride = U; a.bias_b_off = 0; }
         a.k = W.k; a.pad_left = W.pad_left; a.n_rows = T; a.N_total = W.N_total; a.NC = W.NC; a.chunks_per_cta = 1; a.Ty = T; a.B = B;
         a.seg[0].y = pre; a.seg[0].y_ctot = U; a.seg[0].col0 = 0; a.seg[0].col1 = U;
         int trc = launch_convn_tc(a, st);
@@ -647,6 +655,9 @@ int svb_create(int device, svb_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return SVB_ERR_CUDA;
     svb_ctx* c = new svb_ctx();
     c->device = device;
+    if (const char* e = std::getenv("SVB_TC_TMA")) c->opt_tma = std::atoi(e);
+    if (const char* e = std::getenv("SVB_FUSE_RESBLOCK")) c->opt_fuse_rb = std::atoi(e);
+    if (const char* e = std::getenv("SVB_FUSE_MAXC")) c->opt_fuse_maxc = std::atoi(e);
     *out = c;
     return SVB_OK;
 }
@@ -667,6 +678,16 @@ int svb_set_precision(svb_ctx* ctx, int precision) {
     return SVB_OK;
 }
 int svb_get_precision(const svb_ctx* ctx) { return ctx ? ctx->precision : SVB_ERR_INVALID_ARG; }
+
+int svb_set_option(svb_ctx* ctx, const char* name, int value) {
+    if (!ctx || !name) return SVB_ERR_INVALID_ARG;
+    const std::string n(name);
+    if (n == "tma") ctx->opt_tma = value;
+    else if (n == "fuse_resblock") ctx->opt_fuse_rb = value;
+    else if (n == "fuse_maxc") ctx->opt_fuse_maxc = value;
+    else return fail(ctx, SVB_ERR_INVALID_ARG, "unknown option " + n);
+    return SVB_OK;
+}
 
 int svb_debug_enable(svb_ctx* ctx, int on) {
     if (!ctx) return SVB_ERR_INVALID_ARG;
@@ -772,7 +793,8 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
     if (!ctx || !tensors || !cfgp || n_tensors <= 0) return SVB_ERR_INVALID_ARG;
     CU(cudaSetDevice(ctx->device));
     const svb_model_cfg& c = *cfgp;
-    if (c.n_upsamples < 1 || c.n_upsamples > 8 || c.n_resblock_kernels != 3 || c.n_flows != 4 ||
+    if (c.num_mels > 0 && c.snake) return fail(ctx, SVB_ERR_UNSUPPORTED, "mel vocoder has no snake variant");
+    if (c.n_upsamples < 1 || c.n_upsamples > 8 || c.n_resblock_kernels != 3 || (c.num_mels == 0 && c.n_flows != 4) ||
         (c.inter_channels & 1) || c.flow_wn_layers < 1 || (c.n_harmonics != 9 && c.n_harmonics != 1))
         return fail(ctx, SVB_ERR_UNSUPPORTED, "unsupported model configuration");
     for (int i = 0; i < c.n_upsamples; ++i)
@@ -783,6 +805,8 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
     TMap m;
     for (int i = 0; i < n_tensors; ++i)
         if (tensors[i].name && tensors[i].data) m[tensors[i].name] = &tensors[i];
+    const bool melv = c.num_mels > 0;
+    const std::string DP = melv ? "" : "dec.";          // vdecoder/nsf_hifigan checkpoints have no "dec." prefix
     ctx->cfg = c;
     ctx->hop = 1;
     for (int i = 0; i < c.n_upsamples; ++i) ctx->hop *= c.upsample_rates[i];
@@ -791,8 +815,8 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
     HostT w, b;
 
     // ---- flow
-    ctx->flow.assign(c.n_flows, FlowLayer());
-    for (int fl = 0; fl < c.n_flows; ++fl) {
+    ctx->flow.assign(melv ? 0 : c.n_flows, FlowLayer());
+    for (int fl = 0; fl < (melv ? 0 : c.n_flows); ++fl) {
         FlowLayer& F = ctx->flow[fl];
         const std::string p = "flow.flows." + std::to_string(2 * fl) + ".";
         const bool odd = (fl & 1) != 0;           // Flip folded into channel order
@@ -880,30 +904,33 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
 
     // ---- generator
     const int U = c.upsample_initial_channel;
-    if ((rc = folded(ctx, m, "dec.conv_pre", {U, C, 7}, w))) return rc;
-    if ((rc = get_tensor(ctx, m, "dec.conv_pre.bias", {U}, b))) return rc;
-    if ((rc = make_conv(ctx, w.v, b.v, U, C, 7, false, false, ctx->conv_pre))) return rc;
-    ctx->gen_tc_ok = (C == 192 || C == 128 || C == 256) && (U % 256 == 0);
+    const int Cpre = melv ? c.num_mels : C;             // conv_pre input channels: mel bins or the latent z
+    if ((rc = folded(ctx, m, DP + "conv_pre", {U, Cpre, 7}, w))) return rc;
+    if ((rc = get_tensor(ctx, m, DP + "conv_pre.bias", {U}, b))) return rc;
+    if ((rc = make_conv(ctx, w.v, b.v, U, Cpre, 7, false, false, ctx->conv_pre))) return rc;
+    ctx->gen_tc_ok = (Cpre == 192 || Cpre == 128 || Cpre == 256) && (U % 256 == 0);
     for (int i = 0; i < c.n_upsamples; ++i) {
         const int ci_ = U >> i, n_ = (U >> (i + 1)) * c.upsample_rates[i];
         if (!(ci_ == 512 || ci_ == 256 || ci_ == 128 || ci_ == 64 || ci_ == 32) || (n_ % 32)) ctx->gen_tc_ok = false;
     }
     if (ctx->gen_tc_ok) {
         const std::vector<float> wv = w.v, bv = b.v;
-        if ((rc = make_convn(ctx, C, C, U, 256 / convn_mb(C), 7, 3, [&](int col, int ci, int tap) { return wv[((size_t)col * C + ci) * 7 + tap]; },
+        if ((rc = make_convn(ctx, Cpre, Cpre, U, 256 / convn_mb(Cpre), 7, 3, [&](int col, int ci, int tap) { return wv[((size_t)col * Cpre + ci) * 7 + tap]; },
                              [&](int col) { return bv[col]; }, ctx->conv_pre_tc))) return rc;
     }
-    if ((rc = get_tensor(ctx, m, "dec.cond.weight", {U, G, 1}, w))) return rc;
-    if ((rc = get_tensor(ctx, m, "dec.cond.bias", {U}, b))) return rc;
-    if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&ctx->dcond_w_nat))) return rc;
-    if ((rc = make_conv(ctx, w.v, b.v, U, G, 1, false, false, ctx->dcond))) return rc;
-    ctx->dcond_b = ctx->dcond.b;
+    if (!melv) {
+        if ((rc = get_tensor(ctx, m, "dec.cond.weight", {U, G, 1}, w))) return rc;
+        if ((rc = get_tensor(ctx, m, "dec.cond.bias", {U}, b))) return rc;
+        if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&ctx->dcond_w_nat))) return rc;
+        if ((rc = make_conv(ctx, w.v, b.v, U, G, 1, false, false, ctx->dcond))) return rc;
+        ctx->dcond_b = ctx->dcond.b;
+    }
     ctx->stages.assign(c.n_upsamples, Stage());
     for (int i = 0; i < c.n_upsamples; ++i) {
         Stage& S = ctx->stages[i];
         S.Cin = U >> i; S.Cout = U >> (i + 1); S.s = c.upsample_rates[i]; S.k = c.upsample_kernel_sizes[i];
         S.p = (S.k - S.s + 1) / 2;
-        const std::string p = "dec.ups." + std::to_string(i);
+        const std::string p = DP + "ups." + std::to_string(i);
         if ((rc = folded(ctx, m, p, {S.Cin, S.Cout, S.k}, w))) return rc;    // ConvTranspose1d: [Cin][Cout][k]
         if ((rc = get_tensor(ctx, m, p + ".bias", {S.Cout}, b))) return rc;
         std::vector<float> pk((size_t)S.s * S.Cin * 2 * S.Cout);
@@ -920,7 +947,7 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
         // noise conv
         int stride = 1;
         for (int q = i + 1; q < c.n_upsamples; ++q) stride *= c.upsample_rates[q];
-        const std::string np_ = "dec.noise_convs." + std::to_string(i);
+        const std::string np_ = DP + "noise_convs." + std::to_string(i);
         if (i + 1 < c.n_upsamples) { S.noise_K = 2 * stride; S.noise_s = stride; S.noise_p = (stride + 1) / 2; }
         else { S.noise_K = 1; S.noise_s = 1; S.noise_p = 0; }
         if ((rc = get_tensor(ctx, m, np_ + ".weight", {S.Cout, 1, S.noise_K}, w))) return rc;
@@ -955,7 +982,7 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
         S.c2.assign(9, ConvW());
         for (int j = 0; j < 3; ++j) {
             const int k = c.resblock_kernel_sizes[j];
-            const std::string r = "dec.resblocks." + std::to_string(i * 3 + j) + ".";
+            const std::string r = DP + "resblocks." + std::to_string(i * 3 + j) + ".";
             for (int d = 0; d < 3; ++d) {
                 if ((rc = folded(ctx, m, r + "convs1." + std::to_string(d), {S.Cout, S.Cout, k}, w))) return rc;
                 if ((rc = get_tensor(ctx, m, r + "convs1." + std::to_string(d) + ".bias", {S.Cout}, b))) return rc;
@@ -991,12 +1018,12 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
         if ((rc = upload(ctx, w.v.data(), 12 * sizeof(float), (void**)&ctx->snake_filt))) return rc;
     }
     ctx->post_C = U >> c.n_upsamples;
-    if ((rc = folded(ctx, m, "dec.conv_post", {1, ctx->post_C, 7}, w))) return rc;
-    if ((rc = get_tensor(ctx, m, "dec.conv_post.bias", {1}, b))) return rc;
+    if ((rc = folded(ctx, m, DP + "conv_post", {1, ctx->post_C, 7}, w))) return rc;
+    if ((rc = get_tensor(ctx, m, DP + "conv_post.bias", {1}, b))) return rc;
     ctx->post_b = b.v[0];
     if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&ctx->post_w))) return rc;
-    if ((rc = get_tensor(ctx, m, "dec.m_source.l_linear.weight", {1, c.n_harmonics}, w))) return rc;
-    if ((rc = get_tensor(ctx, m, "dec.m_source.l_linear.bias", {1}, b))) return rc;
+    if ((rc = get_tensor(ctx, m, DP + "m_source.l_linear.weight", {1, c.n_harmonics}, w))) return rc;
+    if ((rc = get_tensor(ctx, m, DP + "m_source.l_linear.bias", {1}, b))) return rc;
     ctx->lin_b = b.v[0];
     if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&ctx->lin_w))) return rc;
     ctx->loaded = true;
@@ -1017,6 +1044,7 @@ size_t svb_workspace_bytes(const svb_ctx* ctx, int B, int T) {
 int svb_flow_reverse(svb_ctx* ctx, const float* z_p, const float* g, int gT, const int32_t* lengths,
                      float* z_out, int B, int T, void* ws, size_t ws_bytes, void* stream) {
     PRECHECK();
+    if (ctx->cfg.num_mels > 0) return fail(ctx, SVB_ERR_UNSUPPORTED, "mel vocoder contexts have no flow");
     if (!z_p || !g || !z_out || (gT != 1 && gT != T)) return fail(ctx, SVB_ERR_INVALID_ARG, "bad flow arguments");
     WsPlan pl = plan_ws(ctx->cfg, B, T, gT);
     char* base;
@@ -1034,14 +1062,14 @@ int svb_nsf_source(svb_ctx* ctx, const float* f0, const float* rand_ini, const f
     int rc = ensure_ws(ctx, pl.total, nullptr, 0, &base);
     if (rc) return rc;
     launch_nsf_source(f0, rand_ini, noise, ctx->lin_w, ctx->lin_b, reinterpret_cast<double*>(base + pl.off_phase), har,
-                      B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, (cudaStream_t)stream);
+                      B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, ctx->cfg.num_mels > 0 ? 1 : 0, (cudaStream_t)stream);
     return check_launch(ctx, "nsf_source");
 }
 
 int svb_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const float* har,
                   float* wav, int B, int T, void* ws, size_t ws_bytes, void* stream) {
     PRECHECK();
-    if (!z || !g || !har || !wav || (gT != 1 && gT != T)) return fail(ctx, SVB_ERR_INVALID_ARG, "bad generator arguments");
+    if (!z || (!g && ctx->cfg.num_mels == 0) || !har || !wav || (gT != 1 && gT != T)) return fail(ctx, SVB_ERR_INVALID_ARG, "bad generator arguments");
     WsPlan pl = plan_ws(ctx->cfg, B, T, gT);
     char* base;
     int rc = ensure_ws(ctx, pl.total, ws, ws_bytes, &base);
@@ -1049,10 +1077,28 @@ int svb_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
     return run_generator(ctx, z, g, gT, har, wav, B, T, base, pl, (cudaStream_t)stream);
 }
 
+int svb_vocoder(svb_ctx* ctx, const float* mel, const float* f0, const float* rand_ini, const float* noise,
+                float* wav, int B, int T, void* ws, size_t ws_bytes, void* stream) {
+    PRECHECK();
+    if (ctx->cfg.num_mels <= 0) return fail(ctx, SVB_ERR_UNSUPPORTED, "context was not loaded as a mel vocoder (num_mels == 0)");
+    if (!mel || !f0 || !rand_ini || !wav) return fail(ctx, SVB_ERR_INVALID_ARG, "bad vocoder arguments");
+    WsPlan pl = plan_ws(ctx->cfg, B, T, 1);
+    char* base;
+    int rc = ensure_ws(ctx, pl.total, ws, ws_bytes, &base);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* har = reinterpret_cast<float*>(base + pl.off_har);
+    launch_nsf_source(f0, rand_ini, noise, ctx->lin_w, ctx->lin_b, reinterpret_cast<double*>(base + pl.off_phase), har,
+                      B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, 1, st);
+    if ((rc = dbg_keep(ctx, "har", har, (size_t)B * T * ctx->hop, st))) return rc;
+    return run_generator(ctx, mel, nullptr, 1, har, wav, B, T, base, pl, st);
+}
+
 int svb_infer_tail(svb_ctx* ctx, const float* z_p, const float* g, int gT, const int32_t* lengths,
                    const float* f0, const float* rand_ini, const float* noise,
                    float* wav, int B, int T, void* ws, size_t ws_bytes, void* stream) {
     PRECHECK();
+    if (ctx->cfg.num_mels > 0) return fail(ctx, SVB_ERR_UNSUPPORTED, "mel vocoder contexts: use svb_vocoder");
     if (!z_p || !g || !f0 || !rand_ini || !wav || (gT != 1 && gT != T)) return fail(ctx, SVB_ERR_INVALID_ARG, "bad tail arguments");
     WsPlan pl = plan_ws(ctx->cfg, B, T, gT);
     char* base;
@@ -1070,7 +1116,7 @@ int svb_infer_tail(svb_ctx* ctx, const float* z_p, const float* g, int gT, const
         const double N = (double)T * ctx->hop;
         ProfScope ps(ctx, "nsf_source", st, 0, (double)B * (T * 4.0 + N * 4.0 + (noise ? N * 4.0 * ctx->cfg.n_harmonics : 0.0)));
         launch_nsf_source(f0, rand_ini, noise, ctx->lin_w, ctx->lin_b, reinterpret_cast<double*>(base + pl.off_phase), har,
-                          B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, st);
+                          B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, ctx->cfg.num_mels > 0 ? 1 : 0, st);
     }
     if ((rc = dbg_keep(ctx, "har", har, (size_t)B * T * ctx->hop, st))) return rc;
     ProfScope ps(ctx, "generator", st, 0, 0);

@@ -50,8 +50,12 @@ void launch_snake_alias(const float* x, float* y, const float* ealpha, const flo
 void launch_conv_post(const float* x, const float* w, float bias, float* wav, int B, int C, int N, int K, float slope, cudaStream_t st);
 
 // NSF harmonic source (vdecoder/hifigan/models.py:250-271,307-320) in the closed form of SURVEY §9.7.
+// rand_in_rate = 0: rand_ini is an initial phase (vdecoder/hifigan/models.py:147-150, sample-rate rad_values);
+// rand_in_rate = 1: rand_ini is added to the FIRST FRAME's per-sample phase increment (vdecoder/nsf_hifigan/models.py:146-148,
+//                   where rad_values is built at frame rate and then nearest-upsampled).
 void launch_nsf_source(const float* f0, const float* rand_ini, const float* noise, const float* lin_w, float lin_b,
-                       double* phase_ws /*[B,T,H]*/, float* har, int B, int T, int hop, int n_harm, float sr, cudaStream_t st);
+                       double* phase_ws /*[B,T,H]*/, float* har, int B, int T, int hop, int n_harm, float sr, int rand_in_rate,
+                       cudaStream_t st);
 
 // ---- tensor-core path (kernels_tc.cu) --------------------------------------------------------------
 // One ResBlock "pair": y = x + conv2(lrelu(conv1(lrelu(x)) + b1)) + b2 with out = alpha*y + beta*out_old.

@@ -358,26 +358,34 @@ __device__ __forceinline__ float rad_value(float f0, int h, float sr) {
 }
 
 // one warp per (batch, harmonic): lanes own contiguous chunks of frames, fp64 exclusive scan across lanes
+__device__ __forceinline__ double rad_frame(const float* __restrict__ f0row, const float* __restrict__ ri, int t, int h, float sr, int rand_in_rate) {
+    float r = rad_value(f0row[t], h, sr);
+    if (rand_in_rate && t == 0 && h > 0) r = __fadd_rn(r, ri[h]);      // fp32 add like rad_values[:, 0, :] += rand_ini
+    return (double)r;
+}
+
 __global__ void nsf_phase_kernel(const float* __restrict__ f0, const float* __restrict__ rand_ini, double* __restrict__ phase,
-                                 int B, int T, int H, int hop, float sr) {
+                                 int B, int T, int H, int hop, float sr, int rand_in_rate) {
     const int i = blockIdx.x;                 // b*H + h
     const int lane = threadIdx.x;
     const int b = i / H, h = i % H;
     const int ch = (T + 31) / 32;
     const int t_lo = lane * ch, t_hi = min(T, t_lo + ch);
+    const float* f0row = f0 + (long long)b * T;
+    const float* ri = rand_ini + b * H;
     double local = 0.0;
-    for (int t = t_lo; t < t_hi; ++t) local += (double)rad_value(f0[(long long)b * T + t], h, sr) * (double)hop;
+    for (int t = t_lo; t < t_hi; ++t) local += rad_frame(f0row, ri, t, h, sr, rand_in_rate) * (double)hop;
     double incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         double v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
     }
-    double acc = (incl - local) + ((h == 0) ? 0.0 : (double)rand_ini[b * H + h]);
+    double acc = (incl - local) + ((h == 0 || rand_in_rate) ? 0.0 : (double)ri[h]);
     acc -= floor(acc);
     for (int t = t_lo; t < t_hi; ++t) {
         phase[((long long)b * T + t) * H + h] = acc;
-        acc += (double)rad_value(f0[(long long)b * T + t], h, sr) * (double)hop;
+        acc += rad_frame(f0row, ri, t, h, sr, rand_in_rate) * (double)hop;
         acc -= floor(acc);
     }
 }
@@ -385,7 +393,8 @@ __global__ void nsf_phase_kernel(const float* __restrict__ f0, const float* __re
 template <int H>
 __global__ void __launch_bounds__(256) nsf_source_kernel(const float* __restrict__ f0, const float* __restrict__ noise,
                                                          const double* __restrict__ phase, const float* __restrict__ lin_w, float lin_b,
-                                                         float* __restrict__ har, int T, int hop, float sr, long long N) {
+                                                         float* __restrict__ har, int T, int hop, float sr, long long N,
+                                                         const float* __restrict__ rand_ini, int rand_in_rate) {
     const int b = blockIdx.y;
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
@@ -399,7 +408,9 @@ __global__ void __launch_bounds__(256) nsf_source_kernel(const float* __restrict
     float acc = lin_b;
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-        double r = (double)rad_value(f, h, sr);
+        float rf = rad_value(f, h, sr);
+        if (rand_in_rate && F == 0 && h > 0) rf = __fadd_rn(rf, rand_ini[b * H + h]);
+        double r = (double)rf;
         double ph = ph0[h] + (double)(k + 1) * r;
         ph -= floor(ph);
         float s = sinpif(2.0f * (float)ph) * 0.1f;
@@ -410,15 +421,15 @@ __global__ void __launch_bounds__(256) nsf_source_kernel(const float* __restrict
 }
 
 void launch_nsf_source(const float* f0, const float* rand_ini, const float* noise, const float* lin_w, float lin_b,
-                       double* phase_ws, float* har, int B, int T, int hop, int n_harm, float sr, cudaStream_t st) {
-    nsf_phase_kernel<<<B * n_harm, 32, 0, st>>>(f0, rand_ini, phase_ws, B, T, n_harm, hop, sr);
+                       double* phase_ws, float* har, int B, int T, int hop, int n_harm, float sr, int rand_in_rate, cudaStream_t st) {
+    nsf_phase_kernel<<<B * n_harm, 32, 0, st>>>(f0, rand_ini, phase_ws, B, T, n_harm, hop, sr, rand_in_rate);
     launch_counter()++;
     long long N = (long long)T * hop;
     dim3 grid((unsigned)((N + 255) / 256), B);
     if (n_harm == 9)
-        nsf_source_kernel<9><<<grid, 256, 0, st>>>(f0, noise, phase_ws, lin_w, lin_b, har, T, hop, sr, N);
+        nsf_source_kernel<9><<<grid, 256, 0, st>>>(f0, noise, phase_ws, lin_w, lin_b, har, T, hop, sr, N, rand_ini, rand_in_rate);
     else
-        nsf_source_kernel<1><<<grid, 256, 0, st>>>(f0, noise, phase_ws, lin_w, lin_b, har, T, hop, sr, N);
+        nsf_source_kernel<1><<<grid, 256, 0, st>>>(f0, noise, phase_ws, lin_w, lin_b, har, T, hop, sr, N, rand_ini, rand_in_rate);
     launch_counter()++;
 }
 

@@ -39,6 +39,7 @@ def _cfg_struct(cfg: ModelCfg) -> L.svb_model_cfg:
     s.sampling_rate = cfg.sampling_rate
     s.n_harmonics = cfg.n_harmonics
     s.snake = 1 if cfg.snake else 0
+    s.num_mels = cfg.num_mels
     return s
 
 
@@ -76,7 +77,7 @@ class TailEngine:
         keep = []
         arr_t = []
         for k, v in sd.items():
-            if not k.startswith(TAIL_PREFIXES):
+            if self.cfg.num_mels == 0 and not k.startswith(TAIL_PREFIXES):
                 continue
             t = v.detach()
             if t.dtype not in (torch.float32, torch.float16):
@@ -101,6 +102,9 @@ class TailEngine:
         code = {"fp32": L.PREC_FP32, "tc": L.PREC_TC}[precision]
         L.check(self.lib, self._ctx, self.lib.svb_set_precision(self._ctx, code), "svb_set_precision")
         self.precision = precision
+
+    def set_option(self, name: str, value: int) -> None:
+        L.check(self.lib, self._ctx, self.lib.svb_set_option(self._ctx, name.encode(), int(value)), "svb_set_option")
 
     def debug_enable(self, on: bool = True) -> None:
         L.check(self.lib, self._ctx, self.lib.svb_debug_enable(self._ctx, int(on)), "svb_debug_enable")
@@ -205,6 +209,23 @@ class TailEngine:
         rc = self.lib.svb_generator(self._ctx, z.data_ptr(), g.data_ptr(), g.shape[2], har.data_ptr(), wav.data_ptr(),
                                     B, T, None, 0, self._stream())
         L.check(self.lib, self._ctx, rc, "svb_generator")
+        return wav
+
+    @torch.no_grad()
+    def vocoder(self, mel: torch.Tensor, f0: torch.Tensor, rand_ini: torch.Tensor, har_noise: Optional[torch.Tensor]) -> torch.Tensor:
+        """vdecoder.nsf_hifigan Generator.forward(mel, f0) (vdecoder/nsf_hifigan/models.py:259-278) -> [B,1,N]."""
+        mel = self._f32(mel, "mel"); f0 = self._f32(f0, "f0"); rand_ini = self._f32(rand_ini, "rand_ini")
+        B, _, T = mel.shape
+        N = T * self.cfg.hop
+        nz = None
+        if har_noise is not None:
+            har_noise = self._f32(har_noise, "har_noise")
+            assert har_noise.shape == (B, N, self.cfg.n_harmonics), har_noise.shape
+            nz = har_noise.data_ptr()
+        wav = torch.empty((B, 1, N), dtype=torch.float32, device=self.device)
+        rc = self.lib.svb_vocoder(self._ctx, mel.data_ptr(), f0.data_ptr(), rand_ini.data_ptr(), nz, wav.data_ptr(), B, T,
+                                  None, 0, self._stream())
+        L.check(self.lib, self._ctx, rc, "svb_vocoder")
         return wav
 
     @torch.no_grad()

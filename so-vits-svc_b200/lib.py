@@ -36,7 +36,7 @@ class svb_model_cfg(C.Structure):
         ("upsample_rates", C.c_int32 * 8), ("upsample_kernel_sizes", C.c_int32 * 8),
         ("n_resblock_kernels", C.c_int32), ("resblock_kernel_sizes", C.c_int32 * 4),
         ("resblock_dilations", (C.c_int32 * 3) * 4),
-        ("sampling_rate", C.c_int32), ("n_harmonics", C.c_int32), ("snake", C.c_int32),
+        ("sampling_rate", C.c_int32), ("n_harmonics", C.c_int32), ("snake", C.c_int32), ("num_mels", C.c_int32),
     ]
 
 
@@ -47,12 +47,15 @@ SIGNATURES = {
     "svb_load_weights": (C.c_int, [C.c_void_p, C.POINTER(svb_tensor), C.c_int, C.POINTER(svb_model_cfg)]),
     "svb_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "svb_get_precision": (C.c_int, [C.c_void_p]),
+    "svb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "svb_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "svb_flow_reverse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "svb_nsf_source": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "svb_generator": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "svb_vocoder": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                              C.c_void_p, C.c_size_t, C.c_void_p]),
     "svb_infer_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "svb_infer_tail_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,

@@ -244,3 +244,43 @@ def golden_inputs(cfg: ModelCfg, name: str):
         f0[:, 5:12] = 0.0
         uv = (f0 > 0).float()
     return c, f0, uv, sid
+
+
+def synth_vocoder_state_dict(cfg: ModelCfg, seed: int = 20260923) -> Dict[str, torch.Tensor]:
+    """Seeded weights for the mel-conditioned vdecoder/nsf_hifigan Generator (cfg.num_mels > 0), reference key layout."""
+    from .nsf_hifigan import vocoder_param_shapes
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = OrderedDict()
+    for key, shape in vocoder_param_shapes(cfg).items():
+        leaf = key.rsplit(".", 1)[1]
+        if leaf == "weight_g":
+            continue
+        if leaf == "weight_v":
+            fan = shape[0] * 2 if key.startswith("ups.") else shape[1] * shape[2]
+            v = torch.randn(shape, generator=gen) / math.sqrt(fan)
+            sd[key] = v
+            nrm = v.reshape(shape[0], -1).norm(dim=1).reshape(shape[0], 1, 1)
+            sd[key.replace("weight_v", "weight_g")] = nrm * (torch.rand((shape[0], 1, 1), generator=gen) + 0.5)
+        elif leaf == "bias":
+            sd[key] = torch.randn(shape, generator=gen) * 0.05
+        elif key == "m_source.l_linear.weight":
+            sd[key] = torch.rand(shape, generator=gen) * (2.0 / 3) - 1.0 / 3
+        elif key.startswith("noise_convs."):
+            sd[key] = torch.randn(shape, generator=gen) / math.sqrt(shape[2])
+        else:
+            raise KeyError(key)
+    from .nsf_hifigan import vocoder_param_shapes as _vps
+    return OrderedDict((k, sd[k]) for k in _vps(cfg))
+
+
+VOCODER_H = {"sampling_rate": 44100, "num_mels": 128, "resblock": "1", "resblock_kernel_sizes": [3, 7, 11],
+             "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]], "upsample_rates": [8, 8, 2, 2, 2],
+             "upsample_kernel_sizes": [16, 16, 4, 4, 4], "upsample_initial_channel": 512,
+             "hop_size": 512, "n_fft": 2048, "win_size": 2048, "fmin": 40, "fmax": 16000}
+
+
+def synth_vocoder_inputs(cfg: ModelCfg, B: int, T: int, seed: int = 4321):
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    mel = torch.randn((B, cfg.num_mels, T), generator=gen)                     # standardised log-mel
+    _, f0, _, _ = synth_inputs(cfg, B, T)
+    return mel, f0

@@ -84,6 +84,24 @@ def main():
         print(name, o.shape, float(o.abs().max()))
         np.savez_compressed(os.path.join(HERE, f"ref_infer_{name}.npz"), o=o.numpy(), z_p=taps["z_p"].numpy(),
                             B=B, T=T, seed=52468, noice_scale=0.4, f0=f0.numpy())
+    # mel-conditioned vocoder vdecoder/nsf_hifigan: RNG seeded with 777, draws rand(B,9) then randn(B,N,9)
+    sys.modules["matplotlib"].use = lambda *a, **k: None
+    from vdecoder.nsf_hifigan import models as voc_models
+    from vdecoder.nsf_hifigan.env import AttrDict
+    from sovits_b200 import nsf_hifigan
+    h = AttrDict(synth.VOCODER_H)
+    vcfg = nsf_hifigan.cfg_from_h(h)
+    vsd = synth.synth_vocoder_state_dict(vcfg)
+    G = voc_models.Generator(h).eval()
+    assert set(G.state_dict()) == set(vsd)
+    G.load_state_dict(vsd)
+    B, T = 2, 21
+    mel, f0 = synth.synth_vocoder_inputs(vcfg, B, T)
+    torch.manual_seed(777)
+    with torch.no_grad():
+        o = G(mel, f0)
+    print("vocoder", o.shape, float(o.abs().max()))
+    np.savez_compressed(os.path.join(HERE, "ref_vocoder_b2_t21.npz"), o=o.numpy(), B=B, T=T, seed=777)
     print("done")
 
 

@@ -254,6 +254,30 @@ def test_full_size_properties(cfg, sd, eng):
     assert torch.equal(host[0], outs["fp32"][i].cpu())
 
 
+def test_schedule_options_are_equivalent(cfg, sd, eng):
+    """TMA-fed pair kernels and the pair-vs-fused ResBlock schedules compute the same function."""
+    B, T = 2, 150
+    z_p, g, f0, noise = _case(cfg, sd, B, T)
+    args = [t.to(DEV) for t in (z_p, g, f0, noise["rand_ini"], noise["har_noise"])]
+    eng.set_precision("tc")
+    base = eng.infer_tail(*args)
+    eng.set_option("tma", 1)
+    tma = eng.infer_tail(*args)
+    eng.set_option("tma", 0)
+    eng.set_option("fuse_resblock", 0)
+    pairs = eng.infer_tail(*args)
+    eng.set_option("fuse_resblock", 1)
+    eng.set_option("fuse_maxc", 64)
+    fused64 = eng.infer_tail(*args)
+    eng.set_option("fuse_maxc", 32)
+    eng.set_precision("fp32")
+    ref = eng.infer_tail(*args)
+    for name, o in (("default", base), ("tma", tma), ("pairs-only", pairs), ("fused<=64", fused64)):
+        err = float((o - ref).abs().max())
+        print(f"[parity] schedule {name}: L-inf vs fp32 path = {err:.3e}")
+        assert err < TC_TOL
+
+
 def test_snake_variant_matches_reference_fixture():
     """BASELINE config 4 (vdecoder/hifiganwithsnake): SnakeAlias kernel + fp32 FFMA convolutions vs the reference's own
     waveform; `precision="tc"` must give the same result (the Snake path does not use the LeakyReLU-fused TC kernels)."""
@@ -279,6 +303,41 @@ def test_snake_variant_matches_reference_fixture():
             assert err < (FP32_TOL if precision == "fp32" else TC_TOL)
             outs.append(got)
     e.close()
+
+
+def test_mel_vocoder_matches_reference_fixture():
+    """vdecoder/nsf_hifigan Generator(mel, f0) through svb_vocoder vs the reference's own waveform, and the
+    drop-in module end to end (replaying its RNG draws for the oracle)."""
+    from sovits_b200 import nsf_hifigan
+    from sovits_b200.engine import TailEngine
+    vcfg = nsf_hifigan.cfg_from_h(synth.VOCODER_H)
+    vsd = synth.synth_vocoder_state_dict(vcfg)
+    gold = np.load(os.path.join(GOLD, "ref_vocoder_b2_t21.npz"))
+    B, T = int(gold["B"]), int(gold["T"])
+    mel, f0 = synth.synth_vocoder_inputs(vcfg, B, T)
+    torch.manual_seed(int(gold["seed"]))
+    ri, hn = torch.rand(B, 9), torch.randn(B, T * vcfg.hop, 9)
+    e = TailEngine(vcfg, DEV, "fp32")
+    e.load_state_dict(vsd)
+    for precision, tol in (("fp32", FP32_TOL), ("tc", TC_TOL)):
+        e.set_precision(precision)
+        got = e.vocoder(mel.to(DEV), f0.to(DEV), ri.to(DEV), hn.to(DEV)).cpu()
+        err = float((got - torch.from_numpy(gold["o"])).abs().max())
+        print(f"[parity] mel vocoder {precision}: L-inf vs reference waveform = {err:.3e}")
+        assert err < tol
+    e.close()
+    gen = nsf_hifigan.Generator(synth.VOCODER_H)
+    gen.load_state_dict(vsd)
+    gen = gen.to(DEV).eval()
+    torch.manual_seed(99)
+    o = gen(mel.to(DEV), f0.to(DEV))
+    torch.manual_seed(99)
+    ri2 = torch.rand(B, 9, device=DEV).cpu()
+    hn2 = torch.randn(B, T * vcfg.hop, 9, device=DEV).cpu()
+    ref = O.vocoder(vsd, vcfg, mel, f0, ri2, hn2)
+    err = float((o.cpu() - ref).abs().max())
+    print(f"[parity] mel vocoder module (tc): L-inf vs oracle = {err:.3e}")
+    assert o.shape == (B, 1, T * 512) and err < TC_TOL
 
 
 def test_error_paths(cfg, sd):

@@ -130,3 +130,21 @@ def test_patch_reference_keeps_surface(cfg, sd):
         for m in ("models", "utils", "modules", "vdecoder"):
             for k in [k for k in sys.modules if k == m or k.startswith(m + ".")]:
                 del sys.modules[k]
+
+
+def test_vocoder_surface_matches_reference_layout(tmp_path):
+    """sovits_b200.nsf_hifigan mirrors vdecoder/nsf_hifigan/models.py: load_model(path) reads config.json next to the
+    checkpoint, the module's state_dict has the reference's keys, and it refuses CPU tensors."""
+    from sovits_b200 import nsf_hifigan
+    vcfg = nsf_hifigan.cfg_from_h(synth.VOCODER_H)
+    vsd = synth.synth_vocoder_state_dict(vcfg)
+    with open(tmp_path / "config.json", "w") as f:
+        json.dump(synth.VOCODER_H, f)
+    torch.save({"generator": vsd}, tmp_path / "model")
+    gen, h = nsf_hifigan.load_model(str(tmp_path / "model"), device="cpu")
+    assert h.num_mels == 128 and gen.upp == 512
+    own = gen.state_dict()
+    assert set(own) == set(vsd) and torch.equal(own["ups.1.weight_v"], vsd["ups.1.weight_v"])
+    mel, f0 = synth.synth_vocoder_inputs(vcfg, 1, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gen(mel, f0)

@@ -45,6 +45,20 @@ def test_snake_oracle_matches_reference_fixture():
         assert float((o - torch.from_numpy(g["o"])).abs().max()) < 2e-5
 
 
+def test_vocoder_oracle_matches_reference_fixture():
+    """vdecoder/nsf_hifigan Generator (mel-conditioned, frame-rate SineGen): oracle vs the stored reference run."""
+    from sovits_b200 import nsf_hifigan
+    vcfg = nsf_hifigan.cfg_from_h(synth.VOCODER_H)
+    vsd = synth.synth_vocoder_state_dict(vcfg)
+    g = np.load(os.path.join(GOLD, "ref_vocoder_b2_t21.npz"))
+    B, T = int(g["B"]), int(g["T"])
+    mel, f0 = synth.synth_vocoder_inputs(vcfg, B, T)
+    torch.manual_seed(int(g["seed"]))
+    ri, hn = torch.rand(B, 9), torch.randn(B, T * vcfg.hop, 9)
+    o = O.vocoder(vsd, vcfg, mel, f0, ri, hn)
+    assert float((o - torch.from_numpy(g["o"])).abs().max()) < 2e-5
+
+
 def test_oracle_fp64_close_to_fp32_reference(cfg, sd):
     g = _load("b1_t33")
     c, f0, uv, sid = synth.golden_inputs(cfg, "b1_t33")
