@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+echo "=== tests" ; timeout 1200 python -m pytest tests -m gpu -q -s > gpurun_out/test_all.log 2>&1 ; echo "rc=$?" ; grep -E "passed|failed|Error|error" gpurun_out/test_all.log | tail -6; grep -E "vocoder|schedule|snake" gpurun_out/test_all.log | grep parity
+echo "=== bench" ; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_tc.log 2>&1 ; echo "rc=$?" ; tail -1 gpurun_out/bench_tc.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['frac'], d['roofline_secondary'])"
