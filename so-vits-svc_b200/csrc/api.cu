@@ -69,6 +69,7 @@ struct Stage {
     int noise_K = 0, noise_s = 0, noise_p = 0;
     std::vector<ConvW> c1, c2;     // [branch*3 + d]
     ConvNW up_tc;
+    ConvNW noise_tc;               // wide noise_convs (stage 0): a 2-tap GEMM over 64-sample excitation rows
 };
 
 }  // namespace
@@ -531,8 +532,19 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         } else {
             launch_conv_f32(up, st);
         }
-        if (!(gen_tc && S.up_tc.noise))
+        if (gen_tc && !S.up_tc.noise && S.noise_tc.img) {
+            const ConvNW& W = S.noise_tc;
+            ConvNTC a;
+            a.x = har; a.cin_real = 64; a.cinp = 64; a.Tin = Lout + 1;
+            a.view_bstride = N; a.view_tstride = S.noise_s; a.view_cstride = 1; a.view_off = -S.noise_p; a.view_limit = N;
+            a.w = W.img; a.bias = W.bias; a.k = 2; a.pad_left = 0; a.n_rows = Lout; a.N_total = W.N_total; a.NC = W.NC;
+            a.chunks_per_cta = (W.N_total + W.NC - 1) / W.NC; a.Ty = Lout; a.B = B;
+            a.seg[0].y = X; a.seg[0].y_ctot = S.Cout; a.seg[0].col0 = 0; a.seg[0].col1 = S.Cout; a.seg[0].beta = 1.f;
+            int trc = launch_convn_tc(a, st);
+            if (trc) return fail(ctx, trc, "convn launch failed (noise conv)");
+        } else if (!(gen_tc && S.up_tc.noise)) {
             launch_noise_conv_add(har, S.noise_w, S.noise_b, X, B, S.Cout, Lout, (int)N, S.noise_K, S.noise_s, S.noise_p, st);
+        }
         if ((rc = dbg_keep(ctx, "ups" + std::to_string(i), X, (size_t)B * S.Cout * Lout, st))) return rc;
         static const int fuse_rb = [] { const char* e = std::getenv("SVB_FUSE_RESBLOCK"); return e ? std::atoi(e) : 1; }();
         static const int use_tma = [] { const char* e = std::getenv("SVB_TC_TMA"); return e ? std::atoi(e) : 1; }();
@@ -977,6 +989,13 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
                                  fuse_noise ? &ncol : nullptr, noise_kind))) return rc;
             S.up_tc.noise_stride = s_ * sp;
             S.up_tc.noise_w0 = -S.p * sp - pn_;
+            if (!fuse_noise && Kn == 2 * sp && sp == 64 && (Co % 32) == 0) {
+                // y[co,t] = sum_kk wn[co,kk] har[t*64 - 32 + kk]: rows H[t] = har[64t-32 .. +64) are a strided view of the
+                // excitation; the 128-tap filter is two 64-wide taps on consecutive rows -> convn with Cin = 64, k = 2
+                if ((rc = make_convn(ctx, 64, 64, Co, Co <= 128 ? Co : 128, 2, 0,
+                                     [&](int col, int ci, int tap) { return nwv[(size_t)col * Kn + tap * 64 + ci]; },
+                                     [&](int col) { return nbv[col]; }, S.noise_tc))) return rc;
+            }
         }
         S.c1.assign(9, ConvW());
         S.c2.assign(9, ConvW());

@@ -100,6 +100,9 @@ struct ConvNSeg {                 // destination of a column range [col0, col1)
 struct ConvNTC {
     const float* x = nullptr; int x_ctot = 0, x_c0 = 0, cin_real = 0, Tin = 0;
     int cinp = 0;                  // padded Cin (template selector): 32,64,128,192,256,512
+    // optional strided view of the input (0 = the default [B,C,T] tensor): element (c, t) = x[b*view_bstride + t*view_tstride
+    // + c*view_cstride + view_off], zero outside [0, view_limit).  Used to read the 1-channel excitation as overlapping windows.
+    long long view_bstride = 0; int view_tstride = 0, view_cstride = 0, view_off = 0; long long view_limit = 0;
     int in_act = 0; float in_slope = 0.f;
     const void* w = nullptr;       // fp16 image [chunk][tap][panel][NC rows][swizzled]
     const float* bias = nullptr;   // per column (column order), nullable

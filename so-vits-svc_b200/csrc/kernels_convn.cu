@@ -189,17 +189,27 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
         // ------------------------------------------------------------ workers
         // (1) stage A = act(x)[rows][Cin] as fp16; row r <-> input index i0 - pad_left + r
         {
-            const float* __restrict__ xb = a.x + ((size_t)b * a.x_ctot + a.x_c0) * (size_t)a.Tin;
+            const bool view = a.view_tstride != 0;
+            const float* __restrict__ xb = view ? a.x + (size_t)b * a.view_bstride : a.x + ((size_t)b * a.x_ctot + a.x_c0) * (size_t)a.Tin;
             for (int r = tid; r < RA; r += CN_NWORK) {
                 const int ti = i0 - a.pad_left + r;
                 const bool rv = (ti >= 0) && (ti < a.Tin);
-                const float* __restrict__ xt = xb + (rv ? ti : 0);
+                const float* __restrict__ xt = xb + (rv && !view ? ti : 0);
+                const long long vbase = (long long)ti * a.view_tstride + a.view_off;
                 const uint32_t phase = swz_phase(r, G::RB);
 #pragma unroll 2
                 for (int c0 = 0; c0 < CINP; c0 += 16) {
                     float v[16];
+                    if (view) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = (rv && (c0 + j) < a.cin_real) ? __ldg(xt + (size_t)(c0 + j) * a.Tin) : 0.f;
+                        for (int j = 0; j < 16; ++j) {
+                            const long long idx = vbase + (long long)(c0 + j) * a.view_cstride;
+                            v[j] = (rv && (c0 + j) < a.cin_real && idx >= 0 && idx < a.view_limit) ? __ldg(xb + idx) : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = (rv && (c0 + j) < a.cin_real) ? __ldg(xt + (size_t)(c0 + j) * a.Tin) : 0.f;
+                    }
                     if (a.in_act) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], a.in_slope * v[j]);

@@ -58,6 +58,16 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
+// One lane of a fully converged warp (always the same one).  Issuing tcgen05.mma / commit / bulk copies under
+// `if (elect_one())` instead of `if (lane == 0)` lets ptxas keep the operands in uniform registers and emit the
+// UTCHMMA stream back to back; with a lane test it wraps EVERY instruction in an ELECT / BRA.U.ANY loop
+// (~15 issue slots per MMA, measured ~100 clk per MMA on B200 - longer than an N<=128 MMA itself).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- tcgen05 -------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {   // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
