@@ -103,39 +103,47 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 9) {
-        // ------------------------------------------------------------ weight producer
-        if (lane == 0) {
-            int ring = 0;
-            for (int c = c_lo; c < c_hi; ++c) {
-                const uint8_t* wsrc = static_cast<const uint8_t*>(a.w) + (size_t)c * chunk_bytes;
-                int idx = 0;
-                uint32_t off = 0;
+        // ------------------------------------------------------------ weight producer (whole warp converged, elected lane issues)
+        int ring = 0;
+        for (int c = c_lo; c < c_hi; ++c) {
+            const uint8_t* wsrc = static_cast<const uint8_t*>(a.w) + (size_t)c * chunk_bytes;
+            int idx = 0;
+            uint32_t off = 0;
+            while (idx < n_sb) {
+                uint32_t bytes = 0;
                 while (idx < n_sb) {
-                    uint32_t bytes = 0;
-                    while (idx < n_sb) {
-                        const uint32_t sbb = sb_bytes(idx);
-                        if (bytes && bytes + sbb > (uint32_t)d.stage_bytes) break;
-                        bytes += sbb; ++idx;
-                    }
-                    const int s = ring & 1;
-                    if (ring >= 2) mbar_wait(bar_empty + 8 * s, ((ring >> 1) - 1) & 1);
+                    const uint32_t sbb = sb_bytes(idx);
+                    if (bytes && bytes + sbb > (uint32_t)d.stage_bytes) break;
+                    bytes += sbb; ++idx;
+                }
+                const int s = ring & 1;
+                if (ring >= 2) mbar_wait(bar_empty + 8 * s, ((ring >> 1) - 1) & 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
                     bulk_g2s(ring_base + s * d.stage_bytes, wsrc + off, bytes, bar_full + 8 * s);
-                    off += bytes; ++ring;
                 }
+                __syncwarp();
+                off += bytes; ++ring;
             }
         }
     } else if (warp == 8) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_f16(128, NC);
-            mbar_wait(bar_a, 0);
-            tc_fence_after();
-            int ring = 0;
+        // Warp converged, ONE elected lane runs the whole issue loop (ring / accumulator-buffer waits included); the
+        // body is UTCHMMAs plus descriptor increments only (see pair_tc_kernel for why).
+        const uint32_t idesc = make_idesc_f16(128, NC);
+        mbar_wait(bar_a, 0);
+        tc_fence_after();
+        if (elect_one()) {
+            const uint64_t a_step = (uint64_t)((uint32_t)(a.dil * G::RB) >> 4);
+            const uint64_t sub16 = (uint64_t)((uint32_t)SUB >> 4);
+            uint32_t ring = 0;
             for (int c = c_lo; c < c_hi; ++c) {
                 const int u = c - c_lo, buf = (d.nbuf > 1) ? (u & 1) : 0;
                 if (u >= d.nbuf) { mbar_wait(bar_tempty + 8 * buf, ((u / d.nbuf) - 1) & 1); tc_fence_after(); }
                 const uint32_t dcol = tmem_base + buf * d.bufcols;
+                uint64_t a_tap = make_smem_desc(a_base, G::RB, 0);
+                int pn = 0;
+                uint32_t acc = 0u;
                 int idx = 0;
                 while (idx < n_sb) {
                     // same greedy grouping as the producer
@@ -146,36 +154,37 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                         if (bytes && bytes + sbb > (uint32_t)d.stage_bytes) break;
                         bytes += sbb; ++idx;
                     }
-                    const int s = ring & 1;
-                    mbar_wait(bar_full + 8 * s, (ring >> 1) & 1);
+                    const uint32_t s = ring & 1u;
+                    mbar_wait(bar_full + 8 * s, (ring >> 1) & 1u);
                     tc_fence_after();
-                    uint32_t boff = 0;
-                    for (int sb = g0; sb < idx; ++sb) {
-                        const uint32_t bsub = ring_base + s * d.stage_bytes + boff;
-                        const uint32_t acc0 = (sb > 0) ? 1u : 0u;
-                        if (sb < n_reg) {
-                            const int tap = sb / G::NP, pn = sb % G::NP;
-                            const uint64_t a_d0 = make_smem_desc(a_base + pn * APANEL + (uint32_t)(tap * a.dil) * G::RB, G::RB, 0);
-                            const uint64_t b_d0 = make_smem_desc(bsub, G::RB, 0);
+                    uint64_t bd = make_smem_desc(ring_base + s * d.stage_bytes, G::RB, 0);
+                    const int g_reg = (idx < n_reg ? idx : n_reg);
+                    for (int sb = g0; sb < g_reg; ++sb) {
+                        const uint64_t ad = a_tap + (uint64_t)pn * (uint64_t)(APANEL >> 4);
 #pragma unroll
-                            for (int mb = 0; mb < MB; ++mb) {
+                        for (int mb = 0; mb < MB; ++mb) {
 #pragma unroll
-                                for (int ks = 0; ks < G::KSTEPS; ++ks) {
-                                    const uint64_t ad = a_d0 + (uint64_t)(((uint32_t)(mb * 128) * G::RB + ks * 32) >> 4);
-                                    const uint64_t bd = b_d0 + (uint64_t)((ks * 32) >> 4);
-                                    umma_f16(dcol + mb * d.blkcols, ad, bd, idesc, (ks > 0) ? 1u : acc0);
-                                }
-                            }
-                            boff += SUB;
-                        } else {
+                            for (int ks = 0; ks < G::KSTEPS; ++ks)
+                                umma_f16(dcol + mb * d.blkcols, ad + (uint64_t)(((uint32_t)(mb * 128) * G::RB + ks * 32) >> 4),
+                                         bd + (uint64_t)((ks * 32) >> 4), idesc, (ks > 0) ? 1u : acc);
+                        }
+                        acc = 1u;
+                        bd += sub16;
+                        if (++pn == G::NP) { pn = 0; a_tap += a_step; }
+                    }
+                    if (idx > n_reg) {
+                        // excitation (noise_convs) panels: narrower rows, own swizzle width
+                        uint32_t boff = (uint32_t)(g_reg > g0 ? (g_reg - g0) : 0) * (uint32_t)SUB;
+                        for (int sb = (g0 > n_reg ? g0 : n_reg); sb < idx; ++sb) {
                             const int pnn = sb - n_reg;
                             const uint32_t rbn = (uint32_t)d.noise_rb[pnn];
                             const uint64_t a_d0 = make_smem_desc(base + d.off_noise[pnn], rbn, 0);
-                            const uint64_t b_d0 = make_smem_desc(bsub, rbn, 0);
+                            const uint64_t b_d0 = make_smem_desc(ring_base + s * d.stage_bytes + boff, rbn, 0);
                             for (int mb = 0; mb < MB; ++mb)
                                 for (uint32_t ks = 0; ks < rbn / 32u; ++ks)
                                     umma_f16(dcol + mb * d.blkcols, a_d0 + (uint64_t)(((uint32_t)(mb * 128) * rbn + ks * 32u) >> 4),
-                                             b_d0 + (uint64_t)((ks * 32u) >> 4), idesc, (ks > 0) ? 1u : acc0);
+                                             b_d0 + (uint64_t)((ks * 32u) >> 4), idesc, (ks > 0) ? 1u : acc);
+                            acc = 1u;
                             boff += sb_bytes(sb);
                         }
                     }
@@ -185,6 +194,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                 umma_commit(bar_tfull + 8 * buf);
             }
         }
+        __syncwarp();
     } else {
         // ------------------------------------------------------------ workers
         // (1) stage A = act(x)[rows][Cin] as fp16; row r <-> input index i0 - pad_left + r

@@ -27,6 +27,14 @@ constexpr int RBK_THREADS = 320;
 constexpr int RBK_NWORK = 256;
 constexpr int RBK_PAD = 32;          // >= max |tap offset| = 5*5 = 25
 
+// Phase tracing for tools/bench_rb.cu (compiled only with -DSVB_TRACE): 64 clock64() slots per CTA.
+#ifdef SVB_TRACE
+__device__ long long* g_rb_trace = nullptr;
+#define RB_TRACE(slot) do { if (g_rb_trace) g_rb_trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + (slot)] = clock64(); } while (0)
+#else
+#define RB_TRACE(slot) do { } while (0)
+#endif
+
 struct ResblockParams {
     const float* x; float* out;
     const uint8_t* w[6];             // c1[d0], c2[d0], c1[d1], c2[d1], c1[d2], c2[d2] tensor-core images
@@ -34,7 +42,9 @@ struct ResblockParams {
     int T, k, halo;
     int dil[3];
     float alpha, beta;
+    uint32_t epoch; int skew_clk;    // start skew of the second co-resident CTA (tc_common.cuh)
 };
+__device__ unsigned long long g_rb_ticket[256];
 
 template <int C, int STAGE_KB>
 struct RBGeom {
@@ -83,6 +93,11 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
     float* __restrict__ ob = p.out + (size_t)b * C * p.T;
 
     if (tid == 0) {
+        dephase_first_wave(g_rb_ticket, p.epoch, p.skew_clk, MINB);
+        RB_TRACE(0);
+#ifdef SVB_TRACE
+        { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); if (g_rb_trace) g_rb_trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + 63] = smid; }
+#endif
         for (int s = 0; s < 2; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_a, RBK_NWORK);
         mbar_init(bar_acc, 1);
@@ -97,51 +112,64 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
 
     if (warp == 9) {
         // ------------------------------------------------------------ weight producer: six convolutions back to back
-        if (lane == 0) {
-            int chunk = 0;
-            for (int q = 0; q < 6; ++q) {
-                const uint8_t* wsrc = p.w[q];
-                for (int sb0 = 0; sb0 < k; sb0 += G::SPC, ++chunk) {
-                    const int s = chunk & 1;
-                    if (chunk >= 2) mbar_wait(bar_empty + 8 * s, ((chunk >> 1) - 1) & 1);
-                    const int nsb = (k - sb0) < G::SPC ? (k - sb0) : G::SPC;
-                    const uint32_t bytes = (uint32_t)nsb * G::SUB;
+        int chunk = 0;
+        for (int q = 0; q < 6; ++q) {
+            const uint8_t* wsrc = p.w[q];
+            for (int sb0 = 0; sb0 < k; sb0 += G::SPC, ++chunk) {
+                const int s = chunk & 1;
+                if (chunk >= 2) mbar_wait(bar_empty + 8 * s, ((chunk >> 1) - 1) & 1);
+                const int nsb = (k - sb0) < G::SPC ? (k - sb0) : G::SPC;
+                const uint32_t bytes = (uint32_t)nsb * G::SUB;
+                if (elect_one()) {
                     mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
                     bulk_g2s(ring_base + s * G::STAGE_BYTES, wsrc + (size_t)sb0 * G::SUB, bytes, bar_full + 8 * s);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 8) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(128, C);
-            const int h = (k - 1) / 2;
-            int chunk = 0;
-            for (int q = 0; q < 6; ++q) {
-                mbar_wait(bar_a, q & 1);
-                tc_fence_after();
+        // The whole warp stays converged; ONE elected lane runs the issue loop of a conv (waits on the weight ring
+        // included).  The loop body is kept to the UTCHMMAs plus two descriptor increments: every extra scalar
+        // instruction here is serialised latency in front of an asynchronous 40-clk MMA (measured: the former
+        // div/mod + R2UR heavy body cost ~480 clk per tap and capped the tensor pipe at ~45 %).
+        constexpr uint32_t idesc = make_idesc_f16(128, C);
+        const int h = (k - 1) / 2;
+        const uint32_t nchunk = (uint32_t)((k + G::SPC - 1) / G::SPC);     // ring chunks per conv
+        for (int q = 0; q < 6; ++q) {
+            mbar_wait(bar_a, q & 1);
+            tc_fence_after();
+            if (lane == 0) RB_TRACE(2 + 4 * q + 2);
+            if (elect_one()) {
                 const int cd = (q & 1) ? 1 : p.dil[q >> 1];
-                for (int tap = 0; tap < k; ++tap) {
-                    const int s = chunk & 1;
-                    const int within = tap % G::SPC;
-                    if (within == 0) { mbar_wait(bar_full + 8 * s, (chunk >> 1) & 1); tc_fence_after(); }
-                    const uint32_t a0 = a_base + (uint32_t)(RBK_PAD + (tap - h) * cd) * G::RB;
-                    const uint64_t a_d0 = make_smem_desc(a0, G::RB, 0);
-                    const uint64_t b_d0 = make_smem_desc(ring_base + s * G::STAGE_BYTES + within * G::SUB, G::RB, 0);
-                    const uint32_t acc0 = (tap > 0) ? 1u : 0u;
+                uint64_t ad = make_smem_desc(a_base + (uint32_t)(RBK_PAD - h * cd) * G::RB, G::RB, 0);
+                const uint64_t a_step = (uint64_t)((uint32_t)(cd * G::RB) >> 4);
+                uint32_t chunk = (uint32_t)q * nchunk;
+                uint32_t acc = 0u;
+                for (int tap0 = 0; tap0 < k; tap0 += G::SPC, ++chunk) {
+                    const uint32_t s = chunk & 1u;
+                    mbar_wait(bar_full + 8 * s, (chunk >> 1) & 1u);
+                    tc_fence_after();
+                    uint64_t bd = make_smem_desc(ring_base + s * G::STAGE_BYTES, G::RB, 0);
+                    const int n = (k - tap0) < G::SPC ? (k - tap0) : G::SPC;
+                    for (int i = 0; i < n; ++i) {
 #pragma unroll
-                    for (int mb = 0; mb < MB; ++mb) {
+                        for (int mb = 0; mb < MB; ++mb) {
 #pragma unroll
-                        for (int ks = 0; ks < G::KSTEPS; ++ks) {
-                            const uint64_t ad = a_d0 + (uint64_t)(((uint32_t)(mb * 128) * G::RB + ks * 32) >> 4);
-                            const uint64_t bd = b_d0 + (uint64_t)((ks * 32) >> 4);
-                            umma_f16(tmem_base + ACC0 + mb * C, ad, bd, idesc, (ks > 0) ? 1u : acc0);
+                            for (int ks = 0; ks < G::KSTEPS; ++ks)
+                                umma_f16(tmem_base + ACC0 + mb * C, ad + (uint64_t)(((uint32_t)(mb * 128) * G::RB + ks * 32) >> 4),
+                                         bd + (uint64_t)((ks * 32) >> 4), idesc, (ks > 0) ? 1u : acc);
                         }
+                        acc = 1u;
+                        ad += a_step;
+                        bd += (uint64_t)(G::SUB >> 4);
                     }
-                    if (within == G::SPC - 1 || tap == k - 1) { umma_commit(bar_empty + 8 * s); ++chunk; }
+                    umma_commit(bar_empty + 8 * s);
                 }
                 umma_commit(bar_acc);
             }
+            __syncwarp();
+            if (lane == 0) RB_TRACE(2 + 4 * q + 3);
         }
     } else {
         // ------------------------------------------------------------ workers
@@ -186,11 +214,13 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
         tc_fence_before();
         fence_proxy_async();
         mbar_arrive(bar_a);
+        if (tid == 0) RB_TRACE(1);
 
 #pragma unroll 1
         for (int q = 0; q < 6; ++q) {
             mbar_wait(bar_acc, q & 1);
             tc_fence_after();
+            if (tid == 0) RB_TRACE(2 + 4 * q + 0);
             const float* __restrict__ bq_ = sbias + q * C;
             if ((q & 1) == 0) {
                 // ---- first conv of a pair: mid = lrelu(acc + b1) -> operand tile
@@ -224,6 +254,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(bar_a);
+                if (tid == 0) RB_TRACE(2 + 4 * q + 1);
             } else if (q < 5) {
                 // ---- second conv of pair 0/1: x <- x + acc + b2 (TMEM), operand tile <- lrelu(x)
 #pragma unroll 1
@@ -263,9 +294,11 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(bar_a);
+                if (tid == 0) RB_TRACE(2 + 4 * q + 1);
             } else {
                 // ---- last conv: out = alpha*(x + acc + b2) + beta*out_old for the interior rows
-                const bool has_beta = p.beta != 0.f;
+                const bool red_old = p.beta == 1.f;              // out += y as a fire-and-forget reduction: no read of out
+                const bool has_beta = p.beta != 0.f && !red_old;
 #pragma unroll 1
                 for (int mb = 0; mb < MB; ++mb) {
                     const int row = mb * 128 + rib;
@@ -294,7 +327,8 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
                                     const int j = j4 + e;
                                     float y = p.alpha * (__uint_as_float(r[j]) + b4[e] + __uint_as_float(xr[j]));
                                     if (has_beta) y = fmaf(p.beta, oo[j], y);
-                                    ot[(size_t)(c0 + j) * p.T] = y;
+                                    if (red_old) atomicAdd(ot + (size_t)(c0 + j) * p.T, y);
+                                    else ot[(size_t)(c0 + j) * p.T] = y;
                                 }
                             }
                         }
@@ -302,12 +336,16 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
                 }
             }
         }
+        if (tid == 0) RB_TRACE(2 + 4 * 5 + 1);
         tc_fence_before();
     }
 
     __syncthreads();
+    if (tid == 0) RB_TRACE(30);
     if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
+
+uint32_t g_rb_epoch = 0;         // launch serial number shared by all instantiations (they share g_rb_ticket)
 
 int rb_env_int(const char* name, int dflt) {
     const char* s = std::getenv(name);
@@ -331,6 +369,15 @@ int launch_resblock_t(const ResblockTC& a, cudaStream_t st) {
     int halo = 0;
     for (int d = 0; d < 3; ++d) { p.dil[d] = a.dil[d]; halo += (a.dil[d] + 1) * (a.k - 1) / 2; }
     p.halo = halo;
+    {
+        // first-wave de-phasing (tc_common.cuh): tile period estimate = six conv cycles (MMA at the shared-pipe rate +
+        // epilogue) + load / store phases
+        static const int env_skew = rb_env_int("SVB_RB_SKEW", -1);
+        p.epoch = ++g_rb_epoch;
+        const int mma_clk = (C <= 32 ? 40 : 48) * a.k * MB * (C / 16);
+        const int grid_ctas = (int)(((a.T + (128 * MB - 2 * halo) - 1) / (128 * MB - 2 * halo)) * a.B);
+        p.skew_clk = (MINB < 2 || grid_ctas < 4 * 148 * MINB) ? 0 : (env_skew >= 0 ? env_skew : 6 * (mma_clk + 2000) + 15000);
+    }
     const int TOUT = 128 * MB - 2 * halo;
     if (TOUT < 64) return SVB_ERR_UNSUPPORTED;
     dim3 grid((a.T + TOUT - 1) / TOUT, a.B);

@@ -57,7 +57,20 @@ struct PairParams {
     int T, k, dil;
     float alpha, beta;
     __half* a16_out;     // optional second output: fp16 lrelu(out) in [B][T][C] (the next pair's TMA-loadable operand)
+    int vec4;            // x / out 16-byte aligned and T % 4 == 0: the loader uses 128-bit loads along time
+    int red_out;         // loader pre-writes alpha*x (+ beta*old for beta == 1) into out, epilogue 2 only adds (RED): no x re-read
+    uint32_t epoch; int dephase_clk;   // first-wave start skew (tc_common.cuh: dephase_first_wave)
 };
+__device__ unsigned long long g_pair_ticket[256];
+uint32_t g_pair_epoch = 0;
+
+// Phase tracing for tools/bench_pairtrace.cu (compiled only with -DSVB_TRACE): 16 clock64() slots per CTA.
+#ifdef SVB_TRACE
+__device__ long long* g_pair_trace = nullptr;
+#define PAIR_TRACE(slot) do { if (g_pair_trace) g_pair_trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define PAIR_TRACE(slot) do { } while (0)
+#endif
 
 template <int C, int MB, int STAGE_KB>
 constexpr size_t pair_smem_bytes() {
@@ -104,6 +117,11 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
 
     // ---------------------------------------------------------------- setup
     if (tid == 0) {
+        dephase_first_wave(g_pair_ticket, p.epoch, p.dephase_clk, MINB);
+        PAIR_TRACE(0);
+#ifdef SVB_TRACE
+        { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); if (g_pair_trace) g_pair_trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + 15] = smid; }
+#endif
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_a, NWORK);
         mbar_init(bar_acc, 1);
@@ -122,17 +140,21 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
 
     if (warp == 9) {
         // ------------------------------------------------------------ weight producer (and A-tile TMA issuer)
-        if (lane == 0) {
-            if (TMA_IN) {
-                // the previous pair already wrote lrelu(x) as fp16 [B][T][C]: the tensor map delivers it swizzled, rows
-                // outside [0,T) zero-filled, straight into the A-operand layout - no thread touches the data
-                constexpr int BOX = AROWS / TMA_NBOX;
+        // whole warp converged, one elected lane issues (see elect_one() in tc_common.cuh)
+        if (TMA_IN) {
+            // the previous pair already wrote lrelu(x) as fp16 [B][T][C]: the tensor map delivers it swizzled, rows
+            // outside [0,T) zero-filled, straight into the A-operand layout - no thread touches the data
+            constexpr int BOX = AROWS / TMA_NBOX;
+            if (elect_one()) {
                 tma_prefetch_desc(&tmap);
                 mbar_arrive_expect_tx(bar_tma, (uint32_t)(G::NP * AROWS * G::RB));
                 for (int pn = 0; pn < G::NP; ++pn)
                     for (int bx = 0; bx < TMA_NBOX; ++bx)
                         tma_load_3d(a_base + pn * APANEL + bx * BOX * G::RB, &tmap, pn * G::CPP, tA0 + bx * BOX, b, bar_tma);
             }
+            __syncwarp();
+        }
+        {
             const int total_sb = k * G::NP;
             int chunk = 0;
             for (int conv = 0; conv < 2; ++conv) {
@@ -142,57 +164,138 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
                     if (chunk >= NSTAGE) mbar_wait(bar_empty + 8 * s, ((chunk / NSTAGE) - 1) & 1);
                     const int nsb = (total_sb - sb0) < G::SPC ? (total_sb - sb0) : G::SPC;
                     const uint32_t bytes = (uint32_t)nsb * G::SUB;
-                    mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
-                    bulk_g2s(ring_base + s * G::STAGE_BYTES, wsrc + (size_t)sb0 * G::SUB, bytes, bar_full + 8 * s);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+                        bulk_g2s(ring_base + s * G::STAGE_BYTES, wsrc + (size_t)sb0 * G::SUB, bytes, bar_full + 8 * s);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 8) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(128, C);
-            const int total_sb = k * G::NP;
-            int chunk = 0;
-            for (int conv = 0; conv < 2; ++conv) {
-                if (TMA_IN) { if (conv == 0) mbar_wait(bar_tma, 0); else mbar_wait(bar_a, 0); }
-                else mbar_wait(bar_a, conv);
-                tc_fence_after();
+        // The warp stays converged; ONE elected lane runs the whole issue loop of a conv, ring waits included.  The
+        // body is the UTCHMMAs plus descriptor increments - no div/mod, no per-MMA register->uniform moves: scalar work
+        // here is serialised latency in front of asynchronous MMAs (it used to cap the tensor pipe at ~45 %).
+        constexpr uint32_t idesc = make_idesc_f16(128, C);
+        const int total_sb = k * G::NP;
+        const uint32_t nchunk = (uint32_t)((total_sb + G::SPC - 1) / G::SPC);
+        for (int conv = 0; conv < 2; ++conv) {
+            if (TMA_IN) { if (conv == 0) mbar_wait(bar_tma, 0); else mbar_wait(bar_a, 0); }
+            else mbar_wait(bar_a, conv);
+            tc_fence_after();
+            if (lane == 0) PAIR_TRACE(6 + 2 * conv);
+            if (elect_one()) {
                 const int cd = conv ? 1 : dil;
-                for (int sb = 0; sb < total_sb; ++sb) {
-                    const int s = chunk % NSTAGE;
-                    const int within = sb % G::SPC;
-                    if (within == 0) {
-                        mbar_wait(bar_full + 8 * s, (chunk / NSTAGE) & 1);
-                        tc_fence_after();
-                    }
-                    const int tap = sb / G::NP, pn = sb % G::NP;
-                    const uint32_t bsub = ring_base + s * G::STAGE_BYTES + within * G::SUB;
-                    // descriptors differ only in the 14-bit start-address field: build the constant part once
-                    const uint32_t a0 = a_base + pn * APANEL + (uint32_t)(tap * cd) * G::RB;
-                    const uint64_t a_d0 = make_smem_desc(a0, G::RB, 0);
-                    const uint64_t b_d0 = make_smem_desc(bsub, G::RB, 0);
-                    const uint32_t acc0 = (sb > 0) ? 1u : 0u;
+                uint64_t a_tap = make_smem_desc(a_base, G::RB, 0);            // A descriptor of (tap, panel 0)
+                const uint64_t a_step = (uint64_t)((uint32_t)(cd * G::RB) >> 4);
+                uint32_t chunk = (uint32_t)conv * nchunk;
+                uint32_t acc = 0u;
+                int pn = 0;
+                for (int sb0 = 0; sb0 < total_sb; sb0 += G::SPC, ++chunk) {
+                    const uint32_t s = chunk % NSTAGE;
+                    mbar_wait(bar_full + 8 * s, (chunk / NSTAGE) & 1u);
+                    tc_fence_after();
+                    uint64_t bd = make_smem_desc(ring_base + s * G::STAGE_BYTES, G::RB, 0);
+                    const int n = (total_sb - sb0) < G::SPC ? (total_sb - sb0) : G::SPC;
+                    for (int i = 0; i < n; ++i) {
+                        const uint64_t ad = a_tap + (uint64_t)pn * (uint64_t)(APANEL >> 4);
 #pragma unroll
-                    for (int mb = 0; mb < MB; ++mb) {
+                        for (int mb = 0; mb < MB; ++mb) {
 #pragma unroll
-                        for (int ks = 0; ks < G::KSTEPS; ++ks) {
-                            const uint64_t ad = a_d0 + (uint64_t)(((uint32_t)(mb * 128) * G::RB + ks * 32) >> 4);
-                            const uint64_t bd = b_d0 + (uint64_t)((ks * 32) >> 4);
-                            umma_f16(tmem_base + mb * C, ad, bd, idesc, (ks > 0) ? 1u : acc0);
+                            for (int ks = 0; ks < G::KSTEPS; ++ks)
+                                umma_f16(tmem_base + mb * C, ad + (uint64_t)(((uint32_t)(mb * 128) * G::RB + ks * 32) >> 4),
+                                         bd + (uint64_t)((ks * 32) >> 4), idesc, (ks > 0) ? 1u : acc);
                         }
+                        acc = 1u;
+                        bd += (uint64_t)(G::SUB >> 4);
+                        if (++pn == G::NP) { pn = 0; a_tap += a_step; }
                     }
-                    if (within == G::SPC - 1 || sb == total_sb - 1) {
-                        umma_commit(bar_empty + 8 * s);   // frees the ring stage once these MMAs retire
-                        ++chunk;
-                    }
+                    umma_commit(bar_empty + 8 * s);                           // frees the ring stage once these MMAs retire
                 }
-                umma_commit(bar_acc);                      // accumulators of this conv are complete
+                umma_commit(bar_acc);                                         // accumulators of this conv are complete
             }
+            __syncwarp();
+            if (lane == 0) PAIR_TRACE(7 + 2 * conv);
         }
     } else {
         // ------------------------------------------------------------ workers (warps 0-7)
         // (1) stage A1 = lrelu(x) tile as fp16 [time][channel], zero outside [0,T)  (skipped when the tile comes by TMA)
-        for (int r = tid; !TMA_IN && r < RA1; r += NWORK) {
+        if (!TMA_IN && p.vec4) {
+            // 128-bit loads along time: a lane owns an aligned group of 4 time steps x 8 channels (8 LDG.128 in flight,
+            // 32 KB per CTA), transposes in registers and writes four 16-byte operand chunks.  A warp item is GPI
+            // consecutive groups x CHK chunks, so every load instruction covers GPI*16 contiguous bytes per channel.
+            // When red_out is set the same registers also initialise out = alpha*x (+ old), so that epilogue 2 only
+            // has to ADD the convolution result and never waits on a global load.
+            constexpr int CHK = (C / 8) < 4 ? (C / 8) : 4;
+            constexpr int GPI = 32 / CHK;
+            constexpr int NCB = (C / 8) / CHK;
+            const int sh = tA0 & 3;                       // tA0 - sh is a multiple of 4 (two's complement, tA0 may be negative)
+            const int tAa = tA0 - sh;
+            const int NG = (RA1 + sh + 3) >> 2;
+            const int NGO = (NG + GPI - 1) / GPI;
+            const int g_l = lane % GPI, ch_l = lane / GPI;
+            const bool acc_old = p.beta != 0.f;
+#pragma unroll 1
+            for (int item = warp; item < NGO * NCB; item += NWORK / 32) {
+                const int go = item % NGO, cb = item / NGO;
+                const int g = go * GPI + g_l;
+                const int c0 = (cb * CHK + ch_l) * 8;
+                const int t4 = tAa + 4 * g;
+                const bool gv = (g < NG) && (t4 >= 0) && (t4 < p.T);
+                const float* __restrict__ src = xb + (size_t)c0 * p.T + (gv ? t4 : 0);
+                float4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = gv ? __ldg(reinterpret_cast<const float4*>(src + (size_t)j * p.T)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g < NG) {
+                    uint8_t* pan = sm + (c0 / G::CPP) * APANEL;
+                    const int chunk = (c0 % G::CPP) / 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = 4 * g - sh + i;
+                        if (r >= 0 && r < RA1) {
+                            float w8[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float e = i == 0 ? v[j].x : (i == 1 ? v[j].y : (i == 2 ? v[j].z : v[j].w));
+                                w8[j] = lrelu01(e);
+                            }
+                            store_chunk8(pan + r * G::RB, swz_phase(r, G::RB), chunk, w8, 0xffffffffu);
+                        }
+                    }
+                }
+                if (p.red_out && gv) {
+                    const int o = t4 - t0;
+                    float* __restrict__ dst = ob + (size_t)c0 * p.T + t4;
+                    if (o >= 0 && o + 3 < TOUT) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { v[j].x *= p.alpha; v[j].y *= p.alpha; v[j].z *= p.alpha; v[j].w *= p.alpha; }
+                        if (acc_old) {
+                            float4 od[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) od[j] = *reinterpret_cast<const float4*>(dst + (size_t)j * p.T);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { v[j].x += od[j].x; v[j].y += od[j].y; v[j].z += od[j].z; v[j].w += od[j].w; }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dst + (size_t)j * p.T) = v[j];
+                    } else if (o + 3 >= 0 && o < TOUT) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (o + i >= 0 && o + i < TOUT) {
+                                    float* d = dst + (size_t)j * p.T + i;
+                                    *d = acc_old ? (*d + p.alpha * e[i]) : (p.alpha * e[i]);
+                                }
+                        }
+                    }
+                }
+            }
+            if (p.red_out) __threadfence();              // out = alpha*x must be in L2 before epilogue 2 adds to it
+        }
+        for (int r = tid; !TMA_IN && !p.vec4 && r < RA1; r += NWORK) {
             const int t = tA0 + r;
             const bool valid = (t >= 0) && (t < p.T);
             const float* __restrict__ xt = xb + (valid ? t : 0);
@@ -213,6 +316,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
             fence_proxy_async();
             mbar_arrive(bar_a);
         }
+        if (tid == 0) PAIR_TRACE(1);
 
         const int q = warp & 3, hsel = warp >> 2;
         const int rib = 32 * q + lane;                 // row inside a 128-row block == TMEM lane
@@ -224,6 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
         // (2) epilogue 1: mid = conv1 + b1 -> lrelu -> fp16 -> A2 (in place), zero outside [0,T)
         mbar_wait(bar_acc, 0);
         tc_fence_after();
+        if (tid == 0) PAIR_TRACE(2);
 #pragma unroll 1
         for (int mb = 0; mb < MB; ++mb) {
             const int row = mb * 128 + rib;
@@ -261,13 +366,50 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
         tc_fence_before();
         fence_proxy_async();
         mbar_arrive(bar_a);
+        if (tid == 0) PAIR_TRACE(3);
 
         // (3) epilogue 2: out = alpha*(conv2 + b2 + x) + beta*out_old
         mbar_wait(bar_acc, 1);
         tc_fence_after();
+        if (tid == 0) PAIR_TRACE(4);
         const bool has_beta = p.beta != 0.f;
+        if (p.red_out) {
+            // out already holds alpha*x (+ old): add alpha*(conv2 + b2) with fire-and-forget reductions
 #pragma unroll 1
-        for (int mb = 0; mb < MB; ++mb) {
+            for (int mb = 0; mb < MB; ++mb) {
+                const int o = mb * 128 + rib;
+                const int t = t0 + o;
+                const bool valid = (o < TOUT) && (t < p.T);
+                float* __restrict__ ot = ob + (valid ? t : 0);
+#pragma unroll
+                for (int cc = 0; cc < CH; cc += 2 * CG) {          // two column groups per TMEM round trip
+                    uint32_t r0[16], r1[16];
+                    const int c0 = cbase + cc, c1 = c0 + CG;
+                    const bool two = (cc + CG) < CH;
+                    if (CG == 16) { tmem_ld16(tlane + mb * C + c0, r0); if (two) tmem_ld16(tlane + mb * C + c1, r1); }
+                    else tmem_ld8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r0));
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            if (g == 1 && !two) break;
+                            const int cg0 = g ? c1 : c0;
+                            const uint32_t* rr = g ? r1 : r0;
+#pragma unroll
+                            for (int j4 = 0; j4 < CG; j4 += 4) {
+                                const float4 bq = *reinterpret_cast<const float4*>(sbias + C + cg0 + j4);
+                                atomicAdd(ot + (size_t)(cg0 + j4 + 0) * p.T, p.alpha * (__uint_as_float(rr[j4 + 0]) + bq.x));
+                                atomicAdd(ot + (size_t)(cg0 + j4 + 1) * p.T, p.alpha * (__uint_as_float(rr[j4 + 1]) + bq.y));
+                                atomicAdd(ot + (size_t)(cg0 + j4 + 2) * p.T, p.alpha * (__uint_as_float(rr[j4 + 2]) + bq.z));
+                                atomicAdd(ot + (size_t)(cg0 + j4 + 3) * p.T, p.alpha * (__uint_as_float(rr[j4 + 3]) + bq.w));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll 1
+        for (int mb = 0; !p.red_out && mb < MB; ++mb) {
             const int o = mb * 128 + rib;
             const int t = t0 + o;
             const bool valid = (o < TOUT) && (t < p.T);
@@ -311,11 +453,13 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
                 }
             }
         }
+        if (tid == 0) PAIR_TRACE(5);
         tc_fence_before();
     }
 
     // ---------------------------------------------------------------- teardown
     __syncthreads();
+    if (tid == 0) PAIR_TRACE(10);
     if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
@@ -375,6 +519,18 @@ int launch_pair_t2(const PairTC& a, cudaStream_t st) {
     p.w1 = static_cast<const uint8_t*>(a.w1); p.w2 = static_cast<const uint8_t*>(a.w2);
     p.b1 = a.b1; p.b2 = a.b2; p.T = a.T; p.k = a.k; p.dil = a.dil; p.alpha = a.alpha; p.beta = a.beta;
     p.a16_out = static_cast<__half*>(a.a16_out);
+    {
+        static const int env_vec4 = env_int("SVB_PAIR_VEC4", 1), env_red = env_int("SVB_PAIR_RED", 1);
+        const bool aligned = (a.T % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0);
+        p.vec4 = (!TMA_IN && env_vec4 && aligned) ? 1 : 0;
+        p.red_out = (p.vec4 && env_red && !a.a16_out && a.x != a.out && (a.beta == 0.f || a.beta == 1.f)) ? 1 : 0;
+        // tile period estimate (clk) for the first-wave de-phasing: two MMA phases at the shared-pipe rate + memory phases
+        static const int env_dephase = env_int("SVB_PAIR_DEPHASE", -1);
+        const int mma_clk = (C >= 128 ? C / 2 : (C == 64 ? 48 : 40)) * a.k * (C / 16) * MB;
+        const int grid_ctas = (int)(((a.T + (128 * MB - (a.k - 1)) - 1) / (128 * MB - (a.k - 1))) * a.B);
+        p.epoch = ++g_pair_epoch;
+        p.dephase_clk = (MINB < 2 || grid_ctas < 4 * 148 * MINB) ? 0 : (env_dephase >= 0 ? env_dephase : 2 * mma_clk + 24000);
+    }
     const int TOUT = 128 * MB - (a.k - 1);
     dim3 grid((a.T + TOUT - 1) / TOUT, a.B);
     pair_tc_kernel<C, MB, STAGE_KB, MINB, TMA_IN><<<grid, TC_THREADS, smem, st>>>(p, tmap);

@@ -68,6 +68,42 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---- phase skew of co-resident CTAs ------------------------------------------------------------------
+// Two CTAs that start together on one SM run the same phase sequence in lockstep: both issue MMAs at the same time
+// (sharing the tensor pipe) and both run their loads / epilogues at the same time (pipe idle) - measured with
+// tools/bench_rb.cu.  Sharing the pipe preserves whatever offset the two CTAs have, so the CTA that occupies the "odd"
+// slot of its SM delays its first MMA phase by about half a conv cycle, which puts the pair in anti-phase.
+// sm_ticket() returns how many CTAs of this launch (identified by `epoch`) started on this SM before the caller; its
+// parity identifies the slot as long as the two slots retire alternately.  The counter array needs no reset.
+__device__ __forceinline__ uint32_t sm_ticket(unsigned long long* ctr, uint32_t epoch) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* c = ctr + (smid & 255u);
+    while (true) {
+        const unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(c);
+        if ((uint32_t)(old >> 32) == epoch) return (uint32_t)atomicAdd(c, 1ull);
+        if (atomicCAS(c, old, ((unsigned long long)epoch << 32) | 1ull) == old) return 0u;
+    }
+}
+__device__ __forceinline__ void spin_clocks(int clk) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)clk) { __nanosleep(64); }
+}
+// Launch-wide de-phasing.  All CTAs of a wave start together, take the same time per phase and therefore hit HBM together
+// (every SM loads its tile at once, then every SM sits in its MMA phase with HBM idle) - measured: the load phase of the
+// pair kernel is bandwidth-bound only because of that burst.  The first-wave CTAs (ticket < ctas_per_sm on their SM) wait
+// a golden-ratio-hashed fraction of one tile period before starting; later CTAs inherit the offset of the slot they
+// replace, so the whole launch runs as a steady flow and the block scheduler balances the tail.
+__device__ __forceinline__ void dephase_first_wave(unsigned long long* ctr, uint32_t epoch, int period_clk, uint32_t ctas_per_sm) {
+    if (period_clk <= 0) return;
+    const uint32_t ticket = sm_ticket(ctr, epoch);
+    if (ticket >= ctas_per_sm) return;
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const uint32_t h = ((smid * ctas_per_sm + ticket) * 0x9E3779B1u) >> 16;          // 16 well-spread bits
+    spin_clocks((int)(((unsigned long long)h * (unsigned long long)period_clk) >> 16));
+}
+
 // ---- tcgen05 -------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {   // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
