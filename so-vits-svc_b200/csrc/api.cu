@@ -100,7 +100,8 @@ struct svb_ctx {
     DevBuf host_io;                // device staging for svb_infer_tail_host
     bool debug = false;
     std::map<std::string, DevBuf> dbg;
-    int opt_tma = 0;            // TMA-fed pair kernels (fp16 operand copies): measured neutral on B200, off by default
+    int opt_tma = 0;            // TMA-fed pair kernels (fp16 operand copies written by the previous pair): 13.5 vs 13.3 ms/step
+                                // against the 128-bit thread loader on B200, so off by default; env SVB_TC_TMA overrides
     int opt_fuse_rb = 1;        // fused ResBlock kernel for narrow stages
     int opt_fuse_maxc = 32;     // ... up to this channel count
     bool profile = false;
@@ -547,7 +548,7 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         }
         if ((rc = dbg_keep(ctx, "ups" + std::to_string(i), X, (size_t)B * S.Cout * Lout, st))) return rc;
         static const int fuse_rb = [] { const char* e = std::getenv("SVB_FUSE_RESBLOCK"); return e ? std::atoi(e) : 1; }();
-        static const int use_tma = [] { const char* e = std::getenv("SVB_TC_TMA"); return e ? std::atoi(e) : 1; }();
+        const int use_tma = ctx->opt_tma;
         void* a16[2] = {ws + pl.off_A16, ws + pl.off_B16};
         static const int fuse_maxc = [] { const char* e = std::getenv("SVB_FUSE_MAXC"); return e ? std::atoi(e) : 32; }();
         for (int j = 0; j < nk; ++j) {

