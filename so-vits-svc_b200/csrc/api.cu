@@ -103,7 +103,7 @@ struct svb_ctx {
     int opt_tma = 0;            // TMA-fed pair kernels (fp16 operand copies written by the previous pair): 13.5 vs 13.3 ms/step
                                 // against the 128-bit thread loader on B200, so off by default; env SVB_TC_TMA overrides
     int opt_fuse_rb = 1;        // fused ResBlock kernel for narrow stages
-    int opt_fuse_maxc = 32;     // ... up to this channel count
+    int opt_fuse_maxc = 64;     // ... up to this channel count (C = 64 fused: 12.6 vs 13.15 ms/step against the pair chain)
     bool profile = false;
     struct ProfEntry { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; double flops = 0, bytes = 0; };
     std::map<std::string, ProfEntry> prof;
@@ -547,10 +547,10 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
             launch_noise_conv_add(har, S.noise_w, S.noise_b, X, B, S.Cout, Lout, (int)N, S.noise_K, S.noise_s, S.noise_p, st);
         }
         if ((rc = dbg_keep(ctx, "ups" + std::to_string(i), X, (size_t)B * S.Cout * Lout, st))) return rc;
-        static const int fuse_rb = [] { const char* e = std::getenv("SVB_FUSE_RESBLOCK"); return e ? std::atoi(e) : 1; }();
+        const int fuse_rb = ctx->opt_fuse_rb;
         const int use_tma = ctx->opt_tma;
         void* a16[2] = {ws + pl.off_A16, ws + pl.off_B16};
-        static const int fuse_maxc = [] { const char* e = std::getenv("SVB_FUSE_MAXC"); return e ? std::atoi(e) : 32; }();
+        const int fuse_maxc = ctx->opt_fuse_maxc;
         for (int j = 0; j < nk; ++j) {
             const int k = c.resblock_kernel_sizes[j];
             if (ctx->precision == SVB_PREC_TC && !snake && fuse_rb && S.Cout <= fuse_maxc && S.c1[j * 3].w_tc) {

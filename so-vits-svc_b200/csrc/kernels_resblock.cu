@@ -188,27 +188,38 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
         }
         // (0) load x: fp32 -> TMEM residual, lrelu -> fp16 operand tile
         const int cbase = hsel * CH;
+        static_assert(MB % 2 == 0, "loader batches two row blocks");
 #pragma unroll 1
-        for (int mb = 0; mb < MB; ++mb) {
-            const int row = mb * 128 + rib;
-            const int t = tt0 + row;
-            const bool valid = (t >= 0) && (t < p.T);
-            const float* __restrict__ xt = xb + (valid ? t : 0);
-            uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
-            const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
+        for (int mb0 = 0; mb0 < MB; mb0 += 2) {        // two row blocks (2 x CH loads per thread) in flight at a time
+            float v[2][CH];
 #pragma unroll
-            for (int cc = 0; cc < CH; cc += CG) {
-                const int c0 = cbase + cc;
-                uint32_t r[16];
-                float v[16];
+            for (int u = 0; u < 2; ++u) {
+                const int t = tt0 + (mb0 + u) * 128 + rib;
+                const bool valid = (t >= 0) && (t < p.T);
+                const float* __restrict__ xt = xb + (valid ? t : 0) + (size_t)cbase * p.T;
 #pragma unroll
-                for (int j = 0; j < CG; ++j) { v[j] = valid ? __ldg(xt + (size_t)(c0 + j) * p.T) : 0.f; r[j] = __float_as_uint(v[j]); }
-                if (CG == 16) tmem_st16(tlane + mb * C + c0, r);
-                else tmem_st8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r));
+                for (int j = 0; j < CH; ++j) v[u][j] = valid ? __ldg(xt + (size_t)j * p.T) : 0.f;
+            }
 #pragma unroll
-                for (int j = 0; j < CG; ++j) v[j] = lrelu01(v[j]);
-                store_chunk8(prow, phase, c0 / 8, v, 0xffffffffu);
-                if (CG == 16) store_chunk8(prow, phase, c0 / 8 + 1, v + 8, 0xffffffffu);
+            for (int u = 0; u < 2; ++u) {
+                const int mb = mb0 + u;
+                const int row = mb * 128 + rib;
+                uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
+                const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
+#pragma unroll
+                for (int cc = 0; cc < CH; cc += CG) {
+                    const int c0 = cbase + cc;
+                    uint32_t r[16];
+#pragma unroll
+                    for (int j = 0; j < CG; ++j) r[j] = __float_as_uint(v[u][cc + j]);
+                    if (CG == 16) tmem_st16(tlane + mb * C + c0, r);
+                    else tmem_st8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r));
+                    float w[16];
+#pragma unroll
+                    for (int j = 0; j < CG; ++j) w[j] = lrelu01(v[u][cc + j]);
+                    store_chunk8(prow, phase, c0 / 8, w, 0xffffffffu);
+                    if (CG == 16) store_chunk8(prow, phase, c0 / 8 + 1, w + 8, 0xffffffffu);
+                }
             }
         }
         tmem_st_wait();
@@ -224,32 +235,40 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
             if (tid == 0) RB_TRACE(2 + 4 * q + 0);
             const float* __restrict__ bq_ = sbias + q * C;
             if ((q & 1) == 0) {
-                // ---- first conv of a pair: mid = lrelu(acc + b1) -> operand tile
+                // ---- first conv of a pair: mid = lrelu(acc + b1) -> operand tile (two row blocks per TMEM round trip)
 #pragma unroll 1
-                for (int mb = 0; mb < MB; ++mb) {
-                    const int row = mb * 128 + rib;
-                    const int t = tt0 + row;
-                    const uint32_t keep = ((t >= 0) && (t < p.T)) ? 0xffffffffu : 0u;
-                    uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
-                    const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
+                for (int mb0 = 0; mb0 < MB; mb0 += 2) {
+                    uint32_t r[2][CH];
 #pragma unroll
-                    for (int cc = 0; cc < CH; cc += CG) {
-                        const int c0 = cbase + cc;
-                        uint32_t r[16];
-                        if (CG == 16) tmem_ld16(tlane + ACC0 + mb * C + c0, r);
-                        else tmem_ld8(tlane + ACC0 + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r));
-                        tmem_ld_wait();
-                        float v[16];
+                    for (int u = 0; u < 2; ++u)
 #pragma unroll
-                        for (int j4 = 0; j4 < CG; j4 += 4) {
-                            const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
-                            v[j4 + 0] = lrelu01(__uint_as_float(r[j4 + 0]) + bb.x);
-                            v[j4 + 1] = lrelu01(__uint_as_float(r[j4 + 1]) + bb.y);
-                            v[j4 + 2] = lrelu01(__uint_as_float(r[j4 + 2]) + bb.z);
-                            v[j4 + 3] = lrelu01(__uint_as_float(r[j4 + 3]) + bb.w);
+                        for (int cc = 0; cc < CH; cc += CG) {
+                            if (CG == 16) tmem_ld16(tlane + ACC0 + (mb0 + u) * C + cbase + cc, reinterpret_cast<uint32_t(&)[16]>(r[u][cc]));
+                            else tmem_ld8(tlane + ACC0 + (mb0 + u) * C + cbase + cc, reinterpret_cast<uint32_t(&)[8]>(r[u][cc]));
                         }
-                        store_chunk8(prow, phase, c0 / 8, v, keep);
-                        if (CG == 16) store_chunk8(prow, phase, c0 / 8 + 1, v + 8, keep);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int row = (mb0 + u) * 128 + rib;
+                        const int t = tt0 + row;
+                        const uint32_t keep = ((t >= 0) && (t < p.T)) ? 0xffffffffu : 0u;
+                        uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
+                        const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
+#pragma unroll
+                        for (int cc = 0; cc < CH; cc += CG) {
+                            const int c0 = cbase + cc;
+                            float v[16];
+#pragma unroll
+                            for (int j4 = 0; j4 < CG; j4 += 4) {
+                                const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
+                                v[j4 + 0] = lrelu01(__uint_as_float(r[u][cc + j4 + 0]) + bb.x);
+                                v[j4 + 1] = lrelu01(__uint_as_float(r[u][cc + j4 + 1]) + bb.y);
+                                v[j4 + 2] = lrelu01(__uint_as_float(r[u][cc + j4 + 2]) + bb.z);
+                                v[j4 + 3] = lrelu01(__uint_as_float(r[u][cc + j4 + 3]) + bb.w);
+                            }
+                            store_chunk8(prow, phase, c0 / 8, v, keep);
+                            if (CG == 16) store_chunk8(prow, phase, c0 / 8 + 1, v + 8, keep);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -374,7 +393,7 @@ int launch_resblock_t(const ResblockTC& a, cudaStream_t st) {
         // first-wave de-phasing (tc_common.cuh): tile period estimate = six conv cycles (MMA at the shared-pipe rate +
         // epilogue) + load / store phases
         static const int env_skew = rb_env_int("SVB_RB_SKEW", -1);
-        static const int env_red = rb_env_int("SVB_RB_RED", 0);
+        static const int env_red = rb_env_int("SVB_RB_RED", 1);
         p.red_old = (env_red && a.beta == 1.f) ? 1 : 0;
         p.epoch = ++g_rb_epoch;
         const int mma_clk = (C <= 32 ? 40 : 48) * a.k * MB * (C / 16);

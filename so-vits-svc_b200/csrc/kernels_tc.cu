@@ -369,10 +369,61 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
         if (tid == 0) PAIR_TRACE(3);
 
         // (3) epilogue 2: out = alpha*(conv2 + b2 + x) + beta*out_old
+        const bool has_beta = p.beta != 0.f;
+        // residual loads are software-pipelined one column group ahead; the first group is requested BEFORE waiting for
+        // conv2, so its latency hides behind the MMAs (each group used to expose a full global-load round trip)
+        const bool add_old = p.beta == 1.f;            // xs accumulation: out += y as a fire-and-forget reduction, out is never read
+        const bool pf = !p.red_out && (!has_beta || add_old);
+        constexpr int QPB = CH / CG;                   // column groups per 128-row block (per warp half)
+        constexpr int NQ = MB * QPB;
+        float xa[16], xc[16];
+        auto issue_x = [&](int qq, float (&buf)[16]) {
+            const int o_ = (qq / QPB) * 128 + rib, t_ = t0 + o_;
+            const bool v_ = (o_ < TOUT) && (t_ < p.T);
+            const float* __restrict__ xs_ = xb + (v_ ? t_ : 0) + (size_t)(cbase + (qq % QPB) * CG) * p.T;
+#pragma unroll
+            for (int j = 0; j < CG; ++j) buf[j] = v_ ? __ldg(xs_ + (size_t)j * p.T) : 0.f;
+        };
+        if (pf) issue_x(0, xa);
         mbar_wait(bar_acc, 1);
         tc_fence_after();
         if (tid == 0) PAIR_TRACE(4);
-        const bool has_beta = p.beta != 0.f;
+        if (pf) {
+#pragma unroll
+            for (int qq = 0; qq < NQ; ++qq) {
+                const int mb = qq / QPB, c0 = cbase + (qq % QPB) * CG;
+                const int o = mb * 128 + rib;
+                const int t = t0 + o;
+                const bool valid = (o < TOUT) && (t < p.T);
+                float* __restrict__ ot = ob + (valid ? t : 0);
+                uint32_t r[16];
+                if (CG == 16) tmem_ld16(tlane + mb * C + c0, r);
+                else tmem_ld8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r));
+                if (qq + 1 < NQ) { if (qq & 1) issue_x(qq + 1, xa); else issue_x(qq + 1, xc); }
+                float (&xr)[16] = (qq & 1) ? xc : xa;
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int j4 = 0; j4 < CG; j4 += 4) {
+                        const float4 bq = *reinterpret_cast<const float4*>(sbias + C + c0 + j4);
+                        const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = j4 + e;
+                            const float y = p.alpha * (__uint_as_float(r[j]) + bb[e] + xr[j]);
+                            if (add_old) atomicAdd(ot + (size_t)(c0 + j) * p.T, y);
+                            else ot[(size_t)(c0 + j) * p.T] = y;
+                            xr[j] = lrelu01(y);
+                        }
+                    }
+                    if (p.a16_out) {
+                        uint4* dst = reinterpret_cast<uint4*>(p.a16_out + ((size_t)b * p.T + t) * C + c0);
+                        dst[0] = make_uint4(pack_h2(xr[0], xr[1]), pack_h2(xr[2], xr[3]), pack_h2(xr[4], xr[5]), pack_h2(xr[6], xr[7]));
+                        if (CG == 16) dst[1] = make_uint4(pack_h2(xr[8], xr[9]), pack_h2(xr[10], xr[11]), pack_h2(xr[12], xr[13]), pack_h2(xr[14], xr[15]));
+                    }
+                }
+            }
+        }
         if (p.red_out) {
             // out already holds alpha*x (+ old): add alpha*(conv2 + b2) with fire-and-forget reductions
 #pragma unroll 1
@@ -409,7 +460,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
             }
         }
 #pragma unroll 1
-        for (int mb = 0; !p.red_out && mb < MB; ++mb) {
+        for (int mb = 0; !p.red_out && !pf && mb < MB; ++mb) {
             const int o = mb * 128 + rib;
             const int t = t0 + o;
             const bool valid = (o < TOUT) && (t < p.T);

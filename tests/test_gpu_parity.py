@@ -260,20 +260,28 @@ def test_schedule_options_are_equivalent(cfg, sd, eng):
     z_p, g, f0, noise = _case(cfg, sd, B, T)
     args = [t.to(DEV) for t in (z_p, g, f0, noise["rand_ini"], noise["har_noise"])]
     eng.set_precision("tc")
-    base = eng.infer_tail(*args)                  # defaults: thread-staged 128-bit loader, fused ResBlocks for C <= 32
+
+    def run():
+        n0 = eng.launch_count()
+        out = eng.infer_tail(*args)
+        return out, eng.launch_count() - n0
+
+    base, n_base = run()                          # defaults: thread-staged 128-bit loader, fused ResBlocks for C <= 64
     eng.set_option("tma", 1)                      # pairs 2 and 3 of a ResBlock load their operand tile by TMA
-    tma = eng.infer_tail(*args)
+    tma, n_tma = run()
     eng.set_option("fuse_resblock", 0)
-    pairs_tma = eng.infer_tail(*args)
+    pairs_tma, n_pairs_tma = run()
     eng.set_option("tma", 0)
-    pairs = eng.infer_tail(*args)
+    pairs, n_pairs = run()
     eng.set_option("fuse_resblock", 1)
-    eng.set_option("fuse_maxc", 64)
-    fused64 = eng.infer_tail(*args)
     eng.set_option("fuse_maxc", 32)
+    fused32, n_f32 = run()
+    eng.set_option("fuse_maxc", 64)
+    # the options really select different schedules: 9 pair launches replace each fused ResBlock launch of 3
+    assert n_pairs == n_pairs_tma and n_pairs > n_f32 > n_base, (n_base, n_tma, n_pairs, n_f32)
     eng.set_precision("fp32")
     ref = eng.infer_tail(*args)
-    for name, o in (("default", base), ("tma", tma), ("pairs-only", pairs), ("pairs-only+tma", pairs_tma), ("fused<=64", fused64)):
+    for name, o in (("default", base), ("tma", tma), ("pairs-only", pairs), ("pairs-only+tma", pairs_tma), ("fused<=32", fused32)):
         err = float((o - ref).abs().max())
         print(f"[parity] schedule {name}: L-inf vs fp32 path = {err:.3e}")
         assert err < TC_TOL
