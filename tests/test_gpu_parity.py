@@ -262,9 +262,9 @@ def test_schedule_options_are_equivalent(cfg, sd, eng):
     eng.set_precision("tc")
 
     def run():
-        n0 = eng.launch_count()
+        n0 = eng.launch_count
         out = eng.infer_tail(*args)
-        return out, eng.launch_count() - n0
+        return out, eng.launch_count - n0
 
     base, n_base = run()                          # defaults: thread-staged 128-bit loader, fused ResBlocks for C <= 64
     eng.set_option("tma", 1)                      # pairs 2 and 3 of a ResBlock load their operand tile by TMA
