@@ -159,6 +159,16 @@ SVB_API int svb_debug_resblock(svb_ctx* ctx, int stage, int j, const float* x, f
  * (bench.py's roofline).  Re-enabling clears the counters. */
 SVB_API int svb_profile_enable(svb_ctx* ctx, int on);
 SVB_API int svb_profile_read(svb_ctx* ctx, const char* name, double* total_ms, int64_t* count, double* flops, double* bytes);
+/* ---- enc_p prefix helpers: fused element-wise tails of a transformer layer, time-major [B,L,C] fp32,
+ * no context needed.  Reference: modules/attentions.py:95-106 (x = norm(x + y)), :317-363 (FFN with k-tap convs),
+ * modules/modules.py:23-35 (LayerNorm over channels).
+ *   svb_prefix_add_ln_im2col : y = LayerNorm_C(x + r); if cols != NULL also cols[b,l,t*C+c] = y[b, l+t-(k-1)/2, c] (0 outside)
+ *   svb_prefix_ffn_tail      : y = LayerNorm_C(x + bias + sum_t ya[b, l+t-(k-1)/2, t*C+c])      (ya: [B,L,k*C])           */
+SVB_API int svb_prefix_add_ln_im2col(const float* x, const float* r, const float* gamma, const float* beta, float eps, float* y, float* cols,
+                                     int B, int L, int C, int k, void* stream);
+SVB_API int svb_prefix_ffn_tail(const float* ya, const float* x, const float* bias, const float* gamma, const float* beta, float eps, float* y,
+                                int B, int L, int C, int k, void* stream);
+
 SVB_API const char* svb_version(void);
 
 #ifdef __cplusplus

@@ -1,0 +1,132 @@
+// Fused element-wise tails of the enc_p transformer layers (reference modules/attentions.py:95-106,
+// 317-363 and modules/modules.py:23-35).  The GEMMs of the prefix stay on cuBLAS; what is fused here is the chain of
+// small memory-bound kernels around them, on time-major [B,L,C] fp32 activations:
+//   add_ln_im2col : y = LayerNorm_C(x + r);  cols[b,l,t*C+c] = y[b, l+t-(k-1)/2, c]  (zero outside [0,L))
+//                   = residual add + LayerNorm + F.pad + the k shifted views concatenated for the FFN's first conv
+//   ffn_tail      : y = LayerNorm_C(x + bias + sum_t ya[b, l+t-(k-1)/2, t*C + c])
+//                   = the shift-and-add of the FFN's second conv run as one GEMM against the k stacked tap matrices,
+//                     + bias + residual add + LayerNorm
+// One warp per (b,l) row, mean / variance by two-pass warp reductions in fp32 (torch: same statistics, eps inside sqrt).
+#include "kernels.h"
+#include "../../include/sovits_b200.h"
+
+namespace svb {
+namespace {
+
+constexpr int PF_MAXV = 8;      // values per lane: C <= 256
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) add_ln_im2col_kernel(const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, float* __restrict__ y, float* __restrict__ cols,
+                                                            int B, int L, int C, int k) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= (long long)B * L) return;
+    const int l = (int)(row % L);
+    const int nv = (C + 31) / 32;
+    float v[PF_MAXV];
+    const float* xr = x + row * C;
+    const float* rr = r + row * C;
+#pragma unroll
+    for (int i = 0; i < PF_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = (i < nv && c < C) ? xr[c] + rr[c] : 0.f;
+    }
+    // channels beyond C contribute 0 to the sums only if they are excluded: handle C % 32 != 0 by masking
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PF_MAXV; ++i) if (lane + 32 * i < C) s += v[i];
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PF_MAXV; ++i) if (lane + 32 * i < C) { const float d = v[i] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    const int h = (k - 1) / 2;
+#pragma unroll
+    for (int i = 0; i < PF_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) {
+            const float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+            y[row * C + c] = o;
+            if (cols) {
+                // y[l] is tap t of output row l - t + h
+                for (int t = 0; t < k; ++t) {
+                    const int lo = l - t + h;
+                    if (lo >= 0 && lo < L) cols[(row + (lo - l)) * (long long)(k * C) + t * C + c] = o;
+                }
+                // zero padding: taps of this output row that fall outside [0,L)
+                for (int t = 0; t < k; ++t) {
+                    const int li = l + t - h;
+                    if (li < 0 || li >= L) cols[row * (long long)(k * C) + t * C + c] = 0.f;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ffn_tail_kernel(const float* __restrict__ ya, const float* __restrict__ x, const float* __restrict__ bias,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ y,
+                                                       int B, int L, int C, int k) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= (long long)B * L) return;
+    const int l = (int)(row % L);
+    const int h = (k - 1) / 2;
+    float v[PF_MAXV];
+#pragma unroll
+    for (int i = 0; i < PF_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        float a = 0.f;
+        if (c < C) {
+            a = x[row * C + c] + bias[c];
+            for (int t = 0; t < k; ++t) {
+                const int li = l + t - h;
+                if (li >= 0 && li < L) a += ya[(row + (li - l)) * (long long)(k * C) + t * C + c];
+            }
+        }
+        v[i] = a;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PF_MAXV; ++i) if (lane + 32 * i < C) s += v[i];
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PF_MAXV; ++i) if (lane + 32 * i < C) { const float d = v[i] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < PF_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) y[row * C + c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    }
+}
+
+}  // namespace
+}  // namespace svb
+
+extern "C" {
+
+int svb_prefix_add_ln_im2col(const float* x, const float* r, const float* gamma, const float* beta, float eps, float* y, float* cols, int B, int L, int C,
+                             int k, void* stream) {
+    if (!x || !r || !gamma || !beta || !y || B <= 0 || L <= 0 || C <= 0 || C > 32 * svb::PF_MAXV || k < 1 || k > 7) return SVB_ERR_INVALID_ARG;
+    const long long rows = (long long)B * L;
+    svb::add_ln_im2col_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, r, gamma, beta, eps, y, cols, B, L, C, k);
+    svb::launch_counter()++;
+    return cudaGetLastError() == cudaSuccess ? SVB_OK : SVB_ERR_CUDA;
+}
+
+int svb_prefix_ffn_tail(const float* ya, const float* x, const float* bias, const float* gamma, const float* beta, float eps, float* y, int B, int L, int C,
+                        int k, void* stream) {
+    if (!ya || !x || !bias || !gamma || !beta || !y || B <= 0 || L <= 0 || C <= 0 || C > 32 * svb::PF_MAXV || k < 1 || k > 7) return SVB_ERR_INVALID_ARG;
+    const long long rows = (long long)B * L;
+    svb::ffn_tail_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(ya, x, bias, gamma, beta, eps, y, B, L, C, k);
+    svb::launch_counter()++;
+    return cudaGetLastError() == cudaSuccess ? SVB_OK : SVB_ERR_CUDA;
+}
+
+}  // extern "C"

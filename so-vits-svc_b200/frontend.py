@@ -9,10 +9,58 @@ pad/reshape skewing (attentions.py:275-303) — same sums, far less memory traff
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 from torch import nn
 from torch.nn import functional as F
+
+
+def _cached(mod: nn.Module, name: str, srcs, fn):
+    """Derived weight matrices (tap-stacked conv weights, the fused q/k/v projection) are rebuilt only when a source
+    parameter was re-allocated or written (load_state_dict, .to(), .half())."""
+    key = tuple((t.data_ptr(), t._version, t.dtype) for t in srcs)
+    cache = mod.__dict__.setdefault("_svb_cache", {})
+    hit = cache.get(name)
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            val = fn()
+        cache[name] = (key, val)
+        return val
+    return hit[1]
+
+
+def _fused_tails(x: torch.Tensor):
+    """libsovits_b200 handle when the fused layer tails (csrc/kernels_prefix.cu) apply: CUDA fp32 inference."""
+    if not x.is_cuda or x.dtype != torch.float32 or torch.is_grad_enabled() or os.environ.get("SVB_PREFIX_FUSED", "1") == "0":
+        return None
+    from .lib import load_library
+    return load_library()
+
+
+def _add_ln_im2col(lib, x, r, norm, k):
+    """y = LayerNorm(x + r) and the k shifted copies of y side by side ([B,L,k*C], zero padded) in one kernel."""
+    B, L, C = x.shape
+    x, r = x.contiguous(), r.contiguous()
+    y = torch.empty_like(x)
+    cols = torch.empty((B, L, k * C), dtype=x.dtype, device=x.device)
+    rc = lib.svb_prefix_add_ln_im2col(x.data_ptr(), r.data_ptr(), norm.gamma.data_ptr(), norm.beta.data_ptr(), float(norm.eps),
+                                      y.data_ptr(), cols.data_ptr(), B, L, C, k, torch.cuda.current_stream(x.device).cuda_stream)
+    if rc != 0:
+        raise RuntimeError(f"svb_prefix_add_ln_im2col failed: {lib.svb_strerror(rc).decode()}")
+    return y, cols
+
+
+def _ffn_tail(lib, ya, x, bias, norm, k):
+    """LayerNorm(x + bias + shift-and-add of the k tap slices of ya) in one kernel."""
+    B, L, C = x.shape
+    ya, x = ya.contiguous(), x.contiguous()
+    y = torch.empty_like(x)
+    rc = lib.svb_prefix_ffn_tail(ya.data_ptr(), x.data_ptr(), bias.data_ptr(), norm.gamma.data_ptr(), norm.beta.data_ptr(), float(norm.eps),
+                                 y.data_ptr(), B, L, C, k, torch.cuda.current_stream(x.device).cuda_stream)
+    if rc != 0:
+        raise RuntimeError(f"svb_prefix_ffn_tail failed: {lib.svb_strerror(rc).decode()}")
+    return y
 
 
 def f0_to_coarse(f0: torch.Tensor) -> torch.Tensor:
@@ -99,11 +147,17 @@ class WindowedRelAttention(nn.Module):
         """x: [B,T,C] -> [B,T,C]."""
         B, L, D = x.shape
         h, dk, w = self.n_heads, self.dk, self.window
-        wqkv = torch.cat([self.conv_q.weight[:, :, 0], self.conv_k.weight[:, :, 0], self.conv_v.weight[:, :, 0]], 0)
-        bqkv = torch.cat([self.conv_q.bias, self.conv_k.bias, self.conv_v.bias], 0)
+        scale = 1.0 / math.sqrt(dk)
+        srcs = (self.conv_q.weight, self.conv_k.weight, self.conv_v.weight, self.conv_q.bias, self.conv_k.bias, self.conv_v.bias)
+        if torch.is_grad_enabled():
+            wqkv = torch.cat([self.conv_q.weight[:, :, 0] * scale, self.conv_k.weight[:, :, 0], self.conv_v.weight[:, :, 0]], 0)
+            bqkv = torch.cat([self.conv_q.bias * scale, self.conv_k.bias, self.conv_v.bias], 0)
+        else:       # one projection for q, k, v with the 1/sqrt(dk) of attentions.py:243 folded into the q rows
+            wqkv, bqkv = _cached(self, "qkv", srcs, lambda: (
+                torch.cat([self.conv_q.weight[:, :, 0] * scale, self.conv_k.weight[:, :, 0], self.conv_v.weight[:, :, 0]], 0).contiguous(),
+                torch.cat([self.conv_q.bias * scale, self.conv_k.bias, self.conv_v.bias], 0).contiguous()))
         qkv = F.linear(x, wqkv, bqkv).view(B, L, 3, h, dk).permute(2, 0, 3, 1, 4)      # [3,B,h,L,dk]
-        q = qkv[0] * (1.0 / math.sqrt(dk))
-        k, v = qkv[1], qkv[2]
+        q, k, v = qkv[0], qkv[1], qkv[2]
         scores = q @ k.transpose(-2, -1)                                                  # [B,h,L,L]
         idx, valid = self._band(L, x.device)
         nb = 2 * w + 1
@@ -149,6 +203,21 @@ class ConvFFN(nn.Module):
         wmat = conv.weight.permute(0, 2, 1).reshape(cout, -1)                             # [F, k*C]
         return F.linear(cols, wmat, conv.bias)
 
+    def hidden_from_cols(self, cols):
+        """relu(conv_1) from the k shifted copies of the input laid side by side ([B,L,k*C], tap-major)."""
+        conv = self.conv_1
+        wmat = _cached(self, "w1", (conv.weight,), lambda: conv.weight.permute(0, 2, 1).reshape(conv.weight.shape[0], -1).contiguous())
+        B, L, KC = cols.shape
+        if hasattr(torch, "_addmm_activation"):        # bias + ReLU in the GEMM epilogue (cuBLASLt)
+            return torch._addmm_activation(conv.bias, cols.view(B * L, KC), wmat.t(), use_gelu=False).view(B, L, -1)
+        return torch.relu_(F.linear(cols, wmat, conv.bias))
+
+    def stacked_out(self, hid):
+        """conv_2 as ONE GEMM against the k tap matrices stacked along the output: [B,L,k*Cout], tap-major (no bias)."""
+        conv = self.conv_2
+        wst = _cached(self, "w2", (conv.weight,), lambda: conv.weight.permute(2, 0, 1).reshape(-1, conv.weight.shape[1]).contiguous())
+        return F.linear(hid, wst)
+
     def forward(self, x, x_mask=None):
         """x: [B,T,C]; x_mask: [B,T,1] or None (all ones)."""
         if x_mask is not None:
@@ -184,8 +253,15 @@ class RelEncoder(nn.Module):
         x = x.transpose(1, 2).contiguous()
         if mt is not None:
             x = x * mt
+        lib = _fused_tails(x) if mt is None else None
         with _TF32Like():
             for attn, n1, ffn, n2 in zip(self.attn_layers, self.norm_layers_1, self.ffn_layers, self.norm_layers_2):
+                if lib is not None:
+                    # equal-length batch on the GPU: the element-wise tails of the layer run as two fused kernels
+                    # (csrc/kernels_prefix.cu), the GEMMs stay on cuBLAS
+                    x1, cols = _add_ln_im2col(lib, x, attn(x, None), n1, ffn.kernel_size)
+                    x = _ffn_tail(lib, ffn.stacked_out(ffn.hidden_from_cols(cols)), x1, ffn.conv_2.bias, n2, ffn.kernel_size)
+                    continue
                 x = n1(x + attn(x, attn_mask))
                 x = n2(x + ffn(x, mt))
         if mt is not None:

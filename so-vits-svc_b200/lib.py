@@ -72,6 +72,10 @@ SIGNATURES = {
     "svb_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "svb_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "svb_prefix_add_ln_im2col": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "svb_prefix_ffn_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "svb_version": (C.c_char_p, []),
 }
 

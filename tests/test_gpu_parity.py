@@ -370,3 +370,46 @@ def test_error_paths(cfg, sd):
     with pytest.raises(L.SvbError):
         e.flow_reverse(z, g_bad)
     e.close()
+
+
+def test_prefix_fused_tails_match_torch(monkeypatch):
+    """the fused element-wise tails of an enc_p layer (csrc/kernels_prefix.cu) against the torch ops they
+    replace, and the whole RelEncoder with and without them (odd lengths, boundaries of the k-tap shifts)."""
+    import torch.nn.functional as F
+    from sovits_b200 import frontend as fe
+    from sovits_b200.lib import load_library
+    lib = load_library()
+    g = torch.Generator().manual_seed(11)
+    B, L, C, k = 3, 37, 192, 3
+    x = torch.randn((B, L, C), generator=g).to(DEV)
+    r = torch.randn((B, L, C), generator=g).to(DEV)
+    norm = fe.ChannelNormT(C).to(DEV)
+    with torch.no_grad():
+        norm.gamma.copy_(torch.randn(C, generator=g).to(DEV)); norm.beta.copy_(torch.randn(C, generator=g).to(DEV))
+        y, cols = fe._add_ln_im2col(lib, x, r, norm, k)
+        want = norm(x + r)
+        wp = F.pad(want, (0, 0, (k - 1) // 2, k // 2))
+        wcols = torch.cat([wp[:, t:t + L] for t in range(k)], dim=-1)
+        assert float((y - want).abs().max()) < 2e-5
+        assert float((cols - wcols).abs().max()) < 2e-5
+        ya = torch.randn((B, L, k * C), generator=g).to(DEV)
+        bias = torch.randn(C, generator=g).to(DEV)
+        got = fe._ffn_tail(lib, ya, x, bias, norm, k)
+        yap = F.pad(ya, (0, 0, (k - 1) // 2, k // 2))
+        acc = sum(yap[:, t:t + L, t * C:(t + 1) * C] for t in range(k))
+        want2 = norm(x + acc + bias)
+        assert float((got - want2).abs().max()) < 5e-5
+        enc = fe.RelEncoder(192, 768, 2, 3, 3).to(DEV).eval()
+        xin = torch.randn((2, 192, 75), generator=g).to(DEV)
+        mask = torch.ones(2, 1, 75, device=DEV)
+        prev = torch.backends.cudnn.conv.fp32_precision
+        torch.backends.cudnn.conv.fp32_precision = "ieee"
+        try:
+            fused = enc(xin, mask, True)
+            monkeypatch.setenv("SVB_PREFIX_FUSED", "0")
+            plain = enc(xin, mask, True)
+        finally:
+            torch.backends.cudnn.conv.fp32_precision = prev
+        err = float((fused - plain).abs().max())
+        print(f"[parity] enc_p fused tails vs torch ops: L-inf {err:.2e}")
+        assert err < 1e-4
