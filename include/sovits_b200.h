@@ -169,6 +169,13 @@ SVB_API int svb_prefix_add_ln_im2col(const float* x, const float* r, const float
 SVB_API int svb_prefix_ffn_tail(const float* ya, const float* x, const float* bias, const float* gamma, const float* beta, float eps, float* y,
                                 int B, int L, int C, int k, void* stream);
 
+/*   svb_prefix_rel_softmax   : scores[rows,L] (rows = B*heads*L, row i of each [L,L] matrix) += relk on the 2w+1 band, softmax
+ *                              over the last axis in place, pband[rows,2w+1] = band of p   (attentions.py:246-266)
+ *   svb_prefix_attn_merge    : y[B,L,H*dk] = merge_heads(out[B,H,L,dk] + pband @ embv[2w+1,dk])  (attentions.py:262-267)      */
+SVB_API int svb_prefix_rel_softmax(float* scores, const float* relk, float* pband, int rows, int L, int window, void* stream);
+SVB_API int svb_prefix_attn_merge(const float* out, const float* pband, const float* embv, float* y, int B, int H, int L, int dk, int nb,
+                                  void* stream);
+
 SVB_API const char* svb_version(void);
 
 #ifdef __cplusplus

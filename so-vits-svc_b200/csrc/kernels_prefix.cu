@@ -6,6 +6,8 @@
 //   ffn_tail      : y = LayerNorm_C(x + bias + sum_t ya[b, l+t-(k-1)/2, t*C + c])
 //                   = the shift-and-add of the FFN's second conv run as one GEMM against the k stacked tap matrices,
 //                     + bias + residual add + LayerNorm
+//   rel_softmax   : band add of the relative-key logits + softmax + band extraction of p  (one block per attention row)
+//   attn_merge    : p@v + relative-value term, heads merged back to [B,L,H*dk]
 // One warp per (b,l) row, mean / variance by two-pass warp reductions in fp32 (torch: same statistics, eps inside sqrt).
 #include "kernels.h"
 #include "../../include/sovits_b200.h"
@@ -106,6 +108,68 @@ __global__ void __launch_bounds__(256) ffn_tail_kernel(const float* __restrict__
     }
 }
 
+
+// scores[row, j] += relk[row, j - i + w] on the (2w+1)-wide band (attentions.py:246-250, the relative-key logits), softmax
+// over j (attentions.py:259), probabilities written back in place and the band of p returned for the relative-value term
+// (attentions.py:262-266).  One block per row (b,h,i); the row lives in shared memory.
+__global__ void __launch_bounds__(256) rel_softmax_kernel(float* __restrict__ scores, const float* __restrict__ relk, float* __restrict__ pband, int L, int w) {
+    extern __shared__ float srow[];
+    __shared__ float red[8];
+    const long long row = blockIdx.x;
+    const int i = (int)(row % L);
+    const int nb = 2 * w + 1;
+    float* sr = scores + row * L;
+    const float* rk = relk + row * nb;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float m = -INFINITY;
+    for (int j = tid; j < L; j += 256) {
+        float v = sr[j];
+        const int r = j - i + w;
+        if (r >= 0 && r < nb) v += rk[r];
+        srow[j] = v;
+        m = fmaxf(m, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[wid] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) m = fmaxf(m, red[q]);
+    __syncthreads();
+    float s = 0.f;
+    for (int j = tid; j < L; j += 256) { const float e = __expf(srow[j] - m); srow[j] = e; s += e; }
+    s = warp_sum(s);
+    if (lane == 0) red[wid] = s;
+    __syncthreads();
+    s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q];
+    const float inv = 1.f / s;
+    for (int j = tid; j < L; j += 256) sr[j] = srow[j] * inv;
+    if (tid < nb) {
+        const int j = i + tid - w;
+        pband[row * nb + tid] = (j >= 0 && j < L) ? srow[j] * inv : 0.f;
+    }
+}
+
+// y[b,l,h*dk+d] = out[b,h,l,d] + sum_r pband[b,h,l,r] * embv[r,d]: the relative-value term (attentions.py:262-266) added to
+// p@v and the heads merged back to time-major [B,L,H*dk] (attentions.py:267) in one pass.
+__global__ void __launch_bounds__(256) attn_merge_kernel(const float* __restrict__ out, const float* __restrict__ pband, const float* __restrict__ embv,
+                                                         float* __restrict__ y, int B, int H, int L, int dk, int nb) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long total = (long long)B * L * H * dk;
+    if (idx >= total) return;
+    const int d = (int)(idx % dk);
+    const int h = (int)((idx / dk) % H);
+    const int l = (int)((idx / ((long long)dk * H)) % L);
+    const int b = (int)(idx / ((long long)dk * H * L));
+    const long long rowp = ((long long)b * H + h) * L + l;
+    float a = out[rowp * dk + d];
+    for (int r = 0; r < nb; ++r) a = fmaf(pband[rowp * nb + r], embv[r * dk + d], a);
+    y[idx] = a;
+}
+
 }  // namespace
 }  // namespace svb
 
@@ -125,6 +189,21 @@ int svb_prefix_ffn_tail(const float* ya, const float* x, const float* bias, cons
     if (!ya || !x || !bias || !gamma || !beta || !y || B <= 0 || L <= 0 || C <= 0 || C > 32 * svb::PF_MAXV || k < 1 || k > 7) return SVB_ERR_INVALID_ARG;
     const long long rows = (long long)B * L;
     svb::ffn_tail_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(ya, x, bias, gamma, beta, eps, y, B, L, C, k);
+    svb::launch_counter()++;
+    return cudaGetLastError() == cudaSuccess ? SVB_OK : SVB_ERR_CUDA;
+}
+
+int svb_prefix_rel_softmax(float* scores, const float* relk, float* pband, int rows, int L, int window, void* stream) {
+    if (!scores || !relk || !pband || rows <= 0 || L <= 0 || window < 0 || 2 * window + 1 > 256 || L > 12000) return SVB_ERR_INVALID_ARG;
+    svb::rel_softmax_kernel<<<(unsigned)rows, 256, (size_t)L * sizeof(float), static_cast<cudaStream_t>(stream)>>>(scores, relk, pband, L, window);
+    svb::launch_counter()++;
+    return cudaGetLastError() == cudaSuccess ? SVB_OK : SVB_ERR_CUDA;
+}
+
+int svb_prefix_attn_merge(const float* out, const float* pband, const float* embv, float* y, int B, int H, int L, int dk, int nb, void* stream) {
+    if (!out || !pband || !embv || !y || B <= 0 || H <= 0 || L <= 0 || dk <= 0 || nb <= 0) return SVB_ERR_INVALID_ARG;
+    const long long total = (long long)B * L * H * dk;
+    svb::attn_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, pband, embv, y, B, H, L, dk, nb);
     svb::launch_counter()++;
     return cudaGetLastError() == cudaSuccess ? SVB_OK : SVB_ERR_CUDA;
 }

@@ -159,6 +159,24 @@ class WindowedRelAttention(nn.Module):
         qkv = F.linear(x, wqkv, bqkv).view(B, L, 3, h, dk).permute(2, 0, 3, 1, 4)      # [3,B,h,L,dk]
         q, k, v = qkv[0], qkv[1], qkv[2]
         scores = q @ k.transpose(-2, -1)                                                  # [B,h,L,L]
+        lib = _fused_tails(x) if attn_mask is None else None
+        if lib is not None:
+            # equal-length batch on the GPU: band add + softmax + band extraction, then p@v + relative values + head merge,
+            # as two fused kernels (csrc/kernels_prefix.cu) around the cuBLAS GEMMs
+            nb_ = 2 * w + 1
+            relk = (q @ self.emb_rel_k[0].t()).contiguous()                               # [B,h,L,2w+1]
+            pband = torch.empty_like(relk)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            rc = lib.svb_prefix_rel_softmax(scores.data_ptr(), relk.data_ptr(), pband.data_ptr(), B * h * L, L, w, stream)
+            if rc != 0:
+                raise RuntimeError(f"svb_prefix_rel_softmax failed: {lib.svb_strerror(rc).decode()}")
+            pv = (scores @ v).contiguous()                                                # [B,h,L,dk]
+            merged = torch.empty((B, L, D), dtype=x.dtype, device=x.device)
+            embv = self.emb_rel_v[0].contiguous()
+            rc = lib.svb_prefix_attn_merge(pv.data_ptr(), pband.data_ptr(), embv.data_ptr(), merged.data_ptr(), B, h, L, dk, nb_, stream)
+            if rc != 0:
+                raise RuntimeError(f"svb_prefix_attn_merge failed: {lib.svb_strerror(rc).decode()}")
+            return F.linear(merged, self.conv_o.weight[:, :, 0], self.conv_o.bias)
         idx, valid = self._band(L, x.device)
         nb = 2 * w + 1
         rel_k = (q @ self.emb_rel_k[0].t()) * valid                                       # [B,h,L,2w+1]

@@ -76,6 +76,9 @@ SIGNATURES = {
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "svb_prefix_ffn_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "svb_prefix_rel_softmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "svb_prefix_attn_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p]),
     "svb_version": (C.c_char_p, []),
 }
 
