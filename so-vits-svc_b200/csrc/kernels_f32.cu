@@ -310,37 +310,58 @@ void launch_snake_alias(const float* x, float* y, const float* ealpha, const flo
 // =====================================================================================================
 // conv_post: leaky_relu(slope) -> Conv1d(C->1, K, pad (K-1)/2) -> tanh
 // =====================================================================================================
-__global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w, float bias,
+// 128 threads x 4 consecutive outputs: the lrelu'd input window of a thread (4 + K - 1 <= 12 samples per channel) is read
+// from shared memory with three vector loads and reused for 4*K FMAs, so the kernel is bound by the single HBM pass over
+// the stage-4 tensor instead of by shared-memory loads (was 2 LDS per FMA).
+constexpr int CP_TT = 512, CP_PITCH = CP_TT + 8, CP_MAXK = 9;
+__global__ void __launch_bounds__(128) conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w, float bias,
                                                         float* __restrict__ wav, int C, int N, int K, float slope) {
-    extern __shared__ float sm[];
-    const int TT = 256;
+    extern __shared__ __align__(16) float sm[];
     const int pad = (K - 1) / 2;
-    const int pitch = TT + K - 1;
-    float* xs = sm;               // [C][pitch]
-    float* wsm = sm + C * pitch;  // [C][K]
-    const int b = blockIdx.y, n0 = blockIdx.x * TT;
+    float* xs = sm;                  // [C][CP_PITCH]
+    float* wsm = sm + C * CP_PITCH;  // [C][K]
+    const int b = blockIdx.y, n0 = blockIdx.x * CP_TT;
     const float* xb = x + (long long)b * C * N;
-    for (int idx = threadIdx.x; idx < C * pitch; idx += blockDim.x) {
-        int c = idx / pitch, j = idx - c * pitch;
-        int n = n0 + j - pad;
-        float v = (n >= 0 && n < N) ? xb[(long long)c * N + n] : 0.f;
-        xs[idx] = v > 0.f ? v : v * slope;
+    for (int c = 0; c < C; ++c) {
+        const float* xc = xb + (long long)c * N;
+        for (int j = threadIdx.x; j < CP_PITCH; j += 128) {
+            const int n = n0 + j - pad;
+            const float v = (n >= 0 && n < N) ? __ldg(xc + n) : 0.f;
+            xs[c * CP_PITCH + j] = fmaxf(v, v * slope);
+        }
     }
-    for (int idx = threadIdx.x; idx < C * K; idx += blockDim.x) wsm[idx] = w[idx];
+    for (int idx = threadIdx.x; idx < C * K; idx += 128) wsm[idx] = w[idx];
     __syncthreads();
-    int n = n0 + threadIdx.x;
-    if (n >= N) return;
-    float acc = bias;
-    for (int c = 0; c < C; ++c)
-        for (int k = 0; k < K; ++k) acc = fmaf(wsm[c * K + k], xs[c * pitch + threadIdx.x + k], acc);
-    wav[(long long)b * N + n] = tanhf(acc);
+    const int o = 4 * threadIdx.x;
+    float acc[4] = {bias, bias, bias, bias};
+    for (int c = 0; c < C; ++c) {
+        const float4 a0 = *reinterpret_cast<const float4*>(xs + c * CP_PITCH + o);
+        const float4 a1 = *reinterpret_cast<const float4*>(xs + c * CP_PITCH + o + 4);
+        const float4 a2 = *reinterpret_cast<const float4*>(xs + c * CP_PITCH + o + 8);
+        const float win[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+#pragma unroll
+        for (int k = 0; k < CP_MAXK; ++k) {
+            if (k < K) {
+                const float wk = wsm[c * K + k];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = fmaf(wk, win[i + k], acc[i]);
+            }
+        }
+    }
+    const int n = n0 + o;
+    float* dst = wav + (long long)b * N + n;
+    if (n + 3 < N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+        *reinterpret_cast<float4*>(dst) = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (n + i < N) dst[i] = tanhf(acc[i]);
+    }
 }
 
 void launch_conv_post(const float* x, const float* w, float bias, float* wav, int B, int C, int N, int K, float slope, cudaStream_t st) {
-    const int TT = 256;
-    size_t smem = sizeof(float) * ((size_t)C * (TT + K - 1) + (size_t)C * K);
-    dim3 grid((N + TT - 1) / TT, B);
-    conv_post_kernel<<<grid, 256, smem, st>>>(x, w, bias, wav, C, N, K, slope);
+    size_t smem = sizeof(float) * ((size_t)C * CP_PITCH + (size_t)C * K);
+    dim3 grid((N + CP_TT - 1) / CP_TT, B);
+    conv_post_kernel<<<grid, 128, smem, st>>>(x, w, bias, wav, C, N, K, slope);
     launch_counter()++;
 }
 
