@@ -44,6 +44,7 @@ struct ResblockParams {
     float alpha, beta;
     uint32_t epoch; int skew_clk;    // first-wave de-phasing (tc_common.cuh)
     int red_old;                     // beta == 1 handled with red.global.add instead of load + store
+    int stage_bytes, nstage;         // block-skewed kernel: weight ring geometry (a stage holds one whole conv)
 };
 __device__ unsigned long long g_rb_ticket[256];
 
@@ -365,6 +366,275 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
     if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Block-skewed variant (variant 2, C <= 32 where a whole conv's weights fit one ring stage).  Same data layout and math as
+// resblock_tc_kernel, but the hand-off between the MMA issuer and the epilogue warps is per 128-row block instead of per
+// conv: MMA(block b, conv q+1) only needs the epilogues of blocks b-1, b, b+1 of conv q (its taps reach at most 25 rows
+// into the neighbours), and epilogue(b, q) only needs MMA(b, q) and MMA(b+1, q) (the latter still reads rows of block b).
+// The issuer therefore runs one to two blocks ahead of the epilogue warps and the tensor pipe works while accumulators
+// are being drained, inside ONE CTA - the overlap no longer depends on a second CTA being in a different phase.
+// Barriers: bar_a[b] completes once per round (round 0 = loader, round q+1 = epilogue of conv q), bar_acc[b] once per conv.
+// Every wait of round q only depends on arrivals of round q-1 of the other side, so the protocol cannot deadlock.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int C, int MB, int STAGE_KB, int MINB>
+__global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const ResblockParams p) {
+    using G = RBGeom<C, STAGE_KB>;
+    constexpr int R1 = 128 * MB;
+    constexpr int AROWS = R1 + 2 * RBK_PAD;
+    constexpr int TMEM_COLS = 2 * MB * C;
+    constexpr int ACC0 = MB * C;
+    static_assert(MB >= 2 && MB <= 8 && MB % 2 == 0, "block-skewed ResBlock kernel: 2..8 row blocks");
+    static_assert(C == 16 || C == 32 || C == 64, "block-skewed ResBlock kernel serves C <= 64");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw);
+    const uint32_t a_base = base;
+    const uint32_t ring_base = base + AROWS * G::RB;
+    const uint32_t bar_base = ring_base + (uint32_t)(p.nstage * p.stage_bytes);
+    const uint32_t bar_full = bar_base, bar_empty = bar_base + 16, bar_a = bar_base + 32, bar_acc = bar_base + 32 + 8 * MB;
+    const uint32_t tmem_slot = bar_base + 192;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - base));
+    float* sbias = reinterpret_cast<float*>(sm + (bar_base + 256 - base));     // [6][C]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int k = p.k;
+    const int TOUT = R1 - 2 * p.halo;
+    const int tt0 = blockIdx.x * TOUT - p.halo;
+    const float* __restrict__ xb = p.x + (size_t)b * C * p.T;
+    float* __restrict__ ob = p.out + (size_t)b * C * p.T;
+
+    if (tid == 0) {
+        dephase_first_wave(g_rb_ticket, p.epoch, p.skew_clk, MINB);
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int m = 0; m < MB; ++m) { mbar_init(bar_a + 8 * m, RBK_NWORK); mbar_init(bar_acc + 8 * m, 1); }
+        fence_barrier_init();
+    }
+    if (warp == 8) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+    for (int i = tid; i < 6 * C; i += RBK_THREADS) sbias[i] = __ldg(p.bias[i / C] + (i % C));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 9) {
+        // ------------------------------------------------------------ weight producer: one ring stage per conv
+        // (with a single stage - C = 64, k = 11 - conv q+1 can only be fetched once conv q has been consumed)
+        const int ns = p.nstage;
+        for (int q = 0; q < 6; ++q) {
+            const int s = q % ns, use = q / ns;
+            if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
+            const uint32_t bytes = (uint32_t)k * G::SUB;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+                bulk_g2s(ring_base + s * p.stage_bytes, p.w[q], bytes, bar_full + 8 * s);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------ MMA issuer: block-major inside a conv
+        constexpr uint32_t idesc = make_idesc_f16(128, C);
+        const int h = (k - 1) / 2;
+        if (elect_one()) {
+            for (int q = 0; q < 6; ++q) {
+                const uint32_t s = (uint32_t)(q % p.nstage), par = (uint32_t)q & 1u;
+                mbar_wait(bar_full + 8 * s, (uint32_t)(q / p.nstage) & 1u);
+                const int cd = (q & 1) ? 1 : p.dil[q >> 1];
+                const uint64_t a_step = (uint64_t)((uint32_t)(cd * G::RB) >> 4);
+                const uint64_t a_q = make_smem_desc(a_base + (uint32_t)(RBK_PAD - h * cd) * G::RB, G::RB, 0);
+                const uint64_t b_q = make_smem_desc(ring_base + s * (uint32_t)p.stage_bytes, G::RB, 0);
+#pragma unroll 1
+                for (int mb = 0; mb < MB; ++mb) {
+                    if (mb == 0) { mbar_wait(bar_a, par); mbar_wait(bar_a + 8, par); }
+                    else if (mb + 1 < MB) mbar_wait(bar_a + 8 * (mb + 1), par);
+                    tc_fence_after();
+                    uint64_t ad = a_q + (uint64_t)(((uint32_t)(mb * 128) * G::RB) >> 4);
+                    uint64_t bd = b_q;
+                    uint32_t acc = 0u;
+                    for (int tap = 0; tap < k; ++tap) {
+#pragma unroll
+                        for (int ks = 0; ks < G::KSTEPS; ++ks)
+                            umma_f16(tmem_base + ACC0 + mb * C, ad + (uint64_t)((ks * 32) >> 4), bd + (uint64_t)((ks * 32) >> 4), idesc, (ks > 0) ? 1u : acc);
+                        acc = 1u;
+                        ad += a_step;
+                        bd += (uint64_t)(G::SUB >> 4);
+                    }
+                    umma_commit(bar_acc + 8 * mb);
+                }
+                umma_commit(bar_empty + 8 * s);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ workers
+        const int q4 = warp & 3, hsel = warp >> 2;
+        const int rib = 32 * q4 + lane;
+        constexpr int CH = C / 2;
+        constexpr int CG = CH < 16 ? CH : 16;
+        const uint32_t tlane = tmem_base + ((uint32_t)(32 * q4) << 16);
+        const int cbase = hsel * CH;
+
+        for (int i = tid; i < 2 * RBK_PAD * (G::RB / 16); i += RBK_NWORK) {
+            const int rr = i / (G::RB / 16), ch = i % (G::RB / 16);
+            const int row = rr < RBK_PAD ? rr : (R1 + rr);
+            *reinterpret_cast<uint4*>(sm + swz_offset(row, ch, G::RB)) = make_uint4(0, 0, 0, 0);
+        }
+        // round 0: load x (fp32 -> TMEM residual, lrelu -> fp16 operand rows), two row blocks per batch
+#pragma unroll 1
+        for (int mb0 = 0; mb0 < MB; mb0 += 2) {
+            float v[2][CH];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int t = tt0 + (mb0 + u) * 128 + rib;
+                const bool valid = (t >= 0) && (t < p.T);
+                const float* __restrict__ xt = xb + (valid ? t : 0) + (size_t)cbase * p.T;
+#pragma unroll
+                for (int j = 0; j < CH; ++j) v[u][j] = valid ? __ldg(xt + (size_t)j * p.T) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int mb = mb0 + u;
+                const int row = mb * 128 + rib;
+                uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
+                const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
+#pragma unroll
+                for (int cc = 0; cc < CH; cc += CG) {
+                    const int c0 = cbase + cc;
+                    uint32_t r[16];
+#pragma unroll
+                    for (int j = 0; j < CG; ++j) r[j] = __float_as_uint(v[u][cc + j]);
+                    if (CG == 16) tmem_st16(tlane + mb * C + c0, r);
+                    else tmem_st8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r));
+                    float w[16];
+#pragma unroll
+                    for (int j = 0; j < CG; ++j) w[j] = lrelu01(v[u][cc + j]);
+                    store_chunk8(prow, phase, c0 / 8, w, 0xffffffffu);
+                    if (CG == 16) store_chunk8(prow, phase, c0 / 8 + 1, w + 8, 0xffffffffu);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(bar_a + 8 * mb0);
+            mbar_arrive(bar_a + 8 * (mb0 + 1));
+        }
+
+        const bool red_old = p.red_old != 0;
+        const bool ld_old = p.beta != 0.f && !red_old;
+#pragma unroll 1
+        for (int q = 0; q < 6; ++q) {
+            const uint32_t par = (uint32_t)q & 1u;
+            const float* __restrict__ bq_ = sbias + q * C;
+#pragma unroll 1
+            for (int mb = 0; mb < MB; ++mb) {
+                mbar_wait(bar_acc + 8 * mb, par);
+                if (q < 5 && mb + 1 < MB) mbar_wait(bar_acc + 8 * (mb + 1), par);   // MMA(mb+1, q) still reads rows of this block
+                tc_fence_after();
+                const int row = mb * 128 + rib;
+                const int t = tt0 + row;
+                const uint32_t keep = ((t >= 0) && (t < p.T)) ? 0xffffffffu : 0u;
+                uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
+                const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
+                if ((q & 1) == 0) {
+                    // first conv of a pair: mid = lrelu(acc + b1) -> operand rows
+#pragma unroll
+                    for (int cc = 0; cc < CH; cc += CG) {
+                        const int c0 = cbase + cc;
+                        uint32_t r[16];
+                        if (CG == 16) tmem_ld16(tlane + ACC0 + mb * C + c0, r);
+                        else tmem_ld8(tlane + ACC0 + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r));
+                        tmem_ld_wait();
+                        float v[16];
+#pragma unroll
+                        for (int j4 = 0; j4 < CG; j4 += 4) {
+                            const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
+                            v[j4 + 0] = lrelu01(__uint_as_float(r[j4 + 0]) + bb.x);
+                            v[j4 + 1] = lrelu01(__uint_as_float(r[j4 + 1]) + bb.y);
+                            v[j4 + 2] = lrelu01(__uint_as_float(r[j4 + 2]) + bb.z);
+                            v[j4 + 3] = lrelu01(__uint_as_float(r[j4 + 3]) + bb.w);
+                        }
+                        store_chunk8(prow, phase, c0 / 8, v, keep);
+                        if (CG == 16) store_chunk8(prow, phase, c0 / 8 + 1, v + 8, keep);
+                    }
+                    tc_fence_before();
+                    fence_proxy_async();
+                    mbar_arrive(bar_a + 8 * mb);
+                } else if (q < 5) {
+                    // second conv of pair 0/1: x <- x + acc + b2 (TMEM), operand rows <- lrelu(x)
+#pragma unroll
+                    for (int cc = 0; cc < CH; cc += CG) {
+                        const int c0 = cbase + cc;
+                        uint32_t r[16], xr[16];
+                        if (CG == 16) { tmem_ld16(tlane + ACC0 + mb * C + c0, r); tmem_ld16(tlane + mb * C + c0, xr); }
+                        else { tmem_ld8(tlane + ACC0 + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r)); tmem_ld8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(xr)); }
+                        tmem_ld_wait();
+                        float v[16];
+#pragma unroll
+                        for (int j4 = 0; j4 < CG; j4 += 4) {
+                            const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
+                            v[j4 + 0] = __uint_as_float(r[j4 + 0]) + bb.x + __uint_as_float(xr[j4 + 0]);
+                            v[j4 + 1] = __uint_as_float(r[j4 + 1]) + bb.y + __uint_as_float(xr[j4 + 1]);
+                            v[j4 + 2] = __uint_as_float(r[j4 + 2]) + bb.z + __uint_as_float(xr[j4 + 2]);
+                            v[j4 + 3] = __uint_as_float(r[j4 + 3]) + bb.w + __uint_as_float(xr[j4 + 3]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < CG; ++j) xr[j] = __float_as_uint(v[j]);
+                        if (CG == 16) tmem_st16(tlane + mb * C + c0, xr);
+                        else tmem_st8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(xr));
+#pragma unroll
+                        for (int j = 0; j < CG; ++j) v[j] = lrelu01(v[j]);
+                        store_chunk8(prow, phase, c0 / 8, v, keep);
+                        if (CG == 16) store_chunk8(prow, phase, c0 / 8 + 1, v + 8, keep);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    fence_proxy_async();
+                    mbar_arrive(bar_a + 8 * mb);
+                } else {
+                    // last conv: out = alpha*(x + acc + b2) (+ beta*out_old) for the interior rows
+                    const bool wr = (t >= 0) && (t < p.T) && (row >= p.halo) && (row < R1 - p.halo);
+                    float* __restrict__ ot = ob + (wr ? t : 0);
+#pragma unroll
+                    for (int cc = 0; cc < CH; cc += CG) {
+                        const int c0 = cbase + cc;
+                        uint32_t r[16], xr[16];
+                        float oo[16];
+                        if (CG == 16) { tmem_ld16(tlane + ACC0 + mb * C + c0, r); tmem_ld16(tlane + mb * C + c0, xr); }
+                        else { tmem_ld8(tlane + ACC0 + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r)); tmem_ld8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(xr)); }
+                        if (wr && ld_old) {
+#pragma unroll
+                            for (int j = 0; j < CG; ++j) oo[j] = ot[(size_t)(c0 + j) * p.T];
+                        }
+                        tmem_ld_wait();
+                        if (wr) {
+#pragma unroll
+                            for (int j4 = 0; j4 < CG; j4 += 4) {
+                                const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
+                                const float b4[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int j = j4 + e;
+                                    float y = p.alpha * (__uint_as_float(r[j]) + b4[e] + __uint_as_float(xr[j]));
+                                    if (ld_old) y = fmaf(p.beta, oo[j], y);
+                                    if (red_old) atomicAdd(ot + (size_t)(c0 + j) * p.T, y);
+                                    else ot[(size_t)(c0 + j) * p.T] = y;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
 uint32_t g_rb_epoch = 0;         // launch serial number shared by all instantiations (they share g_rb_ticket)
 
 int rb_env_int(const char* name, int dflt) {
@@ -372,15 +642,27 @@ int rb_env_int(const char* name, int dflt) {
     return s ? std::atoi(s) : dflt;
 }
 
-template <int C, int MB, int STAGE_KB, int MINB>
+template <int C, int MB, int STAGE_KB, int MINB, bool SKEW>
 int launch_resblock_t(const ResblockTC& a, cudaStream_t st) {
     constexpr size_t smem = resblock_smem_bytes<C, MB, STAGE_KB>();
     static_assert((smem + 1024) * MINB <= 228 * 1024, "fused ResBlock kernel shared memory exceeds the SM budget");
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(resblock_tc_kernel<C, MB, STAGE_KB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    auto kernel = [] {
+        if constexpr (SKEW) return resblock_skew_kernel<C, MB, STAGE_KB, MINB>;
+        else return resblock_tc_kernel<C, MB, STAGE_KB, MINB>;
+    }();
+    // block-skewed kernel: a ring stage holds one whole conv (k taps); two stages when they fit next to the operand tile
+    using GG = RBGeom<C, STAGE_KB>;
+    const int stage_bytes = ((a.k * GG::SUB + 1023) / 1024) * 1024;
+    const size_t fixed = 1024 + (size_t)(128 * MB + 2 * RBK_PAD) * GG::RB + 256 + 6 * C * 4;
+    const size_t budget = (size_t)(MINB == 1 ? 227 : 113) * 1024;
+    const int nstage = (fixed + 2 * (size_t)stage_bytes <= budget) ? 2 : 1;
+    const size_t smem_run = SKEW ? fixed + (size_t)nstage * stage_bytes : smem;
+    if (SKEW && smem_run > budget) return SVB_ERR_UNSUPPORTED;
+    static size_t attr_bytes = 0;
+    if (smem_run > attr_bytes) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_run) != cudaSuccess)
             return SVB_ERR_CUDA;
-        attr_set = true;
+        attr_bytes = smem_run;
     }
     ResblockParams p;
     p.x = a.x; p.out = a.out;
@@ -403,7 +685,8 @@ int launch_resblock_t(const ResblockTC& a, cudaStream_t st) {
     const int TOUT = 128 * MB - 2 * halo;
     if (TOUT < 64) return SVB_ERR_UNSUPPORTED;
     dim3 grid((a.T + TOUT - 1) / TOUT, a.B);
-    resblock_tc_kernel<C, MB, STAGE_KB, MINB><<<grid, RBK_THREADS, smem, st>>>(p);
+    p.stage_bytes = stage_bytes; p.nstage = nstage;
+    kernel<<<grid, RBK_THREADS, smem_run, st>>>(p);
     launch_counter()++;
     return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;
 }
@@ -417,19 +700,27 @@ int launch_resblock_tc(const ResblockTC& a, cudaStream_t st) {
         if (a.dil[d] * (a.k - 1) / 2 > RBK_PAD - 1 || a.dil[d] < 1) return SVB_ERR_UNSUPPORTED;
     static const int env_variant = rb_env_int("SVB_RB_VARIANT", -1);
     int variant = a.variant >= 0 ? a.variant : env_variant;
-    if (variant < 0) variant = 1;     // measured: two CTAs/SM win for C <= 32 (profiles/r01/bench_pair_sweep_fused.log)
+    if (variant < 0) variant = 2;     // measured: block-skewed hand-off 11.79 vs 11.98 ms/step; two CTAs/SM for C <= 32
+    if (variant == 2) {               // block-skewed hand-off (resblock_skew_kernel), C <= 32
+        switch (a.C) {
+            case 16: return launch_resblock_t<16, 8, 8, 2, true>(a, st);
+            case 32: return launch_resblock_t<32, 4, 22, 2, true>(a, st);
+            case 64: return launch_resblock_t<64, 4, 32, 1, true>(a, st);
+            default: return SVB_ERR_UNSUPPORTED;
+        }
+    }
     if (variant == 1) {
         switch (a.C) {
-            case 16: return launch_resblock_t<16, 8, 8, 2>(a, st);
-            case 32: return launch_resblock_t<32, 4, 22, 2>(a, st);
-            case 64: return launch_resblock_t<64, 4, 32, 1>(a, st);     // 2 CTAs/SM would leave 256-2*120 = 16 useful rows
+            case 16: return launch_resblock_t<16, 8, 8, 2, false>(a, st);
+            case 32: return launch_resblock_t<32, 4, 22, 2, false>(a, st);
+            case 64: return launch_resblock_t<64, 4, 32, 1, false>(a, st);     // 2 CTAs/SM would leave 256-2*120 = 16 useful rows
             default: return SVB_ERR_UNSUPPORTED;
         }
     }
     switch (a.C) {
-        case 16: return launch_resblock_t<16, 16, 8, 1>(a, st);
-        case 32: return launch_resblock_t<32, 8, 32, 1>(a, st);
-        case 64: return launch_resblock_t<64, 4, 32, 1>(a, st);
+        case 16: return launch_resblock_t<16, 16, 8, 1, false>(a, st);
+        case 32: return launch_resblock_t<32, 8, 32, 1, false>(a, st);
+        case 64: return launch_resblock_t<64, 4, 32, 1, false>(a, st);
         default: return SVB_ERR_UNSUPPORTED;
     }
 }

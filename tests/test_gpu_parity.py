@@ -186,7 +186,7 @@ def test_fused_resblock_matches_pair_chain(cfg, sd, eng, stage):
         for d in range(3):
             ref = eng.debug_pair(stage, j, d, ref, -2)
         want = ref / 3.0 + old
-        for variant in (0, 1):
+        for variant in (0, 1, 2):                 # 2 = block-skewed hand-off (C <= 32; falls back to 1 for C = 64)
             out = old.clone()
             eng.debug_resblock(stage, j, x, variant, out=out, alpha=1.0 / 3.0, beta=1.0)
             rel = float((out - want).abs().max()) / float(want.abs().max())

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+echo "=== tests"; timeout 600 python -m pytest tests -m gpu -q -x -s > gpurun_out/test_final.log 2>&1; echo "rc=$?"; grep -E "passed|failed|Error|error" gpurun_out/test_final.log | tail -3; grep "C=64.*v2" gpurun_out/test_final.log | head -3
+b() { timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['e2e']['ms_per_step'], [x.get('ms_per_step') for x in d['roofline_secondary']])"; }
+echo "=== bench default (skew variant everywhere)"; b
+echo "=== bench SVB_RB_VARIANT=1"; SVB_RB_VARIANT=1 b
