@@ -34,7 +34,6 @@ namespace {
 constexpr int TC_THREADS = 320;
 constexpr int NWORK = 256;           // worker threads (8 warps)
 constexpr int NSTAGE = 2;
-constexpr int MAX_HALO = 64;         // upper bound of the per-variant halo rows (>= max (k-1)*dil = 50)
 constexpr int TMA_NBOX = 3;          // the A tile arrives as 3 row-boxes (box rows must be <= 256 and a multiple of 8)
 template <int MB> struct TileRows { static constexpr int HALO = (MB == 4) ? 64 : 56; static constexpr int AROWS = 128 * MB + HALO; };
 
