@@ -437,3 +437,23 @@ def test_prefix_fused_tails_match_torch(monkeypatch):
         err = float((fused - plain).abs().max())
         print(f"[parity] enc_p fused tails vs torch ops: L-inf {err:.2e}")
         assert err < 1e-4
+
+
+def test_fp16_checkpoint_equals_upcast_weights(cfg, sd):
+    """`compress_model.py --half` checkpoints (compress_model.py:37-41) store fp16 tensors.  The library
+    converts them to fp32 before folding weight norm, so the result must be bit-identical to loading the same values
+    upcast on the host."""
+    from sovits_b200.engine import TailEngine
+    sd16 = {k: (v.half() if v.is_floating_point() else v) for k, v in sd.items()}
+    sd32 = {k: (v.float() if v.is_floating_point() else v) for k, v in sd16.items()}
+    z_p, g, f0, noise = _case(cfg, sd, 2, 40)
+    args = [t.to(DEV) for t in (z_p, sd32["emb_g.weight"][torch.tensor([[0], [1]])].transpose(1, 2).contiguous(), f0,
+                                noise["rand_ini"], noise["har_noise"])]
+    outs = []
+    for weights in (sd16, sd32):
+        e = TailEngine(cfg, DEV, "tc")
+        e.load_state_dict(weights)
+        outs.append(e.infer_tail(*args).cpu())
+        e.close()
+    assert torch.equal(outs[0], outs[1])
+    assert torch.isfinite(outs[0]).all() and float(outs[0].abs().max()) > 1e-3
