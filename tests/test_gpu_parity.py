@@ -108,30 +108,6 @@ def test_flow_reverse_tensor_core(cfg, sd, eng, B, T):
     assert err < 2e-2
 
 
-def test_flow_only_config5(cfg, sd, eng):
-    """SURVEY §8(d) config 5 (flow-only microbench): z_p[1,192,100000] ~ N(0,1), g[1,768,1] ~ N(0,1), mask = ones.  The
-    oracle runs on the GPU through the reference's own ops (strict fp32 convolutions) for this size."""
-    gen = torch.Generator().manual_seed(1234)
-    z_p = torch.randn((1, cfg.inter_channels, 100_000), generator=gen)
-    g = torch.randn((1, cfg.gin_channels, 1), generator=gen)
-    prev = torch.backends.cudnn.conv.fp32_precision
-    torch.backends.cudnn.conv.fp32_precision = "ieee"
-    try:
-        sd_dev = {k: v.to(DEV) for k, v in sd.items() if k.startswith("flow.")}
-        ref = O.flow_reverse(sd_dev, z_p.to(DEV), torch.ones(1, 1, 100_000, device=DEV), g.to(DEV), cfg, torch.float32).cpu()
-    finally:
-        torch.backends.cudnn.conv.fp32_precision = prev
-    eng.set_precision("fp32")
-    got = eng.flow_reverse(z_p.to(DEV), g.to(DEV)).cpu()
-    e32 = float((got - ref).abs().max())
-    eng.set_precision("tc")
-    got_tc = eng.flow_reverse(z_p.to(DEV), g.to(DEV)).cpu()
-    eng.set_precision("fp32")
-    etc = float((got_tc - ref).abs().max())
-    print(f"[parity] config5 flow-only T=100000: fp32 L-inf {e32:.3e}, tc L-inf {etc:.3e} (|z|max {float(ref.abs().max()):.1f})")
-    assert e32 < 5e-4 and etc < 5e-2
-
-
 @pytest.mark.parametrize("B,T", [(2, 24), (1, 33)])
 def test_generator_fp32_stagewise(cfg, sd, eng, B, T):
     z_p, g, f0, noise = _case(cfg, sd, B, T)
@@ -457,3 +433,27 @@ def test_fp16_checkpoint_equals_upcast_weights(cfg, sd):
         e.close()
     assert torch.equal(outs[0], outs[1])
     assert torch.isfinite(outs[0]).all() and float(outs[0].abs().max()) > 1e-3
+
+
+def test_flow_only_config5(cfg, sd, eng):
+    """SURVEY §8(d) config 5 (flow-only microbench): z_p[1,192,100000] ~ N(0,1), g[1,768,1] ~ N(0,1), mask = ones.  The
+    oracle runs on the GPU through the reference's own ops (strict fp32 convolutions) for this size."""
+    gen = torch.Generator().manual_seed(1234)
+    z_p = torch.randn((1, cfg.inter_channels, 100_000), generator=gen)
+    g = torch.randn((1, cfg.gin_channels, 1), generator=gen)
+    prev = torch.backends.cudnn.conv.fp32_precision
+    torch.backends.cudnn.conv.fp32_precision = "ieee"
+    try:
+        sd_dev = {k: v.to(DEV) for k, v in sd.items() if k.startswith("flow.")}
+        ref = O.flow_reverse(sd_dev, z_p.to(DEV), torch.ones(1, 1, 100_000, device=DEV), g.to(DEV), cfg, torch.float32).cpu()
+    finally:
+        torch.backends.cudnn.conv.fp32_precision = prev
+    eng.set_precision("fp32")
+    got = eng.flow_reverse(z_p.to(DEV), g.to(DEV)).cpu()
+    e32 = float((got - ref).abs().max())
+    eng.set_precision("tc")
+    got_tc = eng.flow_reverse(z_p.to(DEV), g.to(DEV)).cpu()
+    eng.set_precision("fp32")
+    etc = float((got_tc - ref).abs().max())
+    print(f"[parity] config5 flow-only T=100000: fp32 L-inf {e32:.3e}, tc L-inf {etc:.3e} (|z|max {float(ref.abs().max()):.1f})")
+    assert e32 < 5e-4 and etc < 5e-2
