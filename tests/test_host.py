@@ -148,3 +148,21 @@ def test_vocoder_surface_matches_reference_layout(tmp_path):
     mel, f0 = synth.synth_vocoder_inputs(vcfg, 1, 8)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         gen(mel, f0)
+
+
+def test_frontend_weight_caches_follow_parameter_updates():
+    """The fused q/k/v projection and the tap-stacked FFN matrices are cached per module; a load_state_dict (in-place copy,
+    bumps the tensor version) or a dtype/device move must invalidate them."""
+    from sovits_b200.frontend import RelEncoder
+    torch.manual_seed(3)
+    a, b = RelEncoder(192, 768, 2, 2, 3).eval(), RelEncoder(192, 768, 2, 2, 3).eval()
+    x, m = torch.randn(2, 192, 30), torch.ones(2, 1, 30)
+    with torch.no_grad():
+        ya0, yb = a(x, m, True), b(x, m, True)
+        assert float((ya0 - yb).abs().max()) > 1e-3            # different random weights
+        a.load_state_dict(b.state_dict())
+        ya1 = a(x, m, True)
+        assert torch.equal(ya1, yb)                             # caches rebuilt from the new weights
+        a.double()
+        ya2 = a(x.double(), m.double(), True)
+        assert ya2.dtype == torch.float64 and float((ya2.float() - yb).abs().max()) < 1e-4
