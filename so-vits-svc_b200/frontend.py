@@ -159,7 +159,7 @@ class WindowedRelAttention(nn.Module):
         qkv = F.linear(x, wqkv, bqkv).view(B, L, 3, h, dk).permute(2, 0, 3, 1, 4)      # [3,B,h,L,dk]
         q, k, v = qkv[0], qkv[1], qkv[2]
         scores = q @ k.transpose(-2, -1)                                                  # [B,h,L,L]
-        lib = _fused_tails(x) if attn_mask is None else None
+        lib = _fused_tails(x) if (attn_mask is None and L <= 12000) else None   # rel_softmax keeps one score row in shared memory
         if lib is not None:
             # equal-length batch on the GPU: band add + softmax + band extraction, then p@v + relative values + head merge,
             # as two fused kernels (csrc/kernels_prefix.cu) around the cuBLAS GEMMs
