@@ -271,7 +271,7 @@ class RelEncoder(nn.Module):
         x = x.transpose(1, 2).contiguous()
         if mt is not None:
             x = x * mt
-        lib = _fused_tails(x) if mt is None else None
+        lib = _fused_tails(x) if (mt is None and x.shape[-1] <= 256 and self.ffn_layers[0].kernel_size <= 7) else None
         with _TF32Like():
             for attn, n1, ffn, n2 in zip(self.attn_layers, self.norm_layers_1, self.ffn_layers, self.norm_layers_2):
                 if lib is not None:
