@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Block-skewed variant (variant 2, C <= 32 where a whole conv's weights fit one ring stage).  Same data layout and math as
+// Block-skewed variant (variant 2, the default; a ring stage holds one whole conv: two stages except C = 64, k = 11).  Same data layout and math as
 // resblock_tc_kernel, but the hand-off between the MMA issuer and the epilogue warps is per 128-row block instead of per
 // conv: MMA(block b, conv q+1) only needs the epilogues of blocks b-1, b, b+1 of conv q (its taps reach at most 25 rows
 // into the neighbours), and epilogue(b, q) only needs MMA(b, q) and MMA(b+1, q) (the latter still reads rows of block b).
@@ -700,8 +700,8 @@ int launch_resblock_tc(const ResblockTC& a, cudaStream_t st) {
         if (a.dil[d] * (a.k - 1) / 2 > RBK_PAD - 1 || a.dil[d] < 1) return SVB_ERR_UNSUPPORTED;
     static const int env_variant = rb_env_int("SVB_RB_VARIANT", -1);
     int variant = a.variant >= 0 ? a.variant : env_variant;
-    if (variant < 0) variant = 2;     // measured: block-skewed hand-off 11.79 vs 11.98 ms/step; two CTAs/SM for C <= 32
-    if (variant == 2) {               // block-skewed hand-off (resblock_skew_kernel), C <= 32
+    if (variant < 0) variant = 2;     // measured: block-skewed hand-off 11.64 vs 11.95 ms/step
+    if (variant == 2) {               // block-skewed hand-off (resblock_skew_kernel): two CTAs/SM for C <= 32, one for C = 64
         switch (a.C) {
             case 16: return launch_resblock_t<16, 8, 8, 2, true>(a, st);
             case 32: return launch_resblock_t<32, 4, 22, 2, true>(a, st);
