@@ -154,6 +154,12 @@ class SynthesizerTrn(_TailMixin, nn.Module):
         self.speaker_map = self.emb_g.to(device)(idx).reshape(1, n_speakers_map, 1, 1, self.gin_channels)
         self.character_mix = True
 
+    def mix_speakers(self, weights):
+        """[T,S] per-frame speaker weights -> time-varying conditioning g [1,gin,T] (models.py:505-509)."""
+        gm = weights.reshape(weights.shape[0], weights.shape[1], 1, 1, 1) * self.speaker_map
+        gm = gm.sum(dim=1)                              # [T,1,1,gin]
+        return gm.transpose(0, -1).transpose(0, -2).squeeze(0)
+
     @torch.no_grad()
     def infer(self, c, f0, uv, g=None, noice_scale=0.35, seed=52468, predict_f0=False, vol=None):
         """models.py:495-532.  ``c`` [B,ssl,T], ``f0``/``uv`` [B,T], ``g`` [B,1] int64 (or [T,S] mix)."""
@@ -165,9 +171,7 @@ class SynthesizerTrn(_TailMixin, nn.Module):
             torch.manual_seed(seed)
         B, _, T = c.shape
         if self.character_mix and len(g) > 1:           # [T,S] mix weights -> g [1,gin,T] (models.py:505-509)
-            gm = g.reshape(g.shape[0], g.shape[1], 1, 1, 1) * self.speaker_map
-            gm = gm.sum(dim=1)                          # [T,1,1,gin]
-            g = gm.transpose(0, -1).transpose(0, -2).squeeze(0)
+            g = self.mix_speakers(g)
         else:
             if g.dim() == 1:
                 g = g.unsqueeze(0)

@@ -141,3 +141,28 @@ def test_polyphase_transposed_conv(cfg, sd):
                 if 0 <= n < L * s:
                     out[0, :, n] = b + w[:, :, ph].t() @ xp[0, :, i0 + 1] + w[:, :, ph + s].t() @ xp[0, :, i0]
         assert torch.allclose(out, ref, atol=1e-10)
+
+
+def test_oracle_tail_with_speaker_mix_conditioning(cfg, sd):
+    """SURVEY §8 f-4 (`EnableCharacterMix`, models.py:456-461,505-509): time-varying g[1,768,T] through flow and generator,
+    against the reference's own speaker-mix run (tests/golden/make_golden_mix.py)."""
+    gold = np.load(os.path.join(GOLD, "ref_infer_mix_t26.npz"))
+    T = int(gold["T"])
+    mix = torch.from_numpy(gold["mix"])                                   # [T, S]
+    g = (mix @ sd["emb_g.weight"]).t().unsqueeze(0).contiguous()          # [1, 768, T]
+    assert float((g - torch.from_numpy(gold["g"])).abs().max()) < 1e-6
+    noise = synth.draw_noise(1, T, cfg, seed=int(gold["seed"]))
+    f0 = torch.from_numpy(gold["f0"])
+    out = O.tail(sd, cfg, torch.from_numpy(gold["z_p"]), g, f0, noise, torch.float32)
+    assert float((out - torch.from_numpy(gold["o"])).abs().max()) < 2e-5
+    # the stand-alone class builds the same g from the mix weights
+    import json
+    import sovits_b200
+    from sovits_b200 import models
+    with open(sovits_b200.DEFAULT_CONFIG) as f:
+        kw = json.load(f)["model"]
+    net = models.SynthesizerTrn(1025, 20, **kw).eval()
+    net.load_state_dict(sd)
+    net.EnableCharacterMix(cfg.n_speakers, "cpu")
+    with torch.no_grad():
+        assert float((net.mix_speakers(mix) - torch.from_numpy(gold["g"])).abs().max()) < 1e-6
