@@ -41,3 +41,26 @@ def test_infer_slices_matches_serial_calls():
             assert err < 2e-4
     finally:
         torch.backends.cudnn.conv.fp32_precision = prev
+
+
+@pytest.mark.skipif(__import__("os").environ.get("SVB_TEST_UNVALIDATED") != "1",
+                    reason="written after the round-1 GPU budget was spent: enable with SVB_TEST_UNVALIDATED=1 (round 2)")
+def test_speaker_mix_matches_reference_fixture():
+    """time-varying conditioning g[1,768,T] (EnableCharacterMix) through the CUDA flow and generator against the
+    reference's own speaker-mix run (tests/golden/make_golden_mix.py).  gT = T runs the fp32 kernels in both precisions."""
+    import os
+    import numpy as np
+    from sovits_b200.engine import TailEngine
+    cfg = load_config()
+    sd = synth.synth_state_dict(cfg)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_infer_mix_t26.npz"))
+    T = int(gold["T"])
+    noise = synth.draw_noise(1, T, cfg, seed=int(gold["seed"]))
+    eng = TailEngine(cfg, DEV, "fp32")
+    eng.load_state_dict(sd)
+    got = eng.infer_tail(torch.from_numpy(gold["z_p"]).to(DEV), torch.from_numpy(gold["g"]).to(DEV), torch.from_numpy(gold["f0"]).to(DEV),
+                         noise["rand_ini"].to(DEV), noise["har_noise"].to(DEV)).cpu()
+    eng.close()
+    err = float((got - torch.from_numpy(gold["o"])).abs().max())
+    print(f"[parity] speaker mix (time-varying g) fp32: L-inf vs reference waveform = {err:.3e}")
+    assert err < 1e-4
