@@ -166,3 +166,39 @@ def test_oracle_tail_with_speaker_mix_conditioning(cfg, sd):
     net.EnableCharacterMix(cfg.n_speakers, "cpu")
     with torch.no_grad():
         assert float((net.mix_speakers(mix) - torch.from_numpy(gold["g"])).abs().max()) < 1e-6
+
+
+def test_fp16_operand_model_explains_the_tensor_core_tolerance(cfg, sd, monkeypatch):
+    """Why `precision="tc"` is held to 2e-2 and lands at about 3e-3: the tcgen05 path rounds the OPERANDS of every
+    convolution (activations and weights) to fp16 and accumulates in fp32.  Emulating exactly that rounding inside the
+    oracle (everything else fp32) reproduces the magnitude measured on the GPU, so the gap is operand rounding, not a
+    kernel defect; the fixtures remain within the stated tolerance under this model."""
+    import torch.nn.functional as F
+    gold = np.load(os.path.join(GOLD, "ref_infer_b2_t24.npz"))
+    B, T = synth.GOLDEN_CASES["b2_t24"]
+    c, f0, uv, sid = synth.golden_inputs(cfg, "b2_t24")
+    noise = synth.draw_noise(B, T, cfg, seed=int(gold["seed"]))
+    g = sd["emb_g.weight"][sid].transpose(1, 2).contiguous()
+    z_p = torch.from_numpy(gold["z_p"])
+    exact = O.tail(sd, cfg, z_p, g, f0, noise, torch.float32)
+
+    real_conv1d, real_convt = F.conv1d, F.conv_transpose1d
+
+    def q(t):
+        return t.half().float()
+
+    def conv1d_q(x, w, b=None, *a, **k):
+        return real_conv1d(q(x), q(w), b, *a, **k)
+
+    def convt_q(x, w, b=None, *a, **k):
+        return real_convt(q(x), q(w), b, *a, **k)
+
+    monkeypatch.setattr(O.F, "conv1d", conv1d_q)
+    monkeypatch.setattr(O.F, "conv_transpose1d", convt_q)
+    rounded = O.tail(sd, cfg, z_p, g, f0, noise, torch.float32)
+    monkeypatch.undo()
+    err_model = float((rounded - exact).abs().max())
+    err_fixture = float((rounded - torch.from_numpy(gold["o"])).abs().max())
+    print(f"[parity] fp16-operand model of the tcgen05 path: L-inf vs fp32 oracle {err_model:.3e}, vs reference fixture {err_fixture:.3e}")
+    assert 2e-4 < err_model < 2e-2          # same order as the measured 2.5-3.4e-3 of the CUDA path (profiles/r01/parity_final.txt)
+    assert err_fixture < 2e-2
