@@ -196,8 +196,14 @@ def test_fp16_operand_model_explains_the_tensor_core_tolerance(cfg, sd, monkeypa
     monkeypatch.setattr(O.F, "conv1d", conv1d_q)
     monkeypatch.setattr(O.F, "conv_transpose1d", convt_q)
     rounded = O.tail(sd, cfg, z_p, g, f0, noise, torch.float32)
+    # the same model with bf16 operands (8 mantissa bits instead of 11): why the kernels use kind::f16 with fp16, not bf16
+    monkeypatch.setattr(O.F, "conv1d", lambda x, w, b=None, *a, **k: real_conv1d(x.bfloat16().float(), w.bfloat16().float(), b, *a, **k))
+    monkeypatch.setattr(O.F, "conv_transpose1d", lambda x, w, b=None, *a, **k: real_convt(x.bfloat16().float(), w.bfloat16().float(), b, *a, **k))
+    err_bf16 = float((O.tail(sd, cfg, z_p, g, f0, noise, torch.float32) - exact).abs().max())
     monkeypatch.undo()
     err_model = float((rounded - exact).abs().max())
+    print(f"[parity] bf16-operand model: L-inf vs fp32 oracle {err_bf16:.3e}")
+    assert err_bf16 > 3 * err_model
     err_fixture = float((rounded - torch.from_numpy(gold["o"])).abs().max())
     print(f"[parity] fp16-operand model of the tcgen05 path: L-inf vs fp32 oracle {err_model:.3e}, vs reference fixture {err_fixture:.3e}")
     assert 2e-4 < err_model < 2e-2          # same order as the measured 2.5-3.4e-3 of the CUDA path (profiles/r01/parity_final.txt)
