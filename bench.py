@@ -10,6 +10,10 @@ A step = one ``SynthesizerTrn.infer`` over a batch of synthetic utterances (BASE
   cpu_baseline : the oracle port of the reference path on the host cores (bounded sample)
 ``--impl reference`` times that CPU port as the reference arm (the reference is pure Python/PyTorch; there is
 no compiled reference to build, and /root/reference does not exist on the GPU box).
+``--impl reference-cuda`` times the same reference ops as plain PyTorch on the B200 (cuDNN/ATen, TF32 default) - the
+denominator of BASELINE.json's ">= 5x the reference's PyTorch-CUDA infer" target.
+Other BASELINE configs: ``--vocoder nsf-snake-hifigan`` (config 4) and ``--workload flow5`` (config 5: flow-only
+microbench, z_p[1,192,100000]; reported in frames/s with the roofline in both FLOP and HBM units).
 """
 import argparse
 import json
@@ -26,6 +30,10 @@ METRIC = "44.1 kHz audio samples/sec"
 UNIT = "samples/s"
 FLOP_PER_SAMPLE_DEC = 1269530.0      # generator FLOPs per output sample
 WORKLOAD = "config2: configs/config.json NSF-HiFiGAN 44.1 kHz, ContentVec768 synthetic feats, batch 8 x 10 s (862 frames)"
+WORKLOAD_SNAKE = "config4: vdecoder/hifiganwithsnake Generator variant (nsf-snake-hifigan), batch 8 x 10 s (862 frames)"
+WORKLOAD_FLOW5 = "config5: flow-only microbench, ResidualCouplingBlock WN stack 192ch x 4 flows, z_p[1,192,100000], g[1,768,1]"
+FLOW_FLOP_PER_FRAME = 14.156e6       # 1 415.6 GFLOP at T = 100 000
+FLOW_BYTES_PER_FRAME_LAYER = 1152.0  # per coupling layer, read 192 ch + write 96 ch fp32
 
 
 def parse_args():
@@ -33,7 +41,9 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
+    ap.add_argument("--vocoder", default="nsf-hifigan", choices=["nsf-hifigan", "nsf-snake-hifigan"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "flow5"])
     ap.add_argument("--precision", default=os.environ.get("SVB_BENCH_PRECISION", "tc"), choices=["tc", "fp32"])
     ap.add_argument("--batch", type=int, default=8, help="utterances per GPU")
     ap.add_argument("--frames", type=int, default=862)
@@ -114,15 +124,15 @@ def pick_threads(cfg, sd):
     return best
 
 
-def cpu_oracle_rate(cfg, sd, T, runs, warmup, threads):
-    """Oracle port of the reference infer on the host cores, one 10 s utterance (B=1) per step."""
+def cpu_oracle_rate(cfg, sd, T, runs, warmup, threads, B=1):
+    """Oracle port of the reference infer on the host cores, B utterances of T frames per step."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import svc_oracle as O
     from sovits_b200 import synth
     torch.set_num_threads(threads)
-    c, f0, uv, sid = synth.synth_inputs(cfg, 1, T)
-    noise = synth.draw_noise(1, T, cfg)
+    c, f0, uv, sid = synth.synth_inputs(cfg, B, T)
+    noise = synth.draw_noise(B, T, cfg)
     times = []
     for i in range(warmup + runs):
         t0 = time.perf_counter()
@@ -130,8 +140,139 @@ def cpu_oracle_rate(cfg, sd, T, runs, warmup, threads):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    N = T * cfg.hop
+    N = B * T * cfg.hop
     return N / (sum(times) / len(times)), times
+
+
+def load_cfg(args):
+    from sovits_b200.config import load_config
+    cfg = load_config()
+    if args.vocoder != "nsf-hifigan":
+        cfg.vocoder_name = args.vocoder
+    return cfg
+
+
+def run_reference_cuda(args):
+    """The reference's own ops (oracle port = F.conv1d / conv_transpose1d / cumsum / sin through cuDNN + ATen, weight norm
+    recomputed every forward like the reference) on cuda:0 with torch defaults (TF32 convolutions)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    import sovits_b200  # noqa: F401
+    from sovits_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import svc_oracle as O
+    cfg = load_cfg(args)
+    dev = torch.device("cuda:0")
+    sd = {k: v.to(dev) for k, v in synth.synth_state_dict(cfg).items()}
+    B, T = args.batch, args.frames
+    c, f0, uv, sid = [t.to(dev) for t in synth.synth_inputs(cfg, B, T)]
+    N = T * cfg.hop
+    torch.manual_seed(52468)
+    noise = {"z_noise": torch.randn(B, cfg.inter_channels, T, device=dev), "rand_ini": torch.rand(B, cfg.n_harmonics, device=dev),
+             "har_noise": torch.randn(B, N, cfg.n_harmonics, device=dev)}
+    torch.backends.cudnn.benchmark = True
+    for _ in range(max(2, args.warmup)):
+        O.infer(sd, cfg, c, f0, uv, sid, noise, noice_scale=0.4)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        O.infer(sd, cfg, c, f0, uv, sid, noise, noice_scale=0.4)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    rate = B * N / (ms * 1e-3)
+    line = {"impl": "reference-cuda", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(2, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 convolutions (cuDNN default) / f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD if args.vocoder == "nsf-hifigan" else WORKLOAD_SNAKE, "global_batch": B, "frames": T,
+                       "samples_per_item": N, "what": "oracle port of the reference ops on cuda:0 (cuDNN + ATen), cudnn.benchmark on"},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_flow5(args):
+    """BASELINE config 5: the flow alone (4 coupling layers, reverse) on z_p[1,192,100000], g[1,768,1], mask = ones."""
+    import torch
+    import sovits_b200  # noqa: F401
+    from sovits_b200 import synth
+    from sovits_b200.engine import TailEngine
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    cfg = load_cfg(args)
+    sd = synth.synth_state_dict(cfg)
+    eng = TailEngine(cfg, dev, args.precision)
+    eng.load_state_dict(sd)
+    T = 100_000
+    gen = torch.Generator().manual_seed(1234)
+    z_host = torch.randn((1, cfg.inter_channels, T), generator=gen).pin_memory()
+    g_host = torch.randn((1, cfg.gin_channels, 1), generator=gen).pin_memory()
+    z_p, g = z_host.to(dev), g_host.to(dev)
+    out_host = torch.empty((1, cfg.inter_channels, T)).pin_memory()
+    flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step_dev():
+        flush.zero_()
+        return eng.flow_reverse(z_p, g)
+
+    def step_e2e():
+        flush.zero_()
+        o = eng.flow_reverse(z_host.to(dev, non_blocking=True), g_host.to(dev, non_blocking=True))
+        out_host.copy_(o, non_blocking=True)
+
+    def timed(fn, steps):
+        # the L2 flush is part of the loop but not of the metric: time it alone and subtract
+        torch.cuda.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        for _ in range(steps):
+            flush.zero_()
+        e[1].record()
+        for _ in range(steps):
+            fn()
+        e[2].record()
+        torch.cuda.synchronize()
+        return (e[1].elapsed_time(e[2]) - e[0].elapsed_time(e[1])) / steps
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    step_e2e()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = eng.launch_count
+    ms = timed(step_dev, args.steps)
+    launches = eng.launch_count - l0
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop()
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        with open(pk_path) as f:
+            peaks = json.load(f)
+    tf_peak, hbm_peak = peaks.get("bf16_tflops", 1590.0), peaks.get("hbm_gbs", 6650.0)
+    flops = FLOW_FLOP_PER_FRAME * T
+    byts = FLOW_BYTES_PER_FRAME_LAYER * 4 * T
+    ach_tf = flops / (ms * 1e-3) / 1e12
+    ach_gb = byts / (ms * 1e-3) / 1e9
+    line = {"metric": "flow frames/sec (config 5 microbench)", "value": T / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate (tcgen05)" if args.precision == "tc" else "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_FLOW5, "frames": T, "precision": args.precision,
+                       "l2": "160 MB flush buffer written before every step (its time is measured and subtracted)"},
+            "e2e": {"value": T / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": z_host.numel() * 4 + g_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
+            "gpu_launches": int(launches), "ffma_fallbacks_in_tc": eng.fallback_count, "clocks": clocks,
+            "roofline": {"kernel": "flow (whole coupling block)", "bound": "tensor", "achieved": ach_tf, "peak": tf_peak, "unit": "TFLOP/s",
+                         "frac": ach_tf / tf_peak, "traffic": None,
+                         "peak_source": "measured burst bf16==fp16 (kernel timed alone)" if peaks else "fallback"},
+            "roofline_hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
+                             "algorithmic_bytes": byts, "note": "SURVEY 8d per-layer figure: 1152 B/frame/layer x 4 layers"}}
+    print(json.dumps(line), flush=True)
 
 
 def run_reference(args):
@@ -141,18 +282,20 @@ def run_reference(args):
     import torch
     import sovits_b200  # noqa: F401
     from sovits_b200 import synth
-    from sovits_b200.config import load_config
-    cfg = load_config()
+    cfg = load_cfg(args)
     sd = synth.synth_state_dict(cfg)
     cores = pick_threads(cfg, sd)
-    rate, times = cpu_oracle_rate(cfg, sd, args.frames, args.steps, max(1, min(args.warmup, 1)), cores)
+    # the CPU arm runs the whole config-2 batch (B utterances x T frames) per step; 1 warm-up
+    rate, times = cpu_oracle_rate(cfg, sd, args.frames, args.steps, 1, cores, B=args.batch)
     ms = 1000.0 * sum(times) / len(times)
-    sample = (f"each step = 1 utterance x {args.frames} frames (1/{args.batch} of the batch) on {cores} host threads "
-              f"(fastest of 8/16/32/64/{os.cpu_count()} on a short probe)")
+    sample = (f"each step = the full batch, {args.batch} utterances x {args.frames} frames, on {cores} host threads "
+              f"(fastest of 8/16/32/64/{os.cpu_count()} on a short probe); 1 warm-up step")
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": args.batch * args.gpus, "frames": args.frames},
+            "config": {"workload": WORKLOAD if args.vocoder == "nsf-hifigan" else WORKLOAD_SNAKE, "global_batch": args.batch,
+                       "frames": args.frames, "samples_per_item": args.frames * cfg.hop, "parallelism": "host cpu",
+                       "note": "rank 0 only; the CPU arm does not scale with --gpus"},
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -164,6 +307,12 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.impl == "reference-cuda":
+        run_reference_cuda(args)
+        return
+    if args.workload == "flow5":
+        run_flow5(args)
         return
     import torch
     import torch.distributed as dist
@@ -181,7 +330,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
-    cfg = load_config()
+    cfg = load_cfg(args)
+    snake = args.vocoder != "nsf-hifigan"
     B, T = args.batch, args.frames
     N = T * cfg.hop
     # ---- weights: rank 0 makes them, one NCCL broadcast (the path's only collective)
@@ -193,6 +343,7 @@ def main():
         sd = synth.synth_state_dict(cfg)
     with open(sovits_b200.DEFAULT_CONFIG) as f:
         kw = json.load(f)["model"]
+    kw["vocoder_name"] = args.vocoder
     net = models.SynthesizerTrn(1025, 20, **kw).eval()
     net.load_state_dict(sd)
     net = net.to(dev)
@@ -248,10 +399,12 @@ def main():
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
 
-    # ---- roofline of the dominant kernel: CUDA events around every launch of it, on the launching stream
+    # ---- roofline: CUDA events around every launch of each kernel family, on the launching stream (svb_profile_enable)
     roof, secondary = None, []
+    fb0 = eng.fallback_count
     eng.profile_enable(True)
-    for _ in range(min(args.steps, 3)):
+    nprof = min(args.steps, 3)
+    for _ in range(nprof):
         step_dev()
     torch.cuda.synchronize()
     peaks = {}
@@ -262,37 +415,61 @@ def main():
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json, sustained bf16==fp16 rate)" if peaks else "fallback"
-    name = "pair_tc" if args.precision == "tc" else "pair_f32"
-    pr = eng.profile_read(name)
-    traffic = None
+    traffic_db = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(name)
+            traffic_db = json.load(open(tpath))
         except Exception:
-            traffic = None
-    if pr and pr["ms"] > 0:
+            traffic_db = {}
+
+    def tensor_entry(name):
+        pr = eng.profile_read(name)
+        if not pr or pr["ms"] <= 0 or pr["flops"] <= 0:
+            return None
         ach = pr["flops"] / (pr["ms"] * 1e-3) / 1e12
-        roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                "traffic": traffic, "launches": pr["count"], "avg_launch_ms": pr["ms"] / pr["count"], "peak_source": peak_src,
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                "traffic": traffic_db.get(name), "launches_per_step": pr["count"] / nprof, "avg_launch_ms": pr["ms"] / pr["count"],
+                "ms_per_step": pr["ms"] / nprof, "peak_source": peak_src,
                 "hbm_gbs_algorithmic": pr["bytes"] / (pr["ms"] * 1e-3) / 1e9}
-    ps = eng.profile_read("nsf_source")
-    if ps and ps["ms"] > 0:
-        a = ps["bytes"] / (ps["ms"] * 1e-3) / 1e9
-        secondary.append({"kernel": "nsf_source", "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak})
+
+    def hbm_entry(name):
+        pr = eng.profile_read(name)
+        if not pr or pr["ms"] <= 0 or pr["bytes"] <= 0:
+            return None
+        a = pr["bytes"] / (pr["ms"] * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
+                "traffic": traffic_db.get(name), "launches_per_step": pr["count"] / nprof, "ms_per_step": pr["ms"] / nprof}
+
+    if args.precision == "tc":
+        tensor_names = ["snake_conv", "pair_tc", "resblock_tc", "ups_tc", "flow_tc"] if snake else ["pair_tc", "resblock_tc", "ups_tc", "flow_tc"]
+    else:
+        tensor_names = ["pair_f32"]
+    entries = [e for e in (tensor_entry(n) for n in tensor_names) if e]
+    if entries:
+        entries.sort(key=lambda e: -e["ms_per_step"])
+        roof = entries[0]                      # the dominant kernel family of this step
+        secondary.extend(entries[1:])
+    for n in ("nsf_source", "conv_post"):
+        e = hbm_entry(n)
+        if e:
+            secondary.append(e)
     for nm in ("flow", "generator"):
         pp = eng.profile_read(nm)
         if pp:
             secondary.append({"kernel": nm, "ms_per_step": pp["ms"] / max(1, pp["count"])})
     eng.profile_enable(False)
+    fallbacks = eng.fallback_count - fb0
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sd_cpu = {k: v.cpu() for k, v in sd.items()}
         cores = pick_threads(cfg, sd_cpu)
-        rate, times = cpu_oracle_rate(cfg, sd_cpu, T, runs=2, warmup=1, threads=cores)
+        cpu_oracle_rate(cfg, sd_cpu, 64, runs=1, warmup=0, threads=cores, B=1)      # short warm-up
+        rate, times = cpu_oracle_rate(cfg, sd_cpu, T, runs=1, warmup=0, threads=cores, B=B)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"oracle port of SynthesizerTrn.infer, 1 utterance x {T} frames, 1 warm-up + 2 timed runs ({sum(times):.1f} s)"}
+               "sample": f"oracle port of SynthesizerTrn.infer, the full batch ({B} utterances x {T} frames) once after a short "
+                         f"warm-up ({sum(times):.1f} s of CPU work)"}
 
     if rank == 0:
         total_samples = float(B * world * N)
@@ -302,14 +479,14 @@ def main():
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16 operands / f32 accumulate (tcgen05)" if args.precision == "tc" else "f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "global_batch": B * world, "frames": T, "samples_per_item": N,
+                "config": {"workload": WORKLOAD_SNAKE if snake else WORKLOAD, "global_batch": B * world, "frames": T, "samples_per_item": N,
                            "parallelism": f"dp{world}", "precision": args.precision,
                            "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
                            "rtf": value / 44100.0},
                 "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_secondary": secondary,
-                "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "ffma_fallbacks_in_tc": int(fallbacks), "clocks": clocks, "roofline": roof,
+                "roofline_secondary": secondary, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -142,6 +142,9 @@ SVB_API const char* svb_strerror(int status);
 SVB_API const char* svb_last_error(const svb_ctx* ctx);
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 SVB_API int64_t svb_launch_count(const svb_ctx* ctx);
+/* number of times a call made in SVB_PREC_TC had to run (part of) its work on the fp32 FFMA kernels (unsupported shapes /
+ * conditioning).  The result is still correct but ~15x slower; the first occurrence also prints one line on stderr. */
+SVB_API int64_t svb_fallback_count(const svb_ctx* ctx);
 /* copies an internal activation ("z","conv_pre","ups0".."ups4","stage0".."stage4") of the LAST
  * svb_generator/svb_infer_tail call into dst (device, fp32, n floats); test hook. */
 SVB_API int svb_debug_enable(svb_ctx* ctx, int on);

@@ -90,7 +90,7 @@ def infer_slices(net, items: Sequence[dict], noice_scale: float = 0.4, seed: int
         x_mask = (torch.arange(Tm, device=dev)[None, :] < lengths[:, None]).to(c.dtype)[:, None, :]
         g = net.emb_g(sid).transpose(1, 2)
         x = net.pre(c) * x_mask + net.emb_uv(uv.long()).transpose(1, 2)
-        all_ones = bool((lengths == Tm).all())
+        all_ones = all(lens[i] == Tm for i in idx)          # host-side: no device sync
         z_p, _, _, _ = net.enc_p(x, x_mask, f0_to_coarse(f0), noice_scale=noice_scale, z_noise=nz["z_noise"], all_ones_mask=all_ones)
         eng = net._engine(dev)
         o = eng.infer_tail(z_p, g, f0, nz["rand_ini"], nz["har_noise"], None if all_ones else lengths)

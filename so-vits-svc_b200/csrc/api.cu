@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstdio>
@@ -30,7 +31,9 @@ struct ConvW {            // folded fp32 weights of one Conv1d, packed [Cin][k][
     float* w = nullptr;
     float* b = nullptr;
     int Cin = 0, Cout = 0, k = 0;
-    void* w_tc = nullptr;  // tensor-core image (fp16, swizzled), when built
+    void* w_tc = nullptr;  // tensor-core image (fp16, swizzled), when built: holds w * tc_scale
+    float tc_scale = 1.f;  // power-of-two range normalisation of the fp16 image (1 unless max|w| leaves [2^-6, 2^6])
+    float* b_tc = nullptr; // bias * tc_scale (what a FIRST conv of a ResBlock pair adds before its LeakyReLU); == b when tc_scale == 1
 };
 
 struct ConvNW {           // tensor-core image of one layer for convn_tc_kernel
@@ -38,6 +41,7 @@ struct ConvNW {           // tensor-core image of one layer for convn_tc_kernel
     float* bias = nullptr;   // per column, column order
     int cinp = 0, cin_real = 0, N_total = 0, NC = 0, k = 1, pad_left = 0;
     int noise = 0, noise_stride = 0, noise_w0 = 0;   // fused noise conv (polyphase ups of the narrow stages)
+    float acc_scale = 1.f;   // 1 / (power-of-two range normalisation applied to the fp16 image)
 };
 
 struct FlowLayer {
@@ -68,6 +72,7 @@ struct Stage {
     float* noise_b = nullptr;
     int noise_K = 0, noise_s = 0, noise_p = 0;
     std::vector<ConvW> c1, c2;     // [branch*3 + d]
+    std::vector<ConvNW> c1n, c2n;  // the same convolutions as convn images (Snake generator: SnakeAlias-loader conv kernel)
     ConvNW up_tc;
     ConvNW noise_tc;               // wide noise_convs (stage 0): a 2-tap GEMM over 64-sample excitation rows
 };
@@ -104,6 +109,8 @@ struct svb_ctx {
                                 // against the 128-bit thread loader on B200, so off by default; env SVB_TC_TMA overrides
     int opt_fuse_rb = 1;        // fused ResBlock kernel for narrow stages
     int opt_fuse_maxc = 64;     // ... up to this channel count (C = 64 fused: 12.6 vs 13.15 ms/step against the pair chain)
+    int64_t ffma_fallbacks = 0;    // times a "tc" call ran (part of) its work on the fp32 FFMA kernels
+    bool warned_fallback = false;
     bool profile = false;
     struct ProfEntry { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; double flops = 0, bytes = 0; };
     std::map<std::string, ProfEntry> prof;
@@ -112,9 +119,33 @@ struct svb_ctx {
 
 namespace {
 
+// Every entry point switches to the context's device for its own duration and restores the caller's current device on
+// every exit path (the reference's Svc(device="cuda:1") never calls torch.cuda.set_device; svb_destroy may run at GC time).
+struct DevGuard {
+    int prev = -1; bool ok = true;
+    explicit DevGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+        else prev = -1;                    // nothing to restore
+    }
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DevGuard(const DevGuard&) = delete;
+    DevGuard& operator=(const DevGuard&) = delete;
+};
+
 int fail(svb_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
     return code;
+}
+
+// A call in SVB_PREC_TC that cannot use the tensor-core kernels still computes the right answer on the FFMA kernels, ~15x
+// slower: count it (svb_fallback_count) and say so once on stderr instead of degrading silently.
+void note_fallback(svb_ctx* c, const char* why) {
+    c->ffma_fallbacks++;
+    if (!c->warned_fallback) {
+        c->warned_fallback = true;
+        std::fprintf(stderr, "[libsovits_b200] warning: precision=tc but running fp32 FFMA kernels (%s); further occurrences are only counted\n", why);
+    }
 }
 
 #define CU(call)                                                                                   \
@@ -213,9 +244,22 @@ int make_conv(svb_ctx* ctx, const std::vector<float>& w, const std::vector<float
     if (Cin == Cout && (k == 3 || k == 7 || k == 11) && (Cin == 16 || Cin == 32 || Cin == 64 || Cin == 128 || Cin == 256)) {
         size_t ib = tc_weight_image_bytes(Cin, k);
         std::vector<uint8_t> img(ib);
-        tc_pack_weight_image(w.data(), Cin, k, img.data());
+        // fp16 range: see make_convn.  LeakyReLU is positively homogeneous, so a pair computes
+        //   x + conv2'(lrelu(conv1'(lrelu x) + s1 b1)) / (s1 s2) + b2   with conv' = the normalised images.
+        float wmax = 0.f;
+        for (float v : w) wmax = std::max(wmax, std::fabs(v));
+        out.tc_scale = 1.f;
+        if (wmax > 0.f && std::isfinite(wmax) && (wmax < 0.015625f || wmax > 64.f)) out.tc_scale = std::exp2(-std::round(std::log2(wmax)));
+        tc_pack_weight_image(w.data(), Cin, k, img.data(), out.tc_scale);
         rc = upload(ctx, img.data(), ib, &out.w_tc);
         if (rc) return rc;
+        out.b_tc = out.b;
+        if (out.tc_scale != 1.f) {
+            std::vector<float> bs(Cout);
+            for (int co = 0; co < Cout; ++co) bs[co] = bb[co] * out.tc_scale;
+            rc = upload(ctx, bs.data(), bs.size() * sizeof(float), (void**)&out.b_tc);
+            if (rc) return rc;
+        }
     }
     return SVB_OK;
 }
@@ -227,7 +271,23 @@ int make_convn(svb_ctx* ctx, int cinp, int cin_real, int N_total, int NC, int k,
     out.noise = ncol ? noise_kind : 0;
     const size_t ib = convn_weight_image_bytes(cinp, N_total, NC, k, out.noise);
     std::vector<uint8_t> img(ib);
-    convn_pack_weight_image(cinp, N_total, NC, k, [&](int col, int ci, int tap) { return ci < cin_real ? wcol(col, ci, tap) : 0.f; }, ncol, out.noise, img.data());
+    // fp16 has a 5-bit exponent (TF32, the reference's CUDA arithmetic, has 8): weights far from 1 would lose bits to
+    // subnormals (< 6e-5) or overflow (> 65504).  Normalise the layer by a power of two (exact) when its largest weight
+    // leaves [2^-6, 2^6]; the epilogue multiplies the fp32 accumulator by the inverse.
+    float wmax = 0.f;
+    for (int col = 0; col < N_total; ++col)
+        for (int ci = 0; ci < cin_real; ++ci)
+            for (int tap = 0; tap < k; ++tap) wmax = std::max(wmax, std::fabs(wcol(col, ci, tap)));
+    if (ncol)
+        for (int col = 0; col < N_total; ++col)
+            for (int u = 0; u < (noise_kind == 2 ? 80 : 16); ++u) wmax = std::max(wmax, std::fabs((*ncol)(col, u)));
+    float wscale = 1.f;
+    if (wmax > 0.f && std::isfinite(wmax) && (wmax < 0.015625f || wmax > 64.f)) wscale = std::exp2(-std::round(std::log2(wmax)));
+    out.acc_scale = 1.f / wscale;
+    std::function<float(int, int)> ncol_s;
+    if (ncol) ncol_s = [&](int col, int u) { return (*ncol)(col, u) * wscale; };
+    convn_pack_weight_image(cinp, N_total, NC, k, [&](int col, int ci, int tap) { return ci < cin_real ? wcol(col, ci, tap) * wscale : 0.f; },
+                            ncol ? &ncol_s : nullptr, out.noise, img.data());
     int rc = upload(ctx, img.data(), ib, &out.img);
     if (rc) return rc;
     std::vector<float> bc(N_total);
@@ -329,6 +389,7 @@ struct ProfScope {
 int check_launch(svb_ctx* ctx, const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, SVB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    if (sticky_launch_error()) { sticky_launch_error() = 0; return fail(ctx, SVB_ERR_CUDA, std::string(what) + ": kernel set-up failed (dynamic shared memory opt-in)"); }
     return SVB_OK;
 }
 
@@ -344,13 +405,14 @@ int run_flow(svb_ctx* ctx, const float* z_p, const float* g, int gT, const int32
     float* gcond = reinterpret_cast<float*>(ws + pl.off_gcond);
     if (y != z_p) CU(cudaMemcpyAsync(y, z_p, (size_t)B * C * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
     const bool use_tc = ctx->precision == SVB_PREC_TC && ctx->flow_tc_ok && gT == 1;
+    if (ctx->precision == SVB_PREC_TC && !use_tc) note_fallback(ctx, gT != 1 ? "flow: time-varying conditioning g" : "flow: unsupported layer shapes");
     for (int fl = c.n_flows - 1; use_tc && fl >= 0; --fl) {
         FlowLayer& F = ctx->flow[fl];
         int trc;
         auto base_args = [&](const ConvNW& W, const float* x, int x_ctot, int x_c0) {
             ConvNTC a;
             a.x = x; a.x_ctot = x_ctot; a.x_c0 = x_c0; a.cin_real = W.cin_real; a.cinp = W.cinp; a.Tin = T;
-            a.w = W.img; a.bias = W.bias; a.k = W.k; a.dil = 1; a.pad_left = W.pad_left;
+            a.w = W.img; a.bias = W.bias; a.acc_scale = W.acc_scale; a.k = W.k; a.dil = 1; a.pad_left = W.pad_left;
             a.n_rows = T; a.N_total = W.N_total; a.NC = W.NC; a.chunks_per_cta = 1; a.Ty = T; a.lengths = lengths; a.B = B;
             return a;
         };
@@ -484,16 +546,18 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         launch_conv_f32(cg, st);
         cp.bias_t = dg; cp.bias_t_ctot = U;
     }
-    // The SnakeAlias variant is a time-domain filter around every activation, not an elementwise op: it runs as its own
-    // kernel in front of the fp32 FFMA convolutions (the tensor-core kernels fuse LeakyReLU and are not used for it).
+    // The SnakeAlias variant is a time-domain filter around every activation, not an elementwise op.  Tensor-core path: it
+    // is computed by the LOADER of the conv kernel (convn_tc_kernel<.., SNAKE>), one launch per convolution; fp32 path: its
+    // own kernel in front of the FFMA convolutions.
     const bool snake = c.snake != 0;
     float* Sb = snake ? reinterpret_cast<float*>(ws + pl.off_S) : nullptr;
-    const bool gen_tc = ctx->precision == SVB_PREC_TC && ctx->gen_tc_ok && (gT == 1 || melv) && !snake;
+    const bool gen_tc = ctx->precision == SVB_PREC_TC && ctx->gen_tc_ok && (gT == 1 || melv);
+    if (ctx->precision == SVB_PREC_TC && !gen_tc) note_fallback(ctx, "generator: conditioning/shape not served by the tensor-core kernels");
     if (gen_tc) {
         const ConvNW& W = ctx->conv_pre_tc;
         ConvNTC a;
         a.x = z; a.x_ctot = Cpre; a.cin_real = W.cin_real; a.cinp = W.cinp; a.Tin = T;
-        a.w = W.img; a.bias = W.bias;
+        a.w = W.img; a.bias = W.bias; a.acc_scale = W.acc_scale;
         if (!melv) { a.bias_b = dg; a.bias_b_stride = U; a.bias_b_off = 0; }
         a.k = W.k; a.pad_left = W.pad_left; a.n_rows = T; a.N_total = W.N_total; a.NC = W.NC; a.chunks_per_cta = 1; a.Ty = T; a.B = B;
         a.seg[0].y = pre; a.seg[0].y_ctot = U; a.seg[0].col0 = 0; a.seg[0].col1 = U;
@@ -511,7 +575,7 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         Stage& S = ctx->stages[i];
         const int Lout = Lin * S.s;
         // x = ups(lrelu(x, 0.1))  as s polyphase 2-tap convs
-        if (snake) launch_snake_alias(cur, Sb, S.snake_in.ealpha, S.snake_in.inv_beta, ctx->snake_filt, B, S.Cin, Lin, st);
+        if (snake && !gen_tc) launch_snake_alias(cur, Sb, S.snake_in.ealpha, S.snake_in.inv_beta, ctx->snake_filt, B, S.Cin, Lin, st);
         ConvF32 up;
         up.x = snake ? Sb : cur; up.x_ctot = S.Cin; up.Cin = S.Cin; up.Tin = Lin;
         up.w = S.up_w; up.bias = S.up_b; up.Cout = S.Cout; up.k = 2; up.dil = 1; up.pad_left = 1;
@@ -522,12 +586,15 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         if (gen_tc) {
             const ConvNW& W = S.up_tc;
             ConvNTC a;
-            a.x = cur; a.x_ctot = S.Cin; a.cin_real = S.Cin; a.cinp = W.cinp; a.Tin = Lin; a.in_act = 1; a.in_slope = 0.1f;
-            a.w = W.img; a.bias = W.bias; a.k = 2; a.pad_left = 1; a.n_rows = Lin + 1; a.N_total = W.N_total; a.NC = W.NC;
+            a.x = cur; a.x_ctot = S.Cin; a.cin_real = S.Cin; a.cinp = W.cinp; a.Tin = Lin; a.in_act = snake ? 0 : 1; a.in_slope = 0.1f;
+            if (snake) { a.snake_ealpha = S.snake_in.ealpha; a.snake_invbeta = S.snake_in.inv_beta; a.snake_filt = ctx->snake_filt; }
+            a.w = W.img; a.bias = W.bias; a.acc_scale = W.acc_scale; a.k = 2; a.pad_left = 1; a.n_rows = Lin + 1; a.N_total = W.N_total; a.NC = W.NC;
             a.chunks_per_cta = (W.N_total + W.NC - 1) / W.NC;
             a.mode = 1; a.s = S.s; a.p = S.p; a.Ty = Lout; a.B = B;
             a.seg[0].y = X; a.seg[0].y_ctot = S.Cout;
             if (W.noise) { a.har = har; a.har_N = (int)N; a.noise_stride = W.noise_stride; a.noise_w0 = W.noise_w0; a.noise_wide = (W.noise == 2); }
+            ProfScope ps(ctx, "ups_tc", st, 2.0 * 2.0 * S.Cin * (double)S.Cout * (double)Lout * B,
+                         ((double)S.Cin * Lin + (double)S.Cout * Lout + (W.noise ? (double)N : 0.0)) * B * sizeof(float));
             int trc = launch_convn_tc(a, st);
             if (trc) return fail(ctx, trc, "convn launch failed (ups)");
         } else {
@@ -538,7 +605,7 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
             ConvNTC a;
             a.x = har; a.cin_real = 64; a.cinp = 64; a.Tin = Lout + 1;
             a.view_bstride = N; a.view_tstride = S.noise_s; a.view_cstride = 1; a.view_off = -S.noise_p; a.view_limit = N;
-            a.w = W.img; a.bias = W.bias; a.k = 2; a.pad_left = 0; a.n_rows = Lout; a.N_total = W.N_total; a.NC = W.NC;
+            a.w = W.img; a.bias = W.bias; a.acc_scale = W.acc_scale; a.k = 2; a.pad_left = 0; a.n_rows = Lout; a.N_total = W.N_total; a.NC = W.NC;
             a.chunks_per_cta = (W.N_total + W.NC - 1) / W.NC; a.Ty = Lout; a.B = B;
             a.seg[0].y = X; a.seg[0].y_ctot = S.Cout; a.seg[0].col0 = 0; a.seg[0].col1 = S.Cout; a.seg[0].beta = 1.f;
             int trc = launch_convn_tc(a, st);
@@ -553,6 +620,41 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         const int fuse_maxc = ctx->opt_fuse_maxc;
         for (int j = 0; j < nk; ++j) {
             const int k = c.resblock_kernel_sizes[j];
+            if (gen_tc && snake && !S.c1n.empty()) {
+                // Snake ResBlock (vdecoder/hifiganwithsnake/models.py:61-72): x = x + c2(a2(c1(a1(x)))) per dilation, every
+                // convolution one tcgen05 launch with the SnakeAlias activation computed by its loader
+                const float* src = X;
+                float* pp[2] = {A, Bb};
+                for (int d = 0; d < 3; ++d) {
+                    const int dil = c.resblock_dilations[j][d];
+                    const bool last = (d == 2);
+                    float* dst = last ? O : pp[d & 1];
+                    auto conv = [&](const ConvNW& W, const SnakeP& act, const float* x, int cdil, float* y, const float* res, float alpha, float beta) {
+                        ConvNTC a;
+                        a.x = x; a.x_ctot = S.Cout; a.cin_real = S.Cout; a.cinp = W.cinp; a.Tin = Lout;
+                        a.snake_ealpha = act.ealpha; a.snake_invbeta = act.inv_beta; a.snake_filt = ctx->snake_filt;
+                        a.w = W.img; a.bias = W.bias; a.acc_scale = W.acc_scale; a.k = k; a.dil = cdil; a.pad_left = cdil * (k - 1) / 2;
+                        a.n_rows = Lout; a.N_total = W.N_total; a.NC = W.NC; a.chunks_per_cta = (W.N_total + W.NC - 1) / W.NC; a.Ty = Lout; a.B = B;
+                        a.seg[0].y = y; a.seg[0].y_ctot = S.Cout; a.seg[0].col0 = 0; a.seg[0].col1 = S.Cout;
+                        a.seg[0].res = res; a.seg[0].res_ctot = S.Cout; a.seg[0].alpha = alpha; a.seg[0].beta = beta;
+                        return launch_convn_tc(a, st);
+                    };
+                    const double cflops = 2.0 * S.Cout * (double)S.Cout * k * (double)Lout * B;
+                    int trc;
+                    {
+                        ProfScope ps(ctx, "snake_conv", st, cflops, 2.0 * S.Cout * (double)Lout * B * sizeof(float));
+                        trc = conv(S.c1n[j * 3 + d], S.acts[j * 6 + 2 * d], src, dil, Tm, nullptr, 1.f, 0.f);
+                    }
+                    if (trc) return fail(ctx, trc, "snake conv launch failed (c1)");
+                    {
+                        ProfScope ps(ctx, "snake_conv", st, cflops, 3.0 * S.Cout * (double)Lout * B * sizeof(float));
+                        trc = conv(S.c2n[j * 3 + d], S.acts[j * 6 + 2 * d + 1], Tm, 1, dst, src, last ? 1.f / nk : 1.f, (last && j > 0) ? 1.f : 0.f);
+                    }
+                    if (trc) return fail(ctx, trc, "snake conv launch failed (c2)");
+                    src = dst;
+                }
+                continue;
+            }
             if (ctx->precision == SVB_PREC_TC && !snake && fuse_rb && S.Cout <= fuse_maxc && S.c1[j * 3].w_tc) {
                 // narrow stages: the whole ResBlock in one kernel (residual stream in TMEM)
                 ResblockTC rb;
@@ -560,7 +662,8 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
                 for (int d = 0; d < 3; ++d) {
                     rb.dil[d] = c.resblock_dilations[j][d];
                     rb.w[2 * d] = S.c1[j * 3 + d].w_tc; rb.w[2 * d + 1] = S.c2[j * 3 + d].w_tc;
-                    rb.bias[2 * d] = S.c1[j * 3 + d].b; rb.bias[2 * d + 1] = S.c2[j * 3 + d].b;
+                    rb.bias[2 * d] = S.c1[j * 3 + d].b_tc; rb.bias[2 * d + 1] = S.c2[j * 3 + d].b;
+                    rb.inv[d] = 1.f / (S.c1[j * 3 + d].tc_scale * S.c2[j * 3 + d].tc_scale);
                 }
                 rb.alpha = 1.f / nk; rb.beta = (j > 0) ? 1.f : 0.f;
                 const double rflops = 3 * 2.0 * 2.0 * S.Cout * (double)S.Cout * k * (double)Lout * B;
@@ -585,7 +688,8 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
                 ProfScope ps(ctx, (ctx->precision == SVB_PREC_TC && W1.w_tc && !snake) ? "pair_tc" : "pair_f32", st, pair_flops, pair_bytes);
                 if (ctx->precision == SVB_PREC_TC && !snake && W1.w_tc && W2.w_tc) {
                     PairTC pt;
-                    pt.x = src; pt.out = dst; pt.w1 = W1.w_tc; pt.w2 = W2.w_tc; pt.b1 = W1.b; pt.b2 = W2.b;
+                    pt.x = src; pt.out = dst; pt.w1 = W1.w_tc; pt.w2 = W2.w_tc; pt.b1 = W1.b_tc; pt.b2 = W2.b;
+                    pt.inv = 1.f / (W1.tc_scale * W2.tc_scale);
                     pt.B = B; pt.C = S.Cout; pt.T = Lout; pt.k = k; pt.dil = dil; pt.alpha = alpha; pt.beta = beta;
                     if (use_tma && pair_tc_supports_tma(S.Cout, -1)) {
                         // pair d writes lrelu(out) as fp16 [B][T][C]; pair d+1 loads its operand tile from it with TMA
@@ -623,11 +727,14 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         cur = tmp;
         Lin = Lout;
     }
-    if (snake) {
-        launch_snake_alias(cur, Sb, ctx->snake_post.ealpha, ctx->snake_post.inv_beta, ctx->snake_filt, B, ctx->post_C, Lin, st);
-        launch_conv_post(Sb, ctx->post_w, ctx->post_b, wav, B, ctx->post_C, Lin, ctx->post_K, 1.0f, st);   // slope 1 = no activation
-    } else {
-        launch_conv_post(cur, ctx->post_w, ctx->post_b, wav, B, ctx->post_C, Lin, ctx->post_K, 0.01f, st);
+    {
+        ProfScope ps(ctx, "conv_post", st, 0, (double)(ctx->post_C + 1) * (double)Lin * B * sizeof(float));
+        if (snake) {
+            launch_snake_alias(cur, Sb, ctx->snake_post.ealpha, ctx->snake_post.inv_beta, ctx->snake_filt, B, ctx->post_C, Lin, st);
+            launch_conv_post(Sb, ctx->post_w, ctx->post_b, wav, B, ctx->post_C, Lin, ctx->post_K, 1.0f, st);   // slope 1 = no activation
+        } else {
+            launch_conv_post(cur, ctx->post_w, ctx->post_b, wav, B, ctx->post_C, Lin, ctx->post_K, 0.01f, st);
+        }
     }
     return check_launch(ctx, "generator");
 }
@@ -656,6 +763,7 @@ const char* svb_strerror(int s) {
 
 const char* svb_last_error(const svb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int64_t svb_launch_count(const svb_ctx*) { return launch_counter(); }
+int64_t svb_fallback_count(const svb_ctx* ctx) { return ctx ? ctx->ffma_fallbacks : -1; }
 
 int svb_create(int device, svb_ctx** out) {
     if (!out) return SVB_ERR_INVALID_ARG;
@@ -665,7 +773,8 @@ int svb_create(int device, svb_ctx** out) {
     cudaDeviceProp p;
     if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return SVB_ERR_CUDA;
     if (p.major != 10) return SVB_ERR_ARCH;   // sm_100a binary only: fail loudly elsewhere
-    if (cudaSetDevice(device) != cudaSuccess) return SVB_ERR_CUDA;
+    DevGuard dg(device);
+    if (!dg.ok) return SVB_ERR_CUDA;
     svb_ctx* c = new svb_ctx();
     c->device = device;
     if (const char* e = std::getenv("SVB_TC_TMA")) c->opt_tma = std::atoi(e);
@@ -677,7 +786,7 @@ int svb_create(int device, svb_ctx** out) {
 
 void svb_destroy(svb_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DevGuard dg(ctx->device);
     for (void* p : ctx->allocs) cudaFree(p);
     if (ctx->ws.p) cudaFree(ctx->ws.p);
     if (ctx->host_io.p) cudaFree(ctx->host_io.p);
@@ -714,7 +823,8 @@ int svb_debug_pair(svb_ctx* ctx, int stage, int j, int d, const float* x, float*
                    float alpha, float beta, void* stream) {
     if (!ctx || !ctx->loaded) return SVB_ERR_NOT_LOADED;
     if (stage < 0 || stage >= ctx->cfg.n_upsamples || j < 0 || j >= 3 || d < 0 || d >= 3 || !x || !out) return SVB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(ctx->device));
+    DevGuard dg__(ctx->device);
+    if (!dg__.ok) return fail(ctx, SVB_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = (cudaStream_t)stream;
     Stage& S = ctx->stages[stage];
     const int k = ctx->cfg.resblock_kernel_sizes[j], dil = ctx->cfg.resblock_dilations[j][d];
@@ -722,7 +832,8 @@ int svb_debug_pair(svb_ctx* ctx, int stage, int j, int d, const float* x, float*
     const ConvW& W2 = S.c2[j * 3 + d];
     if (variant >= 0) {
         PairTC pt;
-        pt.x = x; pt.out = out; pt.w1 = W1.w_tc; pt.w2 = W2.w_tc; pt.b1 = W1.b; pt.b2 = W2.b;
+        pt.x = x; pt.out = out; pt.w1 = W1.w_tc; pt.w2 = W2.w_tc; pt.b1 = W1.b_tc; pt.b2 = W2.b;
+        pt.inv = 1.f / (W1.tc_scale * W2.tc_scale);
         pt.B = B; pt.C = S.Cout; pt.T = L; pt.k = k; pt.dil = dil; pt.alpha = alpha; pt.beta = beta; pt.variant = variant;
         int rc = launch_pair_tc(pt, st);
         if (rc) return fail(ctx, rc, "pair kernel launch failed");
@@ -751,14 +862,16 @@ int svb_debug_resblock(svb_ctx* ctx, int stage, int j, const float* x, float* ou
                        float alpha, float beta, void* stream) {
     if (!ctx || !ctx->loaded) return SVB_ERR_NOT_LOADED;
     if (stage < 0 || stage >= ctx->cfg.n_upsamples || j < 0 || j >= 3 || !x || !out) return SVB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(ctx->device));
+    DevGuard dg__(ctx->device);
+    if (!dg__.ok) return fail(ctx, SVB_ERR_CUDA, "cudaSetDevice failed");
     Stage& S = ctx->stages[stage];
     ResblockTC rb;
     rb.x = x; rb.out = out; rb.B = B; rb.C = S.Cout; rb.T = L; rb.k = ctx->cfg.resblock_kernel_sizes[j];
     for (int d = 0; d < 3; ++d) {
         rb.dil[d] = ctx->cfg.resblock_dilations[j][d];
         rb.w[2 * d] = S.c1[j * 3 + d].w_tc; rb.w[2 * d + 1] = S.c2[j * 3 + d].w_tc;
-        rb.bias[2 * d] = S.c1[j * 3 + d].b; rb.bias[2 * d + 1] = S.c2[j * 3 + d].b;
+        rb.bias[2 * d] = S.c1[j * 3 + d].b_tc; rb.bias[2 * d + 1] = S.c2[j * 3 + d].b;
+        rb.inv[d] = 1.f / (S.c1[j * 3 + d].tc_scale * S.c2[j * 3 + d].tc_scale);
     }
     rb.alpha = alpha; rb.beta = beta; rb.variant = variant;
     int rc = launch_resblock_tc(rb, (cudaStream_t)stream);
@@ -804,7 +917,8 @@ int svb_debug_fetch(svb_ctx* ctx, const char* what, float* dst, size_t n, void* 
 
 int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, const svb_model_cfg* cfgp) {
     if (!ctx || !tensors || !cfgp || n_tensors <= 0) return SVB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(ctx->device));
+    DevGuard dg__(ctx->device);
+    if (!dg__.ok) return fail(ctx, SVB_ERR_CUDA, "cudaSetDevice failed");
     const svb_model_cfg& c = *cfgp;
     if (c.num_mels > 0 && c.snake) return fail(ctx, SVB_ERR_UNSUPPORTED, "mel vocoder has no snake variant");
     if (c.n_upsamples < 1 || c.n_upsamples > 8 || c.n_resblock_kernels != 3 || (c.num_mels == 0 && c.n_flows != 4) ||
@@ -815,6 +929,19 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
             return fail(ctx, SVB_ERR_UNSUPPORTED, "upsample kernel size must be 2x the rate (polyphase 2-tap form)");
     if ((c.upsample_initial_channel >> c.n_upsamples) < 1 || (c.hidden_channels % 8) || (c.inter_channels % 16))
         return fail(ctx, SVB_ERR_UNSUPPORTED, "channel counts must be multiples of 8");
+    // A context may be re-loaded (the Python side re-packs after .to()/.half()/load_state_dict): drop the previous weight
+    // images first, and leave the context "not loaded" unless this call succeeds completely.
+    if (!ctx->allocs.empty() || ctx->loaded) {
+        CU(cudaDeviceSynchronize());
+        for (void* p : ctx->allocs) cudaFree(p);
+        ctx->allocs.clear();
+    }
+    ctx->loaded = false;
+    ctx->flow.clear(); ctx->stages.clear();
+    ctx->conv_pre = ConvW(); ctx->conv_pre_tc = ConvNW(); ctx->dcond = ConvW();
+    ctx->dcond_w_nat = nullptr; ctx->dcond_b = nullptr; ctx->post_w = nullptr; ctx->lin_w = nullptr; ctx->snake_filt = nullptr;
+    ctx->snake_post = SnakeP();
+    ctx->flow_tc_ok = false; ctx->gen_tc_ok = false;
     TMap m;
     for (int i = 0; i < n_tensors; ++i)
         if (tensors[i].name && tensors[i].data) m[tensors[i].name] = &tensors[i];
@@ -1000,6 +1127,8 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
         }
         S.c1.assign(9, ConvW());
         S.c2.assign(9, ConvW());
+        const bool snake_tc = c.snake && ctx->gen_tc_ok && (S.Cout == 256 || S.Cout == 128 || S.Cout == 64 || S.Cout == 32 || S.Cout == 16);
+        if (snake_tc) { S.c1n.assign(9, ConvNW()); S.c2n.assign(9, ConvNW()); }
         for (int j = 0; j < 3; ++j) {
             const int k = c.resblock_kernel_sizes[j];
             const std::string r = DP + "resblocks." + std::to_string(i * 3 + j) + ".";
@@ -1007,9 +1136,18 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
                 if ((rc = folded(ctx, m, r + "convs1." + std::to_string(d), {S.Cout, S.Cout, k}, w))) return rc;
                 if ((rc = get_tensor(ctx, m, r + "convs1." + std::to_string(d) + ".bias", {S.Cout}, b))) return rc;
                 if ((rc = make_conv(ctx, w.v, b.v, S.Cout, S.Cout, k, false, false, S.c1[j * 3 + d]))) return rc;
+                auto as_convn = [&](ConvNW& dstw) {
+                    const std::vector<float> wv = w.v, bv = b.v;
+                    const int Cc = S.Cout;
+                    return make_convn(ctx, Cc, Cc, Cc, Cc, k, 0 /* pad_left is set per launch (dilation) */,
+                                      [&](int col, int ci, int tap) { return wv[((size_t)col * Cc + ci) * k + tap]; },
+                                      [&](int col) { return bv[col]; }, dstw);
+                };
+                if (snake_tc && (rc = as_convn(S.c1n[j * 3 + d]))) return rc;
                 if ((rc = folded(ctx, m, r + "convs2." + std::to_string(d), {S.Cout, S.Cout, k}, w))) return rc;
                 if ((rc = get_tensor(ctx, m, r + "convs2." + std::to_string(d) + ".bias", {S.Cout}, b))) return rc;
                 if ((rc = make_conv(ctx, w.v, b.v, S.Cout, S.Cout, k, false, false, S.c2[j * 3 + d]))) return rc;
+                if (snake_tc && (rc = as_convn(S.c2n[j * 3 + d]))) return rc;
             }
         }
     }
@@ -1059,7 +1197,8 @@ size_t svb_workspace_bytes(const svb_ctx* ctx, int B, int T) {
     if (!ctx) return SVB_ERR_INVALID_ARG;                                              \
     if (!ctx->loaded) return fail(ctx, SVB_ERR_NOT_LOADED, "svb_load_weights first");  \
     if (B < 1 || T < 1) return fail(ctx, SVB_ERR_INVALID_ARG, "B and T must be >= 1"); \
-    CU(cudaSetDevice(ctx->device));
+    DevGuard dg__(ctx->device);                                                        \
+    if (!dg__.ok) return fail(ctx, SVB_ERR_CUDA, "cudaSetDevice failed");
 
 int svb_flow_reverse(svb_ctx* ctx, const float* z_p, const float* g, int gT, const int32_t* lengths,
                      float* z_out, int B, int T, void* ws, size_t ws_bytes, void* stream) {
@@ -1129,6 +1268,8 @@ int svb_infer_tail(svb_ctx* ctx, const float* z_p, const float* g, int gT, const
     float* har = reinterpret_cast<float*>(base + pl.off_har);
     {
         ProfScope ps(ctx, "flow", st, 0, 0);
+        // per frame: 4 coupling layers x (pre 96x192 + 4 x (k5 192x384 + 192x384|192) + post 192x96) MACs (14.156 MFLOP/frame)
+        ProfScope ps2(ctx, ctx->precision == SVB_PREC_TC ? "flow_tc" : "flow_f32", st, 14.156e6 * (double)B * T, 4.0 * 1152.0 * (double)B * T);
         if ((rc = run_flow(ctx, z_p, g, gT, lengths, z, B, T, base, pl, st))) return rc;
     }
     if ((rc = dbg_keep(ctx, "z", z, (size_t)B * ctx->cfg.inter_channels * T, st))) return rc;

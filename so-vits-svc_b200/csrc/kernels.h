@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <functional>
 
 namespace svb {
@@ -67,6 +68,7 @@ struct PairTC {
     const float* b1 = nullptr; const float* b2 = nullptr;
     int B = 1, C = 0, T = 0, k = 3, dil = 1;
     float alpha = 1.f, beta = 0.f;
+    float inv = 1.f;               // 1 / (s1*s2): the weight images hold w1*s1, w2*s2 (power-of-two range normalisation), b1 = s1*bias1
     int variant = -1;              // -1: library default (env SVB_TC_VARIANT), else explicit tile variant
     const void* a16_in = nullptr;  // optional fp16 [B][T][C] copy of lrelu(x): the A tile is then loaded by TMA (tensor map)
     void* a16_out = nullptr;       // optional fp16 [B][T][C] copy of lrelu(out) for the next pair
@@ -75,7 +77,7 @@ bool pair_tc_supports_tma(int C, int variant);
 int launch_pair_tc(const PairTC& a, cudaStream_t st);   // returns 0 or a negative status
 size_t tc_weight_image_bytes(int C, int k);
 // host-side: build the swizzled fp16 image for one conv (w_folded is [Cout][Cin][k] fp32)
-void tc_pack_weight_image(const float* w_folded, int C, int k, void* dst_host);
+void tc_pack_weight_image(const float* w_folded, int C, int k, void* dst_host, float scale = 1.f);
 
 // ---- fused ResBlock1 (three pairs, one branch) for C <= 64 (kernels_resblock.cu) -------------------------------------
 struct ResblockTC {
@@ -85,6 +87,7 @@ struct ResblockTC {
     int B = 1, C = 0, T = 0, k = 3;
     int dil[3] = {1, 3, 5};
     float alpha = 1.f, beta = 0.f;
+    float inv[3] = {1.f, 1.f, 1.f};   // per pair: 1 / (scale of c1's image * scale of c2's image); bias[2d] is pre-multiplied by c1's scale
     int variant = -1;
 };
 int launch_resblock_tc(const ResblockTC& a, cudaStream_t st);
@@ -118,13 +121,37 @@ struct ConvNTC {
     // optional fused noise conv (polyphase mode): excitation window har[b, i*noise_stride + noise_w0 + u], u in [0,16)
     const float* har = nullptr; int har_N = 0; int noise_stride = 0, noise_w0 = 0;
     int noise_wide = 0;            // 1: window of up to 80 samples (64-sample + 16-sample panels) instead of 16
+    float acc_scale = 1.f;         // the image holds w * 2^e (range normalisation at pack time); epilogues use acc * acc_scale
+    // SnakeAlias fused into the loader (vdecoder/hifiganwithsnake/alias/act.py:109-129): A = SnakeAlias(x) per input channel
+    const float* snake_ealpha = nullptr;   // [Cin] e^alpha          (null: plain / LeakyReLU loader)
+    const float* snake_invbeta = nullptr;  // [Cin] 1/(e^beta + 1e-9)
+    const float* snake_filt = nullptr;     // the 12-tap kaiser-sinc filter
+    // time-varying bias (speaker-mix conditioning): bias_t[b, bias_t_c0 + column, row] added per (row, column); plain/gate modes
+    const float* bias_t = nullptr; int bias_t_ctot = 0, bias_t_c0 = 0;
 };
 int launch_convn_tc(const ConvNTC& a, cudaStream_t st);
 int convn_mb(int cinp);
+int convn_snake_mb(int cinp);
 size_t convn_weight_image_bytes(int cinp, int N_total, int NC, int k, int noise);
 void convn_pack_weight_image(int cinp, int N_total, int NC, int k, const std::function<float(int, int, int)>& wcol,
                              const std::function<float(int, int)>* ncol, int noise, void* dst_host);
 
 int64_t& launch_counter();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: track what has been granted per (kernel, device).
+// `granted` is a function-local static array of SVB_MAX_DEV atomics (one per kernel instantiation); setting the attribute
+// twice is idempotent, so concurrent contexts on different devices need no lock.
+constexpr int SVB_MAX_DEV = 64;
+template <typename K>
+inline int ensure_dyn_smem(K kernel, size_t bytes, std::atomic<size_t>* granted) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= SVB_MAX_DEV) return -1;
+    if (bytes > granted[dev].load(std::memory_order_acquire)) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -1;
+        granted[dev].store(bytes, std::memory_order_release);
+    }
+    return 0;
+}
+int& sticky_launch_error();   // set by void launchers whose set-up failed (read + cleared by check_launch in api.cu)
 
 }  // namespace svb

@@ -26,8 +26,11 @@ namespace {
 
 constexpr int CN_THREADS = 320;
 constexpr int CN_NWORK = 256;
-constexpr int CN_HALO = 8;            // >= max (k-1)*dil over the layers served here (k7 -> 6), multiple of 8
+constexpr int CN_HALO_MIN = 8;        // A-tile rows beyond the 128*MB output rows: max(8, roundup8((k-1)*dil)), <= 56 (k11, d5)
+constexpr int CN_HALO_MAX = 56;
 constexpr int CN_NOISE_RB = 32;       // noise panel: 16 fp16 per row
+constexpr int SNK_RUN = 16;           // SnakeAlias loader: outputs per (channel, run) task
+constexpr int SNK_WIN = SNK_RUN + 12; // x samples a run needs: [t0-6, t0+21]
 
 template <int CINP>
 struct CNGeom {
@@ -35,21 +38,76 @@ struct CNGeom {
     static constexpr int NP = CINP / CPP;
     static constexpr int RB = CPP * 2;
     static constexpr int KSTEPS = CPP / 16;
+    // SnakeAlias loader: channels staged per pass (fp32 scratch [SNK_GCH][pitch]); 16 where the operand tile leaves less room
+    static constexpr int SNK_GCH = CINP < 32 ? CINP : ((CINP == 64 || CINP >= 512) ? 16 : 32);
 };
 
 struct ConvNDev {                     // launch-time geometry (host computed)
     int stage_bytes, tmem_cols, bufcols, blkcols, nbuf;
+    int arows;                        // A-tile rows per panel = 128*MB + halo
+    int xs_pitch; uint32_t off_xs;    // SnakeAlias loader: fp32 staging rows [<=32 channels][xs_pitch] (odd pitch)
     int noise_np;                     // noise panels (0, 1 or 2)
     int noise_rb[2];                  // their row bytes (128 -> 64 samples, 32 -> 16 samples)
     uint32_t off_noise[2], off_ring, off_bar, off_bias;   // byte offsets from the 1024-aligned smem base
 };
 
-template <int CINP, int MB, int MINB>
+// ---- SnakeAlias for one (channel, run of SNK_RUN rows) task, everything in registers ---------------------------------
+//   u[2a]   = 2 (f1 x[a+2] + f3 x[a+1] + f5 x[a] + f7 x[a-1] + f9 x[a-2] + f11 x[a-3])        (zero-stuffed 2x upsampling,
+//   u[2a+1] = 2 (f0 x[a+3] + f2 x[a+2] + f4 x[a+1] + f6 x[a] + f8 x[a-1] + f10 x[a-2])         alias/resample.py:35-54)
+//   s[m]    = u[m] + sin^2(e^alpha u[m]) / (e^beta + 1e-9)                                      (alias/act.py SnakeBeta)
+//   y[t]    = sum_j f[j] s[clamp(2t + j - 5, 0, 2L-1)]                                          (alias/filter.py:93-109)
+// with x replicate-padded (indices clamped when the window is staged).  sin^2(z) = (1 - cos 2z)/2 through MUFU.COS
+// (absolute error ~6e-8 |2z|, far inside the fp16 operand rounding that follows).
+// xw[j] = x[t0 - 6 + j]; returns y[t0 + i] in y[i].  EDGE: the tile touches t < 3 or t > L - 4, where s indices clamp
+// (s0 = s[0], sL = s[2L-1] are supplied) and rows outside [0, L) are zero (the conv's own zero padding).
+template <bool EDGE, typename Emit>
+__device__ __forceinline__ void snake_run(const float (&xw)[SNK_WIN], const float (&f)[12], float ea2, float hib, int t0, int L,
+                                          float s0, float sL, Emit&& emit) {
+    float s[12];
+    auto s_val = [&](int jj) -> float {
+        // m = 2*t0 - 5 + jj;  jj even -> m odd (a = t0 - 3 + jj/2), jj odd -> m even (a = t0 - 2 + (jj-1)/2)
+        float u;
+        if ((jj & 1) == 0) {
+            const int q = jj / 2 + 3;          // xw index of x[a]
+            u = f[0] * xw[q + 3];
+            u = fmaf(f[2], xw[q + 2], u); u = fmaf(f[4], xw[q + 1], u); u = fmaf(f[6], xw[q], u);
+            u = fmaf(f[8], xw[q - 1], u); u = fmaf(f[10], xw[q - 2], u);
+        } else {
+            const int q = (jj - 1) / 2 + 4;
+            u = f[1] * xw[q + 2];
+            u = fmaf(f[3], xw[q + 1], u); u = fmaf(f[5], xw[q], u); u = fmaf(f[7], xw[q - 1], u);
+            u = fmaf(f[9], xw[q - 2], u); u = fmaf(f[11], xw[q - 3], u);
+        }
+        u *= 2.f;
+        float v = fmaf(hib, 1.f - __cosf(ea2 * u), u);      // u + (1/beta) * (1 - cos(2 e^alpha u)) / 2
+        if (EDGE) {
+            const int m = 2 * t0 - 5 + jj;
+            v = m < 0 ? s0 : (m > 2 * L - 1 ? sL : v);
+        }
+        return v;
+    };
+#pragma unroll
+    for (int jj = 0; jj < 10; ++jj) s[jj] = s_val(jj);
+#pragma unroll
+    for (int i = 0; i < SNK_RUN; ++i) {
+        s[10] = s_val(2 * i + 10);
+        s[11] = s_val(2 * i + 11);
+        float acc = f[0] * s[0];
+#pragma unroll
+        for (int j = 1; j < 12; ++j) acc = fmaf(f[j], s[j], acc);
+        if (EDGE) { const int t = t0 + i; if (t < 0 || t >= L) acc = 0.f; }
+        emit(i, acc);
+#pragma unroll
+        for (int j = 0; j < 10; ++j) s[j] = s[j + 2];
+    }
+}
+
+template <int CINP, int MB, int MINB, bool SNAKE>
 __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNTC a, const ConvNDev d) {
     using G = CNGeom<CINP>;
     constexpr int R1 = 128 * MB;
-    constexpr int AROWS = R1 + CN_HALO;
-    constexpr int APANEL = AROWS * G::RB;
+    const int AROWS = d.arows;
+    const int APANEL = AROWS * G::RB;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -198,7 +256,71 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
     } else {
         // ------------------------------------------------------------ workers
         // (1) stage A = act(x)[rows][Cin] as fp16; row r <-> input index i0 - pad_left + r
-        {
+        if constexpr (SNAKE) {
+            // SnakeAlias loader.  Per pass of GCH channels: (i) the fp32 window x[c][ti - 6 .. ] of the tile is staged in
+            // shared memory with coalesced loads (indices clamped = replicate padding), (ii) every lane takes one channel
+            // and a run of SNK_RUN rows: window -> registers, 2x upsample -> snake -> low-pass/decimate in registers,
+            // (iii) the fp16 results go to the swizzled operand tile (32 lanes = 32 consecutive channels of one row).
+            constexpr int GCH = G::SNK_GCH;
+            constexpr int LPR = 32 / GCH;                      // runs handled side by side in one warp (2 when GCH = 16)
+            float* xs = reinterpret_cast<float*>(sm + d.off_xs);
+            const int XP = d.xs_pitch;
+            const int n_runs = (RA + SNK_RUN - 1) / SNK_RUN;
+            const int XL = n_runs * SNK_RUN + 12;              // staged samples per channel
+            const int tlo = i0 - a.pad_left - 6;               // time of staged sample 0
+            const int L = a.Tin;
+            const bool edge = (tlo + 6 < 3) || (tlo + XL > L - 4);
+            float f[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) f[j] = __ldg(a.snake_filt + j);
+            const float* __restrict__ xb = a.x + ((size_t)b * a.x_ctot + a.x_c0) * (size_t)L;
+            const int cl = lane % GCH, rsel = lane / GCH;
+#pragma unroll 1
+            for (int cg0 = 0; cg0 < CINP; cg0 += GCH) {
+                for (int c = warp; c < GCH; c += 8) {
+                    const bool cv = (cg0 + c) < a.cin_real;
+                    const float* __restrict__ xc = xb + (size_t)(cv ? cg0 + c : 0) * L;
+                    for (int q = lane; q < XL; q += 32) {
+                        const int ti = min(max(tlo + q, 0), L - 1);
+                        xs[c * XP + q] = cv ? __ldg(xc + ti) : 0.f;
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int c = cg0 + cl;
+                const float ea2 = 2.f * __ldg(a.snake_ealpha + min(c, a.cin_real - 1));
+                const float hib = 0.5f * __ldg(a.snake_invbeta + min(c, a.cin_real - 1));
+                const float* __restrict__ xrow = xs + cl * XP;
+                float s0 = 0.f, sL = 0.f;
+                if (edge) {
+                    // s[0] and s[2L-1] from the clamped signal (only their own tile(s) read them)
+                    auto xat = [&](int t) { const int q = min(max(t, 0), L - 1) - tlo; return (q >= 0 && q < XL) ? xrow[q] : 0.f; };
+                    float u0 = 2.f * (f[1] * xat(2) + f[3] * xat(1) + (f[5] + f[7] + f[9] + f[11]) * xat(0));
+                    float uL = 2.f * ((f[0] + f[2] + f[4] + f[6]) * xat(L - 1) + f[8] * xat(L - 2) + f[10] * xat(L - 3));
+                    s0 = fmaf(hib, 1.f - __cosf(ea2 * u0), u0);
+                    sL = fmaf(hib, 1.f - __cosf(ea2 * uL), uL);
+                }
+#pragma unroll 1
+                for (int run = warp * LPR + rsel; run < n_runs; run += 8 * LPR) {
+                    float xw[SNK_WIN];
+#pragma unroll
+                    for (int j = 0; j < SNK_WIN; ++j) xw[j] = xrow[run * SNK_RUN + j];
+                    const int t0 = tlo + 6 + run * SNK_RUN;
+                    uint8_t* pcol = sm + (c / G::CPP) * APANEL + (c % 8) * 2;
+                    const uint32_t chunk = (uint32_t)(c % G::CPP) / 8u;
+                    const int r0 = run * SNK_RUN;
+                    auto emit = [&](int i, float v) {
+                        const int r = r0 + i;
+                        if (r < AROWS) {
+                            const __half hv = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+                            *reinterpret_cast<__half*>(pcol + r * G::RB + ((chunk ^ swz_phase(r, G::RB)) << 4)) = hv;
+                        }
+                    };
+                    if (edge) snake_run<true>(xw, f, ea2, hib, t0, L, s0, sL, emit);
+                    else snake_run<false>(xw, f, ea2, hib, t0, L, s0, sL, emit);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+        } else {
             const bool view = a.view_tstride != 0;
             const float* __restrict__ xb = view ? a.x + (size_t)b * a.view_bstride : a.x + ((size_t)b * a.x_ctot + a.x_c0) * (size_t)a.Tin;
             for (int r = tid; r < RA; r += CN_NWORK) {
@@ -229,6 +351,8 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                     store_chunk8(prow, phase, (c0 % G::CPP) / 8 + 1, v + 8, 0xffffffffu);
                 }
             }
+        }
+        {
             if (d.noise_np) {
                 // excitation window of output row i: har[i*noise_stride + noise_w0 + u]; panel 0 holds u in [0, rb0/2),
                 // panel 1 the next rb1/2 samples
@@ -279,6 +403,8 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                     const int hc = NC / 2;
                     const int j_lo = hsel * (hc / 2), j_hi = (hsel + 1) * (hc / 2);
                     float* __restrict__ yb = a.seg[0].y + ((size_t)b * a.seg[0].y_ctot + a.seg[0].y_c0 + c * hc) * (size_t)a.Ty + (rowok ? i : 0);
+                    // speaker-mix conditioning: gcond[b, bias_t_c0 + column, row] in the same (permuted) column order as the image
+                    const float* __restrict__ bt = a.bias_t ? a.bias_t + ((size_t)b * a.bias_t_ctot + a.bias_t_c0 + col_base) * (size_t)a.Ty + (rowok ? i : 0) : nullptr;
 #pragma unroll 1
                     for (int j0 = j_lo; j0 < j_hi; j0 += 16) {
                         uint32_t ra[16], rb[16];
@@ -288,8 +414,9 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                         if (rowok) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
-                                const float ta = __uint_as_float(ra[j]) + cb_[j0 + j];
-                                const float sa = __uint_as_float(rb[j]) + cb_[hc + j0 + j];
+                                float ta = fmaf(__uint_as_float(ra[j]), a.acc_scale, cb_[j0 + j]);
+                                float sa = fmaf(__uint_as_float(rb[j]), a.acc_scale, cb_[hc + j0 + j]);
+                                if (bt) { ta += __ldg(bt + (size_t)(j0 + j) * a.Ty); sa += __ldg(bt + (size_t)(hc + j0 + j) * a.Ty); }
                                 yb[(size_t)(j0 + j) * a.Ty] = tanhf(ta) * (1.f / (1.f + expf(-sa)));
                             }
                         }
@@ -297,7 +424,8 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                 } else if (a.mode == 1) {
                     // ---- polyphase: column = co*s + phase; output index n = i*s + phase - p (s is 2 or 8)
                     const ConvNSeg& sg = a.seg[0];
-                    const int w_lo = hsel * (ncols / 2), w_hi = (hsel + 1) * (ncols / 2);
+                    const int n16 = ncols / 16;
+                    const int w_lo = hsel * ((n16 + 1) / 2) * 16, w_hi = hsel ? ncols : ((n16 + 1) / 2) * 16;
                     const long long n0 = (long long)i * a.s - a.p;             // output index of phase 0
                     const bool inner = rowok && n0 >= 0 && n0 + a.s <= a.Ty;
 #pragma unroll 1
@@ -310,10 +438,10 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
 #pragma unroll
                         for (int j4 = 0; j4 < 16; j4 += 4) {
                             const float4 bq = *reinterpret_cast<const float4*>(cb_ + j0 + j4);
-                            v[j4 + 0] = sg.alpha * (__uint_as_float(r[j4 + 0]) + bq.x);
-                            v[j4 + 1] = sg.alpha * (__uint_as_float(r[j4 + 1]) + bq.y);
-                            v[j4 + 2] = sg.alpha * (__uint_as_float(r[j4 + 2]) + bq.z);
-                            v[j4 + 3] = sg.alpha * (__uint_as_float(r[j4 + 3]) + bq.w);
+                            v[j4 + 0] = sg.alpha * fmaf(__uint_as_float(r[j4 + 0]), a.acc_scale, bq.x);
+                            v[j4 + 1] = sg.alpha * fmaf(__uint_as_float(r[j4 + 1]), a.acc_scale, bq.y);
+                            v[j4 + 2] = sg.alpha * fmaf(__uint_as_float(r[j4 + 2]), a.acc_scale, bq.z);
+                            v[j4 + 3] = sg.alpha * fmaf(__uint_as_float(r[j4 + 3]), a.acc_scale, bq.w);
                         }
                         const int col0 = col_base + j0;
                         if (a.s == 8) {
@@ -345,7 +473,8 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                     }
                 } else {
                     // ---- plain: one column per output channel; up to two destination segments
-                    const int w_lo = hsel * (ncols / 2), w_hi = (hsel + 1) * (ncols / 2);   // ncols is a multiple of 32
+                    const int n16 = ncols / 16;                                            // ncols is a multiple of 16
+                    const int w_lo = hsel * ((n16 + 1) / 2) * 16, w_hi = hsel ? ncols : ((n16 + 1) / 2) * 16;
 #pragma unroll 1
                     for (int j0 = w_lo; j0 < w_hi; j0 += 16) {
                         uint32_t r[16];
@@ -353,6 +482,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                         const int col0 = col_base + j0;
                         const ConvNSeg& sg = (a.n_seg > 1 && col0 >= a.seg[1].col0) ? a.seg[1] : a.seg[0];
                         float rr[16], oo[16];
+                        const float* __restrict__ bt = (a.bias_t && rowok) ? a.bias_t + ((size_t)b * a.bias_t_ctot + a.bias_t_c0 + col0) * (size_t)a.Ty + i : nullptr;
                         float* __restrict__ yb = sg.y + ((size_t)b * sg.y_ctot + sg.y_c0 + (col0 - sg.col0)) * (size_t)a.Ty + (rowok ? i : 0);
                         if (rowok && sg.res) {
                             const float* __restrict__ rb_ = sg.res + ((size_t)b * sg.res_ctot + sg.res_c0 + (col0 - sg.col0)) * (size_t)a.Ty + i;
@@ -368,7 +498,8 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                             const bool dead = sg.masked && i >= len;
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
-                                float o = __uint_as_float(r[j]) + cb_[j0 + j];
+                                float o = fmaf(__uint_as_float(r[j]), a.acc_scale, cb_[j0 + j]);
+                                if (bt) o += __ldg(bt + (size_t)j * a.Ty);
                                 if (sg.res) o += rr[j];
                                 o *= sg.alpha;
                                 if (sg.beta != 0.f) o = fmaf(sg.beta, oo[j], o);
@@ -389,9 +520,12 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
 
 int pow2ceil(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 
-template <int CINP, int MB, int MINB>
+template <int CINP, int MB, int MINB, bool SNAKE>
 int launch_convn_t(const ConvNTC& a, cudaStream_t st) {
     using G = CNGeom<CINP>;
+    int halo = ((a.k - 1) * a.dil + 7) & ~7;
+    if (halo < CN_HALO_MIN) halo = CN_HALO_MIN;
+    if (halo > CN_HALO_MAX) return SVB_ERR_UNSUPPORTED;
     const int n_chunks = (a.N_total + a.NC - 1) / a.NC;
     const int cpc = a.chunks_per_cta < 1 ? 1 : a.chunks_per_cta;
     ConvNDev d;
@@ -407,8 +541,18 @@ int launch_convn_t(const ConvNTC& a, cudaStream_t st) {
     int stage = SUB > 16384 ? 32768 : 16384;
     if (SUB > stage) return SVB_ERR_UNSUPPORTED;
     d.stage_bytes = stage;
-    uint32_t off = (uint32_t)G::NP * (128 * MB + CN_HALO) * G::RB;
+    d.arows = 128 * MB + halo;
+    uint32_t off = (uint32_t)G::NP * d.arows * G::RB;
     off = (off + 1023u) & ~1023u;
+    d.xs_pitch = 0; d.off_xs = 0;
+    if (SNAKE) {
+        const int RA = 128 * MB + (a.k - 1) * a.dil;
+        const int xl = ((RA + SNK_RUN - 1) / SNK_RUN) * SNK_RUN + 12;
+        d.xs_pitch = xl | 1;                                   // odd pitch: lanes (channels) hit distinct banks
+        d.off_xs = off;
+        off += (uint32_t)G::SNK_GCH * d.xs_pitch * 4;
+        off = (off + 1023u) & ~1023u;
+    }
     for (int pnn = 0; pnn < 2; ++pnn) {
         d.off_noise[pnn] = off;
         if (pnn < d.noise_np) off += 128 * MB * d.noise_rb[pnn];
@@ -422,14 +566,10 @@ int launch_convn_t(const ConvNTC& a, cudaStream_t st) {
     off += (uint32_t)cpc * a.NC * 4;
     const size_t smem = 1024 + off;
     if (smem > 227 * 1024) return SVB_ERR_UNSUPPORTED;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        if (cudaFuncSetAttribute(convn_tc_kernel<CINP, MB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return SVB_ERR_CUDA;
-        attr_smem = smem;
-    }
+    static std::atomic<size_t> granted[SVB_MAX_DEV];
+    if (ensure_dyn_smem(convn_tc_kernel<CINP, MB, MINB, SNAKE>, smem, granted)) return SVB_ERR_CUDA;
     dim3 grid((a.n_rows + 128 * MB - 1) / (128 * MB), a.B, (n_chunks + cpc - 1) / cpc);
-    convn_tc_kernel<CINP, MB, MINB><<<grid, CN_THREADS, smem, st>>>(a, d);
+    convn_tc_kernel<CINP, MB, MINB, SNAKE><<<grid, CN_THREADS, smem, st>>>(a, d);
     launch_counter()++;
     return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;
 }
@@ -437,17 +577,35 @@ int launch_convn_t(const ConvNTC& a, cudaStream_t st) {
 }  // namespace
 
 int convn_mb(int cinp) { return cinp >= 512 ? 1 : (cinp == 192 ? 1 : 2); }
+// SnakeAlias-loader tiles: one 128-row block for the wide stages so that two CTAs share an SM (one CTA's CUDA-core loader
+// phase overlaps the other's MMA / epilogue phases); C = 256/512 need the whole shared memory for the operand tile.
+int convn_snake_mb(int cinp) { return cinp >= 128 ? 1 : 2; }
 
 int launch_convn_tc(const ConvNTC& a, cudaStream_t st) {
-    if ((a.k - 1) * a.dil > CN_HALO || a.NC % 32 || a.NC > 256 / convn_mb(a.cinp) || a.N_total % 32) return SVB_ERR_UNSUPPORTED;
+    const bool snake = a.snake_ealpha != nullptr;
+    const int mb = snake ? convn_snake_mb(a.cinp) : convn_mb(a.cinp);
+    if (a.NC % 16 || a.NC > 256 / mb || a.N_total % 16) return SVB_ERR_UNSUPPORTED;
     if (a.mode == 1 && !(a.s == 2 || a.s == 8)) return SVB_ERR_UNSUPPORTED;
+    if (a.mode == 2 && (a.NC % 64)) return SVB_ERR_UNSUPPORTED;
+    if (snake) {
+        if (a.view_tstride != 0 || a.in_act || !a.snake_invbeta || !a.snake_filt) return SVB_ERR_INVALID_ARG;
+        switch (a.cinp) {
+            case 512: return launch_convn_t<512, 1, 1, true>(a, st);
+            case 256: return launch_convn_t<256, 1, 1, true>(a, st);
+            case 128: return launch_convn_t<128, 1, 2, true>(a, st);
+            case 64: return launch_convn_t<64, 2, 2, true>(a, st);
+            case 32: return launch_convn_t<32, 2, 2, true>(a, st);
+            case 16: return launch_convn_t<16, 2, 2, true>(a, st);
+            default: return SVB_ERR_UNSUPPORTED;
+        }
+    }
     switch (a.cinp) {
-        case 512: return launch_convn_t<512, 1, 1>(a, st);
-        case 256: return launch_convn_t<256, 2, 1>(a, st);
-        case 192: return launch_convn_t<192, 1, 1>(a, st);
-        case 128: return launch_convn_t<128, 2, 2>(a, st);
-        case 64: return launch_convn_t<64, 2, 2>(a, st);
-        case 32: return launch_convn_t<32, 2, 2>(a, st);
+        case 512: return launch_convn_t<512, 1, 1, false>(a, st);
+        case 256: return launch_convn_t<256, 2, 1, false>(a, st);
+        case 192: return launch_convn_t<192, 1, 1, false>(a, st);
+        case 128: return launch_convn_t<128, 2, 2, false>(a, st);
+        case 64: return launch_convn_t<64, 2, 2, false>(a, st);
+        case 32: return launch_convn_t<32, 2, 2, false>(a, st);
         default: return SVB_ERR_UNSUPPORTED;
     }
 }

@@ -9,6 +9,7 @@
 namespace svb {
 
 int64_t& launch_counter() { static int64_t c = 0; return c; }
+int& sticky_launch_error() { static int e = 0; return e; }
 
 // =====================================================================================================
 // Generic 1-D convolution, fp32.  Block = 256 threads computes TCO output channels x TT time steps.
@@ -124,11 +125,8 @@ static void launch_conv_t(const ConvF32& a, cudaStream_t st) {
     constexpr int G = TCO / 8, TX = CONV_THREADS / G, TT = 4 * TX;
     const int halo = (a.k - 1) * a.dil;
     size_t smem = sizeof(float) * (size_t)(CONV_CK * (TT + halo) + CONV_CK * a.k * TCO);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(conv_f32_kernel<TCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr_set = true;
-    }
+    static std::atomic<size_t> granted[SVB_MAX_DEV];
+    if (smem > 48 * 1024 && ensure_dyn_smem(conv_f32_kernel<TCO>, smem, granted)) { sticky_launch_error() = 1; return; }
     dim3 grid((a.n_out + TT - 1) / TT, ((a.Cout + TCO - 1) / TCO) * a.n_phase, a.B);
     conv_f32_kernel<TCO><<<grid, CONV_THREADS, smem, st>>>(a);
     launch_counter()++;

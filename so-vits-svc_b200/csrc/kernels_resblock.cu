@@ -42,6 +42,7 @@ struct ResblockParams {
     int T, k, halo;
     int dil[3];
     float alpha, beta;
+    float inv[3];                    // per pair 1/(s1*s2) of the range-normalised weight images
     uint32_t epoch; int skew_clk;    // first-wave de-phasing (tc_common.cuh)
     int red_old;                     // beta == 1 handled with red.global.add instead of load + store
     int stage_bytes, nstage;         // block-skewed kernel: weight ring geometry (a stage holds one whole conv)
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
             tc_fence_after();
             if (tid == 0) RB_TRACE(2 + 4 * q + 0);
             const float* __restrict__ bq_ = sbias + q * C;
+            const float inv_q = p.inv[q >> 1];
             if ((q & 1) == 0) {
                 // ---- first conv of a pair: mid = lrelu(acc + b1) -> operand tile (two row blocks per TMEM round trip)
 #pragma unroll 1
@@ -296,10 +298,10 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
 #pragma unroll
                         for (int j4 = 0; j4 < CG; j4 += 4) {
                             const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
-                            v[j4 + 0] = __uint_as_float(r[j4 + 0]) + bb.x + __uint_as_float(xr[j4 + 0]);
-                            v[j4 + 1] = __uint_as_float(r[j4 + 1]) + bb.y + __uint_as_float(xr[j4 + 1]);
-                            v[j4 + 2] = __uint_as_float(r[j4 + 2]) + bb.z + __uint_as_float(xr[j4 + 2]);
-                            v[j4 + 3] = __uint_as_float(r[j4 + 3]) + bb.w + __uint_as_float(xr[j4 + 3]);
+                            v[j4 + 0] = fmaf(__uint_as_float(r[j4 + 0]), inv_q, bb.x) + __uint_as_float(xr[j4 + 0]);
+                            v[j4 + 1] = fmaf(__uint_as_float(r[j4 + 1]), inv_q, bb.y) + __uint_as_float(xr[j4 + 1]);
+                            v[j4 + 2] = fmaf(__uint_as_float(r[j4 + 2]), inv_q, bb.z) + __uint_as_float(xr[j4 + 2]);
+                            v[j4 + 3] = fmaf(__uint_as_float(r[j4 + 3]), inv_q, bb.w) + __uint_as_float(xr[j4 + 3]);
                         }
 #pragma unroll
                         for (int j = 0; j < CG; ++j) xr[j] = __float_as_uint(v[j]);
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
                                     const int j = j4 + e;
-                                    float y = p.alpha * (__uint_as_float(r[j]) + b4[e] + __uint_as_float(xr[j]));
+                                    float y = p.alpha * (fmaf(__uint_as_float(r[j]), inv_q, b4[e]) + __uint_as_float(xr[j]));
                                     if (has_beta) y = fmaf(p.beta, oo[j], y);
                                     if (red_old) atomicAdd(ot + (size_t)(c0 + j) * p.T, y);
                                     else ot[(size_t)(c0 + j) * p.T] = y;
@@ -528,6 +530,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
         for (int q = 0; q < 6; ++q) {
             const uint32_t par = (uint32_t)q & 1u;
             const float* __restrict__ bq_ = sbias + q * C;
+            const float inv_q = p.inv[q >> 1];
 #pragma unroll 1
             for (int mb = 0; mb < MB; ++mb) {
                 mbar_wait(bar_acc + 8 * mb, par);
@@ -575,10 +578,10 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
 #pragma unroll
                         for (int j4 = 0; j4 < CG; j4 += 4) {
                             const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
-                            v[j4 + 0] = __uint_as_float(r[j4 + 0]) + bb.x + __uint_as_float(xr[j4 + 0]);
-                            v[j4 + 1] = __uint_as_float(r[j4 + 1]) + bb.y + __uint_as_float(xr[j4 + 1]);
-                            v[j4 + 2] = __uint_as_float(r[j4 + 2]) + bb.z + __uint_as_float(xr[j4 + 2]);
-                            v[j4 + 3] = __uint_as_float(r[j4 + 3]) + bb.w + __uint_as_float(xr[j4 + 3]);
+                            v[j4 + 0] = fmaf(__uint_as_float(r[j4 + 0]), inv_q, bb.x) + __uint_as_float(xr[j4 + 0]);
+                            v[j4 + 1] = fmaf(__uint_as_float(r[j4 + 1]), inv_q, bb.y) + __uint_as_float(xr[j4 + 1]);
+                            v[j4 + 2] = fmaf(__uint_as_float(r[j4 + 2]), inv_q, bb.z) + __uint_as_float(xr[j4 + 2]);
+                            v[j4 + 3] = fmaf(__uint_as_float(r[j4 + 3]), inv_q, bb.w) + __uint_as_float(xr[j4 + 3]);
                         }
 #pragma unroll
                         for (int j = 0; j < CG; ++j) xr[j] = __float_as_uint(v[j]);
@@ -617,7 +620,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
                                     const int j = j4 + e;
-                                    float y = p.alpha * (__uint_as_float(r[j]) + b4[e] + __uint_as_float(xr[j]));
+                                    float y = p.alpha * (fmaf(__uint_as_float(r[j]), inv_q, b4[e]) + __uint_as_float(xr[j]));
                                     if (ld_old) y = fmaf(p.beta, oo[j], y);
                                     if (red_old) atomicAdd(ot + (size_t)(c0 + j) * p.T, y);
                                     else ot[(size_t)(c0 + j) * p.T] = y;
@@ -658,16 +661,13 @@ int launch_resblock_t(const ResblockTC& a, cudaStream_t st) {
     const int nstage = (fixed + 2 * (size_t)stage_bytes <= budget) ? 2 : 1;
     const size_t smem_run = SKEW ? fixed + (size_t)nstage * stage_bytes : smem;
     if (SKEW && smem_run > budget) return SVB_ERR_UNSUPPORTED;
-    static size_t attr_bytes = 0;
-    if (smem_run > attr_bytes) {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_run) != cudaSuccess)
-            return SVB_ERR_CUDA;
-        attr_bytes = smem_run;
-    }
+    static std::atomic<size_t> granted[SVB_MAX_DEV];
+    if (ensure_dyn_smem(kernel, smem_run, granted)) return SVB_ERR_CUDA;
     ResblockParams p;
     p.x = a.x; p.out = a.out;
     for (int q = 0; q < 6; ++q) { p.w[q] = static_cast<const uint8_t*>(a.w[q]); p.bias[q] = a.bias[q]; }
     p.T = a.T; p.k = a.k; p.alpha = a.alpha; p.beta = a.beta;
+    for (int d = 0; d < 3; ++d) p.inv[d] = a.inv[d];
     int halo = 0;
     for (int d = 0; d < 3; ++d) { p.dil[d] = a.dil[d]; halo += (a.dil[d] + 1) * (a.k - 1) / 2; }
     p.halo = halo;

@@ -54,7 +54,7 @@ struct PairParams {
     const uint8_t* w1; const uint8_t* w2;
     const float* b1; const float* b2;
     int T, k, dil;
-    float alpha, beta;
+    float alpha, beta, inv;
     __half* a16_out;     // optional second output: fp16 lrelu(out) in [B][T][C] (the next pair's TMA-loadable operand)
     int vec4;            // x / out 16-byte aligned and T % 4 == 0: the loader uses 128-bit loads along time
     int red_out;         // loader pre-writes alpha*x (+ beta*old for beta == 1) into out, epilogue 2 only adds (RED): no x re-read
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int j = j4 + e;
-                            const float y = p.alpha * (__uint_as_float(r[j]) + bb[e] + xr[j]);
+                            const float y = p.alpha * (fmaf(__uint_as_float(r[j]), p.inv, bb[e]) + xr[j]);
                             if (add_old) atomicAdd(ot + (size_t)(c0 + j) * p.T, y);
                             else ot[(size_t)(c0 + j) * p.T] = y;
                             xr[j] = lrelu01(y);
@@ -448,10 +448,10 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
 #pragma unroll
                             for (int j4 = 0; j4 < CG; j4 += 4) {
                                 const float4 bq = *reinterpret_cast<const float4*>(sbias + C + cg0 + j4);
-                                atomicAdd(ot + (size_t)(cg0 + j4 + 0) * p.T, p.alpha * (__uint_as_float(rr[j4 + 0]) + bq.x));
-                                atomicAdd(ot + (size_t)(cg0 + j4 + 1) * p.T, p.alpha * (__uint_as_float(rr[j4 + 1]) + bq.y));
-                                atomicAdd(ot + (size_t)(cg0 + j4 + 2) * p.T, p.alpha * (__uint_as_float(rr[j4 + 2]) + bq.z));
-                                atomicAdd(ot + (size_t)(cg0 + j4 + 3) * p.T, p.alpha * (__uint_as_float(rr[j4 + 3]) + bq.w));
+                                atomicAdd(ot + (size_t)(cg0 + j4 + 0) * p.T, p.alpha * fmaf(__uint_as_float(rr[j4 + 0]), p.inv, bq.x));
+                                atomicAdd(ot + (size_t)(cg0 + j4 + 1) * p.T, p.alpha * fmaf(__uint_as_float(rr[j4 + 1]), p.inv, bq.y));
+                                atomicAdd(ot + (size_t)(cg0 + j4 + 2) * p.T, p.alpha * fmaf(__uint_as_float(rr[j4 + 2]), p.inv, bq.z));
+                                atomicAdd(ot + (size_t)(cg0 + j4 + 3) * p.T, p.alpha * fmaf(__uint_as_float(rr[j4 + 3]), p.inv, bq.w));
                             }
                         }
                     }
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairPar
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int j = j4 + e;
-                            float y = p.alpha * (__uint_as_float(r[j]) + bb[e] + xr[j]);
+                            float y = p.alpha * (fmaf(__uint_as_float(r[j]), p.inv, bb[e]) + xr[j]);
                             if (has_beta) y = fmaf(p.beta, oo[j], y);
                             ot[(size_t)(c0 + j) * p.T] = y;
                             xr[j] = lrelu01(y);
@@ -553,12 +553,8 @@ template <int C, int MB, int STAGE_KB, int MINB, bool TMA_IN>
 int launch_pair_t2(const PairTC& a, cudaStream_t st) {
     constexpr size_t smem = pair_smem_bytes<C, MB, STAGE_KB>();
     static_assert(smem * MINB + 1024 * MINB <= 228 * 1024, "pair kernel shared memory exceeds the SM budget");
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(pair_tc_kernel<C, MB, STAGE_KB, MINB, TMA_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return SVB_ERR_CUDA;
-        attr_set = true;
-    }
+    static std::atomic<size_t> granted[SVB_MAX_DEV];
+    if (ensure_dyn_smem(pair_tc_kernel<C, MB, STAGE_KB, MINB, TMA_IN>, smem, granted)) return SVB_ERR_CUDA;
     alignas(64) CUtensorMap tmap;
     std::memset(&tmap, 0, sizeof(tmap));
     if (TMA_IN) {
@@ -567,7 +563,7 @@ int launch_pair_t2(const PairTC& a, cudaStream_t st) {
     PairParams p;
     p.x = a.x; p.out = a.out;
     p.w1 = static_cast<const uint8_t*>(a.w1); p.w2 = static_cast<const uint8_t*>(a.w2);
-    p.b1 = a.b1; p.b2 = a.b2; p.T = a.T; p.k = a.k; p.dil = a.dil; p.alpha = a.alpha; p.beta = a.beta;
+    p.b1 = a.b1; p.b2 = a.b2; p.T = a.T; p.k = a.k; p.dil = a.dil; p.alpha = a.alpha; p.beta = a.beta; p.inv = a.inv;
     p.a16_out = static_cast<__half*>(a.a16_out);
     {
         static const int env_vec4 = env_int("SVB_PAIR_VEC4", 1), env_red = env_int("SVB_PAIR_RED", 0)   /* measured: L2 reductions cost 0.7 ms/step, off */;
@@ -606,7 +602,7 @@ bool pair_tc_supports_tma(int C, int variant) { (void)variant; return C >= 64; }
 size_t tc_weight_image_bytes(int C, int k) { return (size_t)C * C * k * 2; }
 
 // w_folded: [Cout][Cin][k] fp32  ->  image [tap][panel][Cout row][swizzled Cin halves]
-void tc_pack_weight_image(const float* w, int C, int k, void* dst_host) {
+void tc_pack_weight_image(const float* w, int C, int k, void* dst_host, float scale) {
     const int CPP = C < 64 ? C : 64, NP = C / CPP, RB = CPP * 2, SUB = C * RB;
     uint8_t* dst = static_cast<uint8_t*>(dst_host);
     for (int tap = 0; tap < k; ++tap)
@@ -615,7 +611,7 @@ void tc_pack_weight_image(const float* w, int C, int k, void* dst_host) {
             for (int n = 0; n < C; ++n)
                 for (int cc = 0; cc < CPP; ++cc) {
                     const int ci = pn * CPP + cc;
-                    const float v = w[((size_t)n * C + ci) * k + tap];
+                    const float v = w[((size_t)n * C + ci) * k + tap] * scale;
                     const __half h = __float2half_rn(v);
                     const uint32_t off = tc::swz_offset((uint32_t)n, (uint32_t)(cc / 8), (uint32_t)RB) + (cc % 8) * 2;
                     std::memcpy(blk + off, &h, 2);

@@ -190,9 +190,12 @@ __host__ __device__ inline uint32_t swz_offset(uint32_t row, uint32_t chunk, uin
     return a ^ (((a >> 7) & mask) << 4);
 }
 
+// fp32 pair -> packed fp16x2 (a in the low half), round-to-nearest, SATURATING to +-65504: the reference's TF32 operands
+// cannot overflow, so an out-of-range activation must not turn the waveform into inf/NaN here either.
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
 __device__ __forceinline__ float lrelu01(float v) { return fmaxf(v, 0.1f * v); }   // LeakyReLU(0.1): max(v, 0.1 v)
 

@@ -156,6 +156,11 @@ class TailEngine:
     def launch_count(self) -> int:
         return int(self.lib.svb_launch_count(self._ctx))
 
+    @property
+    def fallback_count(self) -> int:
+        """How often a precision="tc" call ran FFMA kernels instead (see svb_fallback_count)."""
+        return int(self.lib.svb_fallback_count(self._ctx))
+
     # ------------------------------------------------------------------ helpers
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -44,8 +44,9 @@ def _add_ln_im2col(lib, x, r, norm, k):
     x, r = x.contiguous(), r.contiguous()
     y = torch.empty_like(x)
     cols = torch.empty((B, L, k * C), dtype=x.dtype, device=x.device)
-    rc = lib.svb_prefix_add_ln_im2col(x.data_ptr(), r.data_ptr(), norm.gamma.data_ptr(), norm.beta.data_ptr(), float(norm.eps),
-                                      y.data_ptr(), cols.data_ptr(), B, L, C, k, torch.cuda.current_stream(x.device).cuda_stream)
+    with torch.cuda.device(x.device):     # raw launches go to the CURRENT device: make it the tensor's device
+        rc = lib.svb_prefix_add_ln_im2col(x.data_ptr(), r.data_ptr(), norm.gamma.data_ptr(), norm.beta.data_ptr(), float(norm.eps),
+                                          y.data_ptr(), cols.data_ptr(), B, L, C, k, torch.cuda.current_stream(x.device).cuda_stream)
     if rc != 0:
         raise RuntimeError(f"svb_prefix_add_ln_im2col failed: {lib.svb_strerror(rc).decode()}")
     return y, cols
@@ -56,8 +57,9 @@ def _ffn_tail(lib, ya, x, bias, norm, k):
     B, L, C = x.shape
     ya, x = ya.contiguous(), x.contiguous()
     y = torch.empty_like(x)
-    rc = lib.svb_prefix_ffn_tail(ya.data_ptr(), x.data_ptr(), bias.data_ptr(), norm.gamma.data_ptr(), norm.beta.data_ptr(), float(norm.eps),
-                                 y.data_ptr(), B, L, C, k, torch.cuda.current_stream(x.device).cuda_stream)
+    with torch.cuda.device(x.device):
+        rc = lib.svb_prefix_ffn_tail(ya.data_ptr(), x.data_ptr(), bias.data_ptr(), norm.gamma.data_ptr(), norm.beta.data_ptr(), float(norm.eps),
+                                     y.data_ptr(), B, L, C, k, torch.cuda.current_stream(x.device).cuda_stream)
     if rc != 0:
         raise RuntimeError(f"svb_prefix_ffn_tail failed: {lib.svb_strerror(rc).decode()}")
     return y
@@ -94,9 +96,11 @@ class ChannelNorm(nn.Module):
 
 
 class _TF32Like:
-    """The reference's 1x1 convolutions run through cuDNN, whose CUDA default is TF32.  The same mixes are
-    plain GEMMs here; let them follow torch's *convolution* precision switch so that `cudnn.conv.fp32_precision='ieee'`
-    still gives a strict-fp32 prefix."""
+    """The reference's 1x1 / k-tap convolutions run through cuDNN, whose CUDA default is TF32.  The same mixes
+    are plain GEMMs here; let exactly THOSE follow torch's *convolution* precision switch (so that
+    `cudnn.conv.fp32_precision='ieee'` still gives a strict-fp32 prefix).  The attention products q@k^T, p@v and the
+    relative-position terms are `torch.matmul` in the reference (modules/attentions.py:243-262): they stay under torch's
+    matmul default (IEEE fp32) and are never wrapped in this context."""
 
     def __enter__(self):
         self.prev = torch.backends.cuda.matmul.allow_tf32
@@ -156,7 +160,8 @@ class WindowedRelAttention(nn.Module):
             wqkv, bqkv = _cached(self, "qkv", srcs, lambda: (
                 torch.cat([self.conv_q.weight[:, :, 0] * scale, self.conv_k.weight[:, :, 0], self.conv_v.weight[:, :, 0]], 0).contiguous(),
                 torch.cat([self.conv_q.bias * scale, self.conv_k.bias, self.conv_v.bias], 0).contiguous()))
-        qkv = F.linear(x, wqkv, bqkv).view(B, L, 3, h, dk).permute(2, 0, 3, 1, 4)      # [3,B,h,L,dk]
+        with _TF32Like():                                                                 # conv_q / conv_k / conv_v
+            qkv = F.linear(x, wqkv, bqkv).view(B, L, 3, h, dk).permute(2, 0, 3, 1, 4)      # [3,B,h,L,dk]
         q, k, v = qkv[0], qkv[1], qkv[2]
         scores = q @ k.transpose(-2, -1)                                                  # [B,h,L,L]
         lib = _fused_tails(x) if (attn_mask is None and L <= 12000) else None   # rel_softmax keeps one score row in shared memory
@@ -167,16 +172,19 @@ class WindowedRelAttention(nn.Module):
             relk = (q @ self.emb_rel_k[0].t()).contiguous()                               # [B,h,L,2w+1]
             pband = torch.empty_like(relk)
             stream = torch.cuda.current_stream(x.device).cuda_stream
-            rc = lib.svb_prefix_rel_softmax(scores.data_ptr(), relk.data_ptr(), pband.data_ptr(), B * h * L, L, w, stream)
+            with torch.cuda.device(x.device):
+                rc = lib.svb_prefix_rel_softmax(scores.data_ptr(), relk.data_ptr(), pband.data_ptr(), B * h * L, L, w, stream)
             if rc != 0:
                 raise RuntimeError(f"svb_prefix_rel_softmax failed: {lib.svb_strerror(rc).decode()}")
             pv = (scores @ v).contiguous()                                                # [B,h,L,dk]
             merged = torch.empty((B, L, D), dtype=x.dtype, device=x.device)
             embv = self.emb_rel_v[0].contiguous()
-            rc = lib.svb_prefix_attn_merge(pv.data_ptr(), pband.data_ptr(), embv.data_ptr(), merged.data_ptr(), B, h, L, dk, nb_, stream)
+            with torch.cuda.device(x.device):
+                rc = lib.svb_prefix_attn_merge(pv.data_ptr(), pband.data_ptr(), embv.data_ptr(), merged.data_ptr(), B, h, L, dk, nb_, stream)
             if rc != 0:
                 raise RuntimeError(f"svb_prefix_attn_merge failed: {lib.svb_strerror(rc).decode()}")
-            return F.linear(merged, self.conv_o.weight[:, :, 0], self.conv_o.bias)
+            with _TF32Like():
+                return F.linear(merged, self.conv_o.weight[:, :, 0], self.conv_o.bias)
         idx, valid = self._band(L, x.device)
         nb = 2 * w + 1
         rel_k = (q @ self.emb_rel_k[0].t()) * valid                                       # [B,h,L,2w+1]
@@ -188,7 +196,8 @@ class WindowedRelAttention(nn.Module):
         rel_w = p.view(B, h, L * L).gather(2, idx.expand(B, h, L * nb)).view(B, h, L, nb) * valid
         out = out + rel_w @ self.emb_rel_v[0]
         out = out.transpose(1, 2).reshape(B, L, D)
-        return F.linear(out, self.conv_o.weight[:, :, 0], self.conv_o.bias)
+        with _TF32Like():
+            return F.linear(out, self.conv_o.weight[:, :, 0], self.conv_o.bias)
 
 
 class ConvFFN(nn.Module):
@@ -202,6 +211,10 @@ class ConvFFN(nn.Module):
         self.conv_2 = nn.Conv1d(filter_channels, channels, kernel_size)
 
     def _conv(self, x, conv):
+        with _TF32Like():
+            return self._conv_impl(x, conv)
+
+    def _conv_impl(self, x, conv):
         k = self.kernel_size
         if k == 1:
             return F.linear(x, conv.weight[:, :, 0], conv.bias)
@@ -226,15 +239,17 @@ class ConvFFN(nn.Module):
         conv = self.conv_1
         wmat = _cached(self, "w1", (conv.weight,), lambda: conv.weight.permute(0, 2, 1).reshape(conv.weight.shape[0], -1).contiguous())
         B, L, KC = cols.shape
-        if hasattr(torch, "_addmm_activation"):        # bias + ReLU in the GEMM epilogue (cuBLASLt)
-            return torch._addmm_activation(conv.bias, cols.view(B * L, KC), wmat.t(), use_gelu=False).view(B, L, -1)
-        return torch.relu_(F.linear(cols, wmat, conv.bias))
+        with _TF32Like():
+            if hasattr(torch, "_addmm_activation"):        # bias + ReLU in the GEMM epilogue (cuBLASLt)
+                return torch._addmm_activation(conv.bias, cols.view(B * L, KC), wmat.t(), use_gelu=False).view(B, L, -1)
+            return torch.relu_(F.linear(cols, wmat, conv.bias))
 
     def stacked_out(self, hid):
         """conv_2 as ONE GEMM against the k tap matrices stacked along the output: [B,L,k*Cout], tap-major (no bias)."""
         conv = self.conv_2
         wst = _cached(self, "w2", (conv.weight,), lambda: conv.weight.permute(2, 0, 1).reshape(-1, conv.weight.shape[1]).contiguous())
-        return F.linear(hid, wst)
+        with _TF32Like():
+            return F.linear(hid, wst)
 
     def forward(self, x, x_mask=None):
         """x: [B,T,C]; x_mask: [B,T,1] or None (all ones)."""
@@ -272,16 +287,15 @@ class RelEncoder(nn.Module):
         if mt is not None:
             x = x * mt
         lib = _fused_tails(x) if (mt is None and x.shape[-1] <= 256 and self.ffn_layers[0].kernel_size <= 7) else None
-        with _TF32Like():
-            for attn, n1, ffn, n2 in zip(self.attn_layers, self.norm_layers_1, self.ffn_layers, self.norm_layers_2):
-                if lib is not None:
-                    # equal-length batch on the GPU: the element-wise tails of the layer run as two fused kernels
-                    # (csrc/kernels_prefix.cu), the GEMMs stay on cuBLAS
-                    x1, cols = _add_ln_im2col(lib, x, attn(x, None), n1, ffn.kernel_size)
-                    x = _ffn_tail(lib, ffn.stacked_out(ffn.hidden_from_cols(cols)), x1, ffn.conv_2.bias, n2, ffn.kernel_size)
-                    continue
-                x = n1(x + attn(x, attn_mask))
-                x = n2(x + ffn(x, mt))
+        for attn, n1, ffn, n2 in zip(self.attn_layers, self.norm_layers_1, self.ffn_layers, self.norm_layers_2):
+            if lib is not None:
+                # equal-length batch on the GPU: the element-wise tails of the layer run as two fused kernels
+                # (csrc/kernels_prefix.cu), the GEMMs stay on cuBLAS
+                x1, cols = _add_ln_im2col(lib, x, attn(x, None), n1, ffn.kernel_size)
+                x = _ffn_tail(lib, ffn.stacked_out(ffn.hidden_from_cols(cols)), x1, ffn.conv_2.bias, n2, ffn.kernel_size)
+                continue
+            x = n1(x + attn(x, attn_mask))
+            x = n2(x + ffn(x, mt))
         if mt is not None:
             x = x * mt
         return x.transpose(1, 2)

@@ -63,6 +63,7 @@ SIGNATURES = {
     "svb_strerror": (C.c_char_p, [C.c_int]),
     "svb_last_error": (C.c_char_p, [C.c_void_p]),
     "svb_launch_count": (C.c_int64, [C.c_void_p]),
+    "svb_fallback_count": (C.c_int64, [C.c_void_p]),
     "svb_debug_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "svb_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "svb_debug_pair": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -76,7 +76,7 @@ class _TailMixin:
     def _mark_dirty(self):
         self._b200_dirty = True
 
-    def _run_tail(self, z_p, c_mask, g, f0):
+    def _run_tail(self, z_p, c_mask, g, f0, lengths=None):
         """models.py:530-531 + the RNG draws of vdecoder/hifigan/models.py:147,266,319."""
         dev = z_p.device
         if dev.type != "cuda":
@@ -88,8 +88,8 @@ class _TailMixin:
         har_noise = torch.randn(B, N, cfg.n_harmonics, device=dev)
         torch.randn(B, N, 1, device=dev)     # draw #4 is discarded by Generator but advances the RNG (:319)
         eng = self._engine(dev)
-        all_ones = bool((c_mask == 1).all()) if c_mask is not None else True
-        lengths = None if all_ones else c_mask[:, 0, :].sum(-1)
+        # `infer` always builds an all-ones mask (c_lengths = ones * T, models.py:503,515), so no length vector is needed and
+        # the mask is NOT inspected on the device (that cost a device->host sync right before the ~100 tail launches).
         o = eng.infer_tail(z_p, g, f0, rand_ini, har_noise, lengths)
         return o.to(z_p.dtype)
 

@@ -2,8 +2,10 @@
 seeded inputs, against the committed reference fixtures, and — at BASELINE's full size — through
 size-independent properties.  Tolerances (waveform in (-1,1), activations O(1..10)):
   * fp32 path  vs oracle/reference fixture:  L-inf <= 1e-4   (T1)
-  * tensor-core path (fp16 operands, fp32 accumulate) vs the same: L-inf <= TC_TOL, the band of the
-    reference's own TF32-vs-fp32 self-disagreement (T2/T3); measured values are printed.
+  * tensor-core path (fp16 operands, fp32 accumulate) vs the same: L-inf <= TC_TOL = 5e-3 (frozen; T3 <= T2 of SURVEY §8d:
+    the reference's own cuDNN-TF32 vs IEEE-fp32 self-disagreement measured on this path at config 2 is 4.4e-3,
+    profiles/r01/ref_pytorch_cuda_baseline.json); measured values are printed.
+  * flow alone on the tensor-core path: L-inf <= FLOW_TC_REL * |z|max (z is not bounded like the waveform).
 """
 import ctypes as C
 import os
@@ -18,7 +20,8 @@ from sovits_b200 import synth
 pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-4
-TC_TOL = 2e-2
+TC_TOL = 5e-3
+FLOW_TC_REL = 1e-3
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 DEV = torch.device("cuda:0")
 
@@ -105,7 +108,7 @@ def test_flow_reverse_tensor_core(cfg, sd, eng, B, T):
     eng.set_precision("fp32")
     err = float((got - ref).abs().max())
     print(f"[parity] flow tc B={B} T={T}: L-inf = {err:.3e} (|z|max {float(ref.abs().max()):.1f})")
-    assert err < 2e-2
+    assert err < FLOW_TC_REL * max(1.0, float(ref.abs().max()))
 
 
 @pytest.mark.parametrize("B,T", [(2, 24), (1, 33)])
@@ -288,8 +291,8 @@ def test_schedule_options_are_equivalent(cfg, sd, eng):
 
 
 def test_snake_variant_matches_reference_fixture():
-    """BASELINE config 4 (vdecoder/hifiganwithsnake): SnakeAlias kernel + fp32 FFMA convolutions vs the reference's own
-    waveform; `precision="tc"` must give the same result (the Snake path does not use the LeakyReLU-fused TC kernels)."""
+    """BASELINE config 4 (vdecoder/hifiganwithsnake) vs the reference's own waveform: fp32 = SnakeAlias kernel + FFMA
+    convolutions; tc = every convolution on tcgen05 with the SnakeAlias activation computed by its loader (no FFMA launch)."""
     from sovits_b200.config import load_config
     from sovits_b200.engine import TailEngine
     cfg_s = load_config()
@@ -305,12 +308,37 @@ def test_snake_variant_matches_reference_fixture():
         outs = []
         for precision in ("fp32", "tc"):
             e.set_precision(precision)
+            fb0 = e.fallback_count
             got = e.infer_tail(torch.from_numpy(gold["z_p"]).to(DEV), g.to(DEV), f0.to(DEV), noise["rand_ini"].to(DEV),
                                noise["har_noise"].to(DEV)).cpu()
             err = float((got - torch.from_numpy(gold["o"])).abs().max())
             print(f"[parity] snake {name} {precision}: L-inf vs reference waveform = {err:.3e}")
             assert err < (FP32_TOL if precision == "fp32" else TC_TOL)
+            assert e.fallback_count == fb0
             outs.append(got)
+        assert not torch.equal(outs[0], outs[1])          # the two precisions really are different code paths
+    # a longer ragged-tile case against the oracle (tile edges, all five stages, both ends of the sequence)
+    import svc_oracle as OO
+    B, T = 2, 45
+    c, f0, uv, sid = synth.synth_inputs(cfg_s, B, T)
+    noise = synth.draw_noise(B, T, cfg_s)
+    g = sd_s["emb_g.weight"][sid].transpose(1, 2).contiguous()
+    gen = torch.Generator().manual_seed(77)
+    z_p = torch.randn((B, cfg_s.inter_channels, T), generator=gen) * 1.4
+    taps = {}
+    ref = OO.tail(sd_s, cfg_s, z_p, g, f0, noise, torch.float32, taps)
+    e.set_precision("tc")
+    e.debug_enable(True)
+    got = e.infer_tail(z_p.to(DEV), g.to(DEV), f0.to(DEV), noise["rand_ini"].to(DEV), noise["har_noise"].to(DEV)).cpu()
+    for name in [f"{k}{i}" for i in range(5) for k in ("ups", "stage")]:
+        t = taps[name]
+        d = e.debug_fetch(name, tuple(t.shape)).cpu()
+        rel = float((d - t).abs().max()) / float(t.abs().max())
+        print(f"[parity] snake tc {name}: relative L-inf {rel:.2e}")
+        assert rel < 1e-2, (name, rel)
+    err = float((got - ref).abs().max())
+    print(f"[parity] snake tc B={B} T={T} vs oracle: L-inf = {err:.3e}")
+    assert err < TC_TOL
     e.close()
 
 
@@ -456,4 +484,101 @@ def test_flow_only_config5(cfg, sd, eng):
     eng.set_precision("fp32")
     etc = float((got_tc - ref).abs().max())
     print(f"[parity] config5 flow-only T=100000: fp32 L-inf {e32:.3e}, tc L-inf {etc:.3e} (|z|max {float(ref.abs().max()):.1f})")
-    assert e32 < 5e-4 and etc < 5e-2
+    assert e32 < 5e-4 and etc < FLOW_TC_REL * float(ref.abs().max())
+
+
+def test_full_size_config2_against_oracle(cfg, sd, eng):
+    """BASELINE config 2 at its own size (8 x 862 frames) against the ORACLE: the reference ops run on the GPU with strict
+    fp32 convolutions (cudnn.conv.fp32_precision='ieee'), the excitation from the fp64 closed form; compared with the CUDA
+    path in both precisions, waveform and every stage tap at full length (full-length tiles, the 1.5-wave stage-0 grid,
+    first-wave de-phasing)."""
+    B, T = 8, 862
+    z_p, g, f0, noise = _case(cfg, sd, B, T)
+    har = O.nsf_source_closed_form(sd, f0, noise["rand_ini"], noise["har_noise"], cfg).float()
+    sd_dev = {k: v.to(DEV) for k, v in sd.items() if k.startswith(("flow.", "dec."))}
+    prev = torch.backends.cudnn.conv.fp32_precision
+    torch.backends.cudnn.conv.fp32_precision = "ieee"
+    taps = {}
+    try:
+        z_ref = O.flow_reverse(sd_dev, z_p.to(DEV), torch.ones(B, 1, T, device=DEV), g.to(DEV), cfg, torch.float32)
+        o_ref = O.generator(sd_dev, z_ref, g.to(DEV), har.to(DEV), cfg, torch.float32, taps)
+    finally:
+        torch.backends.cudnn.conv.fp32_precision = prev
+    taps["z"] = z_ref
+    dv = lambda t: t.to(DEV)
+    for precision, tol, rel_tol in (("fp32", FP32_TOL, 1e-4), ("tc", TC_TOL, 1e-2)):
+        eng.set_precision(precision)
+        eng.debug_enable(True)
+        got = eng.infer_tail(dv(z_p), dv(g), dv(f0), dv(noise["rand_ini"]), dv(noise["har_noise"]))
+        worst = {}
+        for name in ["z", "conv_pre"] + [f"{k}{i}" for i in range(5) for k in ("ups", "stage")]:
+            t = taps[name]
+            d = eng.debug_fetch(name, tuple(t.shape))
+            worst[name] = float((d - t).abs().max()) / max(1.0, float(t.abs().max()))
+            assert worst[name] < rel_tol, (precision, name, worst[name])
+        eng.debug_enable(False)
+        err = float((got - o_ref).abs().max())
+        print(f"[parity] config2 full size {precision}: waveform L-inf vs oracle = {err:.3e}; worst tap {max(worst, key=worst.get)} "
+              f"rel {max(worst.values()):.2e}")
+        assert err < tol, (precision, err)
+    eng.set_precision("fp32")
+
+
+def test_bench_mode_end_to_end_parity(cfg, sd):
+    """The configuration bench.py times: torch defaults for the PyTorch prefix (cuDNN-style TF32 for the conv-equivalent
+    GEMMs, IEEE fp32 for q@k^T / p@v exactly like the reference's CUDA path) + the tensor-core tail, end to end
+    through SynthesizerTrn.infer against the fp32 CPU oracle.  Two independent reduced-precision sources (prefix TF32, tail
+    fp16 operands), each within the reference's own self-disagreement band: bound 2 x TC_TOL."""
+    import json
+    import sovits_b200
+    from sovits_b200 import models
+    with open(sovits_b200.DEFAULT_CONFIG) as f:
+        kw = json.load(f)["model"]
+    net = models.SynthesizerTrn(1025, 20, **kw).eval()
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    net.set_precision("tc")
+    B, T = 2, 120
+    c, f0, uv, sid = synth.synth_inputs(cfg, B, T)
+    N = T * cfg.hop
+    torch.manual_seed(52468)
+    noise = {"z_noise": torch.randn(B, cfg.inter_channels, T, device=DEV).cpu(),
+             "rand_ini": torch.rand(B, cfg.n_harmonics, device=DEV).cpu(),
+             "har_noise": torch.randn(B, N, cfg.n_harmonics, device=DEV).cpu()}
+    ref, _ = O.infer(sd, cfg, c, f0, uv, sid, noise, noice_scale=0.4)
+    assert torch.backends.cudnn.conv.fp32_precision != "ieee"      # torch's CUDA default, as in bench.py
+    o, _ = net.infer(c.to(DEV), f0.to(DEV), uv.to(DEV), g=sid.to(DEV), noice_scale=0.4)
+    err = float((o.cpu() - ref).abs().max())
+    print(f"[parity] bench mode (TF32-like prefix + tc tail) B={B} T={T}: L-inf vs fp32 oracle = {err:.3e}")
+    assert err < 2 * TC_TOL
+    assert net._b200_engine.fallback_count == 0
+
+
+def test_fp16_range_of_the_tensor_core_path(cfg, sd):
+    """fp16 operands have a 5-bit exponent (TF32, the reference's CUDA arithmetic, has 8).  LeakyReLU is positively
+    homogeneous, so scaling every ResBlock's first convolution (weight_g and bias) by s and its second convolution's weight_g
+    by 1/s leaves the network function unchanged - but moves weights and mid activations by s = 1e-4 / 1e+3 in magnitude.
+    The tensor-core path must stay inside TC_TOL of the unscaled reference fixture (power-of-two range normalisation of the
+    weight images, docs in DESIGN.md)."""
+    from sovits_b200.engine import TailEngine
+    gold_name = "b2_t24"
+    gold = np.load(os.path.join(GOLD, f"ref_infer_{gold_name}.npz"))
+    B, T = synth.GOLDEN_CASES[gold_name]
+    c, f0, uv, sid = synth.golden_inputs(cfg, gold_name)
+    noise = synth.draw_noise(B, T, cfg, seed=int(gold["seed"]))
+    g = sd["emb_g.weight"][sid].transpose(1, 2).contiguous()
+    for s in (1e-4, 1e3):
+        sd2 = dict(sd)
+        for k, v in sd.items():
+            if ".convs1." in k and (k.endswith("weight_g") or k.endswith("bias")):
+                sd2[k] = v * s
+            elif ".convs2." in k and k.endswith("weight_g"):
+                sd2[k] = v / s
+        e = TailEngine(cfg, DEV, "tc")
+        e.load_state_dict(sd2)
+        got = e.infer_tail(torch.from_numpy(gold["z_p"]).to(DEV), g.to(DEV), f0.to(DEV), noise["rand_ini"].to(DEV),
+                           noise["har_noise"].to(DEV)).cpu()
+        e.close()
+        err = float((got - torch.from_numpy(gold["o"])).abs().max())
+        print(f"[parity] range test, ResBlock conv1 x{s:g} / conv2 x{1 / s:g} (tc): L-inf vs reference waveform = {err:.3e}")
+        assert torch.isfinite(got).all() and err < TC_TOL

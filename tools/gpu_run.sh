@@ -1,0 +1,24 @@
+#!/bin/bash
+# One gpurun call = one invocation of this script with a list of steps, e.g.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_run.sh tests bench snake flow5 refcuda'
+# Every step runs under its own `timeout`, logs into gpurun_out/ and never aborts the following steps.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+for step in "$@"; do
+  case "$step" in
+    build)   python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 ;;
+    smoke)   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
+    snaketest) timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -s -k "snake" --timeout 300 > gpurun_out/test_snake.log 2>&1; echo "snaketest rc=$?"; tail -5 gpurun_out/test_snake.log ;;
+    tests)   timeout 1500 python -m pytest tests -q -m gpu -s --timeout 600 > gpurun_out/test_gpu.log 2>&1; echo "tests rc=$?"; grep -E "passed|failed|error" gpurun_out/test_gpu.log | tail -3 ;;
+    testsx)  timeout 1500 python -m pytest tests -q -m gpu -x -s --timeout 600 -k "${SVB_K:-}" > gpurun_out/test_gpu_k.log 2>&1; echo "testsx rc=$?"; tail -15 gpurun_out/test_gpu_k.log ;;
+    bench)   timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"; cat gpurun_out/bench_default.json ;;
+    benchq)  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "benchq rc=$?"; cat gpurun_out/bench_quick.json ;;
+    snake)   timeout 600 python bench.py --vocoder nsf-snake-hifigan --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_snake.json 2> gpurun_out/bench_snake.err; echo "snake rc=$?"; cat gpurun_out/bench_snake.json ;;
+    flow5)   timeout 300 python bench.py --workload flow5 --steps 20 --warmup 3 > gpurun_out/bench_flow5.json 2> gpurun_out/bench_flow5.err; echo "flow5 rc=$?"; cat gpurun_out/bench_flow5.json ;;
+    refcuda) timeout 600 python bench.py --impl reference-cuda --steps 3 --warmup 2 > gpurun_out/bench_refcuda.json 2> gpurun_out/bench_refcuda.err; echo "refcuda rc=$?"; cat gpurun_out/bench_refcuda.json ;;
+    refcpu)  timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_refcpu.json 2> gpurun_out/bench_refcpu.err; echo "refcpu rc=$?"; cat gpurun_out/bench_refcpu.json ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1; echo "launches rc=$?" ;;
+    *) echo "unknown step $step" ;;
+  esac
+done
