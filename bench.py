@@ -386,13 +386,19 @@ def main():
         barrier()
         return float(ms.item())
 
+    # clocks are sampled from before the warm-up until after both timed regions (nvidia-smi needs ~0.2 s to produce its first
+    # row; the timed regions are only ~0.1 s each), every 100 ms
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_dev()
     step_e2e()
     eng = net._b200_engine
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 3.0:       # make sure the sampler is running before timing starts
+            step_dev()
     l0 = eng.launch_count
     ms_dev = timed(step_dev, args.steps)
     launches = (eng.launch_count - l0)

@@ -54,6 +54,11 @@ struct FlowLayer {
     ConvW cond;                    // packed variant for time-varying g
     std::vector<ConvW> in_layers, res_skip;
     int in_c0 = 0, out_c0 = 0;     // which half feeds pre / receives post (Flip folded)
+    // fused coupling-layer kernel (kernels_flow.cu): weight block stream, bias sums, conditioning in its chunk order
+    void* fused_img = nullptr;
+    float* fb_gate = nullptr; float* fb_h = nullptr; float* fb_out = nullptr; float* fb_post = nullptr;
+    float* cond_w_perm2 = nullptr; float* cond_b_perm2 = nullptr;   // GEMV form (g[B,gin,1])
+    ConvW cond2;                                                     // packed conv form (time-varying g)
 };
 
 struct SnakeP {           // SnakeAlias parameters of one activation: e^alpha and 1/(e^beta + 1e-9) per channel
@@ -109,6 +114,7 @@ struct svb_ctx {
                                 // against the 128-bit thread loader on B200, so off by default; env SVB_TC_TMA overrides
     int opt_fuse_rb = 1;        // fused ResBlock kernel for narrow stages
     int opt_fuse_maxc = 64;     // ... up to this channel count (C = 64 fused: 12.6 vs 13.15 ms/step against the pair chain)
+    int opt_fuse_flow = 1;      // one kernel per coupling layer (kernels_flow.cu) instead of 10 conv-as-GEMM launches
     int64_t ffma_fallbacks = 0;    // times a "tc" call ran (part of) its work on the fp32 FFMA kernels
     bool warned_fallback = false;
     bool profile = false;
@@ -404,6 +410,29 @@ int run_flow(svb_ctx* ctx, const float* z_p, const float* g, int gT, const int32
     float* out = reinterpret_cast<float*>(ws + pl.off_out);
     float* gcond = reinterpret_cast<float*>(ws + pl.off_gcond);
     if (y != z_p) CU(cudaMemcpyAsync(y, z_p, (size_t)B * C * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const bool fused = ctx->precision == SVB_PREC_TC && ctx->flow_tc_ok && ctx->opt_fuse_flow && !ctx->flow.empty() && ctx->flow[0].fused_img;
+    for (int fl = c.n_flows - 1; fused && fl >= 0; --fl) {
+        // one kernel per coupling layer; the conditioning cond_layer(g) is a GEMV (g[B,gin,1]) or, for speaker-mix g[B,gin,T],
+        // a 1x1 convolution written in the gate's chunk order and added per (frame, column) by the gate epilogue
+        FlowLayer& F = ctx->flow[fl];
+        if (gT == 1) {
+            launch_gemv(F.cond_w_perm2, F.cond_b_perm2, g, gcond, B, 2 * H * L, c.gin_channels, st);
+        } else {
+            ConvF32 cg;
+            cg.x = g; cg.x_ctot = c.gin_channels; cg.Cin = c.gin_channels; cg.Tin = T;
+            cg.w = F.cond2.w; cg.bias = F.cond2.b; cg.Cout = 2 * H * L; cg.k = 1;
+            cg.y = gcond; cg.y_ctot = 2 * H * L; cg.Ty = T; cg.n_out = T; cg.B = B;
+            launch_conv_f32(cg, st);
+        }
+        FlowLayerTC a;
+        a.y = y; a.y_ctot = C; a.in_c0 = F.in_c0; a.out_c0 = F.out_c0;
+        a.w = F.fused_img; a.bias_gate = F.fb_gate; a.bias_h = F.fb_h; a.bias_out = F.fb_out; a.bias_post = F.fb_post;
+        a.gcond = gT == 1 ? gcond : nullptr; a.gcond_t = gT == 1 ? nullptr : gcond;
+        a.lengths = lengths; a.B = B; a.T = T; a.H = H; a.half = half; a.L = L; a.k = c.flow_kernel_size;
+        const int trc = launch_flow_layer_tc(a, st);
+        if (trc) return fail(ctx, trc, "fused coupling-layer kernel launch failed");
+    }
+    if (fused) return check_launch(ctx, "flow");
     const bool use_tc = ctx->precision == SVB_PREC_TC && ctx->flow_tc_ok && gT == 1;
     if (ctx->precision == SVB_PREC_TC && !use_tc) note_fallback(ctx, gT != 1 ? "flow: time-varying conditioning g" : "flow: unsupported layer shapes");
     for (int fl = c.n_flows - 1; use_tc && fl >= 0; --fl) {
@@ -551,14 +580,15 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
     // own kernel in front of the FFMA convolutions.
     const bool snake = c.snake != 0;
     float* Sb = snake ? reinterpret_cast<float*>(ws + pl.off_S) : nullptr;
-    const bool gen_tc = ctx->precision == SVB_PREC_TC && ctx->gen_tc_ok && (gT == 1 || melv);
-    if (ctx->precision == SVB_PREC_TC && !gen_tc) note_fallback(ctx, "generator: conditioning/shape not served by the tensor-core kernels");
+    const bool gen_tc = ctx->precision == SVB_PREC_TC && ctx->gen_tc_ok;
+    if (ctx->precision == SVB_PREC_TC && !gen_tc) note_fallback(ctx, "generator: layer shapes not served by the tensor-core kernels");
     if (gen_tc) {
         const ConvNW& W = ctx->conv_pre_tc;
         ConvNTC a;
         a.x = z; a.x_ctot = Cpre; a.cin_real = W.cin_real; a.cinp = W.cinp; a.Tin = T;
         a.w = W.img; a.bias = W.bias; a.acc_scale = W.acc_scale;
-        if (!melv) { a.bias_b = dg; a.bias_b_stride = U; a.bias_b_off = 0; }
+        if (!melv && gT == 1) { a.bias_b = dg; a.bias_b_stride = U; a.bias_b_off = 0; }
+        else if (!melv) { a.bias_t = dg; a.bias_t_ctot = U; a.bias_t_c0 = 0; }      // speaker mix: cond(g)[b, :, t] per frame
         a.k = W.k; a.pad_left = W.pad_left; a.n_rows = T; a.N_total = W.N_total; a.NC = W.NC; a.chunks_per_cta = 1; a.Ty = T; a.B = B;
         a.seg[0].y = pre; a.seg[0].y_ctot = U; a.seg[0].col0 = 0; a.seg[0].col1 = U;
         int trc = launch_convn_tc(a, st);
@@ -780,6 +810,7 @@ int svb_create(int device, svb_ctx** out) {
     if (const char* e = std::getenv("SVB_TC_TMA")) c->opt_tma = std::atoi(e);
     if (const char* e = std::getenv("SVB_FUSE_RESBLOCK")) c->opt_fuse_rb = std::atoi(e);
     if (const char* e = std::getenv("SVB_FUSE_MAXC")) c->opt_fuse_maxc = std::atoi(e);
+    if (const char* e = std::getenv("SVB_FUSE_FLOW")) c->opt_fuse_flow = std::atoi(e);
     *out = c;
     return SVB_OK;
 }
@@ -807,6 +838,7 @@ int svb_set_option(svb_ctx* ctx, const char* name, int value) {
     if (n == "tma") ctx->opt_tma = value;
     else if (n == "fuse_resblock") ctx->opt_fuse_rb = value;
     else if (n == "fuse_maxc") ctx->opt_fuse_maxc = value;
+    else if (n == "fuse_flow") ctx->opt_fuse_flow = value;
     else return fail(ctx, SVB_ERR_INVALID_ARG, "unknown option " + n);
     return SVB_OK;
 }
@@ -965,6 +997,9 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
         if ((rc = get_tensor(ctx, m, p + "pre.weight", {H, half, 1}, w))) return rc;
         if ((rc = get_tensor(ctx, m, p + "pre.bias", {H}, b))) return rc;
         if ((rc = make_conv(ctx, w.v, b.v, H, half, 1, odd, false, F.pre))) return rc;
+        const std::vector<float> h_pre_w = w.v, h_pre_b = b.v;
+        std::vector<float> h_post_w, h_post_b, h_cond_w, h_cond_b;
+        std::vector<std::vector<float>> h_in_w(L), h_in_b(L), h_rs_w(L), h_rs_b(L);
         const bool flow_tc = (H == 192) && (half <= H) && (half % 32 == 0) && (c.flow_kernel_size - 1 <= 8);
         ctx->flow_tc_ok = flow_tc;
         if (flow_tc) {
@@ -976,6 +1011,7 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
         if ((rc = get_tensor(ctx, m, p + "post.weight", {half, H, 1}, w))) return rc;
         if ((rc = get_tensor(ctx, m, p + "post.bias", {half}, b))) return rc;
         if ((rc = make_conv(ctx, w.v, b.v, half, H, 1, false, odd, F.post))) return rc;
+        h_post_w = w.v; h_post_b = b.v;
         if (flow_tc) {
             const std::vector<float> wv = w.v, bv = b.v;
             if ((rc = make_convn(ctx, H, H, half, half, 1, 0,
@@ -986,6 +1022,7 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
         if ((rc = get_tensor(ctx, m, p + "enc.cond_layer.bias", {2 * H * L}, b))) return rc;
         if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&F.cond_w_nat))) return rc;
         if ((rc = make_conv(ctx, w.v, b.v, 2 * H * L, G, 1, false, false, F.cond))) return rc;
+        h_cond_w = w.v; h_cond_b = b.v;
         // gate kernel column order: chunk c (of H columns) = [tanh channels c*H/2.. | sigmoid channels c*H/2..]
         auto gate_row = [H](int col) { const int cc = col / H, j = col % H, hh = H / 2; return j < hh ? cc * hh + j : H + cc * hh + (j - hh); };
         if (flow_tc) {
@@ -1008,6 +1045,7 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
             if ((rc = folded(ctx, m, q, {2 * H, H, c.flow_kernel_size}, w))) return rc;
             if ((rc = get_tensor(ctx, m, q + ".bias", {2 * H}, b))) return rc;
             if ((rc = make_conv(ctx, w.v, b.v, 2 * H, H, c.flow_kernel_size, false, false, F.in_layers[i]))) return rc;
+            h_in_w[i] = w.v; h_in_b[i] = b.v;
             if (flow_tc) {
                 const int kk = c.flow_kernel_size;
                 const std::vector<float> wv = w.v, bv = b.v;
@@ -1019,6 +1057,7 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
             const int co = (i < L - 1) ? 2 * H : H;
             if ((rc = folded(ctx, m, r, {co, H, 1}, w))) return rc;
             if ((rc = get_tensor(ctx, m, r + ".bias", {co}, b))) return rc;
+            h_rs_w[i] = w.v; h_rs_b[i] = b.v;
             if (flow_tc) {
                 const std::vector<float> wv = w.v, bv = b.v;
                 if ((rc = make_convn(ctx, H, H, co, H, 1, 0, [&](int col, int ci, int) { return wv[(size_t)col * H + ci]; },
@@ -1039,6 +1078,43 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
             } else {
                 if ((rc = make_conv(ctx, w.v, b.v, H, H, 1, false, false, F.res_skip[i]))) return rc;
             }
+        }
+        if (flow_tc && H == 192 && half == 96 && L == 4 && c.flow_kernel_size == 5) {
+            // ---- fused coupling-layer kernel: one block stream + bias sums + conditioning in its own chunk order
+            const int kk = 5;
+            std::vector<uint8_t> img(flow_layer_image_bytes());
+            flow_layer_pack(
+                [&](int co, int ci) { return h_pre_w[(size_t)co * half + (odd ? half - 1 - ci : ci)]; },
+                [&](int i, int row, int ci, int tap) { return h_in_w[i][((size_t)row * H + ci) * kk + tap]; },
+                [&](int i, int row, int ci) { return h_rs_w[i][(size_t)row * H + ci]; },
+                [&](int co, int ci) { return h_post_w[(size_t)(odd ? half - 1 - co : co) * H + ci]; }, img.data());
+            if ((rc = upload(ctx, img.data(), img.size(), &F.fused_img))) return rc;
+            std::vector<float> bg((size_t)L * 2 * H), bh((size_t)L * H), bo(H, 0.f), bp(half);
+            for (int i = 0; i < L; ++i)
+                for (int col = 0; col < 2 * H; ++col) bg[(size_t)i * 2 * H + col] = h_in_b[i][flow_gate_row(col)];
+            for (int ch = 0; ch < H; ++ch) {
+                float acc = h_pre_b[ch];
+                for (int i = 0; i < L; ++i) {
+                    bh[(size_t)i * H + ch] = acc;
+                    if (i < L - 1) { acc += h_rs_b[i][ch]; bo[ch] += h_rs_b[i][H + ch]; }
+                    else bo[ch] += h_rs_b[i][ch];
+                }
+            }
+            for (int co = 0; co < half; ++co) bp[co] = h_post_b[odd ? half - 1 - co : co];
+            if ((rc = upload(ctx, bg.data(), bg.size() * sizeof(float), (void**)&F.fb_gate))) return rc;
+            if ((rc = upload(ctx, bh.data(), bh.size() * sizeof(float), (void**)&F.fb_h))) return rc;
+            if ((rc = upload(ctx, bo.data(), bo.size() * sizeof(float), (void**)&F.fb_out))) return rc;
+            if ((rc = upload(ctx, bp.data(), bp.size() * sizeof(float), (void**)&F.fb_post))) return rc;
+            std::vector<float> wp(h_cond_w.size()), bpc(h_cond_b.size());
+            for (int i = 0; i < L; ++i)
+                for (int col = 0; col < 2 * H; ++col) {
+                    const int src = 2 * H * i + flow_gate_row(col), dst = 2 * H * i + col;
+                    std::memcpy(&wp[(size_t)dst * G], &h_cond_w[(size_t)src * G], sizeof(float) * G);
+                    bpc[dst] = h_cond_b[src];
+                }
+            if ((rc = upload(ctx, wp.data(), wp.size() * sizeof(float), (void**)&F.cond_w_perm2))) return rc;
+            if ((rc = upload(ctx, bpc.data(), bpc.size() * sizeof(float), (void**)&F.cond_b_perm2))) return rc;
+            if ((rc = make_conv(ctx, wp, bpc, 2 * H * L, G, 1, false, false, F.cond2))) return rc;
         }
     }
 

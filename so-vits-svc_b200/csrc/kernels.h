@@ -136,6 +136,25 @@ size_t convn_weight_image_bytes(int cinp, int N_total, int NC, int k, int noise)
 void convn_pack_weight_image(int cinp, int N_total, int NC, int k, const std::function<float(int, int, int)>& wcol,
                              const std::function<float(int, int)>* ncol, int noise, void* dst_host);
 
+// ---- one ResidualCouplingLayer (reverse) per launch (kernels_flow.cu) ------------------------------------------------
+struct FlowLayerTC {
+    float* y = nullptr; int y_ctot = 0, in_c0 = 0, out_c0 = 0;     // [B, 2*half, T] updated in place
+    const void* w = nullptr;                                          // block stream built by flow_layer_pack
+    const float* bias_gate = nullptr;    // [L][2H] in_layers biases, chunk-permuted (flow_gate_row)
+    const float* bias_h = nullptr;       // [L][H]  b_pre + sum_{j<i} b_res_j
+    const float* bias_out = nullptr;     // [H]     sum of the skip biases
+    const float* bias_post = nullptr;    // [half]
+    const float* gcond = nullptr;        // [B][L*2H] cond_layer(g) for g[B,gin,1], chunk-permuted; or null
+    const float* gcond_t = nullptr;      // [B][L*2H][T] for time-varying g (speaker mix); or null
+    const int32_t* lengths = nullptr;
+    int B = 1, T = 0, H = 192, half = 96, L = 4, k = 5;
+};
+int launch_flow_layer_tc(const FlowLayerTC& a, cudaStream_t st);
+size_t flow_layer_image_bytes();
+int flow_gate_row(int col);
+void flow_layer_pack(const std::function<float(int, int)>& pre, const std::function<float(int, int, int, int)>& inl,
+                     const std::function<float(int, int, int)>& rs, const std::function<float(int, int)>& post, void* dst_host);
+
 int64_t& launch_counter();
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: track what has been granted per (kernel, device).

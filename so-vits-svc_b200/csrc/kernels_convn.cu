@@ -45,6 +45,8 @@ struct CNGeom {
 struct ConvNDev {                     // launch-time geometry (host computed)
     int stage_bytes, tmem_cols, bufcols, blkcols, nbuf;
     int arows;                        // A-tile rows per panel = 128*MB + halo
+    int tout;                         // output rows a CTA produces (128*MB; SnakeAlias loader: 128*MB - (k-1)*dil so that the
+                                      // rows it has to activate are exactly 128*MB = 8*MB runs per channel, one per worker warp)
     int xs_pitch; uint32_t off_xs;    // SnakeAlias loader: fp32 staging rows [<=32 channels][xs_pitch] (odd pitch)
     int noise_np;                     // noise panels (0, 1 or 2)
     int noise_rb[2];                  // their row bytes (128 -> 64 samples, 32 -> 16 samples)
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
-    const int i0 = blockIdx.x * R1;                       // first output row of this tile
+    const int i0 = blockIdx.x * d.tout;                   // first output row of this tile
     const int NC = a.NC;
     const int n_chunks = (a.N_total + NC - 1) / NC;
     const int c_lo = blockIdx.z * a.chunks_per_cta;
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
     const int SUBN0 = NC * d.noise_rb[0], SUBN1 = NC * d.noise_rb[1];   // bytes of the noise weight blocks
     const size_t chunk_bytes = (size_t)n_reg * SUB + (d.noise_np > 0 ? SUBN0 : 0) + (d.noise_np > 1 ? SUBN1 : 0);
     auto sb_bytes = [&](int idx) -> uint32_t { return idx < n_reg ? (uint32_t)SUB : (idx == n_reg ? (uint32_t)SUBN0 : (uint32_t)SUBN1); };
-    const int RA = R1 + (a.k - 1) * a.dil;                // A rows touched
+    const int RA = d.tout + (a.k - 1) * a.dil;            // A rows that feed valid output rows
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -275,14 +277,38 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
             for (int j = 0; j < 12; ++j) f[j] = __ldg(a.snake_filt + j);
             const float* __restrict__ xb = a.x + ((size_t)b * a.x_ctot + a.x_c0) * (size_t)L;
             const int cl = lane % GCH, rsel = lane / GCH;
+            // rows past the activated ones are read by the MMAs of the tile's unused output rows: keep them finite (zero)
+            for (int idx = tid; idx < G::NP * (AROWS - n_runs * SNK_RUN) * (G::RB / 16); idx += CN_NWORK) {
+                const int per = (AROWS - n_runs * SNK_RUN) * (G::RB / 16);
+                const int pn = idx / per, rem = idx % per;
+                const int r = n_runs * SNK_RUN + rem / (G::RB / 16), ch = rem % (G::RB / 16);
+                *reinterpret_cast<uint4*>(sm + pn * APANEL + swz_offset(r, ch, G::RB)) = make_uint4(0, 0, 0, 0);
+            }
 #pragma unroll 1
             for (int cg0 = 0; cg0 < CINP; cg0 += GCH) {
-                for (int c = warp; c < GCH; c += 8) {
-                    const bool cv = (cg0 + c) < a.cin_real;
-                    const float* __restrict__ xc = xb + (size_t)(cv ? cg0 + c : 0) * L;
-                    for (int q = lane; q < XL; q += 32) {
-                        const int ti = min(max(tlo + q, 0), L - 1);
-                        xs[c * XP + q] = cv ? __ldg(xc + ti) : 0.f;
+                {
+                    // warp w stages channels w, w+8, ...: all loads of a batch (CPW channels x 4 strides of 32 samples) are
+                    // issued before the first store, so a pass costs ~2 global-load round trips instead of 20
+                    constexpr int CPW = GCH / 8;
+#pragma unroll 1
+                    for (int q0 = lane; q0 < XL; q0 += 128) {
+                        float v[CPW][4];
+#pragma unroll
+                        for (int cc = 0; cc < CPW; ++cc) {
+                            const int c = warp + 8 * cc;
+                            const bool cv = (cg0 + c) < a.cin_real;
+                            const float* __restrict__ xc = xb + (size_t)(cv ? cg0 + c : 0) * L;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int ti = min(max(tlo + q0 + 32 * u, 0), L - 1);
+                                v[cc][u] = cv ? __ldg(xc + ti) : 0.f;
+                            }
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < CPW; ++cc)
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (q0 + 32 * u < XL) xs[(warp + 8 * cc) * XP + q0 + 32 * u] = v[cc][u];
                     }
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -396,7 +422,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
 #pragma unroll 1
             for (int mb = 0; mb < MB; ++mb) {
                 const int i = i0 + mb * 128 + rib;                 // output row
-                const bool rowok = i < a.n_rows;
+                const bool rowok = (i < a.n_rows) && (mb * 128 + rib < d.tout);
                 const uint32_t tcol = tlane + buf * d.bufcols + mb * d.blkcols;
                 if (a.mode == 2) {
                     // ---- gate: cols [0,NC/2) = tanh pre-activations, [NC/2,NC) = sigmoid pre-activations of the same channels
@@ -542,12 +568,13 @@ int launch_convn_t(const ConvNTC& a, cudaStream_t st) {
     if (SUB > stage) return SVB_ERR_UNSUPPORTED;
     d.stage_bytes = stage;
     d.arows = 128 * MB + halo;
+    d.tout = SNAKE ? 128 * MB - (a.k - 1) * a.dil : 128 * MB;
+    if (d.tout < 64) return SVB_ERR_UNSUPPORTED;
     uint32_t off = (uint32_t)G::NP * d.arows * G::RB;
     off = (off + 1023u) & ~1023u;
     d.xs_pitch = 0; d.off_xs = 0;
     if (SNAKE) {
-        const int RA = 128 * MB + (a.k - 1) * a.dil;
-        const int xl = ((RA + SNK_RUN - 1) / SNK_RUN) * SNK_RUN + 12;
+        const int xl = 128 * MB + 12;                          // RA = 128*MB rows -> 8*MB runs of 16
         d.xs_pitch = xl | 1;                                   // odd pitch: lanes (channels) hit distinct banks
         d.off_xs = off;
         off += (uint32_t)G::SNK_GCH * d.xs_pitch * 4;
@@ -568,7 +595,7 @@ int launch_convn_t(const ConvNTC& a, cudaStream_t st) {
     if (smem > 227 * 1024) return SVB_ERR_UNSUPPORTED;
     static std::atomic<size_t> granted[SVB_MAX_DEV];
     if (ensure_dyn_smem(convn_tc_kernel<CINP, MB, MINB, SNAKE>, smem, granted)) return SVB_ERR_CUDA;
-    dim3 grid((a.n_rows + 128 * MB - 1) / (128 * MB), a.B, (n_chunks + cpc - 1) / cpc);
+    dim3 grid((a.n_rows + d.tout - 1) / d.tout, a.B, (n_chunks + cpc - 1) / cpc);
     convn_tc_kernel<CINP, MB, MINB, SNAKE><<<grid, CN_THREADS, smem, st>>>(a, d);
     launch_counter()++;
     return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;

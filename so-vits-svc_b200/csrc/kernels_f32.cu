@@ -356,7 +356,68 @@ __global__ void __launch_bounds__(128) conv_post_kernel(const float* __restrict_
     }
 }
 
+// Register-window form for the shipped shape (C = 16 channels, K = 7, N % 4 == 0): a thread produces 4 consecutive samples
+// and reads, per channel, the aligned 12-sample window [n0-4, n0+8) as three 128-bit loads straight from global memory
+// (neighbouring threads share two of them through L1).  Four channels = 12 LDG.128 are in flight per thread, no shared
+// memory, no block barrier: the kernel is bound by the single HBM pass over the stage-4 tensor.
+template <int C, int K>
+__global__ void __launch_bounds__(256) conv_post_vec_kernel(const float* __restrict__ x, const float* __restrict__ w, float bias,
+                                                            float* __restrict__ wav, int N, float slope) {
+    constexpr int PAD = (K - 1) / 2;
+    static_assert(PAD <= 4 && K - 1 - PAD <= 4, "window is [n0-4, n0+8)");
+    __shared__ float wsm[C * K];
+    for (int i = threadIdx.x; i < C * K; i += 256) wsm[i] = w[i];
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int n0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (n0 >= N) return;
+    const float* __restrict__ xb = x + (size_t)b * C * N;
+    float acc[4] = {bias, bias, bias, bias};
+    const bool inner = (n0 >= 4) && (n0 + 8 <= N);
+#pragma unroll 1
+    for (int c0 = 0; c0 < C; c0 += 4) {
+        float win[4][12];
+        if (inner) {
+            float4 v[4][3];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                for (int u = 0; u < 3; ++u) v[cc][u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)(c0 + cc) * N + n0 - 4 + 4 * u));
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                for (int u = 0; u < 3; ++u) { win[cc][4 * u] = v[cc][u].x; win[cc][4 * u + 1] = v[cc][u].y; win[cc][4 * u + 2] = v[cc][u].z; win[cc][4 * u + 3] = v[cc][u].w; }
+        } else {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                for (int j = 0; j < 12; ++j) { const int n = n0 - 4 + j; win[cc][j] = (n >= 0 && n < N) ? __ldg(xb + (size_t)(c0 + cc) * N + n) : 0.f; }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) win[cc][j] = fmaxf(win[cc][j], win[cc][j] * slope);   // slope <= 1: LeakyReLU (1 = identity)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float wk = wsm[(c0 + cc) * K + k];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = fmaf(wk, win[cc][4 - PAD + i + k], acc[i]);
+            }
+        }
+    }
+    float* dst = wav + (size_t)b * N + n0;
+    if (n0 + 3 < N) *reinterpret_cast<float4*>(dst) = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
+    else
+        for (int i = 0; i < 4; ++i) if (n0 + i < N) dst[i] = tanhf(acc[i]);
+}
+
 void launch_conv_post(const float* x, const float* w, float bias, float* wav, int B, int C, int N, int K, float slope, cudaStream_t st) {
+    if (C == 16 && K == 7 && (N % 4) == 0 && slope <= 1.f && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wav)) & 15u) == 0) {
+        dim3 grid((N / 4 + 255) / 256, B);
+        conv_post_vec_kernel<16, 7><<<grid, 256, 0, st>>>(x, w, bias, wav, N, slope);
+        launch_counter()++;
+        return;
+    }
     size_t smem = sizeof(float) * ((size_t)C * CP_PITCH + (size_t)C * K);
     dim3 grid((N + CP_TT - 1) / CP_TT, B);
     conv_post_kernel<<<grid, 128, smem, st>>>(x, w, bias, wav, C, N, K, slope);
@@ -439,11 +500,64 @@ __global__ void __launch_bounds__(256) nsf_source_kernel(const float* __restrict
     har[(long long)b * N + n] = tanhf(acc);
 }
 
+// Four consecutive samples per thread (hop % 4 == 0, so they share their frame): the 4 x H noise values are H 128-bit loads
+// issued up front (the [B,N,H] noise tensor is 9/10 of the kernel's traffic), the frame's phase base and r are read once,
+// the waveform leaves as one 128-bit store.  Same arithmetic, expression by expression, as nsf_source_kernel.
+template <int H>
+__global__ void __launch_bounds__(256) nsf_source_vec4_kernel(const float* __restrict__ f0, const float* __restrict__ noise,
+                                                              const double* __restrict__ phase, const float* __restrict__ lin_w, float lin_b,
+                                                              float* __restrict__ har, int T, int hop, float sr, long long N,
+                                                              const float* __restrict__ rand_ini, int rand_in_rate) {
+    const int b = blockIdx.y;
+    const long long n0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (n0 >= N) return;
+    float nz[4 * H];
+    if (noise) {
+        const float4* __restrict__ np = reinterpret_cast<const float4*>(noise + ((long long)b * N + n0) * H);
+#pragma unroll
+        for (int j = 0; j < H; ++j) { const float4 q = __ldg(np + j); nz[4 * j] = q.x; nz[4 * j + 1] = q.y; nz[4 * j + 2] = q.z; nz[4 * j + 3] = q.w; }
+    }
+    const int F = (int)(n0 / hop);
+    const int k0 = (int)(n0 - (long long)F * hop);
+    const float f = f0[(long long)b * T + F];
+    const float uv = f > 0.f ? 1.f : 0.f;
+    const float amp = uv * 0.003f + (1.f - uv) * (0.1f / 3.f);
+    const double* __restrict__ ph0 = phase + ((long long)b * T + F) * H;
+    float acc[4] = {lin_b, lin_b, lin_b, lin_b};
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        float rf = rad_value(f, h, sr);
+        if (rand_in_rate && F == 0 && h > 0) rf = __fadd_rn(rf, rand_ini[b * H + h]);
+        const double r = (double)rf;
+        const double p0 = ph0[h];
+        const float lw = lin_w[h];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            double ph = p0 + (double)(k0 + s + 1) * r;
+            ph -= floor(ph);
+            const float sv = sinpif(2.0f * (float)ph) * 0.1f;
+            const float v = sv * uv + (noise ? amp * nz[s * H + h] : 0.f);
+            acc[s] = fmaf(lw, v, acc[s]);
+        }
+    }
+    *reinterpret_cast<float4*>(har + (long long)b * N + n0) = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
+}
+
 void launch_nsf_source(const float* f0, const float* rand_ini, const float* noise, const float* lin_w, float lin_b,
                        double* phase_ws, float* har, int B, int T, int hop, int n_harm, float sr, int rand_in_rate, cudaStream_t st) {
     nsf_phase_kernel<<<B * n_harm, 32, 0, st>>>(f0, rand_ini, phase_ws, B, T, n_harm, hop, sr, rand_in_rate);
     launch_counter()++;
     long long N = (long long)T * hop;
+    const bool vec = (hop % 4 == 0) && ((reinterpret_cast<uintptr_t>(har) & 15u) == 0) && (!noise || (reinterpret_cast<uintptr_t>(noise) & 15u) == 0);
+    if (vec && (n_harm == 9 || n_harm == 1)) {
+        dim3 gridv((unsigned)((N / 4 + 255) / 256), B);
+        if (n_harm == 9)
+            nsf_source_vec4_kernel<9><<<gridv, 256, 0, st>>>(f0, noise, phase_ws, lin_w, lin_b, har, T, hop, sr, N, rand_ini, rand_in_rate);
+        else
+            nsf_source_vec4_kernel<1><<<gridv, 256, 0, st>>>(f0, noise, phase_ws, lin_w, lin_b, har, T, hop, sr, N, rand_ini, rand_in_rate);
+        launch_counter()++;
+        return;
+    }
     dim3 grid((unsigned)((N + 255) / 256), B);
     if (n_harm == 9)
         nsf_source_kernel<9><<<grid, 256, 0, st>>>(f0, noise, phase_ws, lin_w, lin_b, har, T, hop, sr, N, rand_ini, rand_in_rate);

@@ -280,11 +280,16 @@ def test_schedule_options_are_equivalent(cfg, sd, eng):
     eng.set_option("fuse_maxc", 32)
     fused32, n_f32 = run()
     eng.set_option("fuse_maxc", 64)
+    eng.set_option("fuse_flow", 0)                # flow as 10 conv-as-GEMM launches per coupling layer instead of one kernel
+    unfused_flow, n_uf = run()
+    eng.set_option("fuse_flow", 1)
     # the options really select different schedules: 9 pair launches replace each fused ResBlock launch of 3
     assert n_pairs == n_pairs_tma and n_pairs > n_f32 > n_base, (n_base, n_tma, n_pairs, n_f32)
+    assert n_uf == n_base + 4 * 9, (n_uf, n_base)        # 41 launches -> 4 x (conditioning GEMV + 1 kernel)
     eng.set_precision("fp32")
     ref = eng.infer_tail(*args)
-    for name, o in (("default", base), ("tma", tma), ("pairs-only", pairs), ("pairs-only+tma", pairs_tma), ("fused<=32", fused32)):
+    for name, o in (("default", base), ("tma", tma), ("pairs-only", pairs), ("pairs-only+tma", pairs_tma), ("fused<=32", fused32),
+                    ("unfused flow", unfused_flow)):
         err = float((o - ref).abs().max())
         print(f"[parity] schedule {name}: L-inf vs fp32 path = {err:.3e}")
         assert err < TC_TOL
