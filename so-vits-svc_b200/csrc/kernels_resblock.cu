@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
     if (tid == 0) {
         dephase_first_wave(g_rb_ticket, p.epoch, p.skew_clk, MINB);
         for (int s = 0; s < 2; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int m = 0; m < MB; ++m) { mbar_init(bar_a + 8 * m, RBK_NWORK); mbar_init(bar_acc + 8 * m, 1); }
+        for (int m = 0; m < MB; ++m) { mbar_init(bar_a + 8 * m, RBK_NWORK / 2); mbar_init(bar_acc + 8 * m, 1); }
         fence_barrier_init();
     }
     if (warp == 8) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
@@ -472,12 +472,17 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
         __syncwarp();
     } else {
         // ------------------------------------------------------------ workers
-        const int q4 = warp & 3, hsel = warp >> 2;
+        // Two worker groups of four warps: group g owns the row blocks mb = g, g+2, ... and all C channels of its row.  A
+        // block's epilogue is one dependent chain (barrier -> tcgen05.ld -> math -> st.shared -> fences -> arrive) of several
+        // hundred cycles; with all eight warps on the same block the chains of consecutive blocks were serialised and, for the
+        // short k = 3 / C <= 32 convolutions, longer than the MMAs they feed (ncu: tensor pipe 6-13 % active, stalls spread over
+        // scoreboard waits).  Two blocks in flight halve that critical path.
+        const int q4 = warp & 3, grp = warp >> 2;
         const int rib = 32 * q4 + lane;
-        constexpr int CH = C / 2;
-        constexpr int CG = CH < 16 ? CH : 16;
+        constexpr int CH = C;
+        constexpr int CG = 16;
         const uint32_t tlane = tmem_base + ((uint32_t)(32 * q4) << 16);
-        const int cbase = hsel * CH;
+        const int cbase = 0;
 
         for (int i = tid; i < 2 * RBK_PAD * (G::RB / 16); i += RBK_NWORK) {
             const int rr = i / (G::RB / 16), ch = i % (G::RB / 16);
@@ -486,42 +491,32 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
         }
         // round 0: load x (fp32 -> TMEM residual, lrelu -> fp16 operand rows), two row blocks per batch
 #pragma unroll 1
-        for (int mb0 = 0; mb0 < MB; mb0 += 2) {
-            float v[2][CH];
+        for (int mb = grp; mb < MB; mb += 2) {
+            const int t = tt0 + mb * 128 + rib;
+            const bool valid = (t >= 0) && (t < p.T);
+            const float* __restrict__ xt = xb + (valid ? t : 0);
+            const int row = mb * 128 + rib;
+            uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
+            const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
+#pragma unroll 2
+            for (int cc = 0; cc < CH; cc += CG) {
+                float v[16];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int t = tt0 + (mb0 + u) * 128 + rib;
-                const bool valid = (t >= 0) && (t < p.T);
-                const float* __restrict__ xt = xb + (valid ? t : 0) + (size_t)cbase * p.T;
+                for (int j = 0; j < CG; ++j) v[j] = valid ? __ldg(xt + (size_t)(cc + j) * p.T) : 0.f;
+                uint32_t r[16];
 #pragma unroll
-                for (int j = 0; j < CH; ++j) v[u][j] = valid ? __ldg(xt + (size_t)j * p.T) : 0.f;
-            }
+                for (int j = 0; j < CG; ++j) r[j] = __float_as_uint(v[j]);
+                tmem_st16(tlane + mb * C + cc, r);
+                float w[16];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int mb = mb0 + u;
-                const int row = mb * 128 + rib;
-                uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
-                const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
-#pragma unroll
-                for (int cc = 0; cc < CH; cc += CG) {
-                    const int c0 = cbase + cc;
-                    uint32_t r[16];
-#pragma unroll
-                    for (int j = 0; j < CG; ++j) r[j] = __float_as_uint(v[u][cc + j]);
-                    if (CG == 16) tmem_st16(tlane + mb * C + c0, r);
-                    else tmem_st8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r));
-                    float w[16];
-#pragma unroll
-                    for (int j = 0; j < CG; ++j) w[j] = lrelu01(v[u][cc + j]);
-                    store_chunk8(prow, phase, c0 / 8, w, 0xffffffffu);
-                    if (CG == 16) store_chunk8(prow, phase, c0 / 8 + 1, w + 8, 0xffffffffu);
-                }
+                for (int j = 0; j < CG; ++j) w[j] = lrelu01(v[j]);
+                store_chunk8(prow, phase, cc / 8, w, 0xffffffffu);
+                store_chunk8(prow, phase, cc / 8 + 1, w + 8, 0xffffffffu);
             }
             tmem_st_wait();
             tc_fence_before();
             fence_proxy_async();
-            mbar_arrive(bar_a + 8 * mb0);
-            mbar_arrive(bar_a + 8 * (mb0 + 1));
+            mbar_arrive(bar_a + 8 * mb);
         }
 
         const bool red_old = p.red_old != 0;
@@ -532,7 +527,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
             const float* __restrict__ bq_ = sbias + q * C;
             const float inv_q = p.inv[q >> 1];
 #pragma unroll 1
-            for (int mb = 0; mb < MB; ++mb) {
+            for (int mb = grp; mb < MB; mb += 2) {
                 mbar_wait(bar_acc + 8 * mb, par);
                 if (q < 5 && mb + 1 < MB) mbar_wait(bar_acc + 8 * (mb + 1), par);   // MMA(mb+1, q) still reads rows of this block
                 tc_fence_after();
@@ -542,25 +537,32 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                 uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
                 const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
                 if ((q & 1) == 0) {
-                    // first conv of a pair: mid = lrelu(acc + b1) -> operand rows
+                    // first conv of a pair: mid = lrelu(acc + b1) -> operand rows (two column groups per TMEM round trip)
 #pragma unroll
-                    for (int cc = 0; cc < CH; cc += CG) {
-                        const int c0 = cbase + cc;
-                        uint32_t r[16];
-                        if (CG == 16) tmem_ld16(tlane + ACC0 + mb * C + c0, r);
-                        else tmem_ld8(tlane + ACC0 + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r));
+                    for (int cc = 0; cc < CH; cc += 2 * CG) {
+                        uint32_t r0[16], r1[16];
+                        constexpr bool dummy_two = true;
+                        const bool two = dummy_two && (cc + CG) < CH;
+                        tmem_ld16(tlane + ACC0 + mb * C + cc, r0);
+                        if (two) tmem_ld16(tlane + ACC0 + mb * C + cc + CG, r1);
                         tmem_ld_wait();
-                        float v[16];
 #pragma unroll
-                        for (int j4 = 0; j4 < CG; j4 += 4) {
-                            const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
-                            v[j4 + 0] = lrelu01(__uint_as_float(r[j4 + 0]) + bb.x);
-                            v[j4 + 1] = lrelu01(__uint_as_float(r[j4 + 1]) + bb.y);
-                            v[j4 + 2] = lrelu01(__uint_as_float(r[j4 + 2]) + bb.z);
-                            v[j4 + 3] = lrelu01(__uint_as_float(r[j4 + 3]) + bb.w);
+                        for (int g = 0; g < 2; ++g) {
+                            if (g == 1 && !two) break;
+                            const int c0 = cc + g * CG;
+                            const uint32_t* rr = g ? r1 : r0;
+                            float v[16];
+#pragma unroll
+                            for (int j4 = 0; j4 < CG; j4 += 4) {
+                                const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
+                                v[j4 + 0] = lrelu01(__uint_as_float(rr[j4 + 0]) + bb.x);
+                                v[j4 + 1] = lrelu01(__uint_as_float(rr[j4 + 1]) + bb.y);
+                                v[j4 + 2] = lrelu01(__uint_as_float(rr[j4 + 2]) + bb.z);
+                                v[j4 + 3] = lrelu01(__uint_as_float(rr[j4 + 3]) + bb.w);
+                            }
+                            store_chunk8(prow, phase, c0 / 8, v, keep);
+                            store_chunk8(prow, phase, c0 / 8 + 1, v + 8, keep);
                         }
-                        store_chunk8(prow, phase, c0 / 8, v, keep);
-                        if (CG == 16) store_chunk8(prow, phase, c0 / 8 + 1, v + 8, keep);
                     }
                     tc_fence_before();
                     fence_proxy_async();
