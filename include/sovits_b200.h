@@ -83,6 +83,13 @@ typedef struct svb_model_cfg {
     int32_t snake;                   /* 1: vdecoder/hifiganwithsnake (SnakeAlias activations), 0: LeakyReLU */
     int32_t num_mels;                /* > 0: the mel-conditioned vocoder vdecoder/nsf_hifigan (no flow, no speaker
                                         conditioning; conv_pre takes num_mels channels; keys without the "dec." prefix) */
+    /* prior encoder (pre + enc_p); enc_layers = 0: the prefix stays with the caller (PyTorch)               */
+    int32_t ssl_dim;                 /* 768: input channels of `pre` (models.py:400)                                       */
+    int32_t enc_layers;              /* 6   (hps.model.n_layers)                                                          */
+    int32_t enc_heads;               /* 2   (n_heads)                                                                     */
+    int32_t enc_filter;              /* 768 (filter_channels)                                                             */
+    int32_t enc_kernel;              /* 3   (kernel_size of the FFN convolutions)                                         */
+    int32_t enc_window;              /* 4   (attentions.py:74 window_size)                                                */
 } svb_model_cfg;
 
 /* replaces: Svc.load_model's `.to(dev)` of the model (inference/infer_tool.py:189-200) */
@@ -131,6 +138,18 @@ SVB_API int svb_vocoder(svb_ctx* ctx, const float* mel, const float* f0, const f
 SVB_API int svb_infer_tail(svb_ctx* ctx, const float* z_p, const float* g, int gT, const int32_t* lengths,
                    const float* f0, const float* rand_ini, const float* noise,
                    float* wav, int B, int T, void* ws, size_t ws_bytes, void* stream);
+
+/* replaces: `self.pre(c)` (models.py:400,518: Conv1d(ssl_dim -> hidden, k5, pad 2)).  c: [B,ssl_dim,T] -> x: [B,hidden,T].
+ * Needs svb_model_cfg.enc_layers > 0 and the `pre.*` tensors at load time.  Tensor-core arithmetic (fp16 operands). */
+SVB_API int svb_pre_conv(svb_ctx* ctx, const float* c, float* x, int B, int T, void* stream);
+
+/* replaces: TextEncoder.forward (models.py:155-162) after the f0-embedding add, with an all-ones mask:
+ *   x = enc_(x_in) [attentions.Encoder, modules/attentions.py:73-107: 6 x {rel-pos MHA, LayerNorm, k3 FFN, LayerNorm}];
+ *   stats = proj(x);  m, logs = split(stats);  z_p = m + z_noise * exp(logs) * noice_scale.
+ * x_in, z_noise, z_p (and the optional m_p, logs_p): [B,hidden|inter,T] fp32 device tensors.  One tcgen05 GEMM launch per
+ * projection / FFN convolution, one fused attention kernel per layer (scores never leave the SM). */
+SVB_API int svb_enc_p(svb_ctx* ctx, const float* x_in, const float* z_noise, float noice_scale,
+                      float* z_p, float* m_p, float* logs_p, int B, int T, void* stream);
 
 /* Same as svb_infer_tail with HOST buffers: copies inputs H2D, runs, copies wav D2H, synchronises. */
 SVB_API int svb_infer_tail_host(svb_ctx* ctx, const float* z_p, const float* g, int gT,

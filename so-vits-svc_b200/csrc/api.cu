@@ -84,6 +84,20 @@ struct Stage {
 
 }  // namespace
 
+namespace {
+struct EncLayer {
+    ConvNW qkv, o, ffn1, ffn2a, ffn2b;
+    float* ek = nullptr; float* ev = nullptr;
+    float* g1 = nullptr; float* b1 = nullptr; float* g2 = nullptr; float* b2 = nullptr;
+};
+struct Prefix {
+    bool ok = false;
+    int ssl = 0, H = 0, F = 0, heads = 0, k = 0, window = 0, out2 = 0;
+    ConvNW pre_a, pre_b, proj;
+    std::vector<EncLayer> layers;
+};
+}  // namespace
+
 struct svb_ctx {
     int device = 0;
     bool loaded = false;
@@ -106,6 +120,8 @@ struct svb_ctx {
     float* lin_w = nullptr;
     float lin_b = 0.f;
     int hop = 1;
+    Prefix prefix;                 // pre + enc_p on the library's own kernels (svb_pre_conv / svb_enc_p)
+    DevBuf ws_prefix;
     DevBuf ws;                     // library-owned workspace
     DevBuf host_io;                // device staging for svb_infer_tail_host
     bool debug = false;
@@ -397,6 +413,100 @@ int check_launch(svb_ctx* ctx, const char* what) {
     if (e != cudaSuccess) return fail(ctx, SVB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
     if (sticky_launch_error()) { sticky_launch_error() = 0; return fail(ctx, SVB_ERR_CUDA, std::string(what) + ": kernel set-up failed (dynamic shared memory opt-in)"); }
     return SVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- prior encoder (pre + enc_p)
+// Packs `pre` and the six transformer layers of enc_p as conv-as-GEMM images (channel-major activations, like the reference):
+//   pre   Conv1d(768 -> 192, k5)            two K halves of 384 channels (the operand tile of one CTA holds <= 512 channels)
+//   qkv   conv_q | conv_k | conv_v stacked  192 -> 576, the 1/sqrt(dk) of attentions.py:243 folded into the q rows
+//   o     conv_o 192 -> 192;  ffn conv_1 192 -> 768 k3 (+ReLU);  conv_2 768 -> 192 k3 in two K halves;  proj 192 -> 384
+int load_prefix(svb_ctx* ctx, const TMap& m) {
+    const svb_model_cfg& c = ctx->cfg;
+    Prefix& P = ctx->prefix;
+    const int H = c.hidden_channels, F = c.enc_filter, heads = c.enc_heads, k = c.enc_kernel, S = c.ssl_dim, nl = c.enc_layers;
+    const int C2 = 2 * c.inter_channels;
+    if (H != 192 || heads < 1 || H % heads || H / heads != 96 || S != 768 || F != 768 || (k != 1 && k != 3 && k != 5) ||
+        c.enc_window < 0 || c.enc_window > 4 || (C2 % 192))
+        return SVB_OK;                       // shapes the prefix kernels do not serve: the caller keeps the PyTorch prefix
+    int rc;
+    HostT w, b;
+    if ((rc = get_tensor(ctx, m, "pre.weight", {H, S, 5}, w))) return rc;
+    if ((rc = get_tensor(ctx, m, "pre.bias", {H}, b))) return rc;
+    {
+        const std::vector<float> wv = w.v, bv = b.v;
+        for (int half = 0; half < 2; ++half) {
+            if ((rc = make_convn(ctx, 384, 384, H, H, 5, 2,
+                                 [&](int col, int ci, int tap) { return wv[((size_t)col * S + half * 384 + ci) * 5 + tap]; },
+                                 [&](int col) { return half == 0 ? bv[col] : 0.f; }, half == 0 ? P.pre_a : P.pre_b))) return rc;
+        }
+    }
+    P.layers.assign(nl, EncLayer());
+    const float qs = 1.0f / std::sqrt((float)(H / heads));
+    for (int l = 0; l < nl; ++l) {
+        EncLayer& E = P.layers[l];
+        const std::string a = "enc_p.enc_.attn_layers." + std::to_string(l) + ".";
+        HostT wq, wk, wvv, bq, bk, bvv;
+        if ((rc = get_tensor(ctx, m, a + "conv_q.weight", {H, H, 1}, wq)) || (rc = get_tensor(ctx, m, a + "conv_q.bias", {H}, bq)) ||
+            (rc = get_tensor(ctx, m, a + "conv_k.weight", {H, H, 1}, wk)) || (rc = get_tensor(ctx, m, a + "conv_k.bias", {H}, bk)) ||
+            (rc = get_tensor(ctx, m, a + "conv_v.weight", {H, H, 1}, wvv)) || (rc = get_tensor(ctx, m, a + "conv_v.bias", {H}, bvv))) return rc;
+        if ((rc = make_convn(ctx, H, H, 3 * H, H, 1, 0,
+                             [&](int col, int ci, int) { return col < H ? wq.v[(size_t)col * H + ci] * qs : (col < 2 * H ? wk.v[(size_t)(col - H) * H + ci] : wvv.v[(size_t)(col - 2 * H) * H + ci]); },
+                             [&](int col) { return col < H ? bq.v[col] * qs : (col < 2 * H ? bk.v[col - H] : bvv.v[col - 2 * H]); }, E.qkv))) return rc;
+        if ((rc = get_tensor(ctx, m, a + "conv_o.weight", {H, H, 1}, w)) || (rc = get_tensor(ctx, m, a + "conv_o.bias", {H}, b))) return rc;
+        {
+            const std::vector<float> wv = w.v, bv = b.v;
+            if ((rc = make_convn(ctx, H, H, H, H, 1, 0, [&](int col, int ci, int) { return wv[(size_t)col * H + ci]; }, [&](int col) { return bv[col]; }, E.o))) return rc;
+        }
+        const int nbnd = 2 * c.enc_window + 1, dk = H / heads;
+        if ((rc = get_tensor(ctx, m, a + "emb_rel_k", {1, nbnd, dk}, w))) return rc;
+        if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&E.ek))) return rc;
+        if ((rc = get_tensor(ctx, m, a + "emb_rel_v", {1, nbnd, dk}, w))) return rc;
+        if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&E.ev))) return rc;
+        for (int n = 0; n < 2; ++n) {
+            const std::string np_ = "enc_p.enc_.norm_layers_" + std::to_string(n + 1) + "." + std::to_string(l) + ".";
+            if ((rc = get_tensor(ctx, m, np_ + "gamma", {H}, w)) || (rc = get_tensor(ctx, m, np_ + "beta", {H}, b))) return rc;
+            if ((rc = upload(ctx, w.v.data(), H * sizeof(float), (void**)(n ? &E.g2 : &E.g1)))) return rc;
+            if ((rc = upload(ctx, b.v.data(), H * sizeof(float), (void**)(n ? &E.b2 : &E.b1)))) return rc;
+        }
+        const std::string f = "enc_p.enc_.ffn_layers." + std::to_string(l) + ".";
+        if ((rc = get_tensor(ctx, m, f + "conv_1.weight", {F, H, k}, w)) || (rc = get_tensor(ctx, m, f + "conv_1.bias", {F}, b))) return rc;
+        {
+            const std::vector<float> wv = w.v, bv = b.v;
+            if ((rc = make_convn(ctx, H, H, F, H, k, (k - 1) / 2, [&](int col, int ci, int tap) { return wv[((size_t)col * H + ci) * k + tap]; },
+                                 [&](int col) { return bv[col]; }, E.ffn1))) return rc;
+        }
+        if ((rc = get_tensor(ctx, m, f + "conv_2.weight", {H, F, k}, w)) || (rc = get_tensor(ctx, m, f + "conv_2.bias", {H}, b))) return rc;
+        {
+            const std::vector<float> wv = w.v, bv = b.v;
+            for (int half = 0; half < 2; ++half)
+                if ((rc = make_convn(ctx, 384, 384, H, H, k, (k - 1) / 2,
+                                     [&](int col, int ci, int tap) { return wv[((size_t)col * F + half * 384 + ci) * k + tap]; },
+                                     [&](int col) { return half == 0 ? bv[col] : 0.f; }, half == 0 ? E.ffn2a : E.ffn2b))) return rc;
+        }
+    }
+    if ((rc = get_tensor(ctx, m, "enc_p.proj.weight", {C2, H, 1}, w)) || (rc = get_tensor(ctx, m, "enc_p.proj.bias", {C2}, b))) return rc;
+    {
+        const std::vector<float> wv = w.v, bv = b.v;
+        if ((rc = make_convn(ctx, H, H, C2, H, 1, 0, [&](int col, int ci, int) { return wv[(size_t)col * H + ci]; }, [&](int col) { return bv[col]; }, P.proj))) return rc;
+    }
+    P.ssl = S; P.H = H; P.F = F; P.heads = heads; P.k = k; P.window = c.enc_window; P.out2 = C2;
+    P.ok = true;
+    return SVB_OK;
+}
+
+// one plain conv-as-GEMM launch on channel-major tensors: y[B,N,T] = alpha-less (conv_k(x[:, x_c0 : x_c0+cin]) + bias [+ res]) [+ y]
+int prefix_conv(svb_ctx* ctx, const ConvNW& W, const float* x, int x_ctot, int x_c0, float* y, const float* res, float beta, int relu,
+                int B, int T, cudaStream_t st) {
+    ConvNTC a;
+    a.x = x; a.x_ctot = x_ctot; a.x_c0 = x_c0; a.cin_real = W.cin_real; a.cinp = W.cinp; a.Tin = T;
+    a.w = W.img; a.bias = W.bias; a.acc_scale = W.acc_scale; a.k = W.k; a.dil = 1; a.pad_left = W.pad_left;
+    a.n_rows = T; a.N_total = W.N_total; a.NC = W.NC; a.Ty = T; a.B = B; a.out_relu = relu;
+    const int n_chunks = (W.N_total + W.NC - 1) / W.NC;
+    a.chunks_per_cta = n_chunks >= 4 ? 2 : 1;
+    a.seg[0].y = y; a.seg[0].y_ctot = W.N_total; a.seg[0].col0 = 0; a.seg[0].col1 = W.N_total;
+    a.seg[0].res = res; a.seg[0].res_ctot = W.N_total; a.seg[0].beta = beta;
+    const int rc = launch_convn_tc(a, st);
+    return rc ? fail(ctx, rc, "prefix conv launch failed") : SVB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- flow
@@ -820,6 +930,7 @@ void svb_destroy(svb_ctx* ctx) {
     DevGuard dg(ctx->device);
     for (void* p : ctx->allocs) cudaFree(p);
     if (ctx->ws.p) cudaFree(ctx->ws.p);
+    if (ctx->ws_prefix.p) cudaFree(ctx->ws_prefix.p);
     if (ctx->host_io.p) cudaFree(ctx->host_io.p);
     for (auto& kv : ctx->dbg) if (kv.second.p) cudaFree(kv.second.p);
     delete ctx;
@@ -974,6 +1085,7 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
     ctx->dcond_w_nat = nullptr; ctx->dcond_b = nullptr; ctx->post_w = nullptr; ctx->lin_w = nullptr; ctx->snake_filt = nullptr;
     ctx->snake_post = SnakeP();
     ctx->flow_tc_ok = false; ctx->gen_tc_ok = false;
+    ctx->prefix = Prefix();
     TMap m;
     for (int i = 0; i < n_tensors; ++i)
         if (tensors[i].name && tensors[i].data) m[tensors[i].name] = &tensors[i];
@@ -1260,6 +1372,9 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
     if ((rc = get_tensor(ctx, m, DP + "m_source.l_linear.bias", {1}, b))) return rc;
     ctx->lin_b = b.v[0];
     if ((rc = upload(ctx, w.v.data(), w.v.size() * sizeof(float), (void**)&ctx->lin_w))) return rc;
+    if (!melv && c.enc_layers > 0 && m.count("pre.weight") && m.count("enc_p.proj.weight")) {
+        if ((rc = load_prefix(ctx, m))) return rc;
+    }
     ctx->loaded = true;
     return SVB_OK;
 }
@@ -1358,6 +1473,65 @@ int svb_infer_tail(svb_ctx* ctx, const float* z_p, const float* g, int gT, const
     if ((rc = dbg_keep(ctx, "har", har, (size_t)B * T * ctx->hop, st))) return rc;
     ProfScope ps(ctx, "generator", st, 0, 0);
     return run_generator(ctx, z, g, gT, har, wav, B, T, base, pl, st);
+}
+
+int svb_pre_conv(svb_ctx* ctx, const float* c, float* x, int B, int T, void* stream) {
+    PRECHECK();
+    if (!ctx->prefix.ok) return fail(ctx, SVB_ERR_UNSUPPORTED, "the prior encoder was not loaded (enc_layers = 0, missing pre./enc_p. tensors or unsupported shapes)");
+    if (!c || !x) return fail(ctx, SVB_ERR_INVALID_ARG, "bad pre_conv arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Prefix& P = ctx->prefix;
+    int rc;
+    if ((rc = prefix_conv(ctx, P.pre_a, c, P.ssl, 0, x, nullptr, 0.f, 0, B, T, st))) return rc;
+    if ((rc = prefix_conv(ctx, P.pre_b, c, P.ssl, 384, x, nullptr, 1.f, 0, B, T, st))) return rc;
+    return check_launch(ctx, "pre_conv");
+}
+
+int svb_enc_p(svb_ctx* ctx, const float* x_in, const float* z_noise, float noice_scale, float* z_p, float* m_p, float* logs_p,
+              int B, int T, void* stream) {
+    PRECHECK();
+    if (!ctx->prefix.ok) return fail(ctx, SVB_ERR_UNSUPPORTED, "the prior encoder was not loaded (enc_layers = 0, missing pre./enc_p. tensors or unsupported shapes)");
+    if (!x_in || !z_noise || !z_p) return fail(ctx, SVB_ERR_INVALID_ARG, "bad enc_p arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Prefix& P = ctx->prefix;
+    const size_t BT = (size_t)B * T, f = sizeof(float);
+    const size_t need = align_up(BT * 3 * P.H * f, 256) + 4 * align_up(BT * P.H * f, 256) + align_up(BT * P.F * f, 256) + align_up(BT * P.out2 * f, 256);
+    if (ctx->ws_prefix.bytes < need) {
+        if (ctx->ws_prefix.p) { CU(cudaStreamSynchronize(st)); CU(cudaFree(ctx->ws_prefix.p)); }
+        ctx->ws_prefix.p = nullptr; ctx->ws_prefix.bytes = 0;
+        CU(cudaMalloc(&ctx->ws_prefix.p, need));
+        ctx->ws_prefix.bytes = need;
+    }
+    char* wp = static_cast<char*>(ctx->ws_prefix.p);
+    auto take = [&](size_t bytes) { char* r = wp; wp += align_up(bytes, 256); return reinterpret_cast<float*>(r); };
+    float* QKV = take(BT * 3 * P.H * f);
+    float* A = take(BT * P.H * f);
+    float* Y = take(BT * P.H * f);
+    float* X1 = take(BT * P.H * f);
+    float* X = take(BT * P.H * f);
+    float* Hd = take(BT * P.F * f);
+    float* St = take(BT * P.out2 * f);
+    int rc;
+    const float* cur = x_in;
+    ProfScope ps(ctx, "enc_p", st, 0, 0);
+    for (size_t l = 0; l < P.layers.size(); ++l) {
+        const EncLayer& E = P.layers[l];
+        if ((rc = prefix_conv(ctx, E.qkv, cur, P.H, 0, QKV, nullptr, 0.f, 0, B, T, st))) return rc;
+        AttnTC at;
+        at.q = QKV; at.k = QKV + (size_t)P.H * T; at.v = QKV + (size_t)2 * P.H * T; at.ctot = 3 * P.H;
+        at.ek = E.ek; at.ev = E.ev; at.out = A; at.out_ctot = P.H; at.B = B; at.T = T; at.heads = P.heads; at.dk = P.H / P.heads; at.window = P.window;
+        if ((rc = launch_attn_rel_tc(at, st))) return fail(ctx, rc, "attention kernel launch failed");
+        if ((rc = prefix_conv(ctx, E.o, A, P.H, 0, Y, cur, 0.f, 0, B, T, st))) return rc;            // x + conv_o(attn)
+        launch_ln_cm(Y, E.g1, E.b1, 1e-5f, X1, B, P.H, T, st);
+        if ((rc = prefix_conv(ctx, E.ffn1, X1, P.H, 0, Hd, nullptr, 0.f, 1, B, T, st))) return rc;   // relu(conv_1)
+        if ((rc = prefix_conv(ctx, E.ffn2a, Hd, P.F, 0, Y, X1, 0.f, 0, B, T, st))) return rc;        // x1 + conv_2 (first K half)
+        if ((rc = prefix_conv(ctx, E.ffn2b, Hd, P.F, 384, Y, nullptr, 1.f, 0, B, T, st))) return rc; // + second K half
+        launch_ln_cm(Y, E.g2, E.b2, 1e-5f, X, B, P.H, T, st);
+        cur = X;
+    }
+    if ((rc = prefix_conv(ctx, P.proj, cur, P.H, 0, St, nullptr, 0.f, 0, B, T, st))) return rc;
+    launch_prior_sample(St, z_noise, noice_scale, z_p, m_p, logs_p, B, P.out2 / 2, T, st);
+    return check_launch(ctx, "enc_p");
 }
 
 int svb_infer_tail_host(svb_ctx* ctx, const float* z_p, const float* g, int gT,

@@ -121,6 +121,7 @@ struct ConvNTC {
     // optional fused noise conv (polyphase mode): excitation window har[b, i*noise_stride + noise_w0 + u], u in [0,16)
     const float* har = nullptr; int har_N = 0; int noise_stride = 0, noise_w0 = 0;
     int noise_wide = 0;            // 1: window of up to 80 samples (64-sample + 16-sample panels) instead of 16
+    int out_relu = 0;              // plain mode: ReLU after everything else (FFN of enc_p, modules/attentions.py:343-346)
     float acc_scale = 1.f;         // the image holds w * 2^e (range normalisation at pack time); epilogues use acc * acc_scale
     // SnakeAlias fused into the loader (vdecoder/hifiganwithsnake/alias/act.py:109-129): A = SnakeAlias(x) per input channel
     const float* snake_ealpha = nullptr;   // [Cin] e^alpha          (null: plain / LeakyReLU loader)
@@ -154,6 +155,21 @@ size_t flow_layer_image_bytes();
 int flow_gate_row(int col);
 void flow_layer_pack(const std::function<float(int, int)>& pre, const std::function<float(int, int, int, int)>& inl,
                      const std::function<float(int, int, int)>& rs, const std::function<float(int, int)>& post, void* dst_host);
+
+// ---- enc_p attention (kernels_attn.cu): windowed relative-position MHA on channel-major [B,C,T] tensors --------------------
+struct AttnTC {
+    const float* q = nullptr; const float* k = nullptr; const float* v = nullptr;   // bases of the q / k / v channel blocks, [B, ctot, T]
+    int ctot = 0;
+    const float* ek = nullptr; const float* ev = nullptr;     // emb_rel_k / emb_rel_v [2*window+1][dk]
+    float* out = nullptr; int out_ctot = 0;                   // [B, heads*dk, T]
+    const int32_t* lengths = nullptr;
+    int B = 1, T = 0, heads = 2, dk = 96, window = 4;
+};
+int launch_attn_rel_tc(const AttnTC& a, cudaStream_t st);
+
+// channel-major LayerNorm over C of [B,C,T] and the prior sample z = m + noise*exp(logs)*ns (kernels_prefix.cu)
+void launch_ln_cm(const float* x, const float* gamma, const float* beta, float eps, float* y, int B, int C, int T, cudaStream_t st);
+void launch_prior_sample(const float* stats, const float* noise, float ns, float* z, float* m_out, float* logs_out, int B, int C, int T, cudaStream_t st);
 
 int64_t& launch_counter();
 

@@ -1,0 +1,306 @@
+// Windowed relative-position self-attention of enc_p on tcgen05 (sm_100a): one kernel per layer, scores never leave the SM.
+//   reference: modules/attentions.py:198-239 (MultiHeadAttention.attention, heads_share, window_size 4), :246-267 (relative
+//   keys / values), :275-303 (the pad/reshape skewing that this kernel replaces by direct band indexing).
+//     scores[i,j] = q_i . k_j  (q pre-scaled by 1/sqrt(dk))  +  q_i . E_k[j-i+w]          for |j-i| <= w
+//     p = softmax_j(scores)   (keys j >= length are filled with -1e4 like masked_fill, :253)
+//     out_i = sum_j p[i,j] v_j  +  sum_{|m|<=w} p[i,i+m] E_v[m+w]
+// Layout: q, k, v, out are channel-major [B, C, T] fp32 (the reference's layout); head h owns channels [h*dk, (h+1)*dk).
+//
+// One CTA = one (128-query tile, head, utterance).  Two passes over the key tiles (128 keys each):
+//   pass 1: S = Q K^T on the tensor cores (M = 128 queries, N = 128 keys, K = dk = 96), epilogue keeps the running row
+//           maximum and the running sum of exponentials (scalar per row, no rescaling of an accumulator);
+//   pass 2: S again, P = exp(S - max) / sum -> fp16 -> shared memory, O += P V on the tensor cores (N = 96, K = 128).
+// Recomputing S costs 2 x 2.3 GFLOP per layer at config 2 - nothing next to the [B,2,T,T] fp32 score tensor (47 MB) the
+// cuBLAS formulation wrote, re-read for the softmax and re-read again for P V.
+// Operands are staged by the worker warps straight from the fp32 tensors (coalesced along time) into K-major fp16 tiles
+// with the 128-byte hardware swizzle; K and V tiles are double-buffered so staging overlaps the MMAs.
+// TMEM: S at columns [0,128), O at [128,224).
+#include "kernels.h"
+#include "tc_common.cuh"
+#include "../../include/sovits_b200.h"
+
+namespace svb {
+
+using namespace tc;
+
+namespace {
+
+constexpr int AT_THREADS = 288;          // 8 worker warps + 1 MMA warp
+constexpr int AT_NWORK = 256;
+constexpr int AT_DK = 96;
+constexpr int AT_RB = 128;
+constexpr int AT_PANEL = 128 * AT_RB;    // 128 rows x 64 fp16
+constexpr int AT_VPANEL = AT_DK * AT_RB; // V^T: 96 rows (channels) x 64 keys
+constexpr int AT_MAXW = 4;               // window <= 4 -> <= 9 band entries
+constexpr uint32_t OFFA_Q = 0;                              // 2 panels (64 + 32 channels)
+constexpr uint32_t OFFA_K = OFFA_Q + 2 * AT_PANEL;         // 2 buffers x 2 panels
+constexpr uint32_t OFFA_P = OFFA_K + 4 * AT_PANEL;         // 2 panels (128 keys)
+constexpr uint32_t OFFA_V = OFFA_P + 2 * AT_PANEL;         // 2 buffers x 2 panels x 96 rows
+constexpr uint32_t OFFA_BAR = OFFA_V + 4 * AT_VPANEL;
+constexpr uint32_t OFFA_F = OFFA_BAR + 64;                 // floats: relk logits [128][9] | pband [128][9] | stats [2][128][2] | E_k, E_v [9][96] each
+constexpr uint32_t AT_NFLOAT = 128 * 9 * 2 + 2 * 128 * 2 + 2 * 9 * AT_DK;
+constexpr size_t AT_SMEM = 1024 + OFFA_F + AT_NFLOAT * 4;
+constexpr int COL_S = 0, COL_O = 128;
+
+struct AttnParams {
+    const float* q; const float* k; const float* v;   // channel-major bases of this layer's q / k / v ([B, ctot, T] each, may alias one tensor)
+    int ctot;
+    const float* ek; const float* ev;                  // [2w+1][dk]
+    float* out; int out_ctot;
+    const int32_t* lengths;
+    int T, window;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_rel_kernel(const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw);
+    const uint32_t bar_w = base + OFFA_BAR;        // workers -> MMA: operands of the next step staged, S drained (256 arrivals)
+    const uint32_t bar_s = base + OFFA_BAR + 8;    // MMA -> workers: all MMAs issued so far complete (tcgen05.commit)
+    const uint32_t tmem_slot = base + OFFA_BAR + 16;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + OFFA_BAR + 16);
+    float* s_relk = reinterpret_cast<float*>(sm + OFFA_F);   // [128][9]
+    float* s_pband = s_relk + 128 * 9;                        // [128][9]
+    float* s_stat = s_pband + 128 * 9;                        // [2 halves][128][max, sum]
+    float* s_ek = s_stat + 2 * 128 * 2;                       // [9][96]
+    float* s_ev = s_ek + 9 * AT_DK;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int i0 = blockIdx.x * 128;
+    const int T = p.T, w = p.window, nb = 2 * w + 1;
+    const int len = p.lengths ? min(p.lengths[b], T) : T;
+    const int nt = (T + 127) / 128;
+
+    if (tid == 0) {
+        mbar_init(bar_w, AT_NWORK);
+        mbar_init(bar_s, 1);
+        fence_barrier_init();
+    }
+    if (warp == 8) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+    for (int i = tid; i < 9 * AT_DK; i += AT_THREADS) { s_ek[i] = i < nb * AT_DK ? __ldg(p.ek + i) : 0.f; s_ev[i] = i < nb * AT_DK ? __ldg(p.ev + i) : 0.f; }
+    for (int i = tid; i < 128 * 9; i += AT_THREADS) { s_relk[i] = 0.f; s_pband[i] = 0.f; }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const size_t hb = ((size_t)b * p.ctot + (size_t)h * AT_DK) * (size_t)T;     // element offset of this (b, head)
+
+    if (warp == 8) {
+        // ------------------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            const uint64_t q_desc = make_smem_desc(base + OFFA_Q, AT_RB, 0);
+            const uint64_t p_desc = make_smem_desc(base + OFFA_P, AT_RB, 0);
+            constexpr uint32_t idesc_s = make_idesc_f16(128, 128);
+            constexpr uint32_t idesc_o = make_idesc_f16(128, AT_DK);
+            uint32_t n_w = 0;
+            auto s_mma = [&](int jt) {                      // S = Q K_jt^T : K = 96 = panel 0 (4 K-steps) + half of panel 1 (2)
+                const uint64_t k_desc = make_smem_desc(base + OFFA_K + (jt & 1) * 2 * AT_PANEL, AT_RB, 0);
+                for (int pn = 0; pn < 2; ++pn)
+                    for (int ks = 0; ks < (pn ? 2 : 4); ++ks)
+                        umma_f16(tmem_base + COL_S, q_desc + (uint64_t)((uint32_t)(pn * AT_PANEL + ks * 32) >> 4),
+                                 k_desc + (uint64_t)((uint32_t)(pn * AT_PANEL + ks * 32) >> 4), idesc_s, (pn | ks) ? 1u : 0u);
+            };
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int jt = 0; jt <= nt; ++jt) {
+                    // step jt of a pass: [pass 2: O += P_{jt-1} V_{jt-1}]  then  S_jt  (jt < nt).  Step nt of the FIRST pass only consumes
+                    // the workers' last arrival (nothing to issue, nothing to signal).
+                    mbar_wait(bar_w, n_w & 1u); ++n_w;
+                    tc_fence_after();
+                    if (pass == 1 && jt > 0) {
+                        const uint64_t v_desc = make_smem_desc(base + OFFA_V + ((jt - 1) & 1) * 2 * AT_VPANEL, AT_RB, 0);
+                        for (int pn = 0; pn < 2; ++pn)
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_f16(tmem_base + COL_O, p_desc + (uint64_t)((uint32_t)(pn * AT_PANEL + ks * 32) >> 4),
+                                         v_desc + (uint64_t)((uint32_t)(pn * AT_VPANEL + ks * 32) >> 4), idesc_o, (jt > 1 || pn || ks) ? 1u : 0u);
+                    }
+                    if (jt < nt) s_mma(jt);
+                    if (!(pass == 0 && jt == nt)) umma_commit(bar_s);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ workers
+        const int q4 = warp & 3, hsel = warp >> 2;
+        const int row = 32 * q4 + lane;                    // query row of the tile == TMEM lane; also the key / channel row staged
+        const int ti = i0 + row;
+        const uint32_t tlane = tmem_base + ((uint32_t)(32 * q4) << 16);
+        const uint32_t phase = swz_phase(row, AT_RB);
+        uint32_t n_s = 0;
+
+        // stage a [128 time steps][96 channels] tile of a channel-major tensor as a K-major operand (rows = time)
+        auto stage_rows = [&](const float* __restrict__ src, int t_first, uint32_t off, float* dots) {
+            const int t = t_first + row;
+            const bool tv = t < T;
+            const float* __restrict__ xt = src + hb + (size_t)(hsel * 48) * T + (tv ? t : 0);
+#pragma unroll
+            for (int c0 = 0; c0 < 48; c0 += 16) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = tv ? __ldg(xt + (size_t)(c0 + j) * T) : 0.f;
+                const int ch = hsel * 48 + c0;
+                if (dots) {
+#pragma unroll
+                    for (int d = 0; d < 2 * AT_MAXW + 1; ++d) {       // rows d >= 2w+1 of E_k are zero
+                        float acc = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc = fmaf(v[j], s_ek[d * AT_DK + ch + j], acc);
+                        dots[d] += acc;
+                    }
+                }
+                uint8_t* prow = sm + off + (ch / 64) * AT_PANEL + row * AT_RB;
+                store_chunk8(prow, phase, (ch % 64) / 8, v, 0xffffffffu);
+                store_chunk8(prow, phase, (ch % 64) / 8 + 1, v + 8, 0xffffffffu);
+            }
+        };
+        // stage V^T of a key tile: rows = 96 channels, K = 128 keys (two 64-key panels); a thread converts runs of 8 keys
+        auto stage_vt = [&](int j_first, uint32_t off) {
+            for (int it = tid; it < AT_DK * 16; it += AT_NWORK) {
+                const int c = it / 16, ck = it % 16;       // channel row, 8-key chunk
+                const int j = j_first + ck * 8;
+                const float* __restrict__ vp = p.v + hb + (size_t)c * T + j;
+                float v[8];
+                if (j + 7 < T && ((reinterpret_cast<uintptr_t>(vp) & 15u) == 0)) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(vp)), bq = __ldg(reinterpret_cast<const float4*>(vp) + 1);
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bq.x; v[5] = bq.y; v[6] = bq.z; v[7] = bq.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = (j + e < T) ? __ldg(vp + e) : 0.f;
+                }
+                uint8_t* prow = sm + off + (ck / 8) * AT_VPANEL + c * AT_RB;
+                store_chunk8(prow, swz_phase(c, AT_RB), ck % 8, v, 0xffffffffu);
+            }
+        };
+
+        // Q tile + the relative-key logits q_i . E_k[d] (fp32, from the fp32 q)
+        {
+            float dots[2 * AT_MAXW + 1];
+#pragma unroll
+            for (int d = 0; d < 2 * AT_MAXW + 1; ++d) dots[d] = 0.f;
+            stage_rows(p.q, i0, OFFA_Q, dots);
+#pragma unroll
+            for (int d = 0; d < 2 * AT_MAXW + 1; ++d) atomicAdd(&s_relk[row * 9 + d], dots[d]);      // two channel halves per row
+        }
+        stage_rows(p.k, 0, OFFA_K, nullptr);
+        fence_proxy_async();
+        mbar_arrive(bar_w);
+        asm volatile("bar.sync 1, 256;" ::: "memory");        // relk logits of both halves are in shared memory
+        const float* __restrict__ relk = s_relk + row * 9;     // indexed by the (runtime) band position: stays in shared memory
+
+        float m_run = -3.0e38f, l_run = 0.f, m_row = 0.f, inv_l = 0.f;
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) {
+                // combine the two column halves of every row: global maximum and sum
+                s_stat[(hsel * 128 + row) * 2] = m_run; s_stat[(hsel * 128 + row) * 2 + 1] = l_run;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float m0 = s_stat[row * 2], l0 = s_stat[row * 2 + 1], m1 = s_stat[(128 + row) * 2], l1 = s_stat[(128 + row) * 2 + 1];
+                m_row = fmaxf(m0, m1);
+                inv_l = 1.f / (l0 * __expf(m0 - m_row) + l1 * __expf(m1 - m_row));
+                stage_rows(p.k, 0, OFFA_K, nullptr);              // K_0 again (buffer 0 is free: every MMA of pass 1 has completed)
+                stage_vt(0, OFFA_V);
+                fence_proxy_async();
+                mbar_arrive(bar_w);
+            }
+            for (int jt = 0; jt < nt; ++jt) {
+                if (jt + 1 < nt) stage_rows(p.k, (jt + 1) * 128, OFFA_K + ((jt + 1) & 1) * 2 * AT_PANEL, nullptr);
+                mbar_wait(bar_s, n_s & 1u); ++n_s;               // S_jt complete (and, in pass 2, O += P_{jt-1} V_{jt-1})
+                tc_fence_after();
+                if (pass == 1 && jt + 1 < nt) stage_vt((jt + 1) * 128, OFFA_V + ((jt + 1) & 1) * 2 * AT_VPANEL);
+                const int jbase = jt * 128 + hsel * 64;
+                float tmax = -3.0e38f;
+#pragma unroll 1
+                for (int cc = 0; cc < 64; cc += 32) {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(tlane + COL_S + hsel * 64 + cc, r0);
+                    tmem_ld16(tlane + COL_S + hsel * 64 + cc + 16, r1);
+                    tmem_ld_wait();
+                    float sv[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int j = jbase + cc + e;
+                        float s = __uint_as_float(e < 16 ? r0[e] : r1[e - 16]);
+                        const int d = j - ti + w;
+                        if ((unsigned)d < (unsigned)nb) s += relk[d];
+                        if (j >= len) s = -1.0e4f;                  // masked_fill(mask == 0, -1e4)
+                        if (j >= T) s = -3.0e38f;                   // beyond the sequence: not part of the softmax
+                        sv[e] = s;
+                    }
+                    if (pass == 0) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) tmax = fmaxf(tmax, sv[e]);
+                        const float m_new = fmaxf(m_run, tmax);
+                        float acc = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) acc += __expf(sv[e] - m_new);
+                        l_run = l_run * __expf(m_run - m_new) + acc;
+                        m_run = m_new;
+                    } else {
+                        float pv[32];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            pv[e] = __expf(sv[e] - m_row) * inv_l;
+                            const int d = jbase + cc + e - ti + w;
+                            if (d >= 0 && d < nb && jbase + cc + e < T) s_pband[row * 9 + d] = pv[e];
+                        }
+                        uint8_t* prow = sm + OFFA_P + hsel * AT_PANEL + row * AT_RB;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) store_chunk8(prow, phase, cc / 8 + g, pv + 8 * g, 0xffffffffu);
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(bar_w);
+            }
+        }
+        // final: O complete once the last commit lands
+        mbar_wait(bar_s, n_s & 1u); ++n_s;
+        tc_fence_after();
+        asm volatile("bar.sync 1, 256;" ::: "memory");            // band probabilities of both halves visible
+        {
+            const bool wr = ti < T;
+            float pb[2 * AT_MAXW + 1];
+#pragma unroll
+            for (int d = 0; d < 2 * AT_MAXW + 1; ++d) pb[d] = d < nb ? s_pband[row * 9 + d] : 0.f;
+            float* __restrict__ ob = p.out + ((size_t)b * p.out_ctot + (size_t)h * AT_DK + hsel * 48) * (size_t)T + (wr ? ti : 0);
+#pragma unroll
+            for (int cc = 0; cc < 48; cc += 16) {
+                uint32_t r[16];
+                tmem_ld16(tlane + COL_O + hsel * 48 + cc, r);
+                tmem_ld_wait();
+                if (wr) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float o = __uint_as_float(r[j]);
+                        const int c = hsel * 48 + cc + j;
+#pragma unroll
+                        for (int d = 0; d < 2 * AT_MAXW + 1; ++d) o = fmaf(pb[d], s_ev[d * AT_DK + c], o);
+                        ob[(size_t)(cc + j) * T] = o;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+}  // namespace
+
+int launch_attn_rel_tc(const AttnTC& a, cudaStream_t st) {
+    if (a.dk != AT_DK || a.window < 0 || a.window > AT_MAXW || a.heads < 1 || a.T < 1) return SVB_ERR_UNSUPPORTED;
+    static std::atomic<size_t> granted[SVB_MAX_DEV];
+    if (ensure_dyn_smem(attn_rel_kernel, AT_SMEM, granted)) return SVB_ERR_CUDA;
+    AttnParams p;
+    p.q = a.q; p.k = a.k; p.v = a.v; p.ctot = a.ctot; p.ek = a.ek; p.ev = a.ev; p.out = a.out; p.out_ctot = a.out_ctot;
+    p.lengths = a.lengths; p.T = a.T; p.window = a.window;
+    dim3 grid((a.T + 127) / 128, a.heads, a.B);
+    attn_rel_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(p);
+    launch_counter()++;
+    return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;
+}
+
+}  // namespace svb

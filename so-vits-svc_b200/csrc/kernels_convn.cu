@@ -65,6 +65,7 @@ struct ConvNDev {                     // launch-time geometry (host computed)
 template <bool EDGE, typename Emit>
 __device__ __forceinline__ void snake_run(const float (&xw)[SNK_WIN], const float (&f)[12], float ea2, float hib, int t0, int L,
                                           float s0, float sL, Emit&& emit) {
+    // f holds 2 x the filter taps (the gain of the zero-stuffing upsampler folded in, exact); the low-pass sum is halved
     float s[12];
     auto s_val = [&](int jj) -> float {
         // m = 2*t0 - 5 + jj;  jj even -> m odd (a = t0 - 3 + jj/2), jj odd -> m even (a = t0 - 2 + (jj-1)/2)
@@ -80,7 +81,6 @@ __device__ __forceinline__ void snake_run(const float (&xw)[SNK_WIN], const floa
             u = fmaf(f[3], xw[q + 1], u); u = fmaf(f[5], xw[q], u); u = fmaf(f[7], xw[q - 1], u);
             u = fmaf(f[9], xw[q - 2], u); u = fmaf(f[11], xw[q - 3], u);
         }
-        u *= 2.f;
         float v = fmaf(hib, 1.f - __cosf(ea2 * u), u);      // u + (1/beta) * (1 - cos(2 e^alpha u)) / 2
         if (EDGE) {
             const int m = 2 * t0 - 5 + jj;
@@ -97,6 +97,7 @@ __device__ __forceinline__ void snake_run(const float (&xw)[SNK_WIN], const floa
         float acc = f[0] * s[0];
 #pragma unroll
         for (int j = 1; j < 12; ++j) acc = fmaf(f[j], s[j], acc);
+        acc *= 0.5f;
         if (EDGE) { const int t = t0 + i; if (t < 0 || t >= L) acc = 0.f; }
         emit(i, acc);
 #pragma unroll
@@ -263,18 +264,22 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
             // shared memory with coalesced loads (indices clamped = replicate padding), (ii) every lane takes one channel
             // and a run of SNK_RUN rows: window -> registers, 2x upsample -> snake -> low-pass/decimate in registers,
             // (iii) the fp16 results go to the swizzled operand tile (32 lanes = 32 consecutive channels of one row).
+            // The global loads of pass p+1 are issued (into registers) BEFORE the arithmetic of pass p, so their latency
+            // hides behind it; the tile has exactly 128*MB activated rows = 8*MB runs, one round of work per warp and pass.
             constexpr int GCH = G::SNK_GCH;
             constexpr int LPR = 32 / GCH;                      // runs handled side by side in one warp (2 when GCH = 16)
+            constexpr int CPW = GCH / 8;                       // channels a warp stages per pass
+            constexpr int XLC = 128 * MB + 12;                 // staged samples per channel (RA = 128*MB rows)
+            constexpr int NQ = (XLC + 31) / 32;                // strides of 32 samples per channel row
             float* xs = reinterpret_cast<float*>(sm + d.off_xs);
             const int XP = d.xs_pitch;
-            const int n_runs = (RA + SNK_RUN - 1) / SNK_RUN;
-            const int XL = n_runs * SNK_RUN + 12;              // staged samples per channel
+            constexpr int n_runs = 8 * MB;
             const int tlo = i0 - a.pad_left - 6;               // time of staged sample 0
             const int L = a.Tin;
-            const bool edge = (tlo + 6 < 3) || (tlo + XL > L - 4);
+            const bool edge = (tlo + 6 < 3) || (tlo + XLC > L - 4);
             float f[12];
 #pragma unroll
-            for (int j = 0; j < 12; ++j) f[j] = __ldg(a.snake_filt + j);
+            for (int j = 0; j < 12; ++j) f[j] = 2.f * __ldg(a.snake_filt + j);       // 2 x taps, see snake_run
             const float* __restrict__ xb = a.x + ((size_t)b * a.x_ctot + a.x_c0) * (size_t)L;
             const int cl = lane % GCH, rsel = lane / GCH;
             // rows past the activated ones are read by the MMAs of the tile's unused output rows: keep them finite (zero)
@@ -284,34 +289,30 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                 const int r = n_runs * SNK_RUN + rem / (G::RB / 16), ch = rem % (G::RB / 16);
                 *reinterpret_cast<uint4*>(sm + pn * APANEL + swz_offset(r, ch, G::RB)) = make_uint4(0, 0, 0, 0);
             }
-#pragma unroll 1
-            for (int cg0 = 0; cg0 < CINP; cg0 += GCH) {
-                {
-                    // warp w stages channels w, w+8, ...: all loads of a batch (CPW channels x 4 strides of 32 samples) are
-                    // issued before the first store, so a pass costs ~2 global-load round trips instead of 20
-                    constexpr int CPW = GCH / 8;
-#pragma unroll 1
-                    for (int q0 = lane; q0 < XL; q0 += 128) {
-                        float v[CPW][4];
+            float nxt[CPW][NQ];                                // the next pass's samples, in flight
+            auto prefetch = [&](int cg0) {
 #pragma unroll
-                        for (int cc = 0; cc < CPW; ++cc) {
-                            const int c = warp + 8 * cc;
-                            const bool cv = (cg0 + c) < a.cin_real;
-                            const float* __restrict__ xc = xb + (size_t)(cv ? cg0 + c : 0) * L;
+                for (int cc = 0; cc < CPW; ++cc) {
+                    const int c = cg0 + warp + 8 * cc;
+                    const bool cv = c < a.cin_real;
+                    const float* __restrict__ xc = xb + (size_t)(cv ? c : 0) * L;
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int ti = min(max(tlo + q0 + 32 * u, 0), L - 1);
-                                v[cc][u] = cv ? __ldg(xc + ti) : 0.f;
-                            }
-                        }
-#pragma unroll
-                        for (int cc = 0; cc < CPW; ++cc)
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (q0 + 32 * u < XL) xs[(warp + 8 * cc) * XP + q0 + 32 * u] = v[cc][u];
+                    for (int u = 0; u < NQ; ++u) {
+                        const int ti = min(max(tlo + lane + 32 * u, 0), L - 1);
+                        nxt[cc][u] = cv ? __ldg(xc + ti) : 0.f;
                     }
                 }
+            };
+            prefetch(0);
+#pragma unroll 1
+            for (int cg0 = 0; cg0 < CINP; cg0 += GCH) {
+#pragma unroll
+                for (int cc = 0; cc < CPW; ++cc)
+#pragma unroll
+                    for (int u = 0; u < NQ; ++u)
+                        if (lane + 32 * u < XLC) xs[(warp + 8 * cc) * XP + lane + 32 * u] = nxt[cc][u];
                 asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (cg0 + GCH < CINP) prefetch(cg0 + GCH);
                 const int c = cg0 + cl;
                 const float ea2 = 2.f * __ldg(a.snake_ealpha + min(c, a.cin_real - 1));
                 const float hib = 0.5f * __ldg(a.snake_invbeta + min(c, a.cin_real - 1));
@@ -319,27 +320,25 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                 float s0 = 0.f, sL = 0.f;
                 if (edge) {
                     // s[0] and s[2L-1] from the clamped signal (only their own tile(s) read them)
-                    auto xat = [&](int t) { const int q = min(max(t, 0), L - 1) - tlo; return (q >= 0 && q < XL) ? xrow[q] : 0.f; };
-                    float u0 = 2.f * (f[1] * xat(2) + f[3] * xat(1) + (f[5] + f[7] + f[9] + f[11]) * xat(0));
-                    float uL = 2.f * ((f[0] + f[2] + f[4] + f[6]) * xat(L - 1) + f[8] * xat(L - 2) + f[10] * xat(L - 3));
+                    auto xat = [&](int t) { const int q = min(max(t, 0), L - 1) - tlo; return (q >= 0 && q < XLC) ? xrow[q] : 0.f; };
+                    float u0 = f[1] * xat(2) + f[3] * xat(1) + (f[5] + f[7] + f[9] + f[11]) * xat(0);
+                    float uL = (f[0] + f[2] + f[4] + f[6]) * xat(L - 1) + f[8] * xat(L - 2) + f[10] * xat(L - 3);
                     s0 = fmaf(hib, 1.f - __cosf(ea2 * u0), u0);
                     sL = fmaf(hib, 1.f - __cosf(ea2 * uL), uL);
                 }
+                // operand address of (row r0 + i, channel c): the row's swizzle phase depends on i only (r0 is a multiple of 16)
+                uint8_t* const pch = sm + (c / G::CPP) * APANEL + (c % 8) * 2;
+                const uint32_t chunk = (uint32_t)(c % G::CPP) / 8u;
 #pragma unroll 1
                 for (int run = warp * LPR + rsel; run < n_runs; run += 8 * LPR) {
                     float xw[SNK_WIN];
 #pragma unroll
                     for (int j = 0; j < SNK_WIN; ++j) xw[j] = xrow[run * SNK_RUN + j];
                     const int t0 = tlo + 6 + run * SNK_RUN;
-                    uint8_t* pcol = sm + (c / G::CPP) * APANEL + (c % 8) * 2;
-                    const uint32_t chunk = (uint32_t)(c % G::CPP) / 8u;
-                    const int r0 = run * SNK_RUN;
+                    uint8_t* const prun = pch + run * (SNK_RUN * G::RB);
                     auto emit = [&](int i, float v) {
-                        const int r = r0 + i;
-                        if (r < AROWS) {
-                            const __half hv = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
-                            *reinterpret_cast<__half*>(pcol + r * G::RB + ((chunk ^ swz_phase(r, G::RB)) << 4)) = hv;
-                        }
+                        const uint32_t ph = ((uint32_t)(i * G::RB) >> 7) & (uint32_t)(G::RB / 16 - 1);     // compile-time per i
+                        *reinterpret_cast<__half*>(prun + i * G::RB + ((chunk ^ ph) << 4)) = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
                     };
                     if (edge) snake_run<true>(xw, f, ea2, hib, t0, L, s0, sL, emit);
                     else snake_run<false>(xw, f, ea2, hib, t0, L, s0, sL, emit);
@@ -529,6 +528,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                                 if (sg.res) o += rr[j];
                                 o *= sg.alpha;
                                 if (sg.beta != 0.f) o = fmaf(sg.beta, oo[j], o);
+                                if (a.out_relu) o = fmaxf(o, 0.f);
                                 yb[(size_t)j * a.Ty] = dead ? 0.f : o;
                             }
                         }
@@ -603,7 +603,7 @@ int launch_convn_t(const ConvNTC& a, cudaStream_t st) {
 
 }  // namespace
 
-int convn_mb(int cinp) { return cinp >= 512 ? 1 : (cinp == 192 ? 1 : 2); }
+int convn_mb(int cinp) { return cinp >= 384 ? 1 : (cinp == 192 ? 1 : 2); }
 // SnakeAlias-loader tiles: one 128-row block for the wide stages so that two CTAs share an SM (one CTA's CUDA-core loader
 // phase overlaps the other's MMA / epilogue phases); C = 256/512 need the whole shared memory for the operand tile.
 int convn_snake_mb(int cinp) { return cinp >= 128 ? 1 : 2; }
@@ -628,6 +628,7 @@ int launch_convn_tc(const ConvNTC& a, cudaStream_t st) {
     }
     switch (a.cinp) {
         case 512: return launch_convn_t<512, 1, 1, false>(a, st);
+        case 384: return launch_convn_t<384, 1, 1, false>(a, st);
         case 256: return launch_convn_t<256, 2, 1, false>(a, st);
         case 192: return launch_convn_t<192, 1, 1, false>(a, st);
         case 128: return launch_convn_t<128, 2, 2, false>(a, st);

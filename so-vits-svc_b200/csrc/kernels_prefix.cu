@@ -171,6 +171,81 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(const float* __restrict
 }
 
 }  // namespace
+
+// ---- channel-major pieces of the own-kernel enc_p (svb_enc_p): LayerNorm over channels of [B,C,T] and the prior sample ----
+// Block = 32 frames x 8 warps; warp w holds channels w, w+8, ... of its 32 frames in registers (lanes = frames, so every
+// global access is a coalesced 128-byte row segment), statistics are combined across the 8 warps through shared memory.
+// modules/modules.py:23-35 (F.layer_norm over the channel axis, eps inside the square root).
+constexpr int LN_MAXC = 256;
+__global__ void __launch_bounds__(256) ln_cm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    float eps, float* __restrict__ y, int C, int T) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * 32 + lane;
+    const bool tv = t < T;
+    const float* __restrict__ xb = x + (size_t)b * C * T + (tv ? t : 0);
+    float v[LN_MAXC / 8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXC / 8; ++i) {
+        const int c = w + 8 * i;
+        v[i] = (tv && c < C) ? __ldg(xb + (size_t)c * T) : 0.f;
+        s += v[i];
+    }
+    red[w][lane] = s;
+    __syncthreads();
+    float mean = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mean += red[j][lane];
+    mean /= (float)C;
+    __syncthreads();
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXC / 8; ++i) { const int c = w + 8 * i; if (c < C) { const float d = v[i] - mean; q += d * d; } }
+    red[w][lane] = q;
+    __syncthreads();
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) var += red[j][lane];
+    const float rstd = rsqrtf(var / (float)C + eps);
+    if (!tv) return;
+    float* __restrict__ yb = y + (size_t)b * C * T + t;
+#pragma unroll
+    for (int i = 0; i < LN_MAXC / 8; ++i) {
+        const int c = w + 8 * i;
+        if (c < C) yb[(size_t)c * T] = (v[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+    }
+}
+
+void launch_ln_cm(const float* x, const float* gamma, const float* beta, float eps, float* y, int B, int C, int T, cudaStream_t st) {
+    dim3 grid((T + 31) / 32, B);
+    ln_cm_kernel<<<grid, 256, 0, st>>>(x, gamma, beta, eps, y, C, T);
+    launch_counter()++;
+}
+
+// z = m + noise * exp(logs) * noice_scale with stats = [m | logs] ([B, 2C, T]) - models.py:158-160 (mask = ones)
+__global__ void prior_sample_kernel(const float* __restrict__ stats, const float* __restrict__ noise, float ns, float* __restrict__ z,
+                                    float* __restrict__ m_out, float* __restrict__ logs_out, int C, int T, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int t = (int)(i % T);
+    const long long r = i / T;
+    const int c = (int)(r % C);
+    const long long b = r / C;
+    const float m = stats[((b * 2 * C) + c) * (long long)T + t];
+    const float lg = stats[((b * 2 * C) + C + c) * (long long)T + t];
+    z[i] = m + noise[i] * expf(lg) * ns;
+    if (m_out) m_out[i] = m;
+    if (logs_out) logs_out[i] = lg;
+}
+
+void launch_prior_sample(const float* stats, const float* noise, float ns, float* z, float* m_out, float* logs_out, int B, int C, int T, cudaStream_t st) {
+    const long long total = (long long)B * C * T;
+    prior_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(stats, noise, ns, z, m_out, logs_out, C, T, total);
+    launch_counter()++;
+}
+
 }  // namespace svb
 
 extern "C" {

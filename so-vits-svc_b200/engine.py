@@ -14,7 +14,7 @@ import torch
 from . import lib as L
 from .config import ModelCfg
 
-TAIL_PREFIXES = ("flow.", "dec.")
+TAIL_PREFIXES = ("flow.", "dec.", "pre.", "enc_p.")      # pre./enc_p. feed the library's own prior encoder (svb_enc_p)
 
 
 def _cfg_struct(cfg: ModelCfg) -> L.svb_model_cfg:
@@ -40,6 +40,13 @@ def _cfg_struct(cfg: ModelCfg) -> L.svb_model_cfg:
     s.n_harmonics = cfg.n_harmonics
     s.snake = 1 if cfg.snake else 0
     s.num_mels = cfg.num_mels
+    if cfg.num_mels == 0:
+        s.ssl_dim = cfg.ssl_dim
+        s.enc_layers = cfg.n_layers
+        s.enc_heads = cfg.n_heads
+        s.enc_filter = cfg.filter_channels
+        s.enc_kernel = cfg.kernel_size
+        s.enc_window = cfg.enc_window
     return s
 
 
@@ -97,6 +104,7 @@ class TailEngine:
             rc = self.lib.svb_load_weights(self._ctx, arr, len(keep), C.byref(self._cfg_struct))
         L.check(self.lib, self._ctx, rc, "svb_load_weights")
         self.loaded = True
+        self.has_prefix = any(k.startswith(b"enc_p.proj") for k, _ in keep) and any(k.startswith(b"pre.weight") for k, _ in keep)
 
     def set_precision(self, precision: str) -> None:
         code = {"fp32": L.PREC_FP32, "tc": L.PREC_TC}[precision]
@@ -204,6 +212,30 @@ class TailEngine:
         rc = self.lib.svb_nsf_source(self._ctx, f0.data_ptr(), rand_ini.data_ptr(), nz, har.data_ptr(), B, T, self._stream())
         L.check(self.lib, self._ctx, rc, "svb_nsf_source")
         return har
+
+    @torch.no_grad()
+    def pre_conv(self, c: torch.Tensor) -> torch.Tensor:
+        """``self.pre(c)`` (models.py:400,518) on the library's tcgen05 conv kernel: [B,ssl,T] -> [B,hidden,T]."""
+        c = self._f32(c, "c")
+        B, _, T = c.shape
+        x = torch.empty((B, self.cfg.hidden_channels, T), dtype=torch.float32, device=self.device)
+        rc = self.lib.svb_pre_conv(self._ctx, c.data_ptr(), x.data_ptr(), B, T, self._stream())
+        L.check(self.lib, self._ctx, rc, "svb_pre_conv")
+        return x
+
+    @torch.no_grad()
+    def enc_p(self, x_in: torch.Tensor, z_noise: torch.Tensor, noice_scale: float, want_stats: bool = False):
+        """``TextEncoder.forward`` after the f0-embedding add, all-ones mask (models.py:155-162) -> z_p [B,inter,T]
+        (and m_p, logs_p when ``want_stats``)."""
+        x_in = self._f32(x_in, "x_in"); z_noise = self._f32(z_noise, "z_noise")
+        B, _, T = x_in.shape
+        z = torch.empty((B, self.cfg.inter_channels, T), dtype=torch.float32, device=self.device)
+        m = torch.empty_like(z) if want_stats else None
+        lg = torch.empty_like(z) if want_stats else None
+        rc = self.lib.svb_enc_p(self._ctx, x_in.data_ptr(), z_noise.data_ptr(), float(noice_scale), z.data_ptr(),
+                                m.data_ptr() if want_stats else None, lg.data_ptr() if want_stats else None, B, T, self._stream())
+        L.check(self.lib, self._ctx, rc, "svb_enc_p")
+        return (z, m, lg) if want_stats else z
 
     @torch.no_grad()
     def generator(self, z: torch.Tensor, g: torch.Tensor, har: torch.Tensor) -> torch.Tensor:

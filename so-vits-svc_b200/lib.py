@@ -37,6 +37,8 @@ class svb_model_cfg(C.Structure):
         ("n_resblock_kernels", C.c_int32), ("resblock_kernel_sizes", C.c_int32 * 4),
         ("resblock_dilations", (C.c_int32 * 3) * 4),
         ("sampling_rate", C.c_int32), ("n_harmonics", C.c_int32), ("snake", C.c_int32), ("num_mels", C.c_int32),
+        ("ssl_dim", C.c_int32), ("enc_layers", C.c_int32), ("enc_heads", C.c_int32), ("enc_filter", C.c_int32),
+        ("enc_kernel", C.c_int32), ("enc_window", C.c_int32),
     ]
 
 
@@ -58,6 +60,9 @@ SIGNATURES = {
                               C.c_void_p, C.c_size_t, C.c_void_p]),
     "svb_infer_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "svb_pre_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "svb_enc_p": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                            C.c_void_p]),
     "svb_infer_tail_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "svb_strerror": (C.c_char_p, [C.c_int]),

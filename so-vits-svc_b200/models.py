@@ -47,6 +47,7 @@ class _TailMixin:
     draws in the reference's order and the CUDA tail call."""
 
     precision = "tc"
+    own_prefix = True      # precision "tc": pre + enc_p through svb_pre_conv / svb_enc_p instead of cuBLAS / ATen (SURVEY §8 f-3)
 
     def _tail_init(self, cfg: ModelCfg):
         self._b200_cfg = cfg
@@ -178,10 +179,20 @@ class SynthesizerTrn(_TailMixin, nn.Module):
             g = self.emb_g(g).transpose(1, 2)
         x_mask = torch.ones(B, 1, T, dtype=c.dtype, device=c.device)
         v = self.emb_vol(vol[:, :, None]).transpose(1, 2) if (vol is not None and self.vol_embedding) else 0
-        x = self.pre(c) * x_mask + self.emb_uv(uv.long()).transpose(1, 2) + v
         if self.use_automatic_f0_prediction and predict_f0:
             raise NotImplementedError("predict_f0 needs the reference f0_decoder: use patch_reference() (INTEGRATION.md)")
-        z_p, m_p, logs_p, c_mask = self.enc_p(x, x_mask, f0_to_coarse(f0), noice_scale=noice_scale, all_ones_mask=True)
+        eng = self._engine(c.device)
+        if self.precision == "tc" and self.own_prefix and getattr(eng, "has_prefix", False) and c.dtype == torch.float32:
+            # pre + enc_p on the library's own kernels (svb_pre_conv / svb_enc_p): tcgen05 GEMMs + the fused attention kernel.
+            # The embedding gathers stay torch indexing ("a1 stays PyTorch"); RNG draw #1 keeps its place in the stream.
+            x = eng.pre_conv(c) + self.emb_uv(uv.long()).transpose(1, 2) + v
+            x = x + self.enc_p.f0_emb(f0_to_coarse(f0)).transpose(1, 2)
+            z_noise = torch.randn(B, self.cfg.inter_channels, T, dtype=torch.float32, device=c.device)   # models.py:160
+            z_p = eng.enc_p(x, z_noise, noice_scale)
+            c_mask = x_mask
+        else:
+            x = self.pre(c) * x_mask + self.emb_uv(uv.long()).transpose(1, 2) + v
+            z_p, m_p, logs_p, c_mask = self.enc_p(x, x_mask, f0_to_coarse(f0), noice_scale=noice_scale, all_ones_mask=True)
         o = self._run_tail(z_p, c_mask, g, f0)
         return o, f0
 

@@ -220,16 +220,49 @@ def test_full_infer_against_oracle_with_replayed_rng(cfg, sd):
     # IEEE fp32 here so that the strict fp32 comparison measures the library, not cuDNN's TF32.
     old = torch.backends.cudnn.conv.fp32_precision
     torch.backends.cudnn.conv.fp32_precision = "ieee"
-    for precision, tol in (("fp32", 2e-4), ("tc", TC_TOL)):
+    for precision, tol, own in (("fp32", 2e-4, False), ("tc", TC_TOL, False), ("tc", 2 * TC_TOL, True)):
+        # own = the prior encoder on the library's kernels too (fp16-operand GEMMs + fused attention): a second reduced-precision
+        # stage in front of the tail, bounded like the bench-mode test
         net.set_precision(precision)
+        net.own_prefix = own
         o, f0_out = net.infer(c.to(DEV), f0.to(DEV), uv.to(DEV), g=sid.to(DEV), noice_scale=0.4)
         assert o.shape == (B, 1, N) and torch.equal(f0_out.cpu(), f0)
         err = float((o.cpu() - ref).abs().max())
-        print(f"[parity] full infer {precision}: L-inf = {err:.3e}")
+        print(f"[parity] full infer {precision}{' + own prefix' if own else ''}: L-inf = {err:.3e}")
         assert err < tol
         o2, _ = net.infer(c.to(DEV), f0.to(DEV), uv.to(DEV), g=sid.to(DEV), noice_scale=0.4)
         assert torch.equal(o, o2)                       # same seed -> bit-identical (reference behaviour)
     torch.backends.cudnn.conv.fp32_precision = old
+    net.own_prefix = True
+
+
+def test_own_prior_encoder_matches_oracle(cfg, sd):
+    """`pre` and `enc_p` on the library's own kernels (svb_pre_conv, svb_enc_p: tcgen05 conv-as-GEMM launches, the
+    fused relative-position attention kernel, channel-major LayerNorm) against the oracle's fp32 restatement of
+    models.py:155-162 / modules/attentions.py, same noise.  T is not a multiple of the 128-row tiles; the band terms, the
+    sequence end inside a key tile and both heads are exercised."""
+    import torch.nn.functional as F
+    from sovits_b200.engine import TailEngine
+    e = TailEngine(cfg, DEV, "tc")
+    e.load_state_dict(sd)
+    assert e.has_prefix
+    for B, T in ((2, 150), (1, 300)):
+        c, f0, uv, sid = synth.synth_inputs(cfg, B, T)
+        gen = torch.Generator().manual_seed(5)
+        z_noise = torch.randn((B, cfg.inter_channels, T), generator=gen)
+        x_ref, x_mask, _ = O.prologue(sd, c, f0, uv, sid, cfg, torch.float32)
+        pre_ref = F.conv1d(c, sd["pre.weight"], sd["pre.bias"], padding=2)
+        pre_got = e.pre_conv(c.to(DEV)).cpu()
+        rel = float((pre_got - pre_ref).abs().max()) / float(pre_ref.abs().max())
+        print(f"[parity] own pre conv B={B} T={T}: relative L-inf {rel:.2e}")
+        assert rel < 5e-3
+        z_ref, m_ref, logs_ref = O.text_encoder(sd, x_ref, x_mask, O.f0_to_coarse(f0), z_noise, 0.4, cfg, torch.float32)
+        x_in = x_ref + sd["enc_p.f0_emb.weight"][O.f0_to_coarse(f0)].transpose(1, 2)
+        z, m, lg = e.enc_p(x_in.to(DEV), z_noise.to(DEV), 0.4, want_stats=True)
+        errs = {n: float((a.cpu() - r).abs().max()) / max(1.0, float(r.abs().max())) for n, a, r in (("z_p", z, z_ref), ("m", m, m_ref), ("logs", lg, logs_ref))}
+        print(f"[parity] own enc_p B={B} T={T}: relative L-inf {errs} (|z_p|max {float(z_ref.abs().max()):.1f})")
+        assert max(errs.values()) < 1e-2, errs
+    e.close()
 
 
 def test_full_size_properties(cfg, sd, eng):
