@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                     bytes += sbb; ++idx;
                 }
                 const int s = ring & 1;
-                if (ring >= 2) mbar_wait(bar_empty + 8 * s, ((ring >> 1) - 1) & 1);
+                if (ring >= 2) { if (SNAKE) mbar_wait_sleep(bar_empty + 8 * s, ((ring >> 1) - 1) & 1); else mbar_wait(bar_empty + 8 * s, ((ring >> 1) - 1) & 1); }
                 if (elect_one()) {
                     mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
                     bulk_g2s(ring_base + s * d.stage_bytes, wsrc + off, bytes, bar_full + 8 * s);
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
         // Warp converged, ONE elected lane runs the whole issue loop (ring / accumulator-buffer waits included); the
         // body is UTCHMMAs plus descriptor increments only (see pair_tc_kernel for why).
         const uint32_t idesc = make_idesc_f16(128, NC);
-        mbar_wait(bar_a, 0);
+        if (SNAKE) mbar_wait_sleep(bar_a, 0); else mbar_wait(bar_a, 0);
         tc_fence_after();
         if (elect_one()) {
             const uint64_t a_step = (uint64_t)((uint32_t)(a.dil * G::RB) >> 4);
@@ -338,7 +338,9 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                     uint8_t* const prun = pch + run * (SNK_RUN * G::RB);
                     auto emit = [&](int i, float v) {
                         const uint32_t ph = ((uint32_t)(i * G::RB) >> 7) & (uint32_t)(G::RB / 16 - 1);     // compile-time per i
-                        *reinterpret_cast<__half*>(prun + i * G::RB + ((chunk ^ ph) << 4)) = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+                        uint16_t hv;
+                        asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hv) : "f"(v));
+                        *reinterpret_cast<uint16_t*>(prun + i * G::RB + ((chunk ^ ph) << 4)) = hv;
                     };
                     if (edge) snake_run<true>(xw, f, ea2, hib, t0, L, s0, sL, emit);
                     else snake_run<false>(xw, f, ea2, hib, t0, L, s0, sL, emit);
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
         const int len = a.lengths ? a.lengths[b] : 0x7fffffff;
         for (int c = c_lo; c < c_hi; ++c) {
             const int u = c - c_lo, buf = (d.nbuf > 1) ? (u & 1) : 0;
-            mbar_wait(bar_tfull + 8 * buf, (u / d.nbuf) & 1);
+            if (SNAKE) mbar_wait_sleep(bar_tfull + 8 * buf, (u / d.nbuf) & 1, 128); else mbar_wait(bar_tfull + 8 * buf, (u / d.nbuf) & 1);
             tc_fence_after();
             const int col_base = c * NC;
             const int ncols = min(NC, a.N_total - col_base);

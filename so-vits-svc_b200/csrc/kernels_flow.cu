@@ -17,7 +17,7 @@
 //     [384,512)  xin  one 128-column chunk of the in_layer pre-activations (64 tanh + 64 sigmoid channels); also the
 //                     accumulator of the final post GEMM (96 columns).
 //   Shared memory: H16 = fp16 operand copy of h with zero pad rows above / below (3 K-panels x 136 rows x 128 B;
-//     a k5 tap is a row offset of the A descriptor); ACTS = fp16 gate output (3 panels x 128 rows); a 4-stage ring of
+//     a k5 tap is a row offset of the A descriptor); ACTS = fp16 gate output (3 panels x 128 rows); a 7-stage ring of
 //     16 KB weight blocks ([128 output rows][64 input channels], host-swizzled) fed by 1-D bulk TMA copies.  The x0 operand
 //     tile aliases ACTS, the fp16 copy of `out` for the post GEMM aliases H16.
 //   Weights: ONE linear stream of 223 blocks per coupling layer in exactly the order the MMA warp consumes them:
@@ -53,7 +53,8 @@ constexpr int FL_RB = 128;                           // operand row bytes (64 fp
 constexpr int FL_HPANEL = FL_HROWS * FL_RB;          // 17408
 constexpr int FL_APANEL = 128 * FL_RB;               // 16384
 constexpr int FL_BLOCK = 128 * FL_RB;                // one weight block: 128 rows x 64 channels
-constexpr int FL_NSTAGE = 4;
+constexpr int FL_NSTAGE = 7;                         // 112 KB of weights in flight: the MMA stream consumes a 16 KB block every ~260 clk,
+                                                     // an L2 -> shared bulk copy takes several times that under load
 constexpr int FL_NBLK_PRE = 4, FL_NBLK_IN = 15, FL_NBLK_RS = 3, FL_NBLK_POST = 3;
 constexpr int FL_NBLK = FL_NBLK_PRE + FL_L * 3 * (FL_NBLK_IN + FL_NBLK_RS) + FL_NBLK_POST;   // 223
 constexpr int COL_H = 0, COL_OUT = 192, COL_X = 384;
@@ -95,15 +96,16 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_layer_kernel(const FlowPar
     uint8_t* sm = smem_raw + (base - raw);
     const uint32_t h16_base = base + OFF_H16, acts_base = base + OFF_ACTS, ring_base = base + OFF_RING;
     const uint32_t bar_base = base + OFF_BAR;
-    const uint32_t bar_full = bar_base;                      // [4]
-    const uint32_t bar_empty = bar_base + 32;                // [4]
-    const uint32_t bar_a0 = bar_base + 64;                   // x0 operand tile staged          (256 arrivals)
-    const uint32_t bar_hfin = bar_base + 72;                 // h / out accumulators final      (tcgen05.commit)
-    const uint32_t bar_h = bar_base + 80;                    // H16 (or OUT16) operand written  (256 arrivals)
-    const uint32_t bar_x = bar_base + 88;                    // xin chunk complete              (tcgen05.commit)
-    const uint32_t bar_xfree = bar_base + 96;                // gate epilogue done: ACTS panel written, xin free (256 arrivals)
-    const uint32_t tmem_slot = bar_base + 128;
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + 128);
+    static_assert(FL_NSTAGE <= 8, "barrier block holds 8 ring stages");
+    const uint32_t bar_full = bar_base;                      // [8]
+    const uint32_t bar_empty = bar_base + 64;                // [8]
+    const uint32_t bar_a0 = bar_base + 128;                  // x0 operand tile staged          (256 arrivals)
+    const uint32_t bar_hfin = bar_base + 136;                // h / out accumulators final      (tcgen05.commit)
+    const uint32_t bar_h = bar_base + 144;                   // H16 (or OUT16) operand written  (256 arrivals)
+    const uint32_t bar_x = bar_base + 152;                   // xin chunk complete              (tcgen05.commit)
+    const uint32_t bar_xfree = bar_base + 160;               // gate epilogue done: ACTS panel written, xin free (256 arrivals)
+    const uint32_t tmem_slot = bar_base + 192;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + 192);
     float* sb_gate = reinterpret_cast<float*>(sm + OFF_BIAS);
     float* sb_h = sb_gate + FL_L * 2 * FL_H;
     float* sb_out = sb_h + FL_L * FL_H;

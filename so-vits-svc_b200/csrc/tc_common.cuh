@@ -36,6 +36,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Long waits (a role that idles for a whole phase of the others): poll with a back-off so the spinning warp does not eat the
+// issue slots of the warps doing the work (ncu on the SnakeAlias-loader conv: 11 % of all issued instructions were try_wait
+// / branch pairs of the idle MMA and producer warps).
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, unsigned ns = 256) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads, bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

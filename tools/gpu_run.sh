@@ -18,7 +18,7 @@ for step in "$@"; do
     flow5)   timeout 300 python bench.py --workload flow5 --steps 20 --warmup 3 > gpurun_out/bench_flow5.json 2> gpurun_out/bench_flow5.err; echo "flow5 rc=$?"; cat gpurun_out/bench_flow5.json ;;
     refcuda) timeout 600 python bench.py --impl reference-cuda --steps 3 --warmup 2 > gpurun_out/bench_refcuda.json 2> gpurun_out/bench_refcuda.err; echo "refcuda rc=$?"; cat gpurun_out/bench_refcuda.json ;;
     refcpu)  timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_refcpu.json 2> gpurun_out/bench_refcpu.err; echo "refcpu rc=$?"; cat gpurun_out/bench_refcpu.json ;;
-    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1; echo "launches rc=$?" ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1; echo "launches rc=$?" ;;
     ncu_snake) timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:convn_tc_kernel<\\(int\\)128, \\(int\\)1, \\(int\\)2, \\(bool\\)1>" -s 6 -c 3 -f -o gpurun_out/prof_snake128 python bench.py --vocoder nsf-snake-hifigan --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_snake.log 2>&1; echo "ncu_snake rc=$?" ;;
     ncu_main) timeout 900 ncu --set full --clock-control none --import-source on -k "regex:flow_layer_kernel|resblock_skew_kernel" -c 13 -f -o gpurun_out/prof_main python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_main.log 2>&1; echo "ncu_main rc=$?" ;;
     *) echo "unknown step $step" ;;
