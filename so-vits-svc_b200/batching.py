@@ -61,17 +61,20 @@ def pad_batch(items: Sequence[dict], idx: Sequence[int], cfg, device, seed: int 
     c = torch.zeros(B, ssl, Tm, device=device)
     f0 = torch.zeros(B, Tm, device=device)
     uv = torch.zeros(B, Tm, device=device)
+    vol = torch.zeros(B, Tm, device=device) if any("vol" in items[i] and items[i]["vol"] is not None for i in idx) else None
     zn = torch.zeros(B, cfg.inter_channels, Tm, device=device)
     ri = torch.zeros(B, cfg.n_harmonics, device=device)
     hn = torch.zeros(B, Tm * cfg.hop, cfg.n_harmonics, device=device)
     for b, (i, T) in enumerate(zip(idx, Ts)):
         it = items[i]
-        c[b, :, :T], f0[b, :T], uv[b, :T] = it["c"].to(device), it["f0"].to(device), it["uv"].to(device)
+        c[b, :, :T], f0[b, :T], uv[b, :T] = it["c"].to(device).float(), it["f0"].to(device).float(), it["uv"].to(device).float()
+        if vol is not None and it.get("vol") is not None:
+            vol[b, :T] = it["vol"].to(device).float()
         nz = replay_item_noise(T, cfg, device, seed)
         zn[b, :, :T], ri[b], hn[b, :T * cfg.hop] = nz["z_noise"][0], nz["rand_ini"][0], nz["har_noise"][0]
     sid = torch.tensor([[int(items[i]["sid"])] for i in idx], dtype=torch.long, device=device)
     lengths = torch.tensor(Ts, device=device)
-    return c, f0, uv, sid, lengths, {"z_noise": zn, "rand_ini": ri, "har_noise": hn}
+    return c, f0, uv, sid, lengths, {"z_noise": zn, "rand_ini": ri, "har_noise": hn}, vol
 
 
 @torch.no_grad()
@@ -85,11 +88,15 @@ def infer_slices(net, items: Sequence[dict], noice_scale: float = 0.4, seed: int
     out: List[torch.Tensor] = [None] * len(items)       # type: ignore[list-item]
     lens = [int(it["f0"].shape[-1]) for it in items]
     for idx in plan_batches(lens, max_batch, max_pad_ratio):
-        c, f0, uv, sid, lengths, nz = pad_batch(items, idx, cfg, dev, seed)
+        c, f0, uv, sid, lengths, nz, vol = pad_batch(items, idx, cfg, dev, seed)
         B, _, Tm = c.shape
         x_mask = (torch.arange(Tm, device=dev)[None, :] < lengths[:, None]).to(c.dtype)[:, None, :]
         g = net.emb_g(sid).transpose(1, 2)
         x = net.pre(c) * x_mask + net.emb_uv(uv.long()).transpose(1, 2)
+        if vol is not None:
+            if not getattr(net, "vol_embedding", False):
+                raise RuntimeError("items carry `vol` but the model has no volume embedding (vol_embedding=False)")
+            x = x + net.emb_vol(vol[:, :, None]).transpose(1, 2)          # models.py:518-520
         all_ones = all(lens[i] == Tm for i in idx)          # host-side: no device sync
         z_p, _, _, _ = net.enc_p(x, x_mask, f0_to_coarse(f0), noice_scale=noice_scale, z_noise=nz["z_noise"], all_ones_mask=all_ones)
         eng = net._engine(dev)

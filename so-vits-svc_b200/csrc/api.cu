@@ -319,6 +319,16 @@ int make_convn(svb_ctx* ctx, int cinp, int cin_real, int N_total, int NC, int k,
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Column chunks per CTA of a conv-as-GEMM launch: as many as possible (the operand tile is staged once and the epilogue of a
+// chunk overlaps the MMAs of the next), but never so many that the grid falls under two CTAs per SM - the stage-0 upsampler
+// (862 frames -> 56 row tiles) ran on 56 of 148 SMs with all 8 chunks in one CTA.
+int pick_chunks_per_cta(int n_rows, int rows_per_cta, int B, int n_chunks) {
+    const long long tiles = (long long)((n_rows + rows_per_cta - 1) / rows_per_cta) * B;
+    int cpc = n_chunks;
+    while (cpc > 1 && tiles * ((n_chunks + cpc - 1) / cpc) < 2 * 148) cpc = (cpc + 1) / 2;
+    return cpc;
+}
+
 struct WsPlan {
     size_t total = 0;
     size_t off_y, off_h, off_xin, off_acts, off_out, off_gcond, off_dgcond, off_phase;
@@ -729,7 +739,7 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
             a.x = cur; a.x_ctot = S.Cin; a.cin_real = S.Cin; a.cinp = W.cinp; a.Tin = Lin; a.in_act = snake ? 0 : 1; a.in_slope = 0.1f;
             if (snake) { a.snake_ealpha = S.snake_in.ealpha; a.snake_invbeta = S.snake_in.inv_beta; a.snake_filt = ctx->snake_filt; }
             a.w = W.img; a.bias = W.bias; a.acc_scale = W.acc_scale; a.k = 2; a.pad_left = 1; a.n_rows = Lin + 1; a.N_total = W.N_total; a.NC = W.NC;
-            a.chunks_per_cta = (W.N_total + W.NC - 1) / W.NC;
+            a.chunks_per_cta = pick_chunks_per_cta(Lin + 1, 128 * (snake ? convn_snake_mb(W.cinp) : convn_mb(W.cinp)), B, (W.N_total + W.NC - 1) / W.NC);
             a.mode = 1; a.s = S.s; a.p = S.p; a.Ty = Lout; a.B = B;
             a.seg[0].y = X; a.seg[0].y_ctot = S.Cout;
             if (W.noise) { a.har = har; a.har_N = (int)N; a.noise_stride = W.noise_stride; a.noise_w0 = W.noise_w0; a.noise_wide = (W.noise == 2); }

@@ -347,6 +347,27 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
+        } else if (a.view_tstride == CINP && a.view_cstride == 1 && CINP == 64 && (a.view_off & 3) == 0 && (a.view_bstride & 3) == 0 && !a.in_act) {
+            // Strided view whose rows tile a CONTIGUOUS range (row r = samples [r*64 + off, +64) of a 1-channel signal: the
+            // stage-0 noise_convs as a 2-tap GEMM over 64-sample rows).  Element (r, c) = flat[r*64 + c]: load the range with
+            // coalesced 128-bit loads along the flat index and drop each group of 4 samples into its half-chunk of the tile.
+            const float* __restrict__ xb = a.x + (size_t)b * a.view_bstride;
+            const long long flat0 = (long long)(i0 - a.pad_left) * 64 + a.view_off;
+            for (int g = tid; g < RA * 16; g += CN_NWORK) {
+                const int r = g >> 4, c = (g & 15) * 4;
+                const long long idx = flat0 + (long long)g * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx >= 0 && idx + 3 < a.view_limit) v = __ldg(reinterpret_cast<const float4*>(xb + idx));
+                else {
+                    float e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) e[u] = (idx + u >= 0 && idx + u < a.view_limit) ? __ldg(xb + idx + u) : 0.f;
+                    v = make_float4(e[0], e[1], e[2], e[3]);
+                }
+                const uint32_t phase = swz_phase(r, G::RB);
+                uint8_t* pdst = sm + r * G::RB + ((((uint32_t)c >> 3) ^ phase) << 4) + (c & 4) * 2;
+                *reinterpret_cast<uint2*>(pdst) = make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
+            }
         } else {
             const bool view = a.view_tstride != 0;
             const float* __restrict__ xb = view ? a.x + (size_t)b * a.view_bstride : a.x + ((size_t)b * a.x_ctot + a.x_c0) * (size_t)a.Tin;
