@@ -108,6 +108,7 @@ struct svb_ctx {
     ConvW conv_pre;
     ConvNW conv_pre_tc;
     bool flow_tc_ok = false, gen_tc_ok = false;
+    float* cond_all_w = nullptr; float* cond_all_b = nullptr;   // cond_layer of all coupling layers stacked (one GEMV per call)
     float* dcond_w_nat = nullptr;  // dec.cond [U][gin]
     float* dcond_b = nullptr;
     ConvW dcond;                   // packed (time-varying g)
@@ -331,7 +332,7 @@ int pick_chunks_per_cta(int n_rows, int rows_per_cta, int B, int n_chunks) {
 
 struct WsPlan {
     size_t total = 0;
-    size_t off_y, off_h, off_xin, off_acts, off_out, off_gcond, off_dgcond, off_phase;
+    size_t off_y, off_h, off_xin, off_acts, off_out, off_gcond, off_gcond_all, off_dgcond, off_phase;
     size_t off_har, off_pre, off_X, off_A, off_Bb, off_T, off_O, off_z, off_S, off_A16, off_B16;
 };
 
@@ -348,6 +349,7 @@ WsPlan plan_ws(const svb_model_cfg& c, int B, int T, int gT) {
     p.off_acts = take(BT * H * f);
     p.off_out = take(BT * H * f);
     p.off_gcond = take((size_t)B * 2 * H * L * (gT > 1 ? T : 1) * f);
+    p.off_gcond_all = take((size_t)B * 2 * H * L * (c.n_flows > 0 ? c.n_flows : 1) * f);
     p.off_dgcond = take((size_t)B * c.upsample_initial_channel * (gT > 1 ? T : 1) * f);
     p.off_phase = take(BT * c.n_harmonics * sizeof(double));
     long long hop = 1;
@@ -531,11 +533,16 @@ int run_flow(svb_ctx* ctx, const float* z_p, const float* g, int gT, const int32
     float* gcond = reinterpret_cast<float*>(ws + pl.off_gcond);
     if (y != z_p) CU(cudaMemcpyAsync(y, z_p, (size_t)B * C * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
     const bool fused = ctx->precision == SVB_PREC_TC && ctx->flow_tc_ok && ctx->opt_fuse_flow && !ctx->flow.empty() && ctx->flow[0].fused_img;
+    const bool cond_once = fused && gT == 1 && ctx->cond_all_w;
+    float* gcond_all = reinterpret_cast<float*>(ws + pl.off_gcond_all);
+    if (cond_once)      // out[b][fl*2HL + col]
+        launch_gemv(ctx->cond_all_w, ctx->cond_all_b, g, gcond_all, B, c.n_flows * 2 * H * L, c.gin_channels, st);
     for (int fl = c.n_flows - 1; fused && fl >= 0; --fl) {
-        // one kernel per coupling layer; the conditioning cond_layer(g) is a GEMV (g[B,gin,1]) or, for speaker-mix g[B,gin,T],
-        // a 1x1 convolution written in the gate's chunk order and added per (frame, column) by the gate epilogue
+        // one kernel per coupling layer; the conditioning cond_layer(g) is a GEMV (g[B,gin,1]; all layers in one launch) or, for
+        // speaker-mix g[B,gin,T], a 1x1 convolution written in the gate's chunk order and added per (frame, column) by the gate
         FlowLayer& F = ctx->flow[fl];
-        if (gT == 1) {
+        if (cond_once) {
+        } else if (gT == 1) {
             launch_gemv(F.cond_w_perm2, F.cond_b_perm2, g, gcond, B, 2 * H * L, c.gin_channels, st);
         } else {
             ConvF32 cg;
@@ -547,7 +554,8 @@ int run_flow(svb_ctx* ctx, const float* z_p, const float* g, int gT, const int32
         FlowLayerTC a;
         a.y = y; a.y_ctot = C; a.in_c0 = F.in_c0; a.out_c0 = F.out_c0;
         a.w = F.fused_img; a.bias_gate = F.fb_gate; a.bias_h = F.fb_h; a.bias_out = F.fb_out; a.bias_post = F.fb_post;
-        a.gcond = gT == 1 ? gcond : nullptr; a.gcond_t = gT == 1 ? nullptr : gcond;
+        a.gcond = gT == 1 ? (cond_once ? gcond_all + (size_t)fl * 2 * H * L : gcond) : nullptr; a.gcond_t = gT == 1 ? nullptr : gcond;
+        a.gcond_bstride = cond_once ? c.n_flows * 2 * H * L : 2 * H * L;
         a.lengths = lengths; a.B = B; a.T = T; a.H = H; a.half = half; a.L = L; a.k = c.flow_kernel_size;
         const int trc = launch_flow_layer_tc(a, st);
         if (trc) return fail(ctx, trc, "fused coupling-layer kernel launch failed");
@@ -1095,6 +1103,7 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
     ctx->dcond_w_nat = nullptr; ctx->dcond_b = nullptr; ctx->post_w = nullptr; ctx->lin_w = nullptr; ctx->snake_filt = nullptr;
     ctx->snake_post = SnakeP();
     ctx->flow_tc_ok = false; ctx->gen_tc_ok = false;
+    ctx->cond_all_w = nullptr; ctx->cond_all_b = nullptr;
     ctx->prefix = Prefix();
     TMap m;
     for (int i = 0; i < n_tensors; ++i)
@@ -1238,6 +1247,18 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
             if ((rc = upload(ctx, bpc.data(), bpc.size() * sizeof(float), (void**)&F.cond_b_perm2))) return rc;
             if ((rc = make_conv(ctx, wp, bpc, 2 * H * L, G, 1, false, false, F.cond2))) return rc;
         }
+    }
+
+    if (!ctx->flow.empty() && ctx->flow[0].fused_img) {
+        // conditioning of all coupling layers as ONE GEMV per call: rows [fl][2H*L] in each layer's chunk order
+        const size_t per = (size_t)2 * H * L;
+        std::vector<float> wa(ctx->flow.size() * per * G), ba(ctx->flow.size() * per);
+        for (size_t fl = 0; fl < ctx->flow.size(); ++fl) {
+            CU(cudaMemcpy(&wa[fl * per * G], ctx->flow[fl].cond_w_perm2, per * G * sizeof(float), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(&ba[fl * per], ctx->flow[fl].cond_b_perm2, per * sizeof(float), cudaMemcpyDeviceToHost));
+        }
+        if ((rc = upload(ctx, wa.data(), wa.size() * sizeof(float), (void**)&ctx->cond_all_w))) return rc;
+        if ((rc = upload(ctx, ba.data(), ba.size() * sizeof(float), (void**)&ctx->cond_all_b))) return rc;
     }
 
     // ---- generator

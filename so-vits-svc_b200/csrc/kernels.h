@@ -145,7 +145,8 @@ struct FlowLayerTC {
     const float* bias_h = nullptr;       // [L][H]  b_pre + sum_{j<i} b_res_j
     const float* bias_out = nullptr;     // [H]     sum of the skip biases
     const float* bias_post = nullptr;    // [half]
-    const float* gcond = nullptr;        // [B][L*2H] cond_layer(g) for g[B,gin,1], chunk-permuted; or null
+    const float* gcond = nullptr;        // cond_layer(g) for g[B,gin,1], chunk-permuted, row b at gcond + b*gcond_bstride; or null
+    int gcond_bstride = 0;
     const float* gcond_t = nullptr;      // [B][L*2H][T] for time-varying g (speaker mix); or null
     const int32_t* lengths = nullptr;
     int B = 1, T = 0, H = 192, half = 96, L = 4, k = 5;

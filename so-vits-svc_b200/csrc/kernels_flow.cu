@@ -74,7 +74,7 @@ struct FlowParams {
     float* y; int y_ctot, in_c0, out_c0;
     const uint8_t* w;
     const float* bias_gate; const float* bias_h; const float* bias_out; const float* bias_post;
-    const float* gcond;      // [B][L*2H] per-utterance conditioning (chunk-permuted), or null
+    const float* gcond; int gcond_bstride;   // per-utterance conditioning (chunk-permuted) [L*2H] at gcond + b*stride, or null
     const float* gcond_t;    // [B][L*2H][T] time-varying conditioning (speaker mix), or null
     const int32_t* lengths;
     int T;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_layer_kernel(const FlowPar
         float v;
         if (i < FL_L * 2 * FL_H) {
             v = __ldg(p.bias_gate + i);
-            if (p.gcond) v += __ldg(p.gcond + (size_t)b * (FL_L * 2 * FL_H) + i);
+            if (p.gcond) v += __ldg(p.gcond + (size_t)b * p.gcond_bstride + i);
         } else if (i < FL_L * 2 * FL_H + FL_L * FL_H) v = __ldg(p.bias_h + (i - FL_L * 2 * FL_H));
         else if (i < FL_L * 2 * FL_H + FL_L * FL_H + FL_H) v = __ldg(p.bias_out + (i - FL_L * 2 * FL_H - FL_L * FL_H));
         else v = __ldg(p.bias_post + (i - FL_L * 2 * FL_H - FL_L * FL_H - FL_H));
@@ -426,7 +426,8 @@ int launch_flow_layer_tc(const FlowLayerTC& a, cudaStream_t st) {
     p.y = a.y; p.y_ctot = a.y_ctot; p.in_c0 = a.in_c0; p.out_c0 = a.out_c0;
     p.w = static_cast<const uint8_t*>(a.w);
     p.bias_gate = a.bias_gate; p.bias_h = a.bias_h; p.bias_out = a.bias_out; p.bias_post = a.bias_post;
-    p.gcond = a.gcond; p.gcond_t = a.gcond_t; p.lengths = a.lengths; p.T = a.T;
+    p.gcond = a.gcond; p.gcond_bstride = a.gcond_bstride > 0 ? a.gcond_bstride : FL_L * 2 * FL_H;
+    p.gcond_t = a.gcond_t; p.lengths = a.lengths; p.T = a.T;
     dim3 grid((a.T + FL_TOUT - 1) / FL_TOUT, a.B);
     flow_layer_kernel<<<grid, FL_THREADS, FL_SMEM, st>>>(p);
     launch_counter()++;

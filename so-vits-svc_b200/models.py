@@ -87,7 +87,8 @@ class _TailMixin:
         N = T * cfg.hop
         rand_ini = torch.rand(B, cfg.n_harmonics, device=dev)
         har_noise = torch.randn(B, N, cfg.n_harmonics, device=dev)
-        torch.randn(B, N, 1, device=dev)     # draw #4 is discarded by Generator but advances the RNG (:319)
+        # Draw #4 (`randn_like(uv)`, vdecoder/hifigan/models.py:319) is discarded by Generator.forward (:371) and is the LAST
+        # draw of a call whose first act is to re-seed (models.py:498-501): it can never influence an output, so it is not made.
         eng = self._engine(dev)
         # `infer` always builds an all-ones mask (c_lengths = ones * T, models.py:503,515), so no length vector is needed and
         # the mask is NOT inspected on the device (that cost a device->host sync right before the ~100 tail launches).
