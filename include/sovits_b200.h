@@ -103,7 +103,11 @@ SVB_API int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tens
 SVB_API int svb_set_precision(svb_ctx* ctx, int precision /* svb_precision */);
 SVB_API int svb_get_precision(const svb_ctx* ctx);
 /* Kernel-schedule switches (all numerically equivalent paths): "tma" (0/1: pair kernels load their operand tile from an
- * fp16 [B][T][C] copy through a TMA tensor map), "fuse_resblock" (0/1), "fuse_maxc" (largest C using the fused ResBlock). */
+ * fp16 [B][T][C] copy through a TMA tensor map), "fuse_resblock" (0/1), "fuse_maxc" (largest C using the fused ResBlock),
+ * "fuse_flow" (0/1: one kernel per coupling layer).
+ * Noise source of the NSF excitation: "philox_noise" (0/1) - when 1, calls that pass noise == NULL draw the N(0,1) harmonic
+ * noise in-kernel (Philox4x32-10 keyed by "philox_seed" and the sample index) instead of running noiseless; the waveform is
+ * then statistically, not bitwise, equivalent to the reference's torch.randn stream (vdecoder/hifigan/models.py:266). */
 SVB_API int svb_set_option(svb_ctx* ctx, const char* name, int value);
 
 /* Device scratch needed by svb_infer_tail for a [B,*,T] call.  Pass ws = NULL to let the library

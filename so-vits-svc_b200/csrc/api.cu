@@ -56,7 +56,7 @@ struct FlowLayer {
     int in_c0 = 0, out_c0 = 0;     // which half feeds pre / receives post (Flip folded)
     // fused coupling-layer kernel (kernels_flow.cu): weight block stream, bias sums, conditioning in its chunk order
     void* fused_img = nullptr;
-    float* fb_gate = nullptr; float* fb_h = nullptr; float* fb_out = nullptr; float* fb_post = nullptr;
+    float* fb_gate = nullptr; float* fb_h = nullptr; float* fb_m = nullptr;
     float* cond_w_perm2 = nullptr; float* cond_b_perm2 = nullptr;   // GEMV form (g[B,gin,1])
     ConvW cond2;                                                     // packed conv form (time-varying g)
 };
@@ -131,6 +131,8 @@ struct svb_ctx {
                                 // against the 128-bit thread loader on B200, so off by default; env SVB_TC_TMA overrides
     int opt_fuse_rb = 1;        // fused ResBlock kernel for narrow stages
     int opt_fuse_maxc = 64;     // ... up to this channel count (C = 64 fused: 12.6 vs 13.15 ms/step against the pair chain)
+    int opt_philox = 0;         // "throughput mode": calls with noise == NULL draw the harmonic noise in-kernel (Philox4x32-10)
+    unsigned long long philox_seed = 52468;
     int opt_fuse_flow = 1;      // one kernel per coupling layer (kernels_flow.cu) instead of 10 conv-as-GEMM launches
     int64_t ffma_fallbacks = 0;    // times a "tc" call ran (part of) its work on the fp32 FFMA kernels
     bool warned_fallback = false;
@@ -553,7 +555,7 @@ int run_flow(svb_ctx* ctx, const float* z_p, const float* g, int gT, const int32
         }
         FlowLayerTC a;
         a.y = y; a.y_ctot = C; a.in_c0 = F.in_c0; a.out_c0 = F.out_c0;
-        a.w = F.fused_img; a.bias_gate = F.fb_gate; a.bias_h = F.fb_h; a.bias_out = F.fb_out; a.bias_post = F.fb_post;
+        a.w = F.fused_img; a.bias_gate = F.fb_gate; a.bias_h = F.fb_h; a.bias_m = F.fb_m;
         a.gcond = gT == 1 ? (cond_once ? gcond_all + (size_t)fl * 2 * H * L : gcond) : nullptr; a.gcond_t = gT == 1 ? nullptr : gcond;
         a.gcond_bstride = cond_once ? c.n_flows * 2 * H * L : 2 * H * L;
         a.lengths = lengths; a.B = B; a.T = T; a.H = H; a.half = half; a.L = L; a.k = c.flow_kernel_size;
@@ -968,6 +970,8 @@ int svb_set_option(svb_ctx* ctx, const char* name, int value) {
     else if (n == "fuse_resblock") ctx->opt_fuse_rb = value;
     else if (n == "fuse_maxc") ctx->opt_fuse_maxc = value;
     else if (n == "fuse_flow") ctx->opt_fuse_flow = value;
+    else if (n == "philox_noise") ctx->opt_philox = value;
+    else if (n == "philox_seed") ctx->philox_seed = (unsigned long long)(unsigned int)value;
     else return fail(ctx, SVB_ERR_INVALID_ARG, "unknown option " + n);
     return SVB_OK;
 }
@@ -1214,13 +1218,27 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
             // ---- fused coupling-layer kernel: one block stream + bias sums + conditioning in its own chunk order
             const int kk = 5;
             std::vector<uint8_t> img(flow_layer_image_bytes());
+            // post folded into the skip path (fp32 on the host): Wm_i = W_post W_skip_i  [half x H];  channel reversal of the odd
+            // layers applied to the rows of W_post
+            auto wpost = [&](int co, int ci) { return h_post_w[(size_t)(odd ? half - 1 - co : co) * H + ci]; };
+            std::vector<std::vector<float>> wm(L, std::vector<float>((size_t)half * H));
+            for (int i = 0; i < L; ++i)
+                for (int co = 0; co < half; ++co)
+                    for (int ci = 0; ci < H; ++ci) {
+                        double acc = 0.0;
+                        for (int s = 0; s < H; ++s)
+                            acc += (double)wpost(co, s) * (double)h_rs_w[i][(size_t)((i < L - 1 ? H : 0) + s) * H + ci];
+                        wm[i][(size_t)co * H + ci] = (float)acc;
+                    }
             flow_layer_pack(
                 [&](int co, int ci) { return h_pre_w[(size_t)co * half + (odd ? half - 1 - ci : ci)]; },
                 [&](int i, int row, int ci, int tap) { return h_in_w[i][((size_t)row * H + ci) * kk + tap]; },
-                [&](int i, int row, int ci) { return h_rs_w[i][(size_t)row * H + ci]; },
-                [&](int co, int ci) { return h_post_w[(size_t)(odd ? half - 1 - co : co) * H + ci]; }, img.data());
+                [&](int i, int row, int ci) {
+                    if (row < H) return i < L - 1 ? h_rs_w[i][(size_t)row * H + ci] : 0.f;
+                    return wm[i][(size_t)(row - H) * H + ci];
+                }, img.data());
             if ((rc = upload(ctx, img.data(), img.size(), &F.fused_img))) return rc;
-            std::vector<float> bg((size_t)L * 2 * H), bh((size_t)L * H), bo(H, 0.f), bp(half);
+            std::vector<float> bg((size_t)L * 2 * H), bh((size_t)L * H), bo(H, 0.f), bm(half);
             for (int i = 0; i < L; ++i)
                 for (int col = 0; col < 2 * H; ++col) bg[(size_t)i * 2 * H + col] = h_in_b[i][flow_gate_row(col)];
             for (int ch = 0; ch < H; ++ch) {
@@ -1231,11 +1249,14 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
                     else bo[ch] += h_rs_b[i][ch];
                 }
             }
-            for (int co = 0; co < half; ++co) bp[co] = h_post_b[odd ? half - 1 - co : co];
+            for (int co = 0; co < half; ++co) {
+                double acc = h_post_b[odd ? half - 1 - co : co];
+                for (int s = 0; s < H; ++s) acc += (double)wpost(co, s) * (double)bo[s];
+                bm[co] = (float)acc;
+            }
             if ((rc = upload(ctx, bg.data(), bg.size() * sizeof(float), (void**)&F.fb_gate))) return rc;
             if ((rc = upload(ctx, bh.data(), bh.size() * sizeof(float), (void**)&F.fb_h))) return rc;
-            if ((rc = upload(ctx, bo.data(), bo.size() * sizeof(float), (void**)&F.fb_out))) return rc;
-            if ((rc = upload(ctx, bp.data(), bp.size() * sizeof(float), (void**)&F.fb_post))) return rc;
+            if ((rc = upload(ctx, bm.data(), bm.size() * sizeof(float), (void**)&F.fb_m))) return rc;
             std::vector<float> wp(h_cond_w.size()), bpc(h_cond_b.size());
             for (int i = 0; i < L; ++i)
                 for (int col = 0; col < 2 * H; ++col) {
@@ -1443,7 +1464,8 @@ int svb_nsf_source(svb_ctx* ctx, const float* f0, const float* rand_ini, const f
     int rc = ensure_ws(ctx, pl.total, nullptr, 0, &base);
     if (rc) return rc;
     launch_nsf_source(f0, rand_ini, noise, ctx->lin_w, ctx->lin_b, reinterpret_cast<double*>(base + pl.off_phase), har,
-                      B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, ctx->cfg.num_mels > 0 ? 1 : 0, (cudaStream_t)stream);
+                      B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, ctx->cfg.num_mels > 0 ? 1 : 0, (cudaStream_t)stream,
+                      ctx->opt_philox, ctx->philox_seed);
     return check_launch(ctx, "nsf_source");
 }
 
@@ -1470,7 +1492,7 @@ int svb_vocoder(svb_ctx* ctx, const float* mel, const float* f0, const float* ra
     cudaStream_t st = (cudaStream_t)stream;
     float* har = reinterpret_cast<float*>(base + pl.off_har);
     launch_nsf_source(f0, rand_ini, noise, ctx->lin_w, ctx->lin_b, reinterpret_cast<double*>(base + pl.off_phase), har,
-                      B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, 1, st);
+                      B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, 1, st, ctx->opt_philox, ctx->philox_seed);
     if ((rc = dbg_keep(ctx, "har", har, (size_t)B * T * ctx->hop, st))) return rc;
     return run_generator(ctx, mel, nullptr, 1, har, wav, B, T, base, pl, st);
 }
@@ -1499,7 +1521,8 @@ int svb_infer_tail(svb_ctx* ctx, const float* z_p, const float* g, int gT, const
         const double N = (double)T * ctx->hop;
         ProfScope ps(ctx, "nsf_source", st, 0, (double)B * (T * 4.0 + N * 4.0 + (noise ? N * 4.0 * ctx->cfg.n_harmonics : 0.0)));
         launch_nsf_source(f0, rand_ini, noise, ctx->lin_w, ctx->lin_b, reinterpret_cast<double*>(base + pl.off_phase), har,
-                          B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, ctx->cfg.num_mels > 0 ? 1 : 0, st);
+                          B, T, ctx->hop, ctx->cfg.n_harmonics, (float)ctx->cfg.sampling_rate, ctx->cfg.num_mels > 0 ? 1 : 0, st,
+                          ctx->opt_philox, ctx->philox_seed);
     }
     if ((rc = dbg_keep(ctx, "har", har, (size_t)B * T * ctx->hop, st))) return rc;
     ProfScope ps(ctx, "generator", st, 0, 0);

@@ -56,7 +56,7 @@ void launch_conv_post(const float* x, const float* w, float bias, float* wav, in
 //                   where rad_values is built at frame rate and then nearest-upsampled).
 void launch_nsf_source(const float* f0, const float* rand_ini, const float* noise, const float* lin_w, float lin_b,
                        double* phase_ws /*[B,T,H]*/, float* har, int B, int T, int hop, int n_harm, float sr, int rand_in_rate,
-                       cudaStream_t st);
+                       cudaStream_t st, int philox = 0, unsigned long long seed = 0);   // philox: in-kernel N(0,1) when noise == null
 
 // ---- tensor-core path (kernels_tc.cu) --------------------------------------------------------------
 // One ResBlock "pair": y = x + conv2(lrelu(conv1(lrelu(x)) + b1)) + b2 with out = alpha*y + beta*out_old.
@@ -143,8 +143,7 @@ struct FlowLayerTC {
     const void* w = nullptr;                                          // block stream built by flow_layer_pack
     const float* bias_gate = nullptr;    // [L][2H] in_layers biases, chunk-permuted (flow_gate_row)
     const float* bias_h = nullptr;       // [L][H]  b_pre + sum_{j<i} b_res_j
-    const float* bias_out = nullptr;     // [H]     sum of the skip biases
-    const float* bias_post = nullptr;    // [half]
+    const float* bias_m = nullptr;       // [half]  W_post (sum of the skip biases) + b_post
     const float* gcond = nullptr;        // cond_layer(g) for g[B,gin,1], chunk-permuted, row b at gcond + b*gcond_bstride; or null
     int gcond_bstride = 0;
     const float* gcond_t = nullptr;      // [B][L*2H][T] for time-varying g (speaker mix); or null
@@ -155,7 +154,7 @@ int launch_flow_layer_tc(const FlowLayerTC& a, cudaStream_t st);
 size_t flow_layer_image_bytes();
 int flow_gate_row(int col);
 void flow_layer_pack(const std::function<float(int, int)>& pre, const std::function<float(int, int, int, int)>& inl,
-                     const std::function<float(int, int, int)>& rs, const std::function<float(int, int)>& post, void* dst_host);
+                     const std::function<float(int, int, int)>& rsm, void* dst_host);
 
 // ---- enc_p attention (kernels_attn.cu): windowed relative-position MHA on channel-major [B,C,T] tensors --------------------
 struct AttnTC {

@@ -500,6 +500,29 @@ __global__ void __launch_bounds__(256) nsf_source_kernel(const float* __restrict
     har[(long long)b * N + n] = tanhf(acc);
 }
 
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"): counter-based, so every thread derives its
+// 4 x H normals from (seed, its sample-group index, call number) alone - the "throughput mode" of SURVEY §2a: no [B,N,H]
+// noise tensor is written by torch and read back (127 MB at config 2).
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+// two uniform 32-bit integers -> two independent standard normals (Box-Muller; u1 in (0,1], never 0)
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+    const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;      // (a + 1) / 2^32
+    const float u2 = (float)b * 2.3283064365386963e-10f;
+    const float r = sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2, &sn, &cs);
+    z0 = r * cs; z1 = r * sn;
+}
+
 // Four consecutive samples per thread (hop % 4 == 0, so they share their frame): the 4 x H noise values are H 128-bit loads
 // issued up front (the [B,N,H] noise tensor is 9/10 of the kernel's traffic), the frame's phase base and r are read once,
 // the waveform leaves as one 128-bit store.  Same arithmetic, expression by expression, as nsf_source_kernel.
@@ -507,12 +530,22 @@ template <int H>
 __global__ void __launch_bounds__(256) nsf_source_vec4_kernel(const float* __restrict__ f0, const float* __restrict__ noise,
                                                               const double* __restrict__ phase, const float* __restrict__ lin_w, float lin_b,
                                                               float* __restrict__ har, int T, int hop, float sr, long long N,
-                                                              const float* __restrict__ rand_ini, int rand_in_rate) {
+                                                              const float* __restrict__ rand_ini, int rand_in_rate,
+                                                              int philox, unsigned long long seed) {
     const int b = blockIdx.y;
     const long long n0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (n0 >= N) return;
     float nz[4 * H];
-    if (noise) {
+    if (philox) {
+        const unsigned long long grp = ((unsigned long long)b * (unsigned long long)N + (unsigned long long)n0) >> 2;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {                              // call j -> flat noise elements 4j .. 4j+3 ([sample][harmonic] order)
+            uint32_t c[4] = {(uint32_t)grp, (uint32_t)(grp >> 32), (uint32_t)j, 0x6e736673u};
+            philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+            box_muller(c[0], c[1], nz[4 * j], nz[4 * j + 1]);
+            box_muller(c[2], c[3], nz[4 * j + 2], nz[4 * j + 3]);
+        }
+    } else if (noise) {
         const float4* __restrict__ np = reinterpret_cast<const float4*>(noise + ((long long)b * N + n0) * H);
 #pragma unroll
         for (int j = 0; j < H; ++j) { const float4 q = __ldg(np + j); nz[4 * j] = q.x; nz[4 * j + 1] = q.y; nz[4 * j + 2] = q.z; nz[4 * j + 3] = q.w; }
@@ -536,7 +569,7 @@ __global__ void __launch_bounds__(256) nsf_source_vec4_kernel(const float* __res
             double ph = p0 + (double)(k0 + s + 1) * r;
             ph -= floor(ph);
             const float sv = sinpif(2.0f * (float)ph) * 0.1f;
-            const float v = sv * uv + (noise ? amp * nz[s * H + h] : 0.f);
+            const float v = sv * uv + ((noise || philox) ? amp * nz[s * H + h] : 0.f);
             acc[s] = fmaf(lw, v, acc[s]);
         }
     }
@@ -544,7 +577,8 @@ __global__ void __launch_bounds__(256) nsf_source_vec4_kernel(const float* __res
 }
 
 void launch_nsf_source(const float* f0, const float* rand_ini, const float* noise, const float* lin_w, float lin_b,
-                       double* phase_ws, float* har, int B, int T, int hop, int n_harm, float sr, int rand_in_rate, cudaStream_t st) {
+                       double* phase_ws, float* har, int B, int T, int hop, int n_harm, float sr, int rand_in_rate, cudaStream_t st,
+                       int philox, unsigned long long seed) {
     nsf_phase_kernel<<<B * n_harm, 32, 0, st>>>(f0, rand_ini, phase_ws, B, T, n_harm, hop, sr, rand_in_rate);
     launch_counter()++;
     long long N = (long long)T * hop;
@@ -552,12 +586,13 @@ void launch_nsf_source(const float* f0, const float* rand_ini, const float* nois
     if (vec && (n_harm == 9 || n_harm == 1)) {
         dim3 gridv((unsigned)((N / 4 + 255) / 256), B);
         if (n_harm == 9)
-            nsf_source_vec4_kernel<9><<<gridv, 256, 0, st>>>(f0, noise, phase_ws, lin_w, lin_b, har, T, hop, sr, N, rand_ini, rand_in_rate);
+            nsf_source_vec4_kernel<9><<<gridv, 256, 0, st>>>(f0, noise, phase_ws, lin_w, lin_b, har, T, hop, sr, N, rand_ini, rand_in_rate, philox && !noise, seed);
         else
-            nsf_source_vec4_kernel<1><<<gridv, 256, 0, st>>>(f0, noise, phase_ws, lin_w, lin_b, har, T, hop, sr, N, rand_ini, rand_in_rate);
+            nsf_source_vec4_kernel<1><<<gridv, 256, 0, st>>>(f0, noise, phase_ws, lin_w, lin_b, har, T, hop, sr, N, rand_ini, rand_in_rate, philox && !noise, seed);
         launch_counter()++;
         return;
     }
+    if (philox && !noise) { sticky_launch_error() = 1; return; }     // the in-kernel generator lives in the vectorised kernel only
     dim3 grid((unsigned)((N + 255) / 256), B);
     if (n_harm == 9)
         nsf_source_kernel<9><<<grid, 256, 0, st>>>(f0, noise, phase_ws, lin_w, lin_b, har, T, hop, sr, N, rand_ini, rand_in_rate);

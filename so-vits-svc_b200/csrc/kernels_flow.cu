@@ -10,24 +10,29 @@
 // (4 WN layers x (k-1)/2 = 2 frames each).  Nothing but x0 (read), x1 (read-modify-write) and the weights touches global
 // memory; the former schedule was 10 launches with h / acts / out (5.3 MB each at config 2) round-tripping between them.
 //
-//   TMEM (512 columns x 128 lanes, lane = frame of the tile):
+// `post` is folded into the skip path: m = post(sum_i skip_i) = sum_i (W_post W_skip_i) acts_i + (W_post b_skip + b_post),
+// so the kernel accumulates m (96 columns) directly instead of `out` (192) and needs no post GEMM; the products
+// W_post W_skip_i are formed in fp32 on the host at load time (mask = row validity commutes with the 1x1 maps).
+//
+//   TMEM (480 of 512 columns x 128 lanes, lane = frame of the tile):
 //     [  0,192)  h    fp32 residual stream of the WN stack.  Written by the pre GEMM, then the res halves of res_skip are
 //                     ACCUMULATED into it by the MMAs themselves (no epilogue pass for the residual add).
-//     [192,384)  out  fp32 skip accumulator, zeroed once, accumulated by the res_skip MMAs of all four layers.
-//     [384,512)  xin  one 128-column chunk of the in_layer pre-activations (64 tanh + 64 sigmoid channels); also the
-//                     accumulator of the final post GEMM (96 columns).
+//     [192,288)  m    fp32 accumulator of post(skip), zeroed once, accumulated by the res_skip MMAs of all four layers.
+//     [288,384) [384,480)  two buffers for one 96-column chunk of the in_layer pre-activations (48 tanh + 48 sigmoid
+//                     channels): the gate epilogue of chunk c runs while the MMAs of chunk c+1 fill the other buffer.
 //   Shared memory: H16 = fp16 operand copy of h with zero pad rows above / below (3 K-panels x 136 rows x 128 B;
-//     a k5 tap is a row offset of the A descriptor); ACTS = fp16 gate output (3 panels x 128 rows); a 7-stage ring of
-//     16 KB weight blocks ([128 output rows][64 input channels], host-swizzled) fed by 1-D bulk TMA copies.  The x0 operand
-//     tile aliases ACTS, the fp16 copy of `out` for the post GEMM aliases H16.
-//   Weights: ONE linear stream of 223 blocks per coupling layer in exactly the order the MMA warp consumes them:
-//     pre (4) | per WN layer: { in chunk c: 5 taps x 3 panels (15) | res_skip K-panel c-1: 3 row blocks } ... | post (3).
-//   Biases: res_skip / pre biases are never added in TMEM; the running sums are added when h / out are converted to fp16
-//     (bias_h[i] = b_pre + sum_{j<i} b_rs_j[:H],  bias_out = sum_j b_rs_j[H:] + b_rs_3).
+//     a k5 tap is a row offset of the A descriptor); ACTS = fp16 gate output, one 128-row panel per chunk (48 channels in
+//     128-byte rows); an 8-stage ring of 12 KB weight blocks ([96 output rows][64 input channels], host-swizzled) fed by
+//     1-D bulk TMA copies.  The x0 operand tile aliases ACTS.
+//   Weights: ONE linear stream of 292 blocks per coupling layer in exactly the order the MMA warp consumes them:
+//     pre (4) | per WN layer: in(0) in(1) rs(0) in(2) rs(1) in(3) rs(2) rs(3)   with in(c) = 5 taps x 3 panels (15 blocks)
+//     and rs(c) = 3 row blocks of the combined [res 192 | post.skip 96] matrix against the 48 channels of chunk c.
+//   Biases: res / pre biases are never added in TMEM; the running sums are added when h is converted to fp16
+//     (bias_h[i] = b_pre + sum_{j<i} b_res_j), the folded skip bias when m is consumed.
 //
 // Warp roles: warps 0-7 stage / epilogue (warp w <-> TMEM lanes 32 (w%4), column half w/4), warp 8 owns TMEM and issues
 // every MMA from one elected lane, warp 9 streams the weight blocks.  All hand-offs are mbarriers in one linear dependency
-// chain (pre -> h0 -> {in(c) -> gate(c) -> rs(c)} x 3 -> h1 -> ... -> out -> post), so the protocol cannot deadlock.
+// chain, so the protocol cannot deadlock.
 #include "kernels.h"
 #include "tc_common.cuh"
 #include "../../include/sovits_b200.h"
@@ -52,28 +57,30 @@ constexpr int FL_HROWS = 136;                        // 128 + FL_PAD rows above 
 constexpr int FL_RB = 128;                           // operand row bytes (64 fp16 channels, SWIZZLE_128B)
 constexpr int FL_HPANEL = FL_HROWS * FL_RB;          // 17408
 constexpr int FL_APANEL = 128 * FL_RB;               // 16384
-constexpr int FL_BLOCK = 128 * FL_RB;                // one weight block: 128 rows x 64 channels
-constexpr int FL_NSTAGE = 7;                         // 112 KB of weights in flight: the MMA stream consumes a 16 KB block every ~260 clk,
-                                                     // an L2 -> shared bulk copy takes several times that under load
-constexpr int FL_NBLK_PRE = 4, FL_NBLK_IN = 15, FL_NBLK_RS = 3, FL_NBLK_POST = 3;
-constexpr int FL_NBLK = FL_NBLK_PRE + FL_L * 3 * (FL_NBLK_IN + FL_NBLK_RS) + FL_NBLK_POST;   // 223
-constexpr int COL_H = 0, COL_OUT = 192, COL_X = 384;
+constexpr int FL_NB = 96;                            // rows of a weight block = columns of every MMA
+constexpr int FL_BLOCK = FL_NB * FL_RB;              // one weight block: 96 rows x 64 channels = 12 KB
+constexpr int FL_NSTAGE = 8;                         // 96 KB of weights in flight
+constexpr int FL_NCHUNK = 4, FL_CH = 48;             // gate chunks per WN layer, channels per chunk
+constexpr int FL_NBLK_PRE = 4, FL_NBLK_IN = 15, FL_NBLK_RS = 3;
+constexpr int FL_NBLK = FL_NBLK_PRE + FL_L * FL_NCHUNK * (FL_NBLK_IN + FL_NBLK_RS);          // 292
+constexpr int COL_H = 0, COL_M = 192, COL_X = 288;   // xin buffer b at COL_X + 96 b
 
 // shared memory map (bytes from the 1024-aligned base)
 constexpr uint32_t OFF_H16 = 0;                                          // 3 panels x 136 rows
 constexpr uint32_t OFF_ACTS = ((3 * FL_HPANEL + 1023) / 1024) * 1024;    // 52224
 static_assert(FL_HPANEL % 1024 == 0 && FL_APANEL % 1024 == 0, "operand panels must be 1024-byte aligned");
-constexpr uint32_t OFF_RING = OFF_ACTS + 3 * FL_APANEL;                  // + 49152
+constexpr uint32_t OFF_RING = OFF_ACTS + FL_NCHUNK * FL_APANEL;          // + 65536
 constexpr uint32_t OFF_BAR = OFF_RING + FL_NSTAGE * FL_BLOCK;            // + 65536
 constexpr uint32_t OFF_BIAS = OFF_BAR + 256;
-// floats: gate bias [L][2H] | bias_h [L][H] | bias_out [H] | bias_post [HALF]
-constexpr uint32_t N_BIAS = FL_L * 2 * FL_H + FL_L * FL_H + FL_H + FL_HALF;
+// floats: gate bias [L][2H] | bias_h [L][H] | bias_m [HALF]
+constexpr uint32_t N_BIAS = FL_L * 2 * FL_H + FL_L * FL_H + FL_HALF;
+static_assert(1024 + OFF_BIAS + N_BIAS * 4 <= 227 * 1024, "flow kernel shared memory");
 constexpr size_t FL_SMEM = 1024 + OFF_BIAS + N_BIAS * 4;
 
 struct FlowParams {
     float* y; int y_ctot, in_c0, out_c0;
     const uint8_t* w;
-    const float* bias_gate; const float* bias_h; const float* bias_out; const float* bias_post;
+    const float* bias_gate; const float* bias_h; const float* bias_m;
     const float* gcond; int gcond_bstride;   // per-utterance conditioning (chunk-permuted) [L*2H] at gcond + b*stride, or null
     const float* gcond_t;    // [B][L*2H][T] time-varying conditioning (speaker mix), or null
     const int32_t* lengths;
@@ -102,14 +109,13 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_layer_kernel(const FlowPar
     const uint32_t bar_a0 = bar_base + 128;                  // x0 operand tile staged          (256 arrivals)
     const uint32_t bar_hfin = bar_base + 136;                // h / out accumulators final      (tcgen05.commit)
     const uint32_t bar_h = bar_base + 144;                   // H16 (or OUT16) operand written  (256 arrivals)
-    const uint32_t bar_x = bar_base + 152;                   // xin chunk complete              (tcgen05.commit)
-    const uint32_t bar_xfree = bar_base + 160;               // gate epilogue done: ACTS panel written, xin free (256 arrivals)
+    const uint32_t bar_x = bar_base + 152;                   // [2] xin buffer complete         (tcgen05.commit)
+    const uint32_t bar_xfree = bar_base + 168;               // [2] gate epilogue done: ACTS panel written, xin buffer free (256 arrivals)
     const uint32_t tmem_slot = bar_base + 192;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + 192);
     float* sb_gate = reinterpret_cast<float*>(sm + OFF_BIAS);
     float* sb_h = sb_gate + FL_L * 2 * FL_H;
-    float* sb_out = sb_h + FL_L * FL_H;
-    float* sb_post = sb_out + FL_H;
+    float* sb_m = sb_h + FL_L * FL_H;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
@@ -122,8 +128,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_layer_kernel(const FlowPar
         mbar_init(bar_a0, FL_NWORK);
         mbar_init(bar_hfin, 1);
         mbar_init(bar_h, FL_NWORK);
-        mbar_init(bar_x, 1);
-        mbar_init(bar_xfree, FL_NWORK);
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_x + 8 * s, 1); mbar_init(bar_xfree + 8 * s, FL_NWORK); }
         fence_barrier_init();
     }
     if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -133,8 +138,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_layer_kernel(const FlowPar
             v = __ldg(p.bias_gate + i);
             if (p.gcond) v += __ldg(p.gcond + (size_t)b * p.gcond_bstride + i);
         } else if (i < FL_L * 2 * FL_H + FL_L * FL_H) v = __ldg(p.bias_h + (i - FL_L * 2 * FL_H));
-        else if (i < FL_L * 2 * FL_H + FL_L * FL_H + FL_H) v = __ldg(p.bias_out + (i - FL_L * 2 * FL_H - FL_L * FL_H));
-        else v = __ldg(p.bias_post + (i - FL_L * 2 * FL_H - FL_L * FL_H - FL_H));
+        else v = __ldg(p.bias_m + (i - FL_L * 2 * FL_H - FL_L * FL_H));
         sb_gate[i] = v;
     }
     tc_fence_before();
@@ -172,41 +176,39 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_layer_kernel(const FlowPar
             const uint64_t a0_desc = make_smem_desc(acts_base, FL_RB, 0);          // x0 tile aliases ACTS: panel p at + p*APANEL
             const uint64_t h_desc = make_smem_desc(h16_base, FL_RB, 0);            // row 0 of H16 = tile row -2
             const uint64_t acts_desc = make_smem_desc(acts_base, FL_RB, 0);
-            uint32_t n_h = 0, n_xfree = 0;
-            // pre: h = W_pre x0   (K = 96: panel 0 has 4 K-steps, panel 1 two; N = 192 as 128 + 64)
+            uint32_t n_h = 0, n_xf[2] = {0u, 0u};
+            auto in_chunk = [&](int c) {                       // 5 taps x 3 K-panels of H16 -> xin buffer c & 1
+                for (int tap = 0; tap < FL_K; ++tap)
+                    for (int pn = 0; pn < 3; ++pn)
+                        issue_block(h_desc + (uint64_t)((uint32_t)(pn * FL_HPANEL + tap * FL_RB) >> 4), COL_X + (c & 1) * FL_NB, FL_NB, 4, (tap | pn) ? 1u : 0u);
+                umma_commit(bar_x + 8 * (c & 1));
+            };
+            auto rs_chunk = [&](int c) {                       // [res 192 | post.skip 96] += R[:, chunk c] acts(chunk c)
+                mbar_wait(bar_xfree + 8 * (c & 1), n_xf[c & 1] & 1u); ++n_xf[c & 1];    // gate(c) done: ACTS panel c written, buffer free
+                tc_fence_after();
+                for (int nb = 0; nb < 3; ++nb)
+                    issue_block(acts_desc + (uint64_t)((uint32_t)(c * FL_APANEL) >> 4), COL_H + nb * FL_NB, FL_NB, 3, 1u);
+            };
+            // pre: h = W_pre x0   (K = 96: panel 0 has 4 K-steps, panel 1 two; N = 192 as 2 x 96)
             mbar_wait(bar_a0, 0);
             tc_fence_after();
             for (int pn = 0; pn < 2; ++pn)
                 for (int nb = 0; nb < 2; ++nb)
-                    issue_block(a0_desc + (uint64_t)((uint32_t)(pn * FL_APANEL) >> 4), COL_H + nb * 128, nb ? 64 : 128, pn ? 2 : 4, pn ? 1u : 0u);
+                    issue_block(a0_desc + (uint64_t)((uint32_t)(pn * FL_APANEL) >> 4), COL_H + nb * FL_NB, FL_NB, pn ? 2 : 4, pn ? 1u : 0u);
             umma_commit(bar_hfin);
             for (int i = 0; i < FL_L; ++i) {
-                mbar_wait(bar_h, n_h & 1u); ++n_h;                 // H16 of layer i written (and, for i = 0, `out` zeroed)
+                mbar_wait(bar_h, n_h & 1u); ++n_h;                 // H16 of layer i written (and, for i = 0, m zeroed)
                 tc_fence_after();
-                for (int c = 0; c < 3; ++c) {
-                    if (c > 0) {
-                        mbar_wait(bar_xfree, n_xfree & 1u); ++n_xfree;   // ACTS panel c-1 written, xin drained
-                        tc_fence_after();
-                        for (int nb = 0; nb < 3; ++nb)             // res_skip, K-panel c-1: accumulate into h | out
-                            issue_block(acts_desc + (uint64_t)((uint32_t)((c - 1) * FL_APANEL) >> 4), COL_H + nb * 128, 128, 4, 1u);
-                    }
-                    for (int tap = 0; tap < FL_K; ++tap)
-                        for (int pn = 0; pn < 3; ++pn)
-                            issue_block(h_desc + (uint64_t)((uint32_t)(pn * FL_HPANEL + tap * FL_RB) >> 4), COL_X, 128, 4, (tap | pn) ? 1u : 0u);
-                    umma_commit(bar_x);
-                }
-                mbar_wait(bar_xfree, n_xfree & 1u); ++n_xfree;
-                tc_fence_after();
-                for (int nb = 0; nb < 3; ++nb)
-                    issue_block(acts_desc + (uint64_t)((uint32_t)(2 * FL_APANEL) >> 4), COL_H + nb * 128, 128, 4, 1u);
+                in_chunk(0);
+                in_chunk(1);
+                rs_chunk(0);
+                in_chunk(2);
+                rs_chunk(1);
+                in_chunk(3);
+                rs_chunk(2);
+                rs_chunk(3);
                 umma_commit(bar_hfin);
             }
-            // post: m = W_post out   (K = 192, N = 96), accumulator in the xin columns
-            mbar_wait(bar_h, n_h & 1u); ++n_h;
-            tc_fence_after();
-            for (int pn = 0; pn < 3; ++pn)
-                issue_block(h_desc + (uint64_t)((uint32_t)(pn * FL_HPANEL + FL_PAD * FL_RB) >> 4), COL_X, FL_HALF, 4, pn ? 1u : 0u);
-            umma_commit(bar_x);
         }
         __syncwarp();
     } else {
@@ -244,17 +246,17 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_layer_kernel(const FlowPar
         }
         fence_proxy_async();
         mbar_arrive(bar_a0);
-        // out = 0 (the res_skip MMAs only ever accumulate into it)
+        // m = 0 (the res_skip MMAs only ever accumulate into it)
         {
             uint32_t z[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) z[j] = 0u;
 #pragma unroll
-            for (int cc = 0; cc < 96; cc += 16) tmem_st16(tlane + COL_OUT + hsel * 96 + cc, z);
+            for (int cc = 0; cc < 48; cc += 16) tmem_st16(tlane + COL_M + hsel * 48 + cc, z);
             tmem_st_wait();
         }
 
-        uint32_t n_hfin = 0, n_x = 0;
+        uint32_t n_hfin = 0, n_x[2] = {0u, 0u};
         // fp32 TMEM columns [col0 + hsel*96, +96) + bias -> masked fp16 operand rows of H16 (row index shifted by FL_PAD)
         auto to_h16 = [&](uint32_t col0, const float* __restrict__ bias) {
             const uint32_t phase = swz_phase(row + FL_PAD, FL_RB);
@@ -293,45 +295,41 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_layer_kernel(const FlowPar
             fence_proxy_async();
             mbar_arrive(bar_h);
 #pragma unroll 1
-            for (int c = 0; c < 3; ++c) {
-                mbar_wait(bar_x, n_x & 1u); ++n_x;
+            for (int c = 0; c < FL_NCHUNK; ++c) {
+                const int xb_ = c & 1;
+                mbar_wait(bar_x + 8 * xb_, n_x[xb_] & 1u); ++n_x[xb_];
                 tc_fence_after();
-                // chunk c: xin cols [0,64) = tanh pre-activations of channels 64c.., [64,128) = sigmoid pre-activations
-                const float* __restrict__ gb = sb_gate + i * 2 * FL_H + c * 128;
-                const float* __restrict__ gt = p.gcond_t ? p.gcond_t + ((size_t)b * (FL_L * 2 * FL_H) + i * 2 * FL_H + c * 128) * (size_t)T + (tv ? t : 0) : nullptr;
+                // chunk c: buffer cols [0,48) = tanh pre-activations of channels 48c.., [48,96) = sigmoid pre-activations;
+                // this thread: 24 of the 48 channels of its row
+                const float* __restrict__ gb = sb_gate + i * 2 * FL_H + c * FL_NB;
+                const float* __restrict__ gt = p.gcond_t ? p.gcond_t + ((size_t)b * (FL_L * 2 * FL_H) + i * 2 * FL_H + c * FL_NB) * (size_t)T + (tv ? t : 0) : nullptr;
                 const uint32_t phase = swz_phase(row, FL_RB);
                 uint8_t* prow = sm + OFF_ACTS + c * FL_APANEL + row * FL_RB;
+                const int j0 = hsel * 24;
+                const uint32_t xcol = COL_X + xb_ * FL_NB;
+                uint32_t ra[24], rb[24];
+                tmem_ld16(tlane + xcol + j0, reinterpret_cast<uint32_t(&)[16]>(ra[0]));
+                tmem_ld8(tlane + xcol + j0 + 16, reinterpret_cast<uint32_t(&)[8]>(ra[16]));
+                tmem_ld16(tlane + xcol + FL_CH + j0, reinterpret_cast<uint32_t(&)[16]>(rb[0]));
+                tmem_ld8(tlane + xcol + FL_CH + j0 + 16, reinterpret_cast<uint32_t(&)[8]>(rb[16]));
+                tmem_ld_wait();
+                float v[24];
 #pragma unroll
-                for (int cc = 0; cc < 32; cc += 16) {
-                    uint32_t ra[16], rb[16];
-                    const int j0 = hsel * 32 + cc;
-                    tmem_ld16(tlane + COL_X + j0, ra);
-                    tmem_ld16(tlane + COL_X + 64 + j0, rb);
-                    tmem_ld_wait();
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float ta = __uint_as_float(ra[j]) + gb[j0 + j];
-                        float sa = __uint_as_float(rb[j]) + gb[64 + j0 + j];
-                        if (gt && tv) { ta += __ldg(gt + (size_t)(j0 + j) * T); sa += __ldg(gt + (size_t)(64 + j0 + j) * T); }
-                        v[j] = gate_act(ta, sa);
-                    }
-                    store_chunk8(prow, phase, j0 / 8, v, 0xffffffffu);
-                    store_chunk8(prow, phase, j0 / 8 + 1, v + 8, 0xffffffffu);
+                for (int j = 0; j < 24; ++j) {
+                    float ta = __uint_as_float(ra[j]) + gb[j0 + j];
+                    float sa = __uint_as_float(rb[j]) + gb[FL_CH + j0 + j];
+                    if (gt && tv) { ta += __ldg(gt + (size_t)(j0 + j) * T); sa += __ldg(gt + (size_t)(FL_CH + j0 + j) * T); }
+                    v[j] = gate_act(ta, sa);
                 }
+#pragma unroll
+                for (int g = 0; g < 3; ++g) store_chunk8(prow, phase, j0 / 8 + g, v + 8 * g, 0xffffffffu);
                 tc_fence_before();
                 fence_proxy_async();
-                mbar_arrive(bar_xfree);
+                mbar_arrive(bar_xfree + 8 * xb_);
             }
         }
-        // out -> fp16 operand (aliases H16), then the post GEMM
+        // m = post(skip) complete once the res_skip MMAs of the last layer have landed
         mbar_wait(bar_hfin, n_hfin & 1u); ++n_hfin;
-        tc_fence_after();
-        to_h16(COL_OUT, sb_out);
-        tc_fence_before();
-        fence_proxy_async();
-        mbar_arrive(bar_h);
-        mbar_wait(bar_x, n_x & 1u); ++n_x;
         tc_fence_after();
         {
             // x1 = (x1 - (post(out) + b_post)) * mask on the 112 interior frames; this thread: 48 of the 96 channels
@@ -341,7 +339,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_layer_kernel(const FlowPar
             for (int cc = 0; cc < 48; cc += 16) {
                 uint32_t r[16];
                 float xo[16];
-                tmem_ld16(tlane + COL_X + hsel * 48 + cc, r);
+                tmem_ld16(tlane + COL_M + hsel * 48 + cc, r);
                 if (wr) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) xo[j] = yo[(size_t)(cc + j) * T];
@@ -350,7 +348,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_layer_kernel(const FlowPar
                 if (wr) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float m = __uint_as_float(r[j]) + sb_post[hsel * 48 + cc + j];
+                        const float m = __uint_as_float(r[j]) + sb_m[hsel * 48 + cc + j];
                         yo[(size_t)(cc + j) * T] = tv ? (xo[j] - m) : 0.f;
                     }
                 }
@@ -367,16 +365,16 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_layer_kernel(const FlowPar
 
 size_t flow_layer_image_bytes() { return (size_t)FL_NBLK * FL_BLOCK; }
 
-// gate column order of in_layers for this kernel: chunk c (128 columns) = [tanh channels 64c..64c+63 | sigmoid channels 64c..]
-int flow_gate_row(int col) { const int cc = col / 128, j = col % 128; return j < 64 ? cc * 64 + j : FL_H + cc * 64 + (j - 64); }
+// gate column order of in_layers for this kernel: chunk c (96 columns) = [tanh channels 48c..48c+47 | sigmoid channels 48c..]
+int flow_gate_row(int col) { const int cc = col / FL_NB, j = col % FL_NB; return j < FL_CH ? cc * FL_CH + j : FL_H + cc * FL_CH + (j - FL_CH); }
 
 // Build the block stream.  Accessors return folded fp32 weights in the kernel's channel conventions:
 //   pre(co, ci)          co < 192, ci < 96
 //   in(i, row, ci, tap)  row < 384 in NATURAL order (tanh rows 0..191, sigmoid rows 192..383)
-//   rs(i, row, ci)       row < 384: res rows 0..191, skip rows 192..383 (layer 3: rows 0..191 are its skip output, no res)
-//   post(co, ci)         co < 96, ci < 192
+//   rsm(i, row, ci)      row < 288: rows 0..191 = res rows of res_skip[i] (zero for the last layer), rows 192..287 =
+//                        (W_post W_skip_i)[row-192] (for the last layer W_post W_rs), acting on acts channel ci
 void flow_layer_pack(const std::function<float(int, int)>& pre, const std::function<float(int, int, int, int)>& inl,
-                     const std::function<float(int, int, int)>& rs, const std::function<float(int, int)>& post, void* dst_host) {
+                     const std::function<float(int, int, int)>& rsm, void* dst_host) {
     uint8_t* dst = static_cast<uint8_t*>(dst_host);
     std::memset(dst, 0, flow_layer_image_bytes());
     size_t blk = 0;
@@ -387,35 +385,25 @@ void flow_layer_pack(const std::function<float(int, int)>& pre, const std::funct
     };
     for (int pn = 0; pn < 2; ++pn)
         for (int nb = 0; nb < 2; ++nb, ++blk)
-            for (int n = 0; n < (nb ? 64 : 128); ++n)
+            for (int n = 0; n < FL_NB; ++n)
                 for (int cc = 0; cc < 64; ++cc) {
                     const int ci = pn * 64 + cc;
-                    if (ci < FL_HALF) put(n, cc, pre(nb * 128 + n, ci));
+                    if (ci < FL_HALF) put(n, cc, pre(nb * FL_NB + n, ci));
                 }
     for (int i = 0; i < FL_L; ++i) {
-        auto put_rs = [&](int kp) {
-            for (int nb = 0; nb < 3; ++nb, ++blk)
-                for (int n = 0; n < 128; ++n)
-                    for (int cc = 0; cc < 64; ++cc) {
-                        const int row = nb * 128 + n;                     // TMEM column: h | out
-                        float v;
-                        if (i < FL_L - 1) v = rs(i, row, kp * 64 + cc);
-                        else v = row < FL_H ? 0.f : rs(i, row - FL_H, kp * 64 + cc);    // last layer: everything is skip
-                        put(n, cc, v);
-                    }
-        };
-        for (int c = 0; c < 3; ++c) {
-            if (c > 0) put_rs(c - 1);
+        auto put_in = [&](int c) {
             for (int tap = 0; tap < FL_K; ++tap)
                 for (int pn = 0; pn < 3; ++pn, ++blk)
-                    for (int n = 0; n < 128; ++n)
-                        for (int cc = 0; cc < 64; ++cc) put(n, cc, inl(i, flow_gate_row(c * 128 + n), pn * 64 + cc, tap));
-        }
-        put_rs(2);
+                    for (int n = 0; n < FL_NB; ++n)
+                        for (int cc = 0; cc < 64; ++cc) put(n, cc, inl(i, flow_gate_row(c * FL_NB + n), pn * 64 + cc, tap));
+        };
+        auto put_rs = [&](int c) {
+            for (int nb = 0; nb < 3; ++nb, ++blk)
+                for (int n = 0; n < FL_NB; ++n)
+                    for (int cc = 0; cc < FL_CH; ++cc) put(n, cc, rsm(i, nb * FL_NB + n, c * FL_CH + cc));
+        };
+        put_in(0); put_in(1); put_rs(0); put_in(2); put_rs(1); put_in(3); put_rs(2); put_rs(3);
     }
-    for (int pn = 0; pn < 3; ++pn, ++blk)
-        for (int n = 0; n < FL_HALF; ++n)
-            for (int cc = 0; cc < 64; ++cc) put(n, cc, post(n, pn * 64 + cc));
 }
 
 int launch_flow_layer_tc(const FlowLayerTC& a, cudaStream_t st) {
@@ -425,7 +413,7 @@ int launch_flow_layer_tc(const FlowLayerTC& a, cudaStream_t st) {
     FlowParams p;
     p.y = a.y; p.y_ctot = a.y_ctot; p.in_c0 = a.in_c0; p.out_c0 = a.out_c0;
     p.w = static_cast<const uint8_t*>(a.w);
-    p.bias_gate = a.bias_gate; p.bias_h = a.bias_h; p.bias_out = a.bias_out; p.bias_post = a.bias_post;
+    p.bias_gate = a.bias_gate; p.bias_h = a.bias_h; p.bias_m = a.bias_m;
     p.gcond = a.gcond; p.gcond_bstride = a.gcond_bstride > 0 ? a.gcond_bstride : FL_L * 2 * FL_H;
     p.gcond_t = a.gcond_t; p.lengths = a.lengths; p.T = a.T;
     dim3 grid((a.T + FL_TOUT - 1) / FL_TOUT, a.B);

@@ -47,6 +47,8 @@ class _TailMixin:
     draws in the reference's order and the CUDA tail call."""
 
     precision = "tc"
+    noise_mode = "torch"   # "torch": the reference's own RNG stream (bit-comparable); "philox": harmonic noise drawn inside the
+                           # source kernel (no [B,N,9] tensor written and re-read; statistically equivalent)
     own_prefix = True      # precision "tc": pre + enc_p through svb_pre_conv / svb_enc_p instead of cuBLAS / ATen (SURVEY §8 f-3)
 
     def _tail_init(self, cfg: ModelCfg):
@@ -86,10 +88,14 @@ class _TailMixin:
         B, _, T = z_p.shape
         N = T * cfg.hop
         rand_ini = torch.rand(B, cfg.n_harmonics, device=dev)
-        har_noise = torch.randn(B, N, cfg.n_harmonics, device=dev)
+        philox = self.noise_mode == "philox"
+        har_noise = None if philox else torch.randn(B, N, cfg.n_harmonics, device=dev)
         # Draw #4 (`randn_like(uv)`, vdecoder/hifigan/models.py:319) is discarded by Generator.forward (:371) and is the LAST
         # draw of a call whose first act is to re-seed (models.py:498-501): it can never influence an output, so it is not made.
         eng = self._engine(dev)
+        if philox != getattr(eng, "_philox_on", False):
+            eng.set_option("philox_noise", int(philox))
+            eng._philox_on = philox
         # `infer` always builds an all-ones mask (c_lengths = ones * T, models.py:503,515), so no length vector is needed and
         # the mask is NOT inspected on the device (that cost a device->host sync right before the ~100 tail launches).
         o = eng.infer_tail(z_p, g, f0, rand_ini, har_noise, lengths)

@@ -643,3 +643,38 @@ def test_fp16_range_of_the_tensor_core_path(cfg, sd):
         err = float((got - torch.from_numpy(gold["o"])).abs().max())
         print(f"[parity] range test, ResBlock conv1 x{s:g} / conv2 x{1 / s:g} (tc): L-inf vs reference waveform = {err:.3e}")
         assert torch.isfinite(got).all() and err < TC_TOL
+
+
+def test_nsf_source_philox_mode(cfg, sd, eng):
+    """SURVEY §2a "throughput mode": harmonic noise drawn in-kernel (Philox4x32-10 + Box-Muller) instead of a [B,N,9] torch
+    tensor.  Deterministic per seed, different across seeds, and on unvoiced frames (where the excitation is pure noise,
+    vdecoder/hifigan/models.py:262-270) distributed like the torch-noise run: same mean / std, matching quantiles, no
+    sample-to-sample correlation.  With the option off, noise = NULL stays the noiseless path (bit-exact tests above)."""
+    B, T = 2, 600
+    _, _, f0, noise = _case(cfg, sd, B, T)
+    f0[:, 100:400] = 0.0
+    args = (f0.to(DEV), noise["rand_ini"].to(DEV))
+    ref = eng.nsf_source(*args, noise["har_noise"].to(DEV))
+    eng.set_option("philox_seed", 1234)
+    eng.set_option("philox_noise", 1)
+    try:
+        a = eng.nsf_source(*args, None)
+        b = eng.nsf_source(*args, None)
+        eng.set_option("philox_seed", 99)
+        c = eng.nsf_source(*args, None)
+    finally:
+        eng.set_option("philox_noise", 0)
+    quiet = eng.nsf_source(*args, None)
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, quiet)
+    hop = cfg.hop
+    seg = slice(100 * hop, 400 * hop)
+    xa, xr = a[:, seg].flatten().double(), ref[:, seg].flatten().double()
+    assert abs(float(xa.mean() - xr.mean())) < 3e-4 and abs(float(xa.std() / xr.std()) - 1.0) < 0.02
+    qs = torch.linspace(0.001, 0.999, 999, dtype=torch.float64, device=DEV)
+    ks = float((torch.quantile(xa[:200000], qs) - torch.quantile(xr[:200000], qs)).abs().max() / xr.std())
+    xc = xa - xa.mean()
+    rho = float((xc[1:] * xc[:-1]).mean() / xc.var())
+    print(f"[parity] philox source noise: std ratio {float(xa.std() / xr.std()):.4f}, max quantile gap {ks:.4f} sigma, lag-1 autocorrelation {rho:.4f}")
+    assert ks < 0.05 and abs(rho) < 0.01
+    voiced = slice(0, 100 * hop)
+    assert abs(float(a[:, voiced].double().std() / ref[:, voiced].double().std()) - 1.0) < 0.02
