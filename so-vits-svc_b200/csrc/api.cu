@@ -133,6 +133,7 @@ struct svb_ctx {
     int opt_fuse_maxc = 64;     // ... up to this channel count (C = 64 fused: 12.6 vs 13.15 ms/step against the pair chain)
     int opt_philox = 0;         // "throughput mode": calls with noise == NULL draw the harmonic noise in-kernel (Philox4x32-10)
     unsigned long long philox_seed = 52468;
+    int opt_merge_branches = 1; // the three ResBlock branches of a wide, short stage in one pair launch per dilation index
     int opt_fuse_flow = 1;      // one kernel per coupling layer (kernels_flow.cu) instead of 10 conv-as-GEMM launches
     int64_t ffma_fallbacks = 0;    // times a "tc" call ran (part of) its work on the fp32 FFMA kernels
     bool warned_fallback = false;
@@ -336,7 +337,16 @@ struct WsPlan {
     size_t total = 0;
     size_t off_y, off_h, off_xin, off_acts, off_out, off_gcond, off_gcond_all, off_dgcond, off_phase;
     size_t off_har, off_pre, off_X, off_A, off_Bb, off_T, off_O, off_z, off_S, off_A16, off_B16;
+    size_t off_br[6]; size_t br_elems = 0;      // per-branch ping-pong buffers of the branch-merged pair launches
 };
+
+// Branch-merged pair launches (launch_pair_tc_multi) pay a memset of the stage output and private buffers; they win where a
+// single pair launch leaves the GPU half empty: wide stages (pair kernels, C >= 128) with at most ~3 waves of tiles.
+bool merge_branches(int C, int L, int B) {
+    if (C < 128) return false;
+    const long long tiles = (long long)((L + 245) / 246) * B;
+    return tiles <= 3 * 148;
+}
 
 WsPlan plan_ws(const svb_model_cfg& c, int B, int T, int gT) {
     WsPlan p;
@@ -372,6 +382,16 @@ WsPlan plan_ws(const svb_model_cfg& c, int B, int T, int gT) {
     p.off_T = take(maxel * f);
     p.off_O = take(maxel * f);
     p.off_S = c.snake ? take(maxel * f) : 0;
+    // stages whose pair launches have few tiles run their three branches in one launch (run_generator): 3 x 2 private buffers
+    {
+        long long l2 = T;
+        for (int i = 0; i < c.n_upsamples; ++i) {
+            l2 *= c.upsample_rates[i];
+            const int co = c.upsample_initial_channel >> (i + 1);
+            if (merge_branches(co, (int)l2, B)) p.br_elems = std::max(p.br_elems, (size_t)B * co * (size_t)l2);
+        }
+        for (int q = 0; q < 6; ++q) p.off_br[q] = p.br_elems ? take(p.br_elems * f) : 0;
+    }
     p.off_A16 = take(maxel * 2);      // fp16 [B][T][C] copies of lrelu(residual stream) for the TMA-fed pair kernels
     p.off_B16 = take(maxel * 2);
     p.total = o;
@@ -778,7 +798,36 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
         const int use_tma = ctx->opt_tma;
         void* a16[2] = {ws + pl.off_A16, ws + pl.off_B16};
         const int fuse_maxc = ctx->opt_fuse_maxc;
-        for (int j = 0; j < nk; ++j) {
+        bool merged_done = false;
+        if (gen_tc && !snake && nk == 3 && ctx->opt_merge_branches && pl.br_elems >= (size_t)B * S.Cout * (size_t)Lout && merge_branches(S.Cout, Lout, B) &&
+            S.c1[0].w_tc && S.c1[3].w_tc && S.c1[6].w_tc) {
+            // the three branches of this stage advance together: one launch per dilation index, blockIdx.z = branch; every
+            // branch keeps its own ping-pong buffers, the three last pairs accumulate alpha*y into the zeroed stage output
+            CU(cudaMemsetAsync(O, 0, (size_t)B * S.Cout * (size_t)Lout * sizeof(float), st));
+            int trc = 0;
+            for (int d = 0; d < 3 && trc == 0; ++d) {
+                PairTC pt[3];
+                double fl = 0;
+                for (int j = 0; j < 3; ++j) {
+                    const int k = c.resblock_kernel_sizes[j];
+                    const ConvW& W1 = S.c1[j * 3 + d];
+                    const ConvW& W2 = S.c2[j * 3 + d];
+                    float* bufj[2] = {reinterpret_cast<float*>(ws + pl.off_br[2 * j]), reinterpret_cast<float*>(ws + pl.off_br[2 * j + 1])};
+                    pt[j].x = d == 0 ? X : bufj[(d - 1) & 1];
+                    pt[j].out = d == 2 ? O : bufj[d & 1];
+                    pt[j].w1 = W1.w_tc; pt[j].w2 = W2.w_tc; pt[j].b1 = W1.b_tc; pt[j].b2 = W2.b;
+                    pt[j].inv = 1.f / (W1.tc_scale * W2.tc_scale);
+                    pt[j].B = B; pt[j].C = S.Cout; pt[j].T = Lout; pt[j].k = k; pt[j].dil = c.resblock_dilations[j][d];
+                    pt[j].alpha = d == 2 ? 1.f / nk : 1.f; pt[j].beta = d == 2 ? 1.f : 0.f;
+                    fl += 2.0 * 2.0 * S.Cout * (double)S.Cout * k * (double)Lout * B;
+                }
+                ProfScope ps(ctx, "pair_tc", st, fl, 3 * 3.0 * S.Cout * (double)Lout * B * sizeof(float));
+                trc = launch_pair_tc_multi(pt, 3, st);
+            }
+            if (trc == 0) merged_done = true;
+            else if (trc != SVB_ERR_UNSUPPORTED) return fail(ctx, trc, "branch-merged pair launch failed");
+        }
+        for (int j = 0; j < nk && !merged_done; ++j) {
             const int k = c.resblock_kernel_sizes[j];
             if (gen_tc && snake && !S.c1n.empty()) {
                 // Snake ResBlock (vdecoder/hifiganwithsnake/models.py:61-72): x = x + c2(a2(c1(a1(x)))) per dilation, every
@@ -970,6 +1019,7 @@ int svb_set_option(svb_ctx* ctx, const char* name, int value) {
     else if (n == "fuse_resblock") ctx->opt_fuse_rb = value;
     else if (n == "fuse_maxc") ctx->opt_fuse_maxc = value;
     else if (n == "fuse_flow") ctx->opt_fuse_flow = value;
+    else if (n == "merge_branches") ctx->opt_merge_branches = value;
     else if (n == "philox_noise") ctx->opt_philox = value;
     else if (n == "philox_seed") ctx->philox_seed = (unsigned long long)(unsigned int)value;
     else return fail(ctx, SVB_ERR_INVALID_ARG, "unknown option " + n);

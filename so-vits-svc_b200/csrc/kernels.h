@@ -75,6 +75,7 @@ struct PairTC {
 };
 bool pair_tc_supports_tma(int C, int variant);
 int launch_pair_tc(const PairTC& a, cudaStream_t st);   // returns 0 or a negative status
+int launch_pair_tc_multi(const PairTC* av, int nbr, cudaStream_t st);   // up to 3 independent pairs (same C, B, T) in one launch
 size_t tc_weight_image_bytes(int C, int k);
 // host-side: build the swizzled fp16 image for one conv (w_folded is [Cout][Cin][k] fp32)
 void tc_pack_weight_image(const float* w_folded, int C, int k, void* dst_host, float scale = 1.f);

@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include "../../include/sovits_b200.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -60,6 +61,10 @@ struct PairParams {
     int red_out;         // loader pre-writes alpha*x (+ beta*old for beta == 1) into out, epilogue 2 only adds (RED): no x re-read
     uint32_t epoch; int dephase_clk;   // first-wave start skew (tc_common.cuh: dephase_first_wave)
 };
+// Up to three independent pairs (the three ResBlock branches of a stage at the same dilation index) in ONE launch:
+// blockIdx.z selects the branch.  A wide stage with few tiles (stage 0: 232 tiles of C = 256 on 148 SMs = 1.57 waves per
+// launch, i.e. 2 waves of time) is then scheduled as 696 CTAs of mixed length (k = 3 / 7 / 11) = 4.7 waves of the mean.
+struct PairParamsN { PairParams br[3]; };
 __device__ unsigned long long g_pair_ticket[256];
 uint32_t g_pair_epoch = 0;
 
@@ -78,7 +83,9 @@ constexpr size_t pair_smem_bytes() {
 }
 
 template <int C, int MB, int STAGE_KB, int MINB, bool TMA_IN>
-__global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const __grid_constant__ PairParamsN pn_, const __grid_constant__ CUtensorMap tmap) {
+    const PairParams& p = pn_.br[blockIdx.z];
+    if ((int)blockIdx.x * (128 * MB - (p.k - 1)) >= p.T) return;       // this branch has fewer tiles than the widest one
     using G = TCGeom<C, STAGE_KB>;
     constexpr int R1 = 128 * MB;
     constexpr int AROWS = TileRows<MB>::AROWS;
@@ -550,7 +557,8 @@ int make_a16_tmap(CUtensorMap* out, const void* base, int B, int T, int C, int b
 }
 
 template <int C, int MB, int STAGE_KB, int MINB, bool TMA_IN>
-int launch_pair_t2(const PairTC& a, cudaStream_t st) {
+int launch_pair_t2(const PairTC* av, int nbr, cudaStream_t st) {
+    const PairTC& a = av[0];
     constexpr size_t smem = pair_smem_bytes<C, MB, STAGE_KB>();
     static_assert(smem * MINB + 1024 * MINB <= 228 * 1024, "pair kernel shared memory exceeds the SM budget");
     static std::atomic<size_t> granted[SVB_MAX_DEV];
@@ -560,7 +568,11 @@ int launch_pair_t2(const PairTC& a, cudaStream_t st) {
     if (TMA_IN) {
         if (make_a16_tmap(&tmap, a.a16_in, a.B, a.T, C, TileRows<MB>::AROWS / TMA_NBOX) != 0) return SVB_ERR_CUDA;
     }
-    PairParams p;
+    PairParamsN pn;
+    int gx = 0;
+    for (int z = 0; z < 3; ++z) {
+    const PairTC& a = av[z < nbr ? z : 0];
+    PairParams& p = pn.br[z];
     p.x = a.x; p.out = a.out;
     p.w1 = static_cast<const uint8_t*>(a.w1); p.w2 = static_cast<const uint8_t*>(a.w2);
     p.b1 = a.b1; p.b2 = a.b2; p.T = a.T; p.k = a.k; p.dil = a.dil; p.alpha = a.alpha; p.beta = a.beta; p.inv = a.inv;
@@ -574,25 +586,27 @@ int launch_pair_t2(const PairTC& a, cudaStream_t st) {
         static const int env_dephase = env_int("SVB_PAIR_DEPHASE", -1);
         const int mma_clk = (C >= 128 ? C / 2 : (C == 64 ? 48 : 40)) * a.k * (C / 16) * MB;
         const int grid_ctas = (int)(((a.T + (128 * MB - (a.k - 1)) - 1) / (128 * MB - (a.k - 1))) * a.B);
-        p.epoch = ++g_pair_epoch;
+        p.epoch = z == 0 ? ++g_pair_epoch : pn.br[0].epoch;
         p.dephase_clk = (MINB < 2 || grid_ctas < 4 * 148 * MINB) ? 0 : (env_dephase >= 0 ? env_dephase : 2 * mma_clk + 24000);
     }
     const int TOUT = 128 * MB - (a.k - 1);
-    dim3 grid((a.T + TOUT - 1) / TOUT, a.B);
-    pair_tc_kernel<C, MB, STAGE_KB, MINB, TMA_IN><<<grid, TC_THREADS, smem, st>>>(p, tmap);
+    gx = std::max(gx, (a.T + TOUT - 1) / TOUT);
+    }
+    dim3 grid(gx, a.B, nbr);
+    pair_tc_kernel<C, MB, STAGE_KB, MINB, TMA_IN><<<grid, TC_THREADS, smem, st>>>(pn, tmap);
     launch_counter()++;
     return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;
 }
 
 template <int C, int MB, int STAGE_KB, int MINB>
-int launch_pair_t(const PairTC& a, cudaStream_t st) {
+int launch_pair_t(const PairTC* av, int nbr, cudaStream_t st) {
     // the TMA-fed variant exists for the tiles whose row count splits into three 8-row-aligned boxes (MB = 2, 4) and C >= 64
     if constexpr ((MB == 2 || MB == 4) && C >= 64) {
-        if (a.a16_in) return launch_pair_t2<C, MB, STAGE_KB, MINB, true>(a, st);
+        if (av[0].a16_in) return nbr == 1 ? launch_pair_t2<C, MB, STAGE_KB, MINB, true>(av, 1, st) : SVB_ERR_UNSUPPORTED;
     } else {
-        if (a.a16_in) return SVB_ERR_UNSUPPORTED;
+        if (av[0].a16_in) return SVB_ERR_UNSUPPORTED;
     }
-    return launch_pair_t2<C, MB, STAGE_KB, MINB, false>(a, st);
+    return launch_pair_t2<C, MB, STAGE_KB, MINB, false>(av, nbr, st);
 }
 
 }  // namespace
@@ -622,27 +636,36 @@ void tc_pack_weight_image(const float* w, int C, int k, void* dst_host, float sc
 // Tile variants.  variant 0: one CTA per SM with the largest tile (weights amortised over 128*MB rows);
 // variant 1: two CTAs per SM (<= 113 KB smem, <= 256 TMEM columns, <= 102 registers each) so that one CTA's
 // load / epilogue phases overlap the other's MMA phases.  C=256 needs all 512 TMEM columns and stays 1 CTA/SM.
-int launch_pair_tc(const PairTC& a, cudaStream_t st) {
-    if (!(a.k == 3 || a.k == 7 || a.k == 11) || (a.k - 1) * a.dil > 50) return SVB_ERR_UNSUPPORTED;
+int launch_pair_tc(const PairTC& a, cudaStream_t st) { return launch_pair_tc_multi(&a, 1, st); }
+
+// nbr <= 3 pairs with the same C, B, T (different k / dilation / weights / buffers) in one launch
+int launch_pair_tc_multi(const PairTC* av, int nbr, cudaStream_t st) {
+    if (nbr < 1 || nbr > 3) return SVB_ERR_INVALID_ARG;
+    for (int z = 0; z < nbr; ++z) {
+        const PairTC& q = av[z];
+        if (!(q.k == 3 || q.k == 7 || q.k == 11) || (q.k - 1) * q.dil > 50) return SVB_ERR_UNSUPPORTED;
+        if (q.C != av[0].C || q.B != av[0].B || q.T != av[0].T || (nbr > 1 && (q.a16_in || q.a16_out))) return SVB_ERR_INVALID_ARG;
+    }
+    const PairTC& a = av[0];
     static const int env_variant = env_int("SVB_TC_VARIANT", -1);
     int variant = a.variant >= 0 ? a.variant : env_variant;
     if (variant < 0) variant = 1;     // measured on B200 (profiles/r01/bench_pair_sweep_epi.log): two CTAs/SM win for every C that allows it
     if (variant == 1) {
         switch (a.C) {
-            case 16: return launch_pair_t<16, 16, 8, 2>(a, st);
-            case 32: return launch_pair_t<32, 8, 22, 2>(a, st);
-            case 64: return launch_pair_t<64, 4, 16, 2>(a, st);
-            case 128: return launch_pair_t<128, 2, 16, 2>(a, st);
-            case 256: return launch_pair_t<256, 2, 32, 1>(a, st);
+            case 16: return launch_pair_t<16, 16, 8, 2>(av, nbr, st);
+            case 32: return launch_pair_t<32, 8, 22, 2>(av, nbr, st);
+            case 64: return launch_pair_t<64, 4, 16, 2>(av, nbr, st);
+            case 128: return launch_pair_t<128, 2, 16, 2>(av, nbr, st);
+            case 256: return launch_pair_t<256, 2, 32, 1>(av, nbr, st);
             default: return SVB_ERR_UNSUPPORTED;
         }
     }
     switch (a.C) {
-        case 16: return launch_pair_t<16, 16, 32, 1>(a, st);
-        case 32: return launch_pair_t<32, 8, 32, 1>(a, st);
-        case 64: return launch_pair_t<64, 4, 32, 1>(a, st);
-        case 128: return launch_pair_t<128, 4, 32, 1>(a, st);
-        case 256: return launch_pair_t<256, 2, 32, 1>(a, st);
+        case 16: return launch_pair_t<16, 16, 32, 1>(av, nbr, st);
+        case 32: return launch_pair_t<32, 8, 32, 1>(av, nbr, st);
+        case 64: return launch_pair_t<64, 4, 32, 1>(av, nbr, st);
+        case 128: return launch_pair_t<128, 4, 32, 1>(av, nbr, st);
+        case 256: return launch_pair_t<256, 2, 32, 1>(av, nbr, st);
         default: return SVB_ERR_UNSUPPORTED;
     }
 }

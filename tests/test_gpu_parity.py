@@ -339,13 +339,17 @@ def test_schedule_options_are_equivalent(cfg, sd, eng):
     eng.set_option("fuse_flow", 0)                # flow as 10 conv-as-GEMM launches per coupling layer instead of one kernel
     unfused_flow, n_uf = run()
     eng.set_option("fuse_flow", 1)
+    eng.set_option("merge_branches", 0)           # the wide stages' three branches as separate pair launches (9 instead of 3 per stage)
+    unmerged, n_um = run()
+    eng.set_option("merge_branches", 1)
+    assert n_um == n_base + 2 * 6, (n_um, n_base)
     # the options really select different schedules: 9 pair launches replace each fused ResBlock launch of 3
     assert n_pairs == n_pairs_tma and n_pairs > n_f32 > n_base, (n_base, n_tma, n_pairs, n_f32)
     assert n_uf == n_base + 4 * 11 - 5, (n_uf, n_base)   # 4 x 11 launches -> one conditioning GEMV + 4 coupling-layer kernels
     eng.set_precision("fp32")
     ref = eng.infer_tail(*args)
     for name, o in (("default", base), ("tma", tma), ("pairs-only", pairs), ("pairs-only+tma", pairs_tma), ("fused<=32", fused32),
-                    ("unfused flow", unfused_flow)):
+                    ("unfused flow", unfused_flow), ("unmerged branches", unmerged)):
         err = float((o - ref).abs().max())
         print(f"[parity] schedule {name}: L-inf vs fp32 path = {err:.3e}")
         assert err < TC_TOL
