@@ -292,7 +292,7 @@ int make_conv(svb_ctx* ctx, const std::vector<float>& w, const std::vector<float
 
 int make_convn(svb_ctx* ctx, int cinp, int cin_real, int N_total, int NC, int k, int pad_left,
                const std::function<float(int, int, int)>& wcol, const std::function<float(int)>& bcol, ConvNW& out,
-               const std::function<float(int, int)>* ncol = nullptr, int noise_kind = 1) {
+               const std::function<float(int, int)>* ncol = nullptr, int noise_kind = 1, float force_scale = 0.f) {
     out.cinp = cinp; out.cin_real = cin_real; out.N_total = N_total; out.NC = NC; out.k = k; out.pad_left = pad_left;
     out.noise = ncol ? noise_kind : 0;
     const size_t ib = convn_weight_image_bytes(cinp, N_total, NC, k, out.noise);
@@ -309,6 +309,7 @@ int make_convn(svb_ctx* ctx, int cinp, int cin_real, int N_total, int NC, int k,
             for (int u = 0; u < (noise_kind == 2 ? 80 : 16); ++u) wmax = std::max(wmax, std::fabs((*ncol)(col, u)));
     float wscale = 1.f;
     if (wmax > 0.f && std::isfinite(wmax) && (wmax < 0.015625f || wmax > 64.f)) wscale = std::exp2(-std::round(std::log2(wmax)));
+    if (force_scale > 0.f) wscale = force_scale;       // K-chunked layers: both images must share one normalisation
     out.acc_scale = 1.f / wscale;
     std::function<float(int, int)> ncol_s;
     if (ncol) ncol_s = [&](int col, int u) { return (*ncol)(col, u) * wscale; };
@@ -454,6 +455,13 @@ int check_launch(svb_ctx* ctx, const char* what) {
 //   pre   Conv1d(768 -> 192, k5)            two K halves of 384 channels (the operand tile of one CTA holds <= 512 channels)
 //   qkv   conv_q | conv_k | conv_v stacked  192 -> 576, the 1/sqrt(dk) of attentions.py:243 folded into the q rows
 //   o     conv_o 192 -> 192;  ffn conv_1 192 -> 768 k3 (+ReLU);  conv_2 768 -> 192 k3 in two K halves;  proj 192 -> 384
+float shared_pow2_scale(const std::vector<float>& w) {
+    float wmax = 0.f;
+    for (float v : w) wmax = std::max(wmax, std::fabs(v));
+    if (wmax > 0.f && std::isfinite(wmax) && (wmax < 0.015625f || wmax > 64.f)) return std::exp2(-std::round(std::log2(wmax)));
+    return 1.f;
+}
+
 int load_prefix(svb_ctx* ctx, const TMap& m) {
     const svb_model_cfg& c = ctx->cfg;
     Prefix& P = ctx->prefix;
@@ -468,10 +476,11 @@ int load_prefix(svb_ctx* ctx, const TMap& m) {
     if ((rc = get_tensor(ctx, m, "pre.bias", {H}, b))) return rc;
     {
         const std::vector<float> wv = w.v, bv = b.v;
+        const float sc = shared_pow2_scale(wv);
         for (int half = 0; half < 2; ++half) {
             if ((rc = make_convn(ctx, 384, 384, H, H, 5, 2,
                                  [&](int col, int ci, int tap) { return wv[((size_t)col * S + half * 384 + ci) * 5 + tap]; },
-                                 [&](int col) { return half == 0 ? bv[col] : 0.f; }, half == 0 ? P.pre_a : P.pre_b))) return rc;
+                                 [&](int col) { return half == 0 ? bv[col] : 0.f; }, half == 0 ? P.pre_a : P.pre_b, nullptr, 1, sc))) return rc;
         }
     }
     P.layers.assign(nl, EncLayer());
@@ -512,10 +521,11 @@ int load_prefix(svb_ctx* ctx, const TMap& m) {
         if ((rc = get_tensor(ctx, m, f + "conv_2.weight", {H, F, k}, w)) || (rc = get_tensor(ctx, m, f + "conv_2.bias", {H}, b))) return rc;
         {
             const std::vector<float> wv = w.v, bv = b.v;
+            const float sc = shared_pow2_scale(wv);
             for (int half = 0; half < 2; ++half)
                 if ((rc = make_convn(ctx, 384, 384, H, H, k, (k - 1) / 2,
                                      [&](int col, int ci, int tap) { return wv[((size_t)col * F + half * 384 + ci) * k + tap]; },
-                                     [&](int col) { return half == 0 ? bv[col] : 0.f; }, half == 0 ? E.ffn2a : E.ffn2b))) return rc;
+                                     [&](int col) { return half == 0 ? bv[col] : 0.f; }, half == 0 ? E.ffn2a : E.ffn2b, nullptr, 1, sc))) return rc;
         }
     }
     if ((rc = get_tensor(ctx, m, "enc_p.proj.weight", {C2, H, 1}, w)) || (rc = get_tensor(ctx, m, "enc_p.proj.bias", {C2}, b))) return rc;
@@ -530,11 +540,12 @@ int load_prefix(svb_ctx* ctx, const TMap& m) {
 
 // one plain conv-as-GEMM launch on channel-major tensors: y[B,N,T] = alpha-less (conv_k(x[:, x_c0 : x_c0+cin]) + bias [+ res]) [+ y]
 int prefix_conv(svb_ctx* ctx, const ConvNW& W, const float* x, int x_ctot, int x_c0, float* y, const float* res, float beta, int relu,
-                int B, int T, cudaStream_t st) {
+                int B, int T, cudaStream_t st, const ConvNW* W2 = nullptr, int k2_c0 = 0) {
     ConvNTC a;
     a.x = x; a.x_ctot = x_ctot; a.x_c0 = x_c0; a.cin_real = W.cin_real; a.cinp = W.cinp; a.Tin = T;
     a.w = W.img; a.bias = W.bias; a.acc_scale = W.acc_scale; a.k = W.k; a.dil = 1; a.pad_left = W.pad_left;
     a.n_rows = T; a.N_total = W.N_total; a.NC = W.NC; a.Ty = T; a.B = B; a.out_relu = relu;
+    if (W2) { a.w_k2 = W2->img; a.k2_c0 = k2_c0; }       // second K chunk of the same layer (shared normalisation, zero bias)
     const int n_chunks = (W.N_total + W.NC - 1) / W.NC;
     a.chunks_per_cta = n_chunks >= 4 ? 2 : 1;
     a.seg[0].y = y; a.seg[0].y_ctot = W.N_total; a.seg[0].col0 = 0; a.seg[0].col1 = W.N_total;
@@ -1586,8 +1597,7 @@ int svb_pre_conv(svb_ctx* ctx, const float* c, float* x, int B, int T, void* str
     cudaStream_t st = (cudaStream_t)stream;
     const Prefix& P = ctx->prefix;
     int rc;
-    if ((rc = prefix_conv(ctx, P.pre_a, c, P.ssl, 0, x, nullptr, 0.f, 0, B, T, st))) return rc;
-    if ((rc = prefix_conv(ctx, P.pre_b, c, P.ssl, 384, x, nullptr, 1.f, 0, B, T, st))) return rc;
+    if ((rc = prefix_conv(ctx, P.pre_a, c, P.ssl, 0, x, nullptr, 0.f, 0, B, T, st, &P.pre_b, 384))) return rc;     // K = 768 as 2 x 384
     return check_launch(ctx, "pre_conv");
 }
 
@@ -1628,8 +1638,7 @@ int svb_enc_p(svb_ctx* ctx, const float* x_in, const float* z_noise, float noice
         if ((rc = prefix_conv(ctx, E.o, A, P.H, 0, Y, cur, 0.f, 0, B, T, st))) return rc;            // x + conv_o(attn)
         launch_ln_cm(Y, E.g1, E.b1, 1e-5f, X1, B, P.H, T, st);
         if ((rc = prefix_conv(ctx, E.ffn1, X1, P.H, 0, Hd, nullptr, 0.f, 1, B, T, st))) return rc;   // relu(conv_1)
-        if ((rc = prefix_conv(ctx, E.ffn2a, Hd, P.F, 0, Y, X1, 0.f, 0, B, T, st))) return rc;        // x1 + conv_2 (first K half)
-        if ((rc = prefix_conv(ctx, E.ffn2b, Hd, P.F, 384, Y, nullptr, 1.f, 0, B, T, st))) return rc; // + second K half
+        if ((rc = prefix_conv(ctx, E.ffn2a, Hd, P.F, 0, Y, X1, 0.f, 0, B, T, st, &E.ffn2b, 384))) return rc;   // x1 + conv_2, K = 768 as 2 x 384
         launch_ln_cm(Y, E.g2, E.b2, 1e-5f, X, B, P.H, T, st);
         cur = X;
     }

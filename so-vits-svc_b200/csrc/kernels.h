@@ -122,6 +122,9 @@ struct ConvNTC {
     // optional fused noise conv (polyphase mode): excitation window har[b, i*noise_stride + noise_w0 + u], u in [0,16)
     const float* har = nullptr; int har_N = 0; int noise_stride = 0, noise_w0 = 0;
     int noise_wide = 0;            // 1: window of up to 80 samples (64-sample + 16-sample panels) instead of 16
+    // optional second K chunk (input channels [k2_c0, k2_c0 + cinp) against the image w_k2) accumulated into the same
+    // accumulators before the epilogue: a 768-channel input as two operand tiles of 384 (single column chunk only)
+    const void* w_k2 = nullptr; int k2_c0 = 0;
     int out_relu = 0;              // plain mode: ReLU after everything else (FFN of enc_p, modules/attentions.py:343-346)
     float acc_scale = 1.f;         // the image holds w * 2^e (range normalisation at pack time); epilogues use acc * acc_scale
     // SnakeAlias fused into the loader (vdecoder/hifiganwithsnake/alias/act.py:109-129): A = SnakeAlias(x) per input channel

@@ -7,14 +7,18 @@
 // Layout: q, k, v, out are channel-major [B, C, T] fp32 (the reference's layout); head h owns channels [h*dk, (h+1)*dk).
 //
 // One CTA = one (128-query tile, head, utterance).  Two passes over the key tiles (128 keys each):
-//   pass 1: S = Q K^T on the tensor cores (M = 128 queries, N = 128 keys, K = dk = 96), epilogue keeps the running row
-//           maximum and the running sum of exponentials (scalar per row, no rescaling of an accumulator);
+//   pass 1: S = Q K^T on the tensor cores (M = 128 queries, N = 128 keys, K = dk = 96), the softmax warps keep a running
+//           row maximum and sum of exponentials (scalars per row, no accumulator to rescale);
 //   pass 2: S again, P = exp(S - max) / sum -> fp16 -> shared memory, O += P V on the tensor cores (N = 96, K = 128).
 // Recomputing S costs 2 x 2.3 GFLOP per layer at config 2 - nothing next to the [B,2,T,T] fp32 score tensor (47 MB) the
 // cuBLAS formulation wrote, re-read for the softmax and re-read again for P V.
-// Operands are staged by the worker warps straight from the fp32 tensors (coalesced along time) into K-major fp16 tiles
-// with the 128-byte hardware swizzle; K and V tiles are double-buffered so staging overlaps the MMAs.
-// TMEM: S at columns [0,128), O at [128,224).
+//
+// Warp roles (416 threads): warps 0-7 softmax / epilogue (warp w <-> TMEM lanes 32 (w%4), column half w/4),
+// warps 8-11 stagers (convert the fp32 K / V tiles of the NEXT step into K-major fp16 operand tiles while the current one
+// is being consumed; also the Q tile and the relative-key logits), warp 12 owns TMEM and issues the MMAs.
+// K tiles, V tiles and the S accumulators are double-buffered, so the three roles run concurrently (the first version did
+// staging, MMA and softmax one after the other with all eight worker warps: 101 us per layer at config 2).
+//   TMEM  S0 [0,128)  S1 [128,256)  O [256,352).
 #include "kernels.h"
 #include "tc_common.cuh"
 #include "../../include/sovits_b200.h"
@@ -25,8 +29,8 @@ using namespace tc;
 
 namespace {
 
-constexpr int AT_THREADS = 288;          // 8 worker warps + 1 MMA warp
-constexpr int AT_NWORK = 256;
+constexpr int AT_THREADS = 416;          // 8 softmax warps + 4 stager warps + 1 MMA warp
+constexpr int AT_NSOFT = 256, AT_NSTG = 128;
 constexpr int AT_DK = 96;
 constexpr int AT_RB = 128;
 constexpr int AT_PANEL = 128 * AT_RB;    // 128 rows x 64 fp16
@@ -37,10 +41,10 @@ constexpr uint32_t OFFA_K = OFFA_Q + 2 * AT_PANEL;         // 2 buffers x 2 pane
 constexpr uint32_t OFFA_P = OFFA_K + 4 * AT_PANEL;         // 2 panels (128 keys)
 constexpr uint32_t OFFA_V = OFFA_P + 2 * AT_PANEL;         // 2 buffers x 2 panels x 96 rows
 constexpr uint32_t OFFA_BAR = OFFA_V + 4 * AT_VPANEL;
-constexpr uint32_t OFFA_F = OFFA_BAR + 64;                 // floats: relk logits [128][9] | pband [128][9] | stats [2][128][2] | E_k, E_v [9][96] each
+constexpr uint32_t OFFA_F = OFFA_BAR + 128;                // floats: relk logits [128][9] | pband [128][9] | stats [2][128][2] | E_k, E_v [9][96] each
 constexpr uint32_t AT_NFLOAT = 128 * 9 * 2 + 2 * 128 * 2 + 2 * 9 * AT_DK;
 constexpr size_t AT_SMEM = 1024 + OFFA_F + AT_NFLOAT * 4;
-constexpr int COL_S = 0, COL_O = 128;
+constexpr int COL_S = 0, COL_O = 256;
 
 struct AttnParams {
     const float* q; const float* k; const float* v;   // channel-major bases of this layer's q / k / v ([B, ctot, T] each, may alias one tensor)
@@ -56,10 +60,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rel_kernel(const AttnParam
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw);
-    const uint32_t bar_w = base + OFFA_BAR;        // workers -> MMA: operands of the next step staged, S drained (256 arrivals)
-    const uint32_t bar_s = base + OFFA_BAR + 8;    // MMA -> workers: all MMAs issued so far complete (tcgen05.commit)
-    const uint32_t tmem_slot = base + OFFA_BAR + 16;
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + OFFA_BAR + 16);
+    const uint32_t bb = base + OFFA_BAR;
+    const uint32_t bar_q = bb;               // Q tile + relative-key logits staged             (128 stager arrivals)
+    const uint32_t bar_kfull = bb + 8;       // [2] K tile staged                                (128)
+    const uint32_t bar_kfree = bb + 24;      // [2] S-MMA that read the K buffer complete        (tcgen05.commit)
+    const uint32_t bar_vfull = bb + 40;      // [2] V^T tile staged                              (128)
+    const uint32_t bar_vfree = bb + 56;      // [2] O-MMA that read the V buffer complete        (commit)
+    const uint32_t bar_sfull = bb + 72;      // [2] S accumulator complete                       (commit)
+    const uint32_t bar_sfree = bb + 88;      // [2] S accumulator drained by the softmax warps   (256)
+    const uint32_t bar_pfull = bb + 104;     // P tile written                                   (256)
+    const uint32_t bar_pfree = bb + 112;     // O-MMA that read P complete                       (commit)
+    const uint32_t tmem_slot = bb + 120;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + OFFA_BAR + 120);
     float* s_relk = reinterpret_cast<float*>(sm + OFFA_F);   // [128][9]
     float* s_pband = s_relk + 128 * 9;                        // [128][9]
     float* s_stat = s_pband + 128 * 9;                        // [2 halves][128][max, sum]
@@ -74,90 +86,102 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rel_kernel(const AttnParam
     const int nt = (T + 127) / 128;
 
     if (tid == 0) {
-        mbar_init(bar_w, AT_NWORK);
-        mbar_init(bar_s, 1);
+        mbar_init(bar_q, AT_NSTG);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_kfull + 8 * s, AT_NSTG); mbar_init(bar_kfree + 8 * s, 1);
+            mbar_init(bar_vfull + 8 * s, AT_NSTG); mbar_init(bar_vfree + 8 * s, 1);
+            mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sfree + 8 * s, AT_NSOFT);
+        }
+        mbar_init(bar_pfull, AT_NSOFT);
+        mbar_init(bar_pfree, 1);
         fence_barrier_init();
     }
-    if (warp == 8) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+    if (warp == 12) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     for (int i = tid; i < 9 * AT_DK; i += AT_THREADS) { s_ek[i] = i < nb * AT_DK ? __ldg(p.ek + i) : 0.f; s_ev[i] = i < nb * AT_DK ? __ldg(p.ev + i) : 0.f; }
-    for (int i = tid; i < 128 * 9; i += AT_THREADS) { s_relk[i] = 0.f; s_pband[i] = 0.f; }
+    for (int i = tid; i < 128 * 9; i += AT_THREADS) s_pband[i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const size_t hb = ((size_t)b * p.ctot + (size_t)h * AT_DK) * (size_t)T;     // element offset of this (b, head)
 
-    if (warp == 8) {
+    if (warp == 12) {
         // ------------------------------------------------------------ MMA issuer
         if (elect_one()) {
             const uint64_t q_desc = make_smem_desc(base + OFFA_Q, AT_RB, 0);
             const uint64_t p_desc = make_smem_desc(base + OFFA_P, AT_RB, 0);
             constexpr uint32_t idesc_s = make_idesc_f16(128, 128);
             constexpr uint32_t idesc_o = make_idesc_f16(128, AT_DK);
-            uint32_t n_w = 0;
-            auto s_mma = [&](int jt) {                      // S = Q K_jt^T : K = 96 = panel 0 (4 K-steps) + half of panel 1 (2)
-                const uint64_t k_desc = make_smem_desc(base + OFFA_K + (jt & 1) * 2 * AT_PANEL, AT_RB, 0);
+            mbar_wait(bar_q, 0);
+            tc_fence_after();
+            uint32_t n_k[2] = {0u, 0u}, n_sf[2] = {0u, 0u}, n_v[2] = {0u, 0u}, n_p = 0;
+            int g = 0;                                        // S tiles issued so far (both passes): K / S buffer = g & 1
+            auto s_mma = [&]() {                              // S_g = Q K^T : K = 96 = panel 0 (4 K-steps) + half of panel 1 (2)
+                const int sb = g & 1;
+                mbar_wait(bar_kfull + 8 * sb, n_k[sb] & 1u); ++n_k[sb];
+                if (g >= 2) { mbar_wait(bar_sfree + 8 * sb, n_sf[sb] & 1u); ++n_sf[sb]; }
+                tc_fence_after();
+                const uint64_t k_desc = make_smem_desc(base + OFFA_K + sb * 2 * AT_PANEL, AT_RB, 0);
                 for (int pn = 0; pn < 2; ++pn)
                     for (int ks = 0; ks < (pn ? 2 : 4); ++ks)
-                        umma_f16(tmem_base + COL_S, q_desc + (uint64_t)((uint32_t)(pn * AT_PANEL + ks * 32) >> 4),
+                        umma_f16(tmem_base + COL_S + sb * 128, q_desc + (uint64_t)((uint32_t)(pn * AT_PANEL + ks * 32) >> 4),
                                  k_desc + (uint64_t)((uint32_t)(pn * AT_PANEL + ks * 32) >> 4), idesc_s, (pn | ks) ? 1u : 0u);
+                umma_commit(bar_sfull + 8 * sb);
+                umma_commit(bar_kfree + 8 * sb);
+                ++g;
             };
-            for (int pass = 0; pass < 2; ++pass) {
-                for (int jt = 0; jt <= nt; ++jt) {
-                    // step jt of a pass: [pass 2: O += P_{jt-1} V_{jt-1}]  then  S_jt  (jt < nt).  Step nt of the FIRST pass only consumes
-                    // the workers' last arrival (nothing to issue, nothing to signal).
-                    mbar_wait(bar_w, n_w & 1u); ++n_w;
-                    tc_fence_after();
-                    if (pass == 1 && jt > 0) {
-                        const uint64_t v_desc = make_smem_desc(base + OFFA_V + ((jt - 1) & 1) * 2 * AT_VPANEL, AT_RB, 0);
-                        for (int pn = 0; pn < 2; ++pn)
-                            for (int ks = 0; ks < 4; ++ks)
-                                umma_f16(tmem_base + COL_O, p_desc + (uint64_t)((uint32_t)(pn * AT_PANEL + ks * 32) >> 4),
-                                         v_desc + (uint64_t)((uint32_t)(pn * AT_VPANEL + ks * 32) >> 4), idesc_o, (jt > 1 || pn || ks) ? 1u : 0u);
-                    }
-                    if (jt < nt) s_mma(jt);
-                    if (!(pass == 0 && jt == nt)) umma_commit(bar_s);
-                }
+            auto o_mma = [&](int jt) {                        // O += P_jt V_jt
+                const int vb = jt & 1;
+                mbar_wait(bar_vfull + 8 * vb, n_v[vb] & 1u); ++n_v[vb];
+                mbar_wait(bar_pfull, n_p & 1u); ++n_p;
+                tc_fence_after();
+                const uint64_t v_desc = make_smem_desc(base + OFFA_V + vb * 2 * AT_VPANEL, AT_RB, 0);
+                for (int pn = 0; pn < 2; ++pn)
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_f16(tmem_base + COL_O, p_desc + (uint64_t)((uint32_t)(pn * AT_PANEL + ks * 32) >> 4),
+                                 v_desc + (uint64_t)((uint32_t)(pn * AT_VPANEL + ks * 32) >> 4), idesc_o, (jt > 0 || pn || ks) ? 1u : 0u);
+                umma_commit(bar_pfree);
+                umma_commit(bar_vfree + 8 * vb);
+            };
+            for (int jt = 0; jt < nt; ++jt) s_mma();                          // pass 1
+            for (int jt = 0; jt < nt; ++jt) {                                 // pass 2: S runs one tile ahead of O
+                if (jt == 0) s_mma();
+                if (jt + 1 < nt) s_mma();
+                o_mma(jt);
             }
         }
         __syncwarp();
-    } else {
-        // ------------------------------------------------------------ workers
-        const int q4 = warp & 3, hsel = warp >> 2;
-        const int row = 32 * q4 + lane;                    // query row of the tile == TMEM lane; also the key / channel row staged
-        const int ti = i0 + row;
-        const uint32_t tlane = tmem_base + ((uint32_t)(32 * q4) << 16);
+    } else if (warp >= 8) {
+        // ------------------------------------------------------------ stagers (128 threads): thread = row of the tile being staged
+        const int row = tid - 256;
         const uint32_t phase = swz_phase(row, AT_RB);
-        uint32_t n_s = 0;
-
-        // stage a [128 time steps][96 channels] tile of a channel-major tensor as a K-major operand (rows = time)
+        // a [128 time steps][96 channels] tile of a channel-major tensor -> K-major operand rows (rows = time)
         auto stage_rows = [&](const float* __restrict__ src, int t_first, uint32_t off, float* dots) {
             const int t = t_first + row;
             const bool tv = t < T;
-            const float* __restrict__ xt = src + hb + (size_t)(hsel * 48) * T + (tv ? t : 0);
-#pragma unroll
-            for (int c0 = 0; c0 < 48; c0 += 16) {
+            const float* __restrict__ xt = src + hb + (tv ? t : 0);
+#pragma unroll 2
+            for (int c0 = 0; c0 < AT_DK; c0 += 16) {
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = tv ? __ldg(xt + (size_t)(c0 + j) * T) : 0.f;
-                const int ch = hsel * 48 + c0;
                 if (dots) {
 #pragma unroll
                     for (int d = 0; d < 2 * AT_MAXW + 1; ++d) {       // rows d >= 2w+1 of E_k are zero
                         float acc = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc = fmaf(v[j], s_ek[d * AT_DK + ch + j], acc);
+                        for (int j = 0; j < 16; ++j) acc = fmaf(v[j], s_ek[d * AT_DK + c0 + j], acc);
                         dots[d] += acc;
                     }
                 }
-                uint8_t* prow = sm + off + (ch / 64) * AT_PANEL + row * AT_RB;
-                store_chunk8(prow, phase, (ch % 64) / 8, v, 0xffffffffu);
-                store_chunk8(prow, phase, (ch % 64) / 8 + 1, v + 8, 0xffffffffu);
+                uint8_t* prow = sm + off + (c0 / 64) * AT_PANEL + row * AT_RB;
+                store_chunk8(prow, phase, (c0 % 64) / 8, v, 0xffffffffu);
+                store_chunk8(prow, phase, (c0 % 64) / 8 + 1, v + 8, 0xffffffffu);
             }
         };
-        // stage V^T of a key tile: rows = 96 channels, K = 128 keys (two 64-key panels); a thread converts runs of 8 keys
+        // V^T of a key tile: rows = 96 channels, K = 128 keys (two 64-key panels); a thread converts runs of 8 keys
         auto stage_vt = [&](int j_first, uint32_t off) {
-            for (int it = tid; it < AT_DK * 16; it += AT_NWORK) {
+            for (int it = row; it < AT_DK * 16; it += AT_NSTG) {
                 const int c = it / 16, ck = it % 16;       // channel row, 8-key chunk
                 const int j = j_first + ck * 8;
                 const float* __restrict__ vp = p.v + hb + (size_t)c * T + j;
@@ -173,23 +197,43 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rel_kernel(const AttnParam
                 store_chunk8(prow, swz_phase(c, AT_RB), ck % 8, v, 0xffffffffu);
             }
         };
-
-        // Q tile + the relative-key logits q_i . E_k[d] (fp32, from the fp32 q)
-        {
+        {   // Q tile + the relative-key logits q_i . E_k[d] (fp32, from the fp32 q)
             float dots[2 * AT_MAXW + 1];
 #pragma unroll
             for (int d = 0; d < 2 * AT_MAXW + 1; ++d) dots[d] = 0.f;
             stage_rows(p.q, i0, OFFA_Q, dots);
 #pragma unroll
-            for (int d = 0; d < 2 * AT_MAXW + 1; ++d) atomicAdd(&s_relk[row * 9 + d], dots[d]);      // two channel halves per row
+            for (int d = 0; d < 2 * AT_MAXW + 1; ++d) s_relk[row * 9 + d] = dots[d];
+            fence_proxy_async();
+            mbar_arrive(bar_q);
         }
-        stage_rows(p.k, 0, OFFA_K, nullptr);
-        fence_proxy_async();
-        mbar_arrive(bar_w);
-        asm volatile("bar.sync 1, 256;" ::: "memory");        // relk logits of both halves are in shared memory
-        const float* __restrict__ relk = s_relk + row * 9;     // indexed by the (runtime) band position: stays in shared memory
-
+        uint32_t n_kf[2] = {0u, 0u}, n_vf[2] = {0u, 0u};
+        for (int g = 0; g < 2 * nt; ++g) {
+            const int jt = g < nt ? g : g - nt, sb = g & 1;
+            if (g >= 2) { mbar_wait(bar_kfree + 8 * sb, n_kf[sb] & 1u); ++n_kf[sb]; }
+            stage_rows(p.k, jt * 128, OFFA_K + sb * 2 * AT_PANEL, nullptr);
+            fence_proxy_async();
+            mbar_arrive(bar_kfull + 8 * sb);
+            if (g >= nt) {
+                const int vb = jt & 1;
+                if (jt >= 2) { mbar_wait(bar_vfree + 8 * vb, n_vf[vb] & 1u); ++n_vf[vb]; }
+                stage_vt(jt * 128, OFFA_V + vb * 2 * AT_VPANEL);
+                fence_proxy_async();
+                mbar_arrive(bar_vfull + 8 * vb);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ softmax / epilogue warps
+        const int q4 = warp & 3, hsel = warp >> 2;
+        const int row = 32 * q4 + lane;                    // query row of the tile == TMEM lane
+        const int ti = i0 + row;
+        const uint32_t tlane = tmem_base + ((uint32_t)(32 * q4) << 16);
+        const uint32_t phase = swz_phase(row, AT_RB);
+        mbar_wait(bar_q, 0);                               // relative-key logits visible
+        const float* __restrict__ relk = s_relk + row * 9; // indexed by the (runtime) band position: stays in shared memory
+        uint32_t n_s[2] = {0u, 0u}, n_pf = 0;
         float m_run = -3.0e38f, l_run = 0.f, m_row = 0.f, inv_l = 0.f;
+        int g = 0;
         for (int pass = 0; pass < 2; ++pass) {
             if (pass == 1) {
                 // combine the two column halves of every row: global maximum and sum
@@ -198,23 +242,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rel_kernel(const AttnParam
                 const float m0 = s_stat[row * 2], l0 = s_stat[row * 2 + 1], m1 = s_stat[(128 + row) * 2], l1 = s_stat[(128 + row) * 2 + 1];
                 m_row = fmaxf(m0, m1);
                 inv_l = 1.f / (l0 * __expf(m0 - m_row) + l1 * __expf(m1 - m_row));
-                stage_rows(p.k, 0, OFFA_K, nullptr);              // K_0 again (buffer 0 is free: every MMA of pass 1 has completed)
-                stage_vt(0, OFFA_V);
-                fence_proxy_async();
-                mbar_arrive(bar_w);
             }
-            for (int jt = 0; jt < nt; ++jt) {
-                if (jt + 1 < nt) stage_rows(p.k, (jt + 1) * 128, OFFA_K + ((jt + 1) & 1) * 2 * AT_PANEL, nullptr);
-                mbar_wait(bar_s, n_s & 1u); ++n_s;               // S_jt complete (and, in pass 2, O += P_{jt-1} V_{jt-1})
+            for (int jt = 0; jt < nt; ++jt, ++g) {
+                const int sb = g & 1;
+                mbar_wait(bar_sfull + 8 * sb, n_s[sb] & 1u); ++n_s[sb];
                 tc_fence_after();
-                if (pass == 1 && jt + 1 < nt) stage_vt((jt + 1) * 128, OFFA_V + ((jt + 1) & 1) * 2 * AT_VPANEL);
+                if (pass == 1 && jt > 0) { mbar_wait(bar_pfree, n_pf & 1u); ++n_pf; }     // O-MMA of the previous tile has read P
                 const int jbase = jt * 128 + hsel * 64;
                 float tmax = -3.0e38f;
 #pragma unroll 1
                 for (int cc = 0; cc < 64; cc += 32) {
                     uint32_t r0[16], r1[16];
-                    tmem_ld16(tlane + COL_S + hsel * 64 + cc, r0);
-                    tmem_ld16(tlane + COL_S + hsel * 64 + cc + 16, r1);
+                    tmem_ld16(tlane + COL_S + sb * 128 + hsel * 64 + cc, r0);
+                    tmem_ld16(tlane + COL_S + sb * 128 + hsel * 64 + cc + 16, r1);
                     tmem_ld_wait();
                     float sv[32];
 #pragma unroll
@@ -242,20 +282,20 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rel_kernel(const AttnParam
                         for (int e = 0; e < 32; ++e) {
                             pv[e] = __expf(sv[e] - m_row) * inv_l;
                             const int d = jbase + cc + e - ti + w;
-                            if (d >= 0 && d < nb && jbase + cc + e < T) s_pband[row * 9 + d] = pv[e];
+                            if ((unsigned)d < (unsigned)nb && jbase + cc + e < T) s_pband[row * 9 + d] = pv[e];
                         }
                         uint8_t* prow = sm + OFFA_P + hsel * AT_PANEL + row * AT_RB;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) store_chunk8(prow, phase, cc / 8 + g, pv + 8 * g, 0xffffffffu);
+                        for (int gq = 0; gq < 4; ++gq) store_chunk8(prow, phase, cc / 8 + gq, pv + 8 * gq, 0xffffffffu);
                     }
                 }
                 tc_fence_before();
-                fence_proxy_async();
-                mbar_arrive(bar_w);
+                if (pass == 1) { fence_proxy_async(); mbar_arrive(bar_pfull); }
+                mbar_arrive(bar_sfree + 8 * sb);
             }
         }
-        // final: O complete once the last commit lands
-        mbar_wait(bar_s, n_s & 1u); ++n_s;
+        // final: O complete once the last O-MMA has landed
+        mbar_wait(bar_pfree, n_pf & 1u); ++n_pf;
         tc_fence_after();
         asm volatile("bar.sync 1, 256;" ::: "memory");            // band probabilities of both halves visible
         {
@@ -285,7 +325,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rel_kernel(const AttnParam
     }
 
     __syncthreads();
-    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+    if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
     const uint32_t bar_tfull = bar_base + 40;            // [2] accumulator buffer complete
     const uint32_t bar_tempty = bar_base + 56;           // [2] accumulator buffer drained (256 arrivals)
     const uint32_t tmem_slot = bar_base + 72;
+    const uint32_t bar_adone = bar_base + 96;            // MMAs of a K chunk complete: the operand tile may be restaged
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - base));
     float* sbias = reinterpret_cast<float*>(sm + d.off_bias);
 
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
     const size_t chunk_bytes = (size_t)n_reg * SUB + (d.noise_np > 0 ? SUBN0 : 0) + (d.noise_np > 1 ? SUBN1 : 0);
     auto sb_bytes = [&](int idx) -> uint32_t { return idx < n_reg ? (uint32_t)SUB : (idx == n_reg ? (uint32_t)SUBN0 : (uint32_t)SUBN1); };
     const int RA = d.tout + (a.k - 1) * a.dil;            // A rows that feed valid output rows
+    const int nkc = a.w_k2 ? 2 : 1;                       // K chunks (operand tiles staged one after the other)
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -149,6 +151,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
             mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, CN_NWORK);
         }
         mbar_init(bar_a, CN_NWORK);
+        mbar_init(bar_adone, 1);
         fence_barrier_init();
     }
     if (warp == 8) { tmem_alloc(tmem_slot, d.tmem_cols); tmem_relinquish(); }
@@ -166,8 +169,9 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
     if (warp == 9) {
         // ------------------------------------------------------------ weight producer (whole warp converged, elected lane issues)
         int ring = 0;
+        for (int kc = 0; kc < nkc; ++kc)
         for (int c = c_lo; c < c_hi; ++c) {
-            const uint8_t* wsrc = static_cast<const uint8_t*>(a.w) + (size_t)c * chunk_bytes;
+            const uint8_t* wsrc = static_cast<const uint8_t*>(kc ? a.w_k2 : a.w) + (size_t)c * chunk_bytes;
             int idx = 0;
             uint32_t off = 0;
             while (idx < n_sb) {
@@ -198,13 +202,15 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
             const uint64_t a_step = (uint64_t)((uint32_t)(a.dil * G::RB) >> 4);
             const uint64_t sub16 = (uint64_t)((uint32_t)SUB >> 4);
             uint32_t ring = 0;
+            for (int kc = 0; kc < nkc; ++kc)
             for (int c = c_lo; c < c_hi; ++c) {
+                if (kc > 0) { mbar_wait(bar_a, kc & 1); tc_fence_after(); }     // operand tile of this K chunk staged
                 const int u = c - c_lo, buf = (d.nbuf > 1) ? (u & 1) : 0;
                 if (u >= d.nbuf) { mbar_wait(bar_tempty + 8 * buf, ((u / d.nbuf) - 1) & 1); tc_fence_after(); }
                 const uint32_t dcol = tmem_base + buf * d.bufcols;
                 uint64_t a_tap = make_smem_desc(a_base, G::RB, 0);
                 int pn = 0;
-                uint32_t acc = 0u;
+                uint32_t acc = kc > 0 ? 1u : 0u;
                 int idx = 0;
                 while (idx < n_sb) {
                     // same greedy grouping as the producer
@@ -252,13 +258,16 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                     umma_commit(bar_empty + 8 * s);
                     ++ring;
                 }
-                umma_commit(bar_tfull + 8 * buf);
+                if (kc + 1 < nkc) umma_commit(bar_adone); else umma_commit(bar_tfull + 8 * buf);
             }
         }
         __syncwarp();
     } else {
         // ------------------------------------------------------------ workers
         // (1) stage A = act(x)[rows][Cin] as fp16; row r <-> input index i0 - pad_left + r
+        for (int kc = 0; kc < nkc; ++kc) {
+        const int xc0 = kc ? a.k2_c0 : a.x_c0;
+        if (kc > 0) mbar_wait(bar_adone, (kc - 1) & 1);                     // the MMAs have consumed the previous operand tile
         if constexpr (SNAKE) {
             // SnakeAlias loader.  Per pass of GCH channels: (i) the fp32 window x[c][ti - 6 .. ] of the tile is staged in
             // shared memory with coalesced loads (indices clamped = replicate padding), (ii) every lane takes one channel
@@ -280,7 +289,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
             float f[12];
 #pragma unroll
             for (int j = 0; j < 12; ++j) f[j] = 2.f * __ldg(a.snake_filt + j);       // 2 x taps, see snake_run
-            const float* __restrict__ xb = a.x + ((size_t)b * a.x_ctot + a.x_c0) * (size_t)L;
+            const float* __restrict__ xb = a.x + ((size_t)b * a.x_ctot + xc0) * (size_t)L;
             const int cl = lane % GCH, rsel = lane / GCH;
             // rows past the activated ones are read by the MMAs of the tile's unused output rows: keep them finite (zero)
             for (int idx = tid; idx < G::NP * (AROWS - n_runs * SNK_RUN) * (G::RB / 16); idx += CN_NWORK) {
@@ -370,7 +379,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
             }
         } else {
             const bool view = a.view_tstride != 0;
-            const float* __restrict__ xb = view ? a.x + (size_t)b * a.view_bstride : a.x + ((size_t)b * a.x_ctot + a.x_c0) * (size_t)a.Tin;
+            const float* __restrict__ xb = view ? a.x + (size_t)b * a.view_bstride : a.x + ((size_t)b * a.x_ctot + xc0) * (size_t)a.Tin;
             for (int r = tid; r < RA; r += CN_NWORK) {
                 const int ti = i0 - a.pad_left + r;
                 const bool rv = (ti >= 0) && (ti < a.Tin);
@@ -429,6 +438,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
             fence_proxy_async();
             mbar_arrive(bar_a);
         }
+        }   // K chunks
         // (2) per-chunk epilogues
         const int q = warp & 3, hsel = warp >> 2;
         const int rib = 32 * q + lane;
@@ -637,6 +647,7 @@ int launch_convn_tc(const ConvNTC& a, cudaStream_t st) {
     if (a.NC % 16 || a.NC > 256 / mb || a.N_total % 16) return SVB_ERR_UNSUPPORTED;
     if (a.mode == 1 && !(a.s == 2 || a.s == 8)) return SVB_ERR_UNSUPPORTED;
     if (a.mode == 2 && (a.NC % 64)) return SVB_ERR_UNSUPPORTED;
+    if (a.w_k2 && (a.N_total > a.NC || a.har || snake)) return SVB_ERR_UNSUPPORTED;      // K chunking: one column chunk, plain loader
     if (snake) {
         if (a.view_tstride != 0 || a.in_act || !a.snake_invbeta || !a.snake_filt) return SVB_ERR_INVALID_ARG;
         switch (a.cinp) {
