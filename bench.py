@@ -453,7 +453,9 @@ def main():
                 "traffic": traffic_db.get(name), "launches_per_step": pr["count"] / nprof, "ms_per_step": pr["ms"] / nprof}
 
     if args.precision == "tc":
-        tensor_names = ["snake_conv", "pair_tc", "resblock_tc", "ups_tc", "flow_tc"] if snake else ["pair_tc", "resblock_tc", "ups_tc", "flow_tc"]
+        tensor_names = ["pair_tc", "resblock_tc", "ups_tc", "flow_tc", "enc_gemm", "enc_attn"]
+        if snake:
+            tensor_names.insert(0, "snake_conv")
     else:
         tensor_names = ["pair_f32"]
     entries = [e for e in (tensor_entry(n) for n in tensor_names) if e]
@@ -465,7 +467,7 @@ def main():
         e = hbm_entry(n)
         if e:
             secondary.append(e)
-    for nm in ("flow", "generator"):
+    for nm in ("enc_p", "flow", "generator"):
         pp = eng.profile_read(nm)
         if pp:
             secondary.append({"kernel": nm, "ms_per_step": pp["ms"] / max(1, pp["count"])})

@@ -550,6 +550,8 @@ int prefix_conv(svb_ctx* ctx, const ConvNW& W, const float* x, int x_ctot, int x
     a.chunks_per_cta = n_chunks >= 4 ? 2 : 1;
     a.seg[0].y = y; a.seg[0].y_ctot = W.N_total; a.seg[0].col0 = 0; a.seg[0].col1 = W.N_total;
     a.seg[0].res = res; a.seg[0].res_ctot = W.N_total; a.seg[0].beta = beta;
+    ProfScope ps(ctx, "enc_gemm", st, 2.0 * (double)W.cin_real * (W2 ? 2 : 1) * W.k * W.N_total * (double)T * B,
+                 ((double)W.cin_real * (W2 ? 2 : 1) + W.N_total) * (double)T * B * sizeof(float));
     const int rc = launch_convn_tc(a, st);
     return rc ? fail(ctx, rc, "prefix conv launch failed") : SVB_OK;
 }
@@ -1634,7 +1636,11 @@ int svb_enc_p(svb_ctx* ctx, const float* x_in, const float* z_noise, float noice
         AttnTC at;
         at.q = QKV; at.k = QKV + (size_t)P.H * T; at.v = QKV + (size_t)2 * P.H * T; at.ctot = 3 * P.H;
         at.ek = E.ek; at.ev = E.ev; at.out = A; at.out_ctot = P.H; at.B = B; at.T = T; at.heads = P.heads; at.dk = P.H / P.heads; at.window = P.window;
-        if ((rc = launch_attn_rel_tc(at, st))) return fail(ctx, rc, "attention kernel launch failed");
+        {
+            // 2 x (S = QK^T twice, P V once): 3 x 2 x T x T x dk per (batch, head)
+            ProfScope pa(ctx, "enc_attn", st, 3.0 * 2.0 * (double)T * T * at.dk * P.heads * B, 4.0 * P.H * (double)T * B * sizeof(float));
+            if ((rc = launch_attn_rel_tc(at, st))) return fail(ctx, rc, "attention kernel launch failed");
+        }
         if ((rc = prefix_conv(ctx, E.o, A, P.H, 0, Y, cur, 0.f, 0, B, T, st))) return rc;            // x + conv_o(attn)
         launch_ln_cm(Y, E.g1, E.b1, 1e-5f, X1, B, P.H, T, st);
         if ((rc = prefix_conv(ctx, E.ffn1, X1, P.H, 0, Hd, nullptr, 0.f, 1, B, T, st))) return rc;   // relu(conv_1)

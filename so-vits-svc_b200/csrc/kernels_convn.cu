@@ -380,14 +380,20 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
         } else {
             const bool view = a.view_tstride != 0;
             const float* __restrict__ xb = view ? a.x + (size_t)b * a.view_bstride : a.x + ((size_t)b * a.x_ctot + xc0) * (size_t)a.Tin;
-            for (int r = tid; r < RA; r += CN_NWORK) {
+            // one-block tiles (MB = 1) have ~130 rows for 256 loader threads: two threads share a row (half of the channels
+            // each) and keep 48 loads in flight, so the tile costs 2-4 global round trips instead of 6-12 (the small GEMMs of
+            // enc_p are a chain of such latencies: ~31 us per launch before, of which the loader was about a third)
+            constexpr int NSPLIT = (MB == 1 && (CINP % 32) == 0 && CINP >= 192) ? 2 : 1;
+            constexpr int RP = CN_NWORK / NSPLIT, CSPAN = CINP / NSPLIT;
+            const int cbeg = (tid / RP) * CSPAN;
+            for (int r = tid % RP; r < RA; r += RP) {
                 const int ti = i0 - a.pad_left + r;
                 const bool rv = (ti >= 0) && (ti < a.Tin);
                 const float* __restrict__ xt = xb + (rv && !view ? ti : 0);
                 const long long vbase = (long long)ti * a.view_tstride + a.view_off;
                 const uint32_t phase = swz_phase(r, G::RB);
-#pragma unroll 2
-                for (int c0 = 0; c0 < CINP; c0 += 16) {
+#pragma unroll NSPLIT == 2 ? 3 : 2
+                for (int c0 = cbeg; c0 < cbeg + CSPAN; c0 += 16) {
                     float v[16];
                     if (view) {
 #pragma unroll
@@ -533,6 +539,19 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                     // ---- plain: one column per output channel; up to two destination segments
                     const int n16 = ncols / 16;                                            // ncols is a multiple of 16
                     const int w_lo = hsel * ((n16 + 1) / 2) * 16, w_hi = hsel ? ncols : ((n16 + 1) / 2) * 16;
+                    // the residual of column group j0+16 is requested while group j0 is processed (one exposed global round
+                    // trip per row block instead of one per 16 columns)
+                    float rnext[16];
+                    auto issue_res = [&](int j0) {
+                        const int col0 = col_base + j0;
+                        const ConvNSeg& sg = (a.n_seg > 1 && col0 >= a.seg[1].col0) ? a.seg[1] : a.seg[0];
+                        if (rowok && sg.res && j0 < w_hi) {
+                            const float* __restrict__ rb_ = sg.res + ((size_t)b * sg.res_ctot + sg.res_c0 + (col0 - sg.col0)) * (size_t)a.Ty + i;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) rnext[j] = __ldg(rb_ + (size_t)j * a.Ty);
+                        }
+                    };
+                    issue_res(w_lo);
 #pragma unroll 1
                     for (int j0 = w_lo; j0 < w_hi; j0 += 16) {
                         uint32_t r[16];
@@ -542,11 +561,9 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                         float rr[16], oo[16];
                         const float* __restrict__ bt = (a.bias_t && rowok) ? a.bias_t + ((size_t)b * a.bias_t_ctot + a.bias_t_c0 + col0) * (size_t)a.Ty + i : nullptr;
                         float* __restrict__ yb = sg.y + ((size_t)b * sg.y_ctot + sg.y_c0 + (col0 - sg.col0)) * (size_t)a.Ty + (rowok ? i : 0);
-                        if (rowok && sg.res) {
-                            const float* __restrict__ rb_ = sg.res + ((size_t)b * sg.res_ctot + sg.res_c0 + (col0 - sg.col0)) * (size_t)a.Ty + i;
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) rr[j] = __ldg(rb_ + (size_t)j * a.Ty);
-                        }
+                        for (int j = 0; j < 16; ++j) rr[j] = rnext[j];
+                        issue_res(j0 + 16);
                         if (rowok && sg.beta != 0.f) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) oo[j] = yb[(size_t)j * a.Ty];
