@@ -39,7 +39,12 @@ class HostPipeline:
         self._slot = (k + 1) % self.depth
         host = (c, f0, uv, g)
         if self._in_dev[k] is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(self._in_dev[k], host)):
-            self._in_dev[k] = [torch.empty(h.shape, dtype=h.dtype, device=dev) for h in host]
+            if self._computed[k] is not None:
+                self._computed[k].synchronize()                       # (rare) shape change: the old buffers are still being read
+            with torch.cuda.stream(self.s_in):                        # blocks come from the COPY stream's pool: a block recycled from
+                self._in_dev[k] = [torch.empty(h.shape, dtype=h.dtype, device=dev) for h in host]   # the compute stream could still
+            for t in self._in_dev[k]:                                 # be in use by a kernel in flight there
+                t.record_stream(cur)
             self._computed[k] = None
         if self._computed[k] is not None:
             self.s_in.wait_event(self._computed[k])                   # the kernels that read this slot's inputs have finished
