@@ -1611,16 +1611,23 @@ int svb_enc_p(svb_ctx* ctx, const float* x_in, const float* z_noise, float noice
     cudaStream_t st = (cudaStream_t)stream;
     const Prefix& P = ctx->prefix;
     const size_t BT = (size_t)B * T, f = sizeof(float);
-    const size_t need = align_up(BT * 3 * P.H * f, 256) + 4 * align_up(BT * P.H * f, 256) + align_up(BT * P.F * f, 256) + align_up(BT * P.out2 * f, 256);
+    // fp16 tile images of q, k (32 KB per 128-row tile and head) and V^T (24 KB) for the attention kernel
+    const int tiles = (T + 127) / 128;
+    const size_t n_img = (size_t)B * P.heads * tiles;
+    const size_t img_bytes = align_up(n_img * 32768, 1024) * 2 + align_up(n_img * 24576, 1024);
+    const size_t need = img_bytes + 4 * align_up(BT * P.H * f, 256) + align_up(BT * P.F * f, 256) + align_up(BT * P.out2 * f, 256);
     if (ctx->ws_prefix.bytes < need) {
         if (ctx->ws_prefix.p) { CU(cudaStreamSynchronize(st)); CU(cudaFree(ctx->ws_prefix.p)); }
         ctx->ws_prefix.p = nullptr; ctx->ws_prefix.bytes = 0;
         CU(cudaMalloc(&ctx->ws_prefix.p, need));
         ctx->ws_prefix.bytes = need;
+        // rows of the last tile beyond T are never written by the projection GEMM: they must be finite (p = 0 multiplies them)
+        CU(cudaMemsetAsync(ctx->ws_prefix.p, 0, need, st));
     }
     char* wp = static_cast<char*>(ctx->ws_prefix.p);
+    char* q_img = wp; char* k_img = q_img + align_up(n_img * 32768, 1024); char* v_img = k_img + align_up(n_img * 32768, 1024);
+    wp += img_bytes;
     auto take = [&](size_t bytes) { char* r = wp; wp += align_up(bytes, 256); return reinterpret_cast<float*>(r); };
-    float* QKV = take(BT * 3 * P.H * f);
     float* A = take(BT * P.H * f);
     float* Y = take(BT * P.H * f);
     float* X1 = take(BT * P.H * f);
@@ -1632,9 +1639,18 @@ int svb_enc_p(svb_ctx* ctx, const float* x_in, const float* z_noise, float noice
     ProfScope ps(ctx, "enc_p", st, 0, 0);
     for (size_t l = 0; l < P.layers.size(); ++l) {
         const EncLayer& E = P.layers[l];
-        if ((rc = prefix_conv(ctx, E.qkv, cur, P.H, 0, QKV, nullptr, 0.f, 0, B, T, st))) return rc;
+        {   // q | k | v projection; the epilogue writes the attention kernel's fp16 operand tiles directly
+            ConvNTC a;
+            const ConvNW& W = E.qkv;
+            a.x = cur; a.x_ctot = P.H; a.cin_real = W.cin_real; a.cinp = W.cinp; a.Tin = T;
+            a.w = W.img; a.bias = W.bias; a.acc_scale = W.acc_scale; a.k = 1; a.pad_left = 0;
+            a.n_rows = T; a.N_total = W.N_total; a.NC = W.NC; a.chunks_per_cta = 1; a.Ty = T; a.B = B;
+            a.mode = 3; a.att_q = q_img; a.att_k = k_img; a.att_v = v_img; a.att_heads = P.heads; a.att_tiles = tiles;
+            ProfScope ps(ctx, "enc_gemm", st, 2.0 * P.H * 3.0 * P.H * (double)T * B, 0);
+            if ((rc = launch_convn_tc(a, st))) return fail(ctx, rc, "qkv projection launch failed");
+        }
         AttnTC at;
-        at.q = QKV; at.k = QKV + (size_t)P.H * T; at.v = QKV + (size_t)2 * P.H * T; at.ctot = 3 * P.H;
+        at.q_img = q_img; at.k_img = k_img; at.v_img = v_img;
         at.ek = E.ek; at.ev = E.ev; at.out = A; at.out_ctot = P.H; at.B = B; at.T = T; at.heads = P.heads; at.dk = P.H / P.heads; at.window = P.window;
         {
             // 2 x (S = QK^T twice, P V once): 3 x 2 x T x T x dk per (batch, head)

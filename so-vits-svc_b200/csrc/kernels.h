@@ -114,7 +114,11 @@ struct ConvNTC {
     int k = 1, dil = 1, pad_left = 0;
     int n_rows = 0;                // output rows (time steps of the GEMM's M dimension)
     int N_total = 0, NC = 0, chunks_per_cta = 1;
-    int mode = 0;                  // 0 plain (column == channel), 1 polyphase (column = co*s + phase), 2 tanh*sigmoid gate
+    int mode = 0;                  // 0 plain (column == channel), 1 polyphase (column = co*s + phase), 2 tanh*sigmoid gate,
+                                   // 3 attention operands: columns = [q | k | v] x heads x dk(96); the epilogue writes fp16 shared-memory
+                                   // IMAGES of the attention kernel's tiles (att_q / att_k: [b][head][tile][2 panels][128 rows][128 B],
+                                   // att_v: [b][head][tile][2 panels][96 rows][128 B] = V^T), swizzled, ready for 1-D bulk copies
+    void* att_q = nullptr; void* att_k = nullptr; void* att_v = nullptr; int att_heads = 0, att_tiles = 0;
     int s = 1, p = 0, Ty = 0;      // polyphase stride / padding; Ty = length of the output time axis
     ConvNSeg seg[2]; int n_seg = 1;
     const int32_t* lengths = nullptr;
@@ -162,8 +166,9 @@ void flow_layer_pack(const std::function<float(int, int)>& pre, const std::funct
 
 // ---- enc_p attention (kernels_attn.cu): windowed relative-position MHA on channel-major [B,C,T] tensors --------------------
 struct AttnTC {
-    const float* q = nullptr; const float* k = nullptr; const float* v = nullptr;   // bases of the q / k / v channel blocks, [B, ctot, T]
-    int ctot = 0;
+    // fp16 tile images written by the q/k/v projection GEMM (ConvNTC mode 3): q_img / k_img [B][heads][tiles][2][128][128 B],
+    // v_img [B][heads][tiles][2][96][128 B] (V^T), tiles = ceil(T / 128)
+    const void* q_img = nullptr; const void* k_img = nullptr; const void* v_img = nullptr;
     const float* ek = nullptr; const float* ev = nullptr;     // emb_rel_k / emb_rel_v [2*window+1][dk]
     float* out = nullptr; int out_ctot = 0;                   // [B, heads*dk, T]
     const int32_t* lengths = nullptr;

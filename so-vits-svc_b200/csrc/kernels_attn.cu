@@ -13,11 +13,12 @@
 // Recomputing S costs 2 x 2.3 GFLOP per layer at config 2 - nothing next to the [B,2,T,T] fp32 score tensor (47 MB) the
 // cuBLAS formulation wrote, re-read for the softmax and re-read again for P V.
 //
-// Warp roles (416 threads): warps 0-7 softmax / epilogue (warp w <-> TMEM lanes 32 (w%4), column half w/4),
-// warps 8-11 stagers (convert the fp32 K / V tiles of the NEXT step into K-major fp16 operand tiles while the current one
-// is being consumed; also the Q tile and the relative-key logits), warp 12 owns TMEM and issues the MMAs.
-// K tiles, V tiles and the S accumulators are double-buffered, so the three roles run concurrently (the first version did
-// staging, MMA and softmax one after the other with all eight worker warps: 101 us per layer at config 2).
+// Operands arrive ready-made: the q/k/v projection GEMM (convn epilogue mode 3) writes fp16 shared-memory IMAGES of this
+// kernel's tiles (Q / K: [128 rows][96 channels] as two swizzled K-major panels; V^T: [96 channels][128 keys]), so a tile is
+// ONE 1-D bulk TMA copy issued by a producer thread - no per-thread global loads or conversions here (versions 1 and 2
+// staged the fp32 tensors with the worker warps: 93-117 us per layer at config 2, bound by those load round trips).
+// Warp roles (320 threads): warps 0-7 softmax / epilogue (warp w <-> TMEM lanes 32 (w%4), column half w/4), warp 8 streams
+// the tiles (3-stage K ring, 2-stage V ring), warp 9 owns TMEM and issues the MMAs; S is double-buffered in TMEM.
 //   TMEM  S0 [0,128)  S1 [128,256)  O [256,352).
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -29,26 +30,27 @@ using namespace tc;
 
 namespace {
 
-constexpr int AT_THREADS = 416;          // 8 softmax warps + 4 stager warps + 1 MMA warp
-constexpr int AT_NSOFT = 256, AT_NSTG = 128;
+constexpr int AT_THREADS = 320;          // 8 softmax warps + producer warp + MMA warp
+constexpr int AT_NSOFT = 256;
+constexpr int AT_KST = 3;                // K ring stages
 constexpr int AT_DK = 96;
 constexpr int AT_RB = 128;
 constexpr int AT_PANEL = 128 * AT_RB;    // 128 rows x 64 fp16
 constexpr int AT_VPANEL = AT_DK * AT_RB; // V^T: 96 rows (channels) x 64 keys
 constexpr int AT_MAXW = 4;               // window <= 4 -> <= 9 band entries
 constexpr uint32_t OFFA_Q = 0;                              // 2 panels (64 + 32 channels)
-constexpr uint32_t OFFA_K = OFFA_Q + 2 * AT_PANEL;         // 2 buffers x 2 panels
-constexpr uint32_t OFFA_P = OFFA_K + 4 * AT_PANEL;         // 2 panels (128 keys)
+constexpr uint32_t OFFA_K = OFFA_Q + 2 * AT_PANEL;         // AT_KST buffers x 2 panels
+constexpr uint32_t OFFA_P = OFFA_K + AT_KST * 2 * AT_PANEL;   // 2 panels (128 keys)
 constexpr uint32_t OFFA_V = OFFA_P + 2 * AT_PANEL;         // 2 buffers x 2 panels x 96 rows
 constexpr uint32_t OFFA_BAR = OFFA_V + 4 * AT_VPANEL;
-constexpr uint32_t OFFA_F = OFFA_BAR + 128;                // floats: relk logits [128][9] | pband [128][9] | stats [2][128][2] | E_k, E_v [9][96] each
+constexpr uint32_t OFFA_F = OFFA_BAR + 160;                // floats: relk logits [128][9] | pband [128][9] | stats [2][128][2] | E_k, E_v [9][96] each
 constexpr uint32_t AT_NFLOAT = 128 * 9 * 2 + 2 * 128 * 2 + 2 * 9 * AT_DK;
 constexpr size_t AT_SMEM = 1024 + OFFA_F + AT_NFLOAT * 4;
 constexpr int COL_S = 0, COL_O = 256;
 
 struct AttnParams {
-    const float* q; const float* k; const float* v;   // channel-major bases of this layer's q / k / v ([B, ctot, T] each, may alias one tensor)
-    int ctot;
+    const uint8_t* q_img; const uint8_t* k_img; const uint8_t* v_img;   // fp16 tile images [b][head][tile][...] (convn mode 3)
+    int heads, tiles;
     const float* ek; const float* ev;                  // [2w+1][dk]
     float* out; int out_ctot;
     const int32_t* lengths;
@@ -61,17 +63,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rel_kernel(const AttnParam
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw);
     const uint32_t bb = base + OFFA_BAR;
-    const uint32_t bar_q = bb;               // Q tile + relative-key logits staged             (128 stager arrivals)
-    const uint32_t bar_kfull = bb + 8;       // [2] K tile staged                                (128)
-    const uint32_t bar_kfree = bb + 24;      // [2] S-MMA that read the K buffer complete        (tcgen05.commit)
-    const uint32_t bar_vfull = bb + 40;      // [2] V^T tile staged                              (128)
-    const uint32_t bar_vfree = bb + 56;      // [2] O-MMA that read the V buffer complete        (commit)
-    const uint32_t bar_sfull = bb + 72;      // [2] S accumulator complete                       (commit)
-    const uint32_t bar_sfree = bb + 88;      // [2] S accumulator drained by the softmax warps   (256)
-    const uint32_t bar_pfull = bb + 104;     // P tile written                                   (256)
-    const uint32_t bar_pfree = bb + 112;     // O-MMA that read P complete                       (commit)
-    const uint32_t tmem_slot = bb + 120;
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + OFFA_BAR + 120);
+    const uint32_t bar_q = bb;               // Q tile landed                                    (bulk-copy transaction bytes)
+    const uint32_t bar_kfull = bb + 8;       // [3] K tile landed                                (tx)
+    const uint32_t bar_kfree = bb + 32;      // [3] S-MMA that read the K buffer complete        (tcgen05.commit)
+    const uint32_t bar_vfull = bb + 56;      // [2] V^T tile landed                              (tx)
+    const uint32_t bar_vfree = bb + 72;      // [2] O-MMA that read the V buffer complete        (commit)
+    const uint32_t bar_sfull = bb + 88;      // [2] S accumulator complete                       (commit)
+    const uint32_t bar_sfree = bb + 104;     // [2] S accumulator drained by the softmax warps   (256)
+    const uint32_t bar_pfull = bb + 120;     // P tile written                                   (256)
+    const uint32_t bar_pfree = bb + 128;     // O-MMA that read P complete                       (commit)
+    const uint32_t tmem_slot = bb + 136;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + OFFA_BAR + 136);
     float* s_relk = reinterpret_cast<float*>(sm + OFFA_F);   // [128][9]
     float* s_pband = s_relk + 128 * 9;                        // [128][9]
     float* s_stat = s_pband + 128 * 9;                        // [2 halves][128][max, sum]
@@ -86,26 +88,26 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rel_kernel(const AttnParam
     const int nt = (T + 127) / 128;
 
     if (tid == 0) {
-        mbar_init(bar_q, AT_NSTG);
+        mbar_init(bar_q, 1);
+        for (int s = 0; s < AT_KST; ++s) { mbar_init(bar_kfull + 8 * s, 1); mbar_init(bar_kfree + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(bar_kfull + 8 * s, AT_NSTG); mbar_init(bar_kfree + 8 * s, 1);
-            mbar_init(bar_vfull + 8 * s, AT_NSTG); mbar_init(bar_vfree + 8 * s, 1);
+            mbar_init(bar_vfull + 8 * s, 1); mbar_init(bar_vfree + 8 * s, 1);
             mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sfree + 8 * s, AT_NSOFT);
         }
         mbar_init(bar_pfull, AT_NSOFT);
         mbar_init(bar_pfree, 1);
         fence_barrier_init();
     }
-    if (warp == 12) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     for (int i = tid; i < 9 * AT_DK; i += AT_THREADS) { s_ek[i] = i < nb * AT_DK ? __ldg(p.ek + i) : 0.f; s_ev[i] = i < nb * AT_DK ? __ldg(p.ev + i) : 0.f; }
-    for (int i = tid; i < 128 * 9; i += AT_THREADS) s_pband[i] = 0.f;
+    for (int i = tid; i < 128 * 9; i += AT_THREADS) { s_pband[i] = 0.f; s_relk[i] = 0.f; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    const size_t hb = ((size_t)b * p.ctot + (size_t)h * AT_DK) * (size_t)T;     // element offset of this (b, head)
+    const size_t bh = ((size_t)b * p.heads + h) * (size_t)p.tiles;             // first tile image of this (b, head)
 
-    if (warp == 12) {
+    if (warp == 9) {
         // ------------------------------------------------------------ MMA issuer
         if (elect_one()) {
             const uint64_t q_desc = make_smem_desc(base + OFFA_Q, AT_RB, 0);
@@ -114,20 +116,20 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rel_kernel(const AttnParam
             constexpr uint32_t idesc_o = make_idesc_f16(128, AT_DK);
             mbar_wait(bar_q, 0);
             tc_fence_after();
-            uint32_t n_k[2] = {0u, 0u}, n_sf[2] = {0u, 0u}, n_v[2] = {0u, 0u}, n_p = 0;
-            int g = 0;                                        // S tiles issued so far (both passes): K / S buffer = g & 1
+            uint32_t n_sf[2] = {0u, 0u}, n_v[2] = {0u, 0u}, n_p = 0;
+            int g = 0;                                        // S tiles issued so far (both passes): K stage = g % 3, S buffer = g & 1
             auto s_mma = [&]() {                              // S_g = Q K^T : K = 96 = panel 0 (4 K-steps) + half of panel 1 (2)
-                const int sb = g & 1;
-                mbar_wait(bar_kfull + 8 * sb, n_k[sb] & 1u); ++n_k[sb];
+                const int sb = g & 1, ks_ = g % AT_KST;
+                mbar_wait(bar_kfull + 8 * ks_, (uint32_t)(g / AT_KST) & 1u);
                 if (g >= 2) { mbar_wait(bar_sfree + 8 * sb, n_sf[sb] & 1u); ++n_sf[sb]; }
                 tc_fence_after();
-                const uint64_t k_desc = make_smem_desc(base + OFFA_K + sb * 2 * AT_PANEL, AT_RB, 0);
+                const uint64_t k_desc = make_smem_desc(base + OFFA_K + ks_ * 2 * AT_PANEL, AT_RB, 0);
                 for (int pn = 0; pn < 2; ++pn)
                     for (int ks = 0; ks < (pn ? 2 : 4); ++ks)
                         umma_f16(tmem_base + COL_S + sb * 128, q_desc + (uint64_t)((uint32_t)(pn * AT_PANEL + ks * 32) >> 4),
                                  k_desc + (uint64_t)((uint32_t)(pn * AT_PANEL + ks * 32) >> 4), idesc_s, (pn | ks) ? 1u : 0u);
                 umma_commit(bar_sfull + 8 * sb);
-                umma_commit(bar_kfree + 8 * sb);
+                umma_commit(bar_kfree + 8 * ks_);
                 ++g;
             };
             auto o_mma = [&](int jt) {                        // O += P_jt V_jt
@@ -151,77 +153,26 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rel_kernel(const AttnParam
             }
         }
         __syncwarp();
-    } else if (warp >= 8) {
-        // ------------------------------------------------------------ stagers (128 threads): thread = row of the tile being staged
-        const int row = tid - 256;
-        const uint32_t phase = swz_phase(row, AT_RB);
-        // a [128 time steps][96 channels] tile of a channel-major tensor -> K-major operand rows (rows = time)
-        auto stage_rows = [&](const float* __restrict__ src, int t_first, uint32_t off, float* dots) {
-            const int t = t_first + row;
-            const bool tv = t < T;
-            const float* __restrict__ xt = src + hb + (tv ? t : 0);
-#pragma unroll 2
-            for (int c0 = 0; c0 < AT_DK; c0 += 16) {
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = tv ? __ldg(xt + (size_t)(c0 + j) * T) : 0.f;
-                if (dots) {
-#pragma unroll
-                    for (int d = 0; d < 2 * AT_MAXW + 1; ++d) {       // rows d >= 2w+1 of E_k are zero
-                        float acc = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) acc = fmaf(v[j], s_ek[d * AT_DK + c0 + j], acc);
-                        dots[d] += acc;
-                    }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------ tile producer: one elected lane, 1-D bulk copies of tile images
+        constexpr uint32_t QK_BYTES = 2 * AT_PANEL, V_BYTES = 2 * AT_VPANEL;
+        if (elect_one()) {
+            mbar_arrive_expect_tx(bar_q, QK_BYTES);
+            bulk_g2s(base + OFFA_Q, p.q_img + (bh + blockIdx.x) * (size_t)QK_BYTES, QK_BYTES, bar_q);
+            for (int g = 0; g < 2 * nt; ++g) {
+                const int jt = g < nt ? g : g - nt, ks_ = g % AT_KST;
+                if (g >= AT_KST) mbar_wait(bar_kfree + 8 * ks_, (uint32_t)(g / AT_KST - 1) & 1u);
+                mbar_arrive_expect_tx(bar_kfull + 8 * ks_, QK_BYTES);
+                bulk_g2s(base + OFFA_K + ks_ * QK_BYTES, p.k_img + (bh + jt) * (size_t)QK_BYTES, QK_BYTES, bar_kfull + 8 * ks_);
+                if (g >= nt) {
+                    const int vb = jt & 1;
+                    if (jt >= 2) mbar_wait(bar_vfree + 8 * vb, (uint32_t)(jt / 2 - 1) & 1u);
+                    mbar_arrive_expect_tx(bar_vfull + 8 * vb, V_BYTES);
+                    bulk_g2s(base + OFFA_V + vb * V_BYTES, p.v_img + (bh + jt) * (size_t)V_BYTES, V_BYTES, bar_vfull + 8 * vb);
                 }
-                uint8_t* prow = sm + off + (c0 / 64) * AT_PANEL + row * AT_RB;
-                store_chunk8(prow, phase, (c0 % 64) / 8, v, 0xffffffffu);
-                store_chunk8(prow, phase, (c0 % 64) / 8 + 1, v + 8, 0xffffffffu);
-            }
-        };
-        // V^T of a key tile: rows = 96 channels, K = 128 keys (two 64-key panels); a thread converts runs of 8 keys
-        auto stage_vt = [&](int j_first, uint32_t off) {
-            for (int it = row; it < AT_DK * 16; it += AT_NSTG) {
-                const int c = it / 16, ck = it % 16;       // channel row, 8-key chunk
-                const int j = j_first + ck * 8;
-                const float* __restrict__ vp = p.v + hb + (size_t)c * T + j;
-                float v[8];
-                if (j + 7 < T && ((reinterpret_cast<uintptr_t>(vp) & 15u) == 0)) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(vp)), bq = __ldg(reinterpret_cast<const float4*>(vp) + 1);
-                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bq.x; v[5] = bq.y; v[6] = bq.z; v[7] = bq.w;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = (j + e < T) ? __ldg(vp + e) : 0.f;
-                }
-                uint8_t* prow = sm + off + (ck / 8) * AT_VPANEL + c * AT_RB;
-                store_chunk8(prow, swz_phase(c, AT_RB), ck % 8, v, 0xffffffffu);
-            }
-        };
-        {   // Q tile + the relative-key logits q_i . E_k[d] (fp32, from the fp32 q)
-            float dots[2 * AT_MAXW + 1];
-#pragma unroll
-            for (int d = 0; d < 2 * AT_MAXW + 1; ++d) dots[d] = 0.f;
-            stage_rows(p.q, i0, OFFA_Q, dots);
-#pragma unroll
-            for (int d = 0; d < 2 * AT_MAXW + 1; ++d) s_relk[row * 9 + d] = dots[d];
-            fence_proxy_async();
-            mbar_arrive(bar_q);
-        }
-        uint32_t n_kf[2] = {0u, 0u}, n_vf[2] = {0u, 0u};
-        for (int g = 0; g < 2 * nt; ++g) {
-            const int jt = g < nt ? g : g - nt, sb = g & 1;
-            if (g >= 2) { mbar_wait(bar_kfree + 8 * sb, n_kf[sb] & 1u); ++n_kf[sb]; }
-            stage_rows(p.k, jt * 128, OFFA_K + sb * 2 * AT_PANEL, nullptr);
-            fence_proxy_async();
-            mbar_arrive(bar_kfull + 8 * sb);
-            if (g >= nt) {
-                const int vb = jt & 1;
-                if (jt >= 2) { mbar_wait(bar_vfree + 8 * vb, n_vf[vb] & 1u); ++n_vf[vb]; }
-                stage_vt(jt * 128, OFFA_V + vb * 2 * AT_VPANEL);
-                fence_proxy_async();
-                mbar_arrive(bar_vfull + 8 * vb);
             }
         }
+        __syncwarp();
     } else {
         // ------------------------------------------------------------ softmax / epilogue warps
         const int q4 = warp & 3, hsel = warp >> 2;
@@ -229,7 +180,31 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rel_kernel(const AttnParam
         const int ti = i0 + row;
         const uint32_t tlane = tmem_base + ((uint32_t)(32 * q4) << 16);
         const uint32_t phase = swz_phase(row, AT_RB);
-        mbar_wait(bar_q, 0);                               // relative-key logits visible
+        mbar_wait(bar_q, 0);                               // Q tile landed
+        {   // relative-key logits q_i . E_k[d] from the fp16 q row (this thread: 48 of the 96 channels), halves combined in smem
+            float dots[2 * AT_MAXW + 1];
+#pragma unroll
+            for (int d = 0; d < 2 * AT_MAXW + 1; ++d) dots[d] = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < 48; cc += 8) {
+                const int ch = hsel * 48 + cc;
+                const uint4 raw4 = *reinterpret_cast<const uint4*>(sm + OFFA_Q + (ch / 64) * AT_PANEL + row * AT_RB + ((((uint32_t)(ch % 64) / 8u) ^ phase) << 4));
+                const __half2* h2 = reinterpret_cast<const __half2*>(&raw4);
+                float qv[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f2 = __half22float2(h2[e]); qv[2 * e] = f2.x; qv[2 * e + 1] = f2.y; }
+#pragma unroll
+                for (int d = 0; d < 2 * AT_MAXW + 1; ++d) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc = fmaf(qv[e], s_ek[d * AT_DK + ch + e], acc);
+                    dots[d] += acc;
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < 2 * AT_MAXW + 1; ++d) atomicAdd(&s_relk[row * 9 + d], dots[d]);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
         const float* __restrict__ relk = s_relk + row * 9; // indexed by the (runtime) band position: stays in shared memory
         uint32_t n_s[2] = {0u, 0u}, n_pf = 0;
         float m_run = -3.0e38f, l_run = 0.f, m_row = 0.f, inv_l = 0.f;
@@ -325,17 +300,20 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rel_kernel(const AttnParam
     }
 
     __syncthreads();
-    if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace
 
 int launch_attn_rel_tc(const AttnTC& a, cudaStream_t st) {
     if (a.dk != AT_DK || a.window < 0 || a.window > AT_MAXW || a.heads < 1 || a.T < 1) return SVB_ERR_UNSUPPORTED;
+    if (!a.q_img || !a.k_img || !a.v_img) return SVB_ERR_INVALID_ARG;
     static std::atomic<size_t> granted[SVB_MAX_DEV];
     if (ensure_dyn_smem(attn_rel_kernel, AT_SMEM, granted)) return SVB_ERR_CUDA;
     AttnParams p;
-    p.q = a.q; p.k = a.k; p.v = a.v; p.ctot = a.ctot; p.ek = a.ek; p.ev = a.ev; p.out = a.out; p.out_ctot = a.out_ctot;
+    p.q_img = static_cast<const uint8_t*>(a.q_img); p.k_img = static_cast<const uint8_t*>(a.k_img); p.v_img = static_cast<const uint8_t*>(a.v_img);
+    p.heads = a.heads; p.tiles = (a.T + 127) / 128;
+    p.ek = a.ek; p.ev = a.ev; p.out = a.out; p.out_ctot = a.out_ctot;
     p.lengths = a.lengths; p.T = a.T; p.window = a.window;
     dim3 grid((a.T + 127) / 128, a.heads, a.B);
     attn_rel_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(p);

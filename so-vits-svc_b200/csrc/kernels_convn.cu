@@ -462,7 +462,41 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                 const int i = i0 + mb * 128 + rib;                 // output row
                 const bool rowok = (i < a.n_rows) && (mb * 128 + rib < d.tout);
                 const uint32_t tcol = tlane + buf * d.bufcols + mb * d.blkcols;
-                if (a.mode == 2) {
+                if (a.mode == 3) {
+                    // ---- attention operand images (dk = 96: panel 0 = channels 0..63, panel 1 = 64..95 in 128-byte rows)
+                    const int w_lo = hsel * (ncols / 2), w_hi = (hsel + 1) * (ncols / 2);      // ncols = heads*96, a multiple of 32
+                    const int tile = i >> 7, trow = i & 127;
+#pragma unroll 1
+                    for (int j0 = w_lo; j0 < w_hi; j0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(tcol + j0, r);
+                        tmem_ld_wait();
+                        if (!rowok) continue;
+                        float v[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), a.acc_scale, cb_[j0 + j]);
+                        const int col0 = col_base + j0;                       // global column: [q | k | v] blocks of heads*96
+                        const int hd96 = a.att_heads * 96;
+                        const int which = col0 / hd96, hc = col0 % hd96, head = hc / 96, ch = hc % 96;     // 16 | 96: a group never straddles
+                        const size_t bh = ((size_t)b * a.att_heads + head) * a.att_tiles + tile;
+                        if (which < 2) {
+                            uint8_t* img = static_cast<uint8_t*>(which == 0 ? a.att_q : a.att_k) + bh * (size_t)(2 * 128 * 128);
+                            uint8_t* prow = img + (ch / 64) * (128 * 128) + trow * 128;
+                            const uint32_t phase = (uint32_t)trow & 7u;
+                            store_chunk8(prow, phase, (ch % 64) / 8, v, 0xffffffffu);
+                            store_chunk8(prow, phase, (ch % 64) / 8 + 1, v + 8, 0xffffffffu);
+                        } else {
+                            uint8_t* img = static_cast<uint8_t*>(a.att_v) + bh * (size_t)(2 * 96 * 128);
+                            const int kp = trow >> 6, kc = (trow & 63) >> 3, ko = (trow & 7) * 2;       // key panel, 8-key chunk, byte in chunk
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int c = ch + j;
+                                const __half hv = __float2half_rn(fminf(fmaxf(v[j], -65504.f), 65504.f));
+                                *reinterpret_cast<__half*>(img + kp * (96 * 128) + c * 128 + (((uint32_t)kc ^ ((uint32_t)c & 7u)) << 4) + ko) = hv;
+                            }
+                        }
+                    }
+                } else if (a.mode == 2) {
                     // ---- gate: cols [0,NC/2) = tanh pre-activations, [NC/2,NC) = sigmoid pre-activations of the same channels
                     const int hc = NC / 2;
                     const int j_lo = hsel * (hc / 2), j_hi = (hsel + 1) * (hc / 2);
@@ -664,6 +698,7 @@ int launch_convn_tc(const ConvNTC& a, cudaStream_t st) {
     if (a.NC % 16 || a.NC > 256 / mb || a.N_total % 16) return SVB_ERR_UNSUPPORTED;
     if (a.mode == 1 && !(a.s == 2 || a.s == 8)) return SVB_ERR_UNSUPPORTED;
     if (a.mode == 2 && (a.NC % 64)) return SVB_ERR_UNSUPPORTED;
+    if (a.mode == 3 && (!a.att_q || !a.att_k || !a.att_v || a.att_heads < 1 || a.NC != a.att_heads * 96 || a.N_total != 3 * a.NC)) return SVB_ERR_INVALID_ARG;
     if (a.w_k2 && (a.N_total > a.NC || a.har || snake)) return SVB_ERR_UNSUPPORTED;      // K chunking: one column chunk, plain loader
     if (snake) {
         if (a.view_tstride != 0 || a.in_act || !a.snake_invbeta || !a.snake_filt) return SVB_ERR_INVALID_ARG;
