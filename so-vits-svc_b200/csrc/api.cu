@@ -1644,7 +1644,9 @@ int svb_enc_p(svb_ctx* ctx, const float* x_in, const float* z_noise, float noice
             const ConvNW& W = E.qkv;
             a.x = cur; a.x_ctot = P.H; a.cin_real = W.cin_real; a.cinp = W.cinp; a.Tin = T;
             a.w = W.img; a.bias = W.bias; a.acc_scale = W.acc_scale; a.k = 1; a.pad_left = 0;
-            a.n_rows = T; a.N_total = W.N_total; a.NC = W.NC; a.chunks_per_cta = 1; a.Ty = T; a.B = B;
+            a.n_rows = T; a.N_total = W.N_total; a.NC = W.NC; a.Ty = T; a.B = B;
+            // one wave: 7 x 8 x 3 = 168 one-CTA-per-SM blocks would need two; with two chunks per CTA the grid is 112
+            a.chunks_per_cta = ((T + 127) / 128) * B * 3 > 148 ? 2 : 1;
             a.mode = 3; a.att_q = q_img; a.att_k = k_img; a.att_v = v_img; a.att_heads = P.heads; a.att_tiles = tiles;
             ProfScope ps(ctx, "enc_gemm", st, 2.0 * P.H * 3.0 * P.H * (double)T * B, 0);
             if ((rc = launch_convn_tc(a, st))) return fail(ctx, rc, "qkv projection launch failed");

@@ -105,7 +105,10 @@ __device__ __forceinline__ void snake_run(const float (&xw)[SNK_WIN], const floa
     }
 }
 
-template <int CINP, int MB, int MINB, bool SNAKE>
+// MODE is the epilogue (ConvNTC::mode) as a template parameter: the small latency-bound launches of the prior encoder execute
+// every instruction once per CTA, and ncu showed "no instruction" (fetch) stalls second only to scoreboard waits with all four
+// epilogues in one body; VIEW = strided-view loader (stage-0 noise conv) compiled in.
+template <int CINP, int MB, int MINB, bool SNAKE, int MODE, bool VIEW>
 __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNTC a, const ConvNDev d) {
     using G = CNGeom<CINP>;
     constexpr int R1 = 128 * MB;
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                         bd += sub16;
                         if (++pn == G::NP) { pn = 0; a_tap += a_step; }
                     }
-                    if (idx > n_reg) {
+                    if (MODE == 1 && idx > n_reg) {
                         // excitation (noise_convs) panels: narrower rows, own swizzle width
                         uint32_t boff = (uint32_t)(g_reg > g0 ? (g_reg - g0) : 0) * (uint32_t)SUB;
                         for (int sb = (g0 > n_reg ? g0 : n_reg); sb < idx; ++sb) {
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
-        } else if (a.view_tstride == CINP && a.view_cstride == 1 && CINP == 64 && (a.view_off & 3) == 0 && (a.view_bstride & 3) == 0 && !a.in_act) {
+        } else if (VIEW && a.view_tstride == CINP && a.view_cstride == 1 && CINP == 64 && (a.view_off & 3) == 0 && (a.view_bstride & 3) == 0 && !a.in_act) {
             // Strided view whose rows tile a CONTIGUOUS range (row r = samples [r*64 + off, +64) of a 1-channel signal: the
             // stage-0 noise_convs as a 2-tap GEMM over 64-sample rows).  Element (r, c) = flat[r*64 + c]: load the range with
             // coalesced 128-bit loads along the flat index and drop each group of 4 samples into its half-chunk of the tile.
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                 *reinterpret_cast<uint2*>(pdst) = make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
             }
         } else {
-            const bool view = a.view_tstride != 0;
+            const bool view = VIEW && a.view_tstride != 0;
             const float* __restrict__ xb = view ? a.x + (size_t)b * a.view_bstride : a.x + ((size_t)b * a.x_ctot + xc0) * (size_t)a.Tin;
             // one-block tiles (MB = 1) have ~130 rows for 256 loader threads: two threads share a row (half of the channels
             // each) and keep 48 loads in flight, so the tile costs 2-4 global round trips instead of 6-12 (the small GEMMs of
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
             }
         }
         {
-            if (d.noise_np) {
+            if (MODE == 1 && d.noise_np) {
                 // excitation window of output row i: har[i*noise_stride + noise_w0 + u]; panel 0 holds u in [0, rb0/2),
                 // panel 1 the next rb1/2 samples
                 const float* __restrict__ hb = a.har + (size_t)b * a.har_N;
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                 const int i = i0 + mb * 128 + rib;                 // output row
                 const bool rowok = (i < a.n_rows) && (mb * 128 + rib < d.tout);
                 const uint32_t tcol = tlane + buf * d.bufcols + mb * d.blkcols;
-                if (a.mode == 3) {
+                if constexpr (MODE == 3) {
                     // ---- attention operand images (dk = 96: panel 0 = channels 0..63, panel 1 = 64..95 in 128-byte rows)
                     const int w_lo = hsel * (ncols / 2), w_hi = (hsel + 1) * (ncols / 2);      // ncols = heads*96, a multiple of 32
                     const int tile = i >> 7, trow = i & 127;
@@ -496,7 +499,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                             }
                         }
                     }
-                } else if (a.mode == 2) {
+                } else if constexpr (MODE == 2) {
                     // ---- gate: cols [0,NC/2) = tanh pre-activations, [NC/2,NC) = sigmoid pre-activations of the same channels
                     const int hc = NC / 2;
                     const int j_lo = hsel * (hc / 2), j_hi = (hsel + 1) * (hc / 2);
@@ -519,7 +522,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                             }
                         }
                     }
-                } else if (a.mode == 1) {
+                } else if constexpr (MODE == 1) {
                     // ---- polyphase: column = co*s + phase; output index n = i*s + phase - p (s is 2 or 8)
                     const ConvNSeg& sg = a.seg[0];
                     const int n16 = ncols / 16;
@@ -630,8 +633,8 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
 
 int pow2ceil(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 
-template <int CINP, int MB, int MINB, bool SNAKE>
-int launch_convn_t(const ConvNTC& a, cudaStream_t st) {
+template <int CINP, int MB, int MINB, bool SNAKE, int MODE, bool VIEW>
+int launch_convn_m(const ConvNTC& a, cudaStream_t st) {
     using G = CNGeom<CINP>;
     int halo = ((a.k - 1) * a.dil + 7) & ~7;
     if (halo < CN_HALO_MIN) halo = CN_HALO_MIN;
@@ -678,11 +681,28 @@ int launch_convn_t(const ConvNTC& a, cudaStream_t st) {
     const size_t smem = 1024 + off;
     if (smem > 227 * 1024) return SVB_ERR_UNSUPPORTED;
     static std::atomic<size_t> granted[SVB_MAX_DEV];
-    if (ensure_dyn_smem(convn_tc_kernel<CINP, MB, MINB, SNAKE>, smem, granted)) return SVB_ERR_CUDA;
+    if (ensure_dyn_smem(convn_tc_kernel<CINP, MB, MINB, SNAKE, MODE, VIEW>, smem, granted)) return SVB_ERR_CUDA;
     dim3 grid((a.n_rows + d.tout - 1) / d.tout, a.B, (n_chunks + cpc - 1) / cpc);
-    convn_tc_kernel<CINP, MB, MINB, SNAKE><<<grid, CN_THREADS, smem, st>>>(a, d);
+    convn_tc_kernel<CINP, MB, MINB, SNAKE, MODE, VIEW><<<grid, CN_THREADS, smem, st>>>(a, d);
     launch_counter()++;
     return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;
+}
+
+// which epilogues exist per operand width: plain everywhere; polyphase for the upsamplers (512..32); gate (unfused flow) and
+// attention images (q/k/v projection) for the 192-channel layers; the strided view only for the 64-channel stage-0 noise conv
+template <int CINP, int MB, int MINB, bool SNAKE>
+int launch_convn_t(const ConvNTC& a, cudaStream_t st) {
+    constexpr bool POLY = (CINP == 512 || CINP == 256 || CINP == 128 || CINP == 64 || CINP == 32);
+    if (a.mode == 0) {
+        if constexpr (CINP == 64 && !SNAKE) { if (a.view_tstride != 0) return launch_convn_m<CINP, MB, MINB, SNAKE, 0, true>(a, st); }
+        if (a.view_tstride != 0) return SVB_ERR_UNSUPPORTED;
+        return launch_convn_m<CINP, MB, MINB, SNAKE, 0, false>(a, st);
+    }
+    if (a.view_tstride != 0) return SVB_ERR_UNSUPPORTED;
+    if (a.mode == 1) { if constexpr (POLY) return launch_convn_m<CINP, MB, MINB, SNAKE, 1, false>(a, st); }
+    if (a.mode == 2) { if constexpr (CINP == 192 && !SNAKE) return launch_convn_m<CINP, MB, MINB, SNAKE, 2, false>(a, st); }
+    if (a.mode == 3) { if constexpr (CINP == 192 && !SNAKE) return launch_convn_m<CINP, MB, MINB, SNAKE, 3, false>(a, st); }
+    return SVB_ERR_UNSUPPORTED;
 }
 
 }  // namespace
