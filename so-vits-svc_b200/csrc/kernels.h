@@ -196,6 +196,18 @@ inline int ensure_dyn_smem(K kernel, size_t bytes, std::atomic<size_t>* granted)
     }
     return 0;
 }
+// Number of SMs of the current device (persistent kernels size their grid by it); 148 if the query fails.
+inline int sm_count() {
+    static std::atomic<int> cached[SVB_MAX_DEV];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= SVB_MAX_DEV) return 148;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
 int& sticky_launch_error();   // set by void launchers whose set-up failed (read + cleared by check_launch in api.cu)
 
 }  // namespace svb

@@ -46,6 +46,7 @@ struct ResblockParams {
     uint32_t epoch; int skew_clk;    // first-wave de-phasing (tc_common.cuh)
     int red_old;                     // beta == 1 handled with red.global.add instead of load + store
     int stage_bytes, nstage;         // block-skewed kernel: weight ring geometry (a stage holds one whole conv)
+    int tiles_per_item, B;           // block-skewed kernel: persistent tile list (item-major)
 };
 __device__ unsigned long long g_rb_ticket[256];
 
@@ -386,6 +387,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
     constexpr int AROWS = R1 + 2 * RBK_PAD;
     constexpr int TMEM_COLS = 2 * MB * C;
     constexpr int ACC0 = MB * C;
+    constexpr int NBG = MB / 2;                      // row blocks per worker group
     static_assert(MB >= 2 && MB <= 8 && MB % 2 == 0, "block-skewed ResBlock kernel: 2..8 row blocks");
     static_assert(C == 16 || C == 32 || C == 64, "block-skewed ResBlock kernel serves C <= 64");
 
@@ -402,18 +404,37 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
     float* sbias = reinterpret_cast<float*>(sm + (bar_base + 256 - base));     // [6][C]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.y;
     const int k = p.k;
     const int TOUT = R1 - 2 * p.halo;
-    const int tt0 = blockIdx.x * TOUT - p.halo;
-    const float* __restrict__ xb = p.x + (size_t)b * C * p.T;
-    float* __restrict__ ob = p.out + (size_t)b * C * p.T;
+    // Persistent tile loop: CTA c owns the tiles c, c + gridDim.x, ... of the (item, tile) list.  The load of the next tile's
+    // block b is issued by the thread that has just finished the last epilogue of block b, so the x read, the output
+    // reduction and the first MMAs of the next tile overlap the tail of this one inside the CTA (before: load + final
+    // epilogue = 16 k of a 53 k clk tile with the tensor pipe idle unless the co-resident CTA happened to be in an MMA phase).
+    const int ntile = p.tiles_per_item * p.B;
+    const int niter = (ntile - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (tid == 0) {
         dephase_first_wave(g_rb_ticket, p.epoch, p.skew_clk, MINB);
         for (int s = 0; s < 2; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int m = 0; m < MB; ++m) { mbar_init(bar_a + 8 * m, RBK_NWORK / 2); mbar_init(bar_acc + 8 * m, 1); }
         fence_barrier_init();
+    }
+    // The first x tile of a worker (its row of every block its group owns, all channels) is requested before the set-up
+    // barrier: one HBM latency per tile instead of one per block.
+    float xin[NBG * C];
+    if (warp < 8) {
+        const int grp0 = warp >> 2, rib0 = 32 * (warp & 3) + lane;
+        const int g0 = (int)blockIdx.x;
+        const int tt00 = (g0 % p.tiles_per_item) * TOUT - p.halo;
+        const float* __restrict__ xb0 = p.x + (size_t)(g0 / p.tiles_per_item) * C * p.T;
+#pragma unroll
+        for (int i = 0; i < NBG; ++i) {
+            const int t = tt00 + (grp0 + 2 * i) * 128 + rib0;
+            const bool valid = (t >= 0) && (t < p.T);
+            const float* __restrict__ xt = xb0 + (valid ? t : 0);
+#pragma unroll
+            for (int c = 0; c < C; ++c) xin[i * C + c] = valid ? __ldg(xt + (size_t)c * p.T) : 0.f;
+        }
     }
     if (warp == 8) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
     for (int i = tid; i < 6 * C; i += RBK_THREADS) sbias[i] = __ldg(p.bias[i / C] + (i % C));
@@ -426,8 +447,10 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
         // ------------------------------------------------------------ weight producer: one ring stage per conv
         // (with a single stage - C = 64, k = 11 - conv q+1 can only be fetched once conv q has been consumed)
         const int ns = p.nstage;
-        for (int q = 0; q < 6; ++q) {
-            const int s = q % ns, use = q / ns;
+        const int nconv = 6 * niter;
+        for (int gq = 0; gq < nconv; ++gq) {
+            const int q = gq % 6;
+            const int s = gq % ns, use = gq / ns;
             if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
             const uint32_t bytes = (uint32_t)k * G::SUB;
             if (elect_one()) {
@@ -441,9 +464,11 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
         constexpr uint32_t idesc = make_idesc_f16(128, C);
         const int h = (k - 1) / 2;
         if (elect_one()) {
-            for (int q = 0; q < 6; ++q) {
-                const uint32_t s = (uint32_t)(q % p.nstage), par = (uint32_t)q & 1u;
-                mbar_wait(bar_full + 8 * s, (uint32_t)(q / p.nstage) & 1u);
+            const int nconv = 6 * niter;
+            int q = 0;
+            for (int gq = 0; gq < nconv; ++gq, q = (q == 5 ? 0 : q + 1)) {
+                const uint32_t s = (uint32_t)(gq % p.nstage), par = (uint32_t)q & 1u;
+                mbar_wait(bar_full + 8 * s, (uint32_t)(gq / p.nstage) & 1u);
                 const int cd = (q & 1) ? 1 : p.dil[q >> 1];
                 const uint64_t a_step = (uint64_t)((uint32_t)(cd * G::RB) >> 4);
                 const uint64_t a_q = make_smem_desc(a_base + (uint32_t)(RBK_PAD - h * cd) * G::RB, G::RB, 0);
@@ -474,42 +499,32 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
         // ------------------------------------------------------------ workers
         // Two worker groups of four warps: group g owns the row blocks mb = g, g+2, ... and all C channels of its row.  A
         // block's epilogue is one dependent chain (barrier -> tcgen05.ld -> math -> st.shared -> fences -> arrive) of several
-        // hundred cycles; with all eight warps on the same block the chains of consecutive blocks were serialised and, for the
-        // short k = 3 / C <= 32 convolutions, longer than the MMAs they feed (ncu: tensor pipe 6-13 % active, stalls spread over
-        // scoreboard waits).  Two blocks in flight halve that critical path.
+        // hundred cycles; two blocks in flight halve that critical path.
         const int q4 = warp & 3, grp = warp >> 2;
         const int rib = 32 * q4 + lane;
         constexpr int CH = C;
         constexpr int CG = 16;
         const uint32_t tlane = tmem_base + ((uint32_t)(32 * q4) << 16);
-        const int cbase = 0;
 
         for (int i = tid; i < 2 * RBK_PAD * (G::RB / 16); i += RBK_NWORK) {
             const int rr = i / (G::RB / 16), ch = i % (G::RB / 16);
             const int row = rr < RBK_PAD ? rr : (R1 + rr);
             *reinterpret_cast<uint4*>(sm + swz_offset(row, ch, G::RB)) = make_uint4(0, 0, 0, 0);
         }
-        // round 0: load x (fp32 -> TMEM residual, lrelu -> fp16 operand rows), two row blocks per batch
-#pragma unroll 1
-        for (int mb = grp; mb < MB; mb += 2) {
-            const int t = tt0 + mb * 128 + rib;
-            const bool valid = (t >= 0) && (t < p.T);
-            const float* __restrict__ xt = xb + (valid ? t : 0);
+        // x rows of one block: fp32 -> TMEM residual, lrelu -> fp16 operand rows, then hand the block to the issuer
+        auto put_block = [&](int mb, const float* v) {
             const int row = mb * 128 + rib;
             uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
             const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
-#pragma unroll 2
-            for (int cc = 0; cc < CH; cc += CG) {
-                float v[16];
 #pragma unroll
-                for (int j = 0; j < CG; ++j) v[j] = valid ? __ldg(xt + (size_t)(cc + j) * p.T) : 0.f;
+            for (int cc = 0; cc < CH; cc += CG) {
                 uint32_t r[16];
 #pragma unroll
-                for (int j = 0; j < CG; ++j) r[j] = __float_as_uint(v[j]);
+                for (int j = 0; j < CG; ++j) r[j] = __float_as_uint(v[cc + j]);
                 tmem_st16(tlane + mb * C + cc, r);
                 float w[16];
 #pragma unroll
-                for (int j = 0; j < CG; ++j) w[j] = lrelu01(v[j]);
+                for (int j = 0; j < CG; ++j) w[j] = lrelu01(v[cc + j]);
                 store_chunk8(prow, phase, cc / 8, w, 0xffffffffu);
                 store_chunk8(prow, phase, cc / 8 + 1, w + 8, 0xffffffffu);
             }
@@ -517,117 +532,140 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(bar_a + 8 * mb);
-        }
+        };
+#pragma unroll
+        for (int i = 0; i < NBG; ++i) put_block(grp + 2 * i, xin + i * C);
 
         const bool red_old = p.red_old != 0;
         const bool ld_old = p.beta != 0.f && !red_old;
 #pragma unroll 1
-        for (int q = 0; q < 6; ++q) {
-            const uint32_t par = (uint32_t)q & 1u;
-            const float* __restrict__ bq_ = sbias + q * C;
-            const float inv_q = p.inv[q >> 1];
+        for (int it = 0; it < niter; ++it) {
+            const int g = (int)blockIdx.x + it * (int)gridDim.x;
+            const int tt0 = (g % p.tiles_per_item) * TOUT - p.halo;
+            float* __restrict__ ob = p.out + (size_t)(g / p.tiles_per_item) * C * p.T;
+            const bool has_next = it + 1 < niter;
+            const int gn = g + (int)gridDim.x;
+            const int tt0n = (gn % p.tiles_per_item) * TOUT - p.halo;
+            const float* __restrict__ xbn = p.x + (size_t)(has_next ? gn / p.tiles_per_item : 0) * C * p.T;
 #pragma unroll 1
-            for (int mb = grp; mb < MB; mb += 2) {
-                mbar_wait(bar_acc + 8 * mb, par);
-                if (q < 5 && mb + 1 < MB) mbar_wait(bar_acc + 8 * (mb + 1), par);   // MMA(mb+1, q) still reads rows of this block
-                tc_fence_after();
-                const int row = mb * 128 + rib;
-                const int t = tt0 + row;
-                const uint32_t keep = ((t >= 0) && (t < p.T)) ? 0xffffffffu : 0u;
-                uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
-                const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
-                if ((q & 1) == 0) {
-                    // first conv of a pair: mid = lrelu(acc + b1) -> operand rows (two column groups per TMEM round trip)
+            for (int q = 0; q < 6; ++q) {
+                const uint32_t par = (uint32_t)q & 1u;
+                const float* __restrict__ bq_ = sbias + q * C;
+                const float inv_q = p.inv[q >> 1];
+#pragma unroll 1
+                for (int mb = grp; mb < MB; mb += 2) {
+                    float xn[C];
+                    if (q == 5 && has_next) {
+                        // next tile, same block: the loads fly while this block's output is reduced into HBM
+                        const int tn = tt0n + mb * 128 + rib;
+                        const bool valid = (tn >= 0) && (tn < p.T);
+                        const float* __restrict__ xt = xbn + (valid ? tn : 0);
 #pragma unroll
-                    for (int cc = 0; cc < CH; cc += 2 * CG) {
-                        uint32_t r0[16], r1[16];
-                        constexpr bool dummy_two = true;
-                        const bool two = dummy_two && (cc + CG) < CH;
-                        tmem_ld16(tlane + ACC0 + mb * C + cc, r0);
-                        if (two) tmem_ld16(tlane + ACC0 + mb * C + cc + CG, r1);
-                        tmem_ld_wait();
+                        for (int c = 0; c < C; ++c) xn[c] = valid ? ldg_nc_v(xt + (size_t)c * p.T) : 0.f;
+                    }
+                    mbar_wait(bar_acc + 8 * mb, par);
+                    if (q < 5 && mb + 1 < MB) mbar_wait(bar_acc + 8 * (mb + 1), par);   // MMA(mb+1, q) still reads rows of this block
+                    tc_fence_after();
+                    const int row = mb * 128 + rib;
+                    const int t = tt0 + row;
+                    const uint32_t keep = ((t >= 0) && (t < p.T)) ? 0xffffffffu : 0u;
+                    uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
+                    const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
+                    if ((q & 1) == 0) {
+                        // first conv of a pair: mid = lrelu(acc + b1) -> operand rows (two column groups per TMEM round trip)
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            if (g == 1 && !two) break;
-                            const int c0 = cc + g * CG;
-                            const uint32_t* rr = g ? r1 : r0;
+                        for (int cc = 0; cc < CH; cc += 2 * CG) {
+                            uint32_t r0[16], r1[16];
+                            const bool two = (cc + CG) < CH;
+                            tmem_ld16(tlane + ACC0 + mb * C + cc, r0);
+                            if (two) tmem_ld16(tlane + ACC0 + mb * C + cc + CG, r1);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int gg = 0; gg < 2; ++gg) {
+                                if (gg == 1 && !two) break;
+                                const int c0 = cc + gg * CG;
+                                const uint32_t* rr = gg ? r1 : r0;
+                                float v[16];
+#pragma unroll
+                                for (int j4 = 0; j4 < CG; j4 += 4) {
+                                    const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
+                                    v[j4 + 0] = lrelu01(__uint_as_float(rr[j4 + 0]) + bb.x);
+                                    v[j4 + 1] = lrelu01(__uint_as_float(rr[j4 + 1]) + bb.y);
+                                    v[j4 + 2] = lrelu01(__uint_as_float(rr[j4 + 2]) + bb.z);
+                                    v[j4 + 3] = lrelu01(__uint_as_float(rr[j4 + 3]) + bb.w);
+                                }
+                                store_chunk8(prow, phase, c0 / 8, v, keep);
+                                store_chunk8(prow, phase, c0 / 8 + 1, v + 8, keep);
+                            }
+                        }
+                        tc_fence_before();
+                        fence_proxy_async();
+                        mbar_arrive(bar_a + 8 * mb);
+                    } else if (q < 5) {
+                        // second conv of pair 0/1: x <- x + acc + b2 (TMEM), operand rows <- lrelu(x)
+#pragma unroll
+                        for (int cc = 0; cc < CH; cc += CG) {
+                            uint32_t r[16], xr[16];
+                            tmem_ld16(tlane + ACC0 + mb * C + cc, r);
+                            tmem_ld16(tlane + mb * C + cc, xr);
+                            tmem_ld_wait();
                             float v[16];
 #pragma unroll
                             for (int j4 = 0; j4 < CG; j4 += 4) {
-                                const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
-                                v[j4 + 0] = lrelu01(__uint_as_float(rr[j4 + 0]) + bb.x);
-                                v[j4 + 1] = lrelu01(__uint_as_float(rr[j4 + 1]) + bb.y);
-                                v[j4 + 2] = lrelu01(__uint_as_float(rr[j4 + 2]) + bb.z);
-                                v[j4 + 3] = lrelu01(__uint_as_float(rr[j4 + 3]) + bb.w);
+                                const float4 bb = *reinterpret_cast<const float4*>(bq_ + cc + j4);
+                                v[j4 + 0] = fmaf(__uint_as_float(r[j4 + 0]), inv_q, bb.x) + __uint_as_float(xr[j4 + 0]);
+                                v[j4 + 1] = fmaf(__uint_as_float(r[j4 + 1]), inv_q, bb.y) + __uint_as_float(xr[j4 + 1]);
+                                v[j4 + 2] = fmaf(__uint_as_float(r[j4 + 2]), inv_q, bb.z) + __uint_as_float(xr[j4 + 2]);
+                                v[j4 + 3] = fmaf(__uint_as_float(r[j4 + 3]), inv_q, bb.w) + __uint_as_float(xr[j4 + 3]);
                             }
-                            store_chunk8(prow, phase, c0 / 8, v, keep);
-                            store_chunk8(prow, phase, c0 / 8 + 1, v + 8, keep);
+#pragma unroll
+                            for (int j = 0; j < CG; ++j) xr[j] = __float_as_uint(v[j]);
+                            tmem_st16(tlane + mb * C + cc, xr);
+#pragma unroll
+                            for (int j = 0; j < CG; ++j) v[j] = lrelu01(v[j]);
+                            store_chunk8(prow, phase, cc / 8, v, keep);
+                            store_chunk8(prow, phase, cc / 8 + 1, v + 8, keep);
                         }
-                    }
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(bar_a + 8 * mb);
-                } else if (q < 5) {
-                    // second conv of pair 0/1: x <- x + acc + b2 (TMEM), operand rows <- lrelu(x)
+                        tmem_st_wait();
+                        tc_fence_before();
+                        fence_proxy_async();
+                        mbar_arrive(bar_a + 8 * mb);
+                    } else {
+                        // last conv: out = alpha*(x + acc + b2) (+ beta*out_old) for the interior rows
+                        const bool wr = (t >= 0) && (t < p.T) && (row >= p.halo) && (row < R1 - p.halo);
+                        float* __restrict__ ot = ob + (wr ? t : 0);
 #pragma unroll
-                    for (int cc = 0; cc < CH; cc += CG) {
-                        const int c0 = cbase + cc;
-                        uint32_t r[16], xr[16];
-                        if (CG == 16) { tmem_ld16(tlane + ACC0 + mb * C + c0, r); tmem_ld16(tlane + mb * C + c0, xr); }
-                        else { tmem_ld8(tlane + ACC0 + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r)); tmem_ld8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(xr)); }
-                        tmem_ld_wait();
-                        float v[16];
+                        for (int cc = 0; cc < CH; cc += CG) {
+                            uint32_t r[16], xr[16];
+                            float oo[16];
+                            tmem_ld16(tlane + ACC0 + mb * C + cc, r);
+                            tmem_ld16(tlane + mb * C + cc, xr);
+                            if (wr && ld_old) {
 #pragma unroll
-                        for (int j4 = 0; j4 < CG; j4 += 4) {
-                            const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
-                            v[j4 + 0] = fmaf(__uint_as_float(r[j4 + 0]), inv_q, bb.x) + __uint_as_float(xr[j4 + 0]);
-                            v[j4 + 1] = fmaf(__uint_as_float(r[j4 + 1]), inv_q, bb.y) + __uint_as_float(xr[j4 + 1]);
-                            v[j4 + 2] = fmaf(__uint_as_float(r[j4 + 2]), inv_q, bb.z) + __uint_as_float(xr[j4 + 2]);
-                            v[j4 + 3] = fmaf(__uint_as_float(r[j4 + 3]), inv_q, bb.w) + __uint_as_float(xr[j4 + 3]);
-                        }
+                                for (int j = 0; j < CG; ++j) oo[j] = ot[(size_t)(cc + j) * p.T];
+                            }
+                            tmem_ld_wait();
+                            if (wr) {
 #pragma unroll
-                        for (int j = 0; j < CG; ++j) xr[j] = __float_as_uint(v[j]);
-                        if (CG == 16) tmem_st16(tlane + mb * C + c0, xr);
-                        else tmem_st8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(xr));
+                                for (int j4 = 0; j4 < CG; j4 += 4) {
+                                    const float4 bb = *reinterpret_cast<const float4*>(bq_ + cc + j4);
+                                    const float b4[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                        for (int j = 0; j < CG; ++j) v[j] = lrelu01(v[j]);
-                        store_chunk8(prow, phase, c0 / 8, v, keep);
-                        if (CG == 16) store_chunk8(prow, phase, c0 / 8 + 1, v + 8, keep);
-                    }
-                    tmem_st_wait();
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(bar_a + 8 * mb);
-                } else {
-                    // last conv: out = alpha*(x + acc + b2) (+ beta*out_old) for the interior rows
-                    const bool wr = (t >= 0) && (t < p.T) && (row >= p.halo) && (row < R1 - p.halo);
-                    float* __restrict__ ot = ob + (wr ? t : 0);
-#pragma unroll
-                    for (int cc = 0; cc < CH; cc += CG) {
-                        const int c0 = cbase + cc;
-                        uint32_t r[16], xr[16];
-                        float oo[16];
-                        if (CG == 16) { tmem_ld16(tlane + ACC0 + mb * C + c0, r); tmem_ld16(tlane + mb * C + c0, xr); }
-                        else { tmem_ld8(tlane + ACC0 + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(r)); tmem_ld8(tlane + mb * C + c0, reinterpret_cast<uint32_t(&)[8]>(xr)); }
-                        if (wr && ld_old) {
-#pragma unroll
-                            for (int j = 0; j < CG; ++j) oo[j] = ot[(size_t)(c0 + j) * p.T];
-                        }
-                        tmem_ld_wait();
-                        if (wr) {
-#pragma unroll
-                            for (int j4 = 0; j4 < CG; j4 += 4) {
-                                const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
-                                const float b4[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const int j = j4 + e;
-                                    float y = p.alpha * (fmaf(__uint_as_float(r[j]), inv_q, b4[e]) + __uint_as_float(xr[j]));
-                                    if (ld_old) y = fmaf(p.beta, oo[j], y);
-                                    if (red_old) atomicAdd(ot + (size_t)(c0 + j) * p.T, y);
-                                    else ot[(size_t)(c0 + j) * p.T] = y;
+                                    for (int e = 0; e < 4; ++e) {
+                                        const int j = j4 + e;
+                                        float y = p.alpha * (fmaf(__uint_as_float(r[j]), inv_q, b4[e]) + __uint_as_float(xr[j]));
+                                        if (ld_old) y = fmaf(p.beta, oo[j], y);
+                                        if (red_old) atomicAdd(ot + (size_t)(cc + j) * p.T, y);
+                                        else ot[(size_t)(cc + j) * p.T] = y;
+                                    }
                                 }
                             }
+                        }
+                        if (has_next) {
+                            // rows of this block are still read by the last MMAs of blocks mb-1 .. mb+1 of this tile
+                            if (mb + 1 < MB) mbar_wait(bar_acc + 8 * (mb + 1), par);
+                            tc_fence_after();
+                            put_block(mb, xn);
                         }
                     }
                 }
@@ -688,6 +726,14 @@ int launch_resblock_t(const ResblockTC& a, cudaStream_t st) {
     if (TOUT < 64) return SVB_ERR_UNSUPPORTED;
     dim3 grid((a.T + TOUT - 1) / TOUT, a.B);
     p.stage_bytes = stage_bytes; p.nstage = nstage;
+    p.tiles_per_item = (int)grid.x; p.B = a.B;
+    if (SKEW) {
+        // persistent: one CTA per resident slot walks the (item, tile) list; SVB_RB_PERSIST=0 launches one CTA per tile
+        static const int env_persist = rb_env_int("SVB_RB_PERSIST", 1);
+        const int ntile = (int)grid.x * a.B;
+        const int slots = sm_count() * MINB;
+        grid = dim3(env_persist ? (ntile < slots ? ntile : slots) : ntile, 1);
+    }
     kernel<<<grid, RBK_THREADS, smem_run, st>>>(p);
     launch_counter()++;
     return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;

@@ -110,6 +110,13 @@ __device__ __forceinline__ void dephase_first_wave(unsigned long long* ctr, uint
     spin_clocks((int)(((unsigned long long)h * (unsigned long long)period_clk) >> 16));
 }
 
+// Read-only global load the compiler may not move across barrier waits (prefetch of the next tile).
+__device__ __forceinline__ float ldg_nc_v(const float* ptr) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(ptr));
+    return v;
+}
+
 // ---- tcgen05 -------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {   // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");

@@ -13,7 +13,8 @@ for step in "$@"; do
     tests)   timeout 1500 python -m pytest tests -q -m gpu -s --timeout 600 > gpurun_out/test_gpu.log 2>&1; echo "tests rc=$?"; grep -E "passed|failed|error" gpurun_out/test_gpu.log | tail -3 ;;
     testsx)  timeout 1500 python -m pytest tests -q -m gpu -x -s --timeout 600 -k "${SVB_K:-}" > gpurun_out/test_gpu_k.log 2>&1; echo "testsx rc=$?"; tail -15 gpurun_out/test_gpu_k.log ;;
     bench)   timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"; cat gpurun_out/bench_default.json ;;
-    benchq)  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "benchq rc=$?"; cat gpurun_out/bench_quick.json ;;
+    benchq)  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "benchq rc=$?"; python tools/bench_brief.py gpurun_out/bench_quick.json ;;
+    benchq0) SVB_RB_PERSIST=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick0.json 2> gpurun_out/bench_quick0.err; echo "benchq0 rc=$?"; python tools/bench_brief.py gpurun_out/bench_quick0.json ;;
     snake)   timeout 600 python bench.py --vocoder nsf-snake-hifigan --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_snake.json 2> gpurun_out/bench_snake.err; echo "snake rc=$?"; cat gpurun_out/bench_snake.json ;;
     flow5)   timeout 300 python bench.py --workload flow5 --steps 20 --warmup 3 > gpurun_out/bench_flow5.json 2> gpurun_out/bench_flow5.err; echo "flow5 rc=$?"; cat gpurun_out/bench_flow5.json ;;
     refcuda) timeout 600 python bench.py --impl reference-cuda --steps 3 --warmup 2 > gpurun_out/bench_refcuda.json 2> gpurun_out/bench_refcuda.err; echo "refcuda rc=$?"; cat gpurun_out/bench_refcuda.json ;;
