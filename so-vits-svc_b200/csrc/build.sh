@@ -11,5 +11,7 @@ for f in kernels_f32 kernels_tc kernels_convn kernels_resblock kernels_flow kern
     $NVCC $FLAGS ${EXTRA_NVCC_FLAGS} -c $f.cu -o build/$f.o
   fi
 done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT build/kernels_f32.o build/kernels_tc.o build/kernels_convn.o build/kernels_resblock.o build/kernels_flow.o build/kernels_attn.o build/kernels_prefix.o build/api.o -lcudart
+# link next to the target and rename: a snapshot taken while we build never sees a half-written library
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT.tmp build/kernels_f32.o build/kernels_tc.o build/kernels_convn.o build/kernels_resblock.o build/kernels_flow.o build/kernels_attn.o build/kernels_prefix.o build/api.o -lcudart
+mv -f $OUT.tmp $OUT
 echo "built $OUT"

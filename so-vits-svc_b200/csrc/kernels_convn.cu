@@ -65,7 +65,8 @@ struct ConvNDev {                     // launch-time geometry (host computed)
 template <bool EDGE, typename Emit>
 __device__ __forceinline__ void snake_run(const float (&xw)[SNK_WIN], const float (&f)[12], float ea2, float hib, int t0, int L,
                                           float s0, float sL, Emit&& emit) {
-    // f holds 2 x the filter taps (the gain of the zero-stuffing upsampler folded in, exact); the low-pass sum is halved
+    // f holds 2 x the filter taps (the gain of the zero-stuffing upsampler folded in, exact); the low-pass therefore returns
+    // 2 y, and the factor 1/2 rides on the accumulator scale of the convolution that consumes the operand
     float s[12];
     auto s_val = [&](int jj) -> float {
         // m = 2*t0 - 5 + jj;  jj even -> m odd (a = t0 - 3 + jj/2), jj odd -> m even (a = t0 - 2 + (jj-1)/2)
@@ -96,8 +97,7 @@ __device__ __forceinline__ void snake_run(const float (&xw)[SNK_WIN], const floa
         s[11] = s_val(2 * i + 11);
         float acc = f[0] * s[0];
 #pragma unroll
-        for (int j = 1; j < 12; ++j) acc = fmaf(f[j], s[j], acc);
-        acc *= 0.5f;
+        for (int j = 1; j < 12; ++j) acc = fmaf(f[j], s[j], acc);       // = 2 y[t0 + i]: launch_convn_tc halves acc_scale (exact)
         if (EDGE) { const int t = t0 + i; if (t < 0 || t >= L) acc = 0.f; }
         emit(i, acc);
 #pragma unroll
@@ -302,16 +302,25 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                 *reinterpret_cast<uint4*>(sm + pn * APANEL + swz_offset(r, ch, G::RB)) = make_uint4(0, 0, 0, 0);
             }
             float nxt[CPW][NQ];                                // the next pass's samples, in flight
+            // interior tiles (every staged index inside [0, L)) read with constant offsets from one pointer per channel; only
+            // the first / last tiles of a sequence pay for the clamps (ncu: the staging was 17 % of the executed instructions)
+            const bool ld_inner = (tlo >= 0) && (tlo + 32 * NQ <= L);
             auto prefetch = [&](int cg0) {
 #pragma unroll
                 for (int cc = 0; cc < CPW; ++cc) {
                     const int c = cg0 + warp + 8 * cc;
                     const bool cv = c < a.cin_real;
                     const float* __restrict__ xc = xb + (size_t)(cv ? c : 0) * L;
+                    if (ld_inner) {
+                        const float* __restrict__ xl = xc + tlo + lane;
 #pragma unroll
-                    for (int u = 0; u < NQ; ++u) {
-                        const int ti = min(max(tlo + lane + 32 * u, 0), L - 1);
-                        nxt[cc][u] = cv ? __ldg(xc + ti) : 0.f;
+                        for (int u = 0; u < NQ; ++u) nxt[cc][u] = cv ? __ldg(xl + 32 * u) : 0.f;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < NQ; ++u) {
+                            const int ti = min(max(tlo + lane + 32 * u, 0), L - 1);
+                            nxt[cc][u] = cv ? __ldg(xc + ti) : 0.f;
+                        }
                     }
                 }
             };
@@ -326,7 +335,8 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (cg0 + GCH < CINP) prefetch(cg0 + GCH);
                 const int c = cg0 + cl;
-                const float ea2 = 2.f * __ldg(a.snake_ealpha + min(c, a.cin_real - 1));
+                float ea2 = 2.f * __ldg(a.snake_ealpha + min(c, a.cin_real - 1));
+                asm volatile("" : "+f"(ea2));          // keep the product: otherwise every sample pays an extra u + u
                 const float hib = 0.5f * __ldg(a.snake_invbeta + min(c, a.cin_real - 1));
                 const float* __restrict__ xrow = xs + cl * XP;
                 float s0 = 0.f, sL = 0.f;
@@ -435,6 +445,7 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
                         for (int uu = 0; uu < 16; ++uu) {
                             const long long hi = h0 + uu;
                             v[uu] = (hi >= 0 && hi < a.har_N) ? __ldg(hb + hi) : 0.f;
+                            if (SNAKE) v[uu] *= 2.f;           // same factor as the 2 x activation the SnakeAlias loader stages
                         }
                         uint8_t* prow = sm + d.off_noise[pnn] + r * rbn;
                         const uint32_t phase = swz_phase(r, rbn);
@@ -722,13 +733,15 @@ int launch_convn_tc(const ConvNTC& a, cudaStream_t st) {
     if (a.w_k2 && (a.N_total > a.NC || a.har || snake)) return SVB_ERR_UNSUPPORTED;      // K chunking: one column chunk, plain loader
     if (snake) {
         if (a.view_tstride != 0 || a.in_act || !a.snake_invbeta || !a.snake_filt) return SVB_ERR_INVALID_ARG;
+        ConvNTC h = a;
+        h.acc_scale = 0.5f * a.acc_scale;        // the SnakeAlias loader stages 2 x the activation (snake_run)
         switch (a.cinp) {
-            case 512: return launch_convn_t<512, 1, 1, true>(a, st);
-            case 256: return launch_convn_t<256, 1, 1, true>(a, st);
-            case 128: return launch_convn_t<128, 1, 2, true>(a, st);
-            case 64: return launch_convn_t<64, 2, 2, true>(a, st);
-            case 32: return launch_convn_t<32, 2, 2, true>(a, st);
-            case 16: return launch_convn_t<16, 2, 2, true>(a, st);
+            case 512: return launch_convn_t<512, 1, 1, true>(h, st);
+            case 256: return launch_convn_t<256, 1, 1, true>(h, st);
+            case 128: return launch_convn_t<128, 1, 2, true>(h, st);
+            case 64: return launch_convn_t<64, 2, 2, true>(h, st);
+            case 32: return launch_convn_t<32, 2, 2, true>(h, st);
+            case 16: return launch_convn_t<16, 2, 2, true>(h, st);
             default: return SVB_ERR_UNSUPPORTED;
         }
     }

@@ -31,8 +31,12 @@ constexpr int RBK_PAD = 32;          // >= max |tap offset| = 5*5 = 25
 #ifdef SVB_TRACE
 __device__ long long* g_rb_trace = nullptr;
 #define RB_TRACE(slot) do { if (g_rb_trace) g_rb_trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + (slot)] = clock64(); } while (0)
+// block-skewed kernel (tools/bench_rbskew.cu): 256 slots per CTA, [q][mb][what] of the CTA's SECOND tile (steady state);
+// what = 0 issuer about to issue MMA(q, mb), 1 worker starts waiting for the accumulators, 2 sees them, 3 has handed the block on
+#define SK_TRACE(it, q, mb, w) do { if (g_rb_trace && (it) == 1) g_rb_trace[(size_t)blockIdx.x * 256 + (((q) * 8 + (mb)) * 4 + (w))] = clock64(); } while (0)
 #else
 #define RB_TRACE(slot) do { } while (0)
+#define SK_TRACE(it, q, mb, w) do { } while (0)
 #endif
 
 struct ResblockParams {
@@ -47,6 +51,7 @@ struct ResblockParams {
     int red_old;                     // beta == 1 handled with red.global.add instead of load + store
     int stage_bytes, nstage;         // block-skewed kernel: weight ring geometry (a stage holds one whole conv)
     int tiles_per_item, B;           // block-skewed kernel: persistent tile list (item-major)
+    int pf_q;                        // conv index at which the next tile is prefetched into L2 (-1: off)
 };
 __device__ unsigned long long g_rb_ticket[256];
 
@@ -478,6 +483,11 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                     if (mb == 0) { mbar_wait(bar_a, par); mbar_wait(bar_a + 8, par); }
                     else if (mb + 1 < MB) mbar_wait(bar_a + 8 * (mb + 1), par);
                     tc_fence_after();
+                    SK_TRACE(gq / 6, q, mb, 0);
+#ifdef SVB_TRACE
+                    if (g_rb_trace && q == 0 && mb == 0 && gq / 6 < 8) g_rb_trace[(size_t)blockIdx.x * 256 + 200 + gq / 6] = clock64();   // tile starts
+                    if (g_rb_trace && gq == 0) { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); g_rb_trace[(size_t)blockIdx.x * 256 + 255] = smid; }
+#endif
                     uint64_t ad = a_q + (uint64_t)(((uint32_t)(mb * 128) * G::RB) >> 4);
                     uint64_t bd = b_q;
                     uint32_t acc = 0u;
@@ -555,6 +565,16 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
 #pragma unroll 1
                 for (int mb = grp; mb < MB; mb += 2) {
                     float xn[C];
+                    if (q == p.pf_q && has_next) {
+                        // pull the next tile's lines of this warp into L2 two convolutions ahead (no registers held): the
+                        // demand loads below then pay an L2 hit instead of a loaded-DRAM round trip
+                        const int tw = tt0n + mb * 128 + 32 * q4;                 // first time step of this warp's rows
+#pragma unroll
+                        for (int c = lane; c < 2 * C; c += 32) {
+                            const int tp = tw + ((c >= C) ? 31 : 0);              // the 32 steps may straddle two 128-byte lines
+                            if (tp >= 0 && tp < p.T) prefetch_l2(xbn + (size_t)(c % C) * p.T + tp);
+                        }
+                    }
                     if (q == 5 && has_next) {
                         // next tile, same block: the loads fly while this block's output is reduced into HBM
                         const int tn = tt0n + mb * 128 + rib;
@@ -563,9 +583,11 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
 #pragma unroll
                         for (int c = 0; c < C; ++c) xn[c] = valid ? ldg_nc_v(xt + (size_t)c * p.T) : 0.f;
                     }
+                    if (q4 == 0 && lane == 0) SK_TRACE(it, q, mb, 1);
                     mbar_wait(bar_acc + 8 * mb, par);
                     if (q < 5 && mb + 1 < MB) mbar_wait(bar_acc + 8 * (mb + 1), par);   // MMA(mb+1, q) still reads rows of this block
                     tc_fence_after();
+                    if (q4 == 0 && lane == 0) SK_TRACE(it, q, mb, 2);
                     const int row = mb * 128 + rib;
                     const int t = tt0 + row;
                     const uint32_t keep = ((t >= 0) && (t < p.T)) ? 0xffffffffu : 0u;
@@ -668,6 +690,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                             put_block(mb, xn);
                         }
                     }
+                    if (q4 == 0 && lane == 0) SK_TRACE(it, q, mb, 3);
                 }
             }
         }
@@ -730,6 +753,8 @@ int launch_resblock_t(const ResblockTC& a, cudaStream_t st) {
     if (SKEW) {
         // persistent: one CTA per resident slot walks the (item, tile) list; SVB_RB_PERSIST=0 launches one CTA per tile
         static const int env_persist = rb_env_int("SVB_RB_PERSIST", 1);
+        static const int env_pf = rb_env_int("SVB_RB_PF", 3);
+        p.pf_q = env_pf;
         const int ntile = (int)grid.x * a.B;
         const int slots = sm_count() * MINB;
         grid = dim3(env_persist ? (ntile < slots ? ntile : slots) : ntile, 1);
@@ -752,7 +777,11 @@ int launch_resblock_tc(const ResblockTC& a, cudaStream_t st) {
     if (variant == 2) {               // block-skewed hand-off (resblock_skew_kernel): two CTAs/SM for C <= 32, one for C = 64
         switch (a.C) {
             case 16: return launch_resblock_t<16, 8, 8, 2, true>(a, st);
-            case 32: return launch_resblock_t<32, 4, 22, 2, true>(a, st);
+            case 32: {
+                static const int env_c32 = rb_env_int("SVB_RB_C32_ONE", 0);     // experiment: one CTA/SM with 1024-row tiles
+                if (env_c32) return launch_resblock_t<32, 8, 22, 1, true>(a, st);
+                return launch_resblock_t<32, 4, 22, 2, true>(a, st);
+            }
             case 64: return launch_resblock_t<64, 4, 32, 1, true>(a, st);
             default: return SVB_ERR_UNSUPPORTED;
         }

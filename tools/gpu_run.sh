@@ -15,6 +15,14 @@ for step in "$@"; do
     bench)   timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"; cat gpurun_out/bench_default.json ;;
     benchq)  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "benchq rc=$?"; python tools/bench_brief.py gpurun_out/bench_quick.json ;;
     benchq0) SVB_RB_PERSIST=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick0.json 2> gpurun_out/bench_quick0.err; echo "benchq0 rc=$?"; python tools/bench_brief.py gpurun_out/bench_quick0.json ;;
+    ab)      # A/B of environment switches: SVB_AB="VAR=1;VAR2=0 VAR3=5" -> one quick bench per ';'-separated setting
+             IFS=';' read -ra SETS <<< "${SVB_AB:-}"
+             for e in "${SETS[@]}"; do
+               tag=$(echo "$e" | tr -c 'A-Za-z0-9=_\n' '_')
+               env $e timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > "gpurun_out/bench_ab_$tag.json" 2> "gpurun_out/bench_ab_$tag.err"
+               echo "ab [$e] rc=$?"; python tools/bench_brief.py "gpurun_out/bench_ab_$tag.json" | head -4
+             done ;;
+    rbskew)  for cfg in "16 3" "16 7" "32 7" "64 7" "64 3"; do timeout 120 tools/bench_rbskew $cfg; done > gpurun_out/rbskew.log 2>&1; echo "rbskew rc=$?"; grep -E "per launch|period|conv" gpurun_out/rbskew.log | head -60 ;;
     snake)   timeout 600 python bench.py --vocoder nsf-snake-hifigan --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_snake.json 2> gpurun_out/bench_snake.err; echo "snake rc=$?"; cat gpurun_out/bench_snake.json ;;
     flow5)   timeout 300 python bench.py --workload flow5 --steps 20 --warmup 3 > gpurun_out/bench_flow5.json 2> gpurun_out/bench_flow5.err; echo "flow5 rc=$?"; cat gpurun_out/bench_flow5.json ;;
     refcuda) timeout 600 python bench.py --impl reference-cuda --steps 3 --warmup 2 > gpurun_out/bench_refcuda.json 2> gpurun_out/bench_refcuda.err; echo "refcuda rc=$?"; cat gpurun_out/bench_refcuda.json ;;
