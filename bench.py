@@ -398,7 +398,8 @@ def main():
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_dev()
-    step_e2e()
+    for _ in range(max(args.warmup, 3)):     # every pipeline slot allocates its pinned / device buffers on first use
+        step_e2e()
     eng = net._b200_engine
     if sampler:
         t_wait = time.time()

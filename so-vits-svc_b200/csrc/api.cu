@@ -1680,7 +1680,10 @@ int svb_infer_tail_host(svb_ctx* ctx, const float* z_p, const float* g, int gT,
     const size_t N = (size_t)T * ctx->hop;
     const size_t n_zp = (size_t)B * c.inter_channels * T, n_g = (size_t)B * c.gin_channels * gT, n_f0 = (size_t)B * T,
                  n_ri = (size_t)B * c.n_harmonics, n_nz = noise ? (size_t)B * N * c.n_harmonics : 0, n_wav = (size_t)B * N;
-    const size_t need = (n_zp + n_g + n_f0 + n_ri + n_nz + n_wav + 64) * sizeof(float);
+    // every sub-buffer starts on a 256-byte boundary: the kernels pick their 128-bit code paths by pointer alignment, and a
+    // host call must run exactly the kernels a device call with torch-allocated tensors runs (bit-identical results)
+    auto al = [](size_t n) { return (n + 63) & ~(size_t)63; };
+    const size_t need = (al(n_zp) + al(n_g) + al(n_f0) + al(n_ri) + al(n_nz) + al(n_wav)) * sizeof(float);
     if (ctx->host_io.bytes < need) {
         if (ctx->host_io.p) CU(cudaFree(ctx->host_io.p));
         ctx->host_io.p = nullptr; ctx->host_io.bytes = 0;
@@ -1688,11 +1691,11 @@ int svb_infer_tail_host(svb_ctx* ctx, const float* z_p, const float* g, int gT,
         ctx->host_io.bytes = need;
     }
     float* d = static_cast<float*>(ctx->host_io.p);
-    float* d_zp = d; d += n_zp;
-    float* d_g = d; d += n_g;
-    float* d_f0 = d; d += n_f0;
-    float* d_ri = d; d += n_ri;
-    float* d_nz = d; d += n_nz;
+    float* d_zp = d; d += al(n_zp);
+    float* d_g = d; d += al(n_g);
+    float* d_f0 = d; d += al(n_f0);
+    float* d_ri = d; d += al(n_ri);
+    float* d_nz = d; d += al(n_nz);
     float* d_wav = d;
     cudaStream_t st = 0;
     CU(cudaMemcpyAsync(d_zp, z_p, n_zp * sizeof(float), cudaMemcpyHostToDevice, st));

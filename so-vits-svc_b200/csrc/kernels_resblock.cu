@@ -52,6 +52,7 @@ struct ResblockParams {
     int stage_bytes, nstage;         // block-skewed kernel: weight ring geometry (a stage holds one whole conv)
     int tiles_per_item, B;           // block-skewed kernel: persistent tile list (item-major)
     int pf_q;                        // conv index at which the next tile is prefetched into L2 (-1: off)
+    int dual;                        // block-skewed kernel: two MMA issuers (warp 8: even row blocks, warp 9: odd ones + the weight ring)
 };
 __device__ unsigned long long g_rb_ticket[256];
 
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
 
     if (tid == 0) {
         dephase_first_wave(g_rb_ticket, p.epoch, p.skew_clk, MINB);
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, p.dual ? 2 : 1); }
         for (int m = 0; m < MB; ++m) { mbar_init(bar_a + 8 * m, RBK_NWORK / 2); mbar_init(bar_acc + 8 * m, 1); }
         fence_barrier_init();
     }
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp == 9) {
+    if (warp == 9 && !p.dual) {
         // ------------------------------------------------------------ weight producer: one ring stage per conv
         // (with a single stage - C = 64, k = 11 - conv q+1 can only be fetched once conv q has been consumed)
         const int ns = p.nstage;
@@ -464,29 +465,61 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
             }
             __syncwarp();
         }
-    } else if (warp == 8) {
-        // ------------------------------------------------------------ MMA issuer: block-major inside a conv
+    } else if (warp == 8 || warp == 9) {
+        // ------------------------------------------------------------ MMA issuer(s): block-major inside a conv
+        // One issuing thread spends ~700 clk of serial scalar work per row block (barrier polls, descriptor arithmetic, the
+        // commit) on top of the MMAs themselves - measured with tools/bench_rbskew.cu: issue-to-issue 850 / 1000 / 1200 clk
+        // for k = 3 / 7 / 11 at C = 16 while the epilogue groups sit waiting for accumulators.  MMAs into different
+        // accumulators are independent, so in dual mode two threads share the work: warp 8 issues the even row blocks, warp
+        // 9 the odd ones and, between its blocks, keeps the weight ring filled (non-blocking polls of the empty barrier).
+        // Each issuer waits for the previous round of blocks mb-1, mb, mb+1 itself; a ring stage is released by both commits.
         constexpr uint32_t idesc = make_idesc_f16(128, C);
         const int h = (k - 1) / 2;
+        const int first = p.dual ? warp - 8 : 0, step = p.dual ? 2 : 1;
+        const bool feeds = p.dual && warp == 9;
         if (elect_one()) {
             const int nconv = 6 * niter;
+            const int ns = p.nstage;
+            const uint32_t wbytes = (uint32_t)k * G::SUB;
+            int next_load = 0;                                   // dual mode, warp 9: next conv whose weights have to be requested
+            auto try_refill = [&](bool block) {                  // conv L goes into stage L % ns once conv L - ns has been consumed
+                if (next_load >= nconv) return;
+                const int L = next_load;
+                const uint32_t sl = (uint32_t)(L % ns);
+                if (L >= ns) {
+                    const uint32_t bar = bar_empty + 8 * sl, par = (uint32_t)(L / ns - 1) & 1u;
+                    if (block) mbar_wait(bar, par);
+                    else if (!mbar_try_wait(bar, par)) return;
+                }
+                mbar_arrive_expect_tx(bar_full + 8 * sl, wbytes);
+                bulk_g2s(ring_base + sl * p.stage_bytes, p.w[L % 6], wbytes, bar_full + 8 * sl);
+                ++next_load;
+            };
+            if (feeds) { try_refill(true); if (ns > 1) try_refill(true); }
             int q = 0;
             for (int gq = 0; gq < nconv; ++gq, q = (q == 5 ? 0 : q + 1)) {
-                const uint32_t s = (uint32_t)(gq % p.nstage), par = (uint32_t)q & 1u;
-                mbar_wait(bar_full + 8 * s, (uint32_t)(gq / p.nstage) & 1u);
+                const uint32_t s = (uint32_t)(gq % ns), par = (uint32_t)q & 1u;
+                mbar_wait(bar_full + 8 * s, (uint32_t)(gq / ns) & 1u);
                 const int cd = (q & 1) ? 1 : p.dil[q >> 1];
                 const uint64_t a_step = (uint64_t)((uint32_t)(cd * G::RB) >> 4);
                 const uint64_t a_q = make_smem_desc(a_base + (uint32_t)(RBK_PAD - h * cd) * G::RB, G::RB, 0);
                 const uint64_t b_q = make_smem_desc(ring_base + s * (uint32_t)p.stage_bytes, G::RB, 0);
 #pragma unroll 1
-                for (int mb = 0; mb < MB; ++mb) {
-                    if (mb == 0) { mbar_wait(bar_a, par); mbar_wait(bar_a + 8, par); }
-                    else if (mb + 1 < MB) mbar_wait(bar_a + 8 * (mb + 1), par);
+                for (int mb = first; mb < MB; mb += step) {
+                    if (feeds && next_load <= gq + ns - 1) try_refill(false);
+                    if (step == 1) {
+                        if (mb == 0) { mbar_wait(bar_a, par); mbar_wait(bar_a + 8, par); }
+                        else if (mb + 1 < MB) mbar_wait(bar_a + 8 * (mb + 1), par);
+                    } else {
+                        if (mb == 1) mbar_wait(bar_a, par);                       // (block mb - 1 was covered by this thread's previous block otherwise)
+                        mbar_wait(bar_a + 8 * mb, par);
+                        if (mb + 1 < MB) mbar_wait(bar_a + 8 * (mb + 1), par);
+                    }
                     tc_fence_after();
                     SK_TRACE(gq / 6, q, mb, 0);
 #ifdef SVB_TRACE
                     if (g_rb_trace && q == 0 && mb == 0 && gq / 6 < 8) g_rb_trace[(size_t)blockIdx.x * 256 + 200 + gq / 6] = clock64();   // tile starts
-                    if (g_rb_trace && gq == 0) { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); g_rb_trace[(size_t)blockIdx.x * 256 + 255] = smid; }
+                    if (g_rb_trace && gq == 0 && mb == 0) { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); g_rb_trace[(size_t)blockIdx.x * 256 + 255] = smid; }
 #endif
                     uint64_t ad = a_q + (uint64_t)(((uint32_t)(mb * 128) * G::RB) >> 4);
                     uint64_t bd = b_q;
@@ -502,6 +535,9 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                     umma_commit(bar_acc + 8 * mb);
                 }
                 umma_commit(bar_empty + 8 * s);
+                // the next conv's weights must have been requested before anybody waits for them (single-stage ring: only now,
+                // once this conv has been consumed by both issuers)
+                if (feeds && next_load <= gq + 1) try_refill(true);
             }
         }
         __syncwarp();
@@ -585,7 +621,9 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                     }
                     if (q4 == 0 && lane == 0) SK_TRACE(it, q, mb, 1);
                     mbar_wait(bar_acc + 8 * mb, par);
-                    if (q < 5 && mb + 1 < MB) mbar_wait(bar_acc + 8 * (mb + 1), par);   // MMA(mb+1, q) still reads rows of this block
+                    // MMA(mb+1, q) still reads operand rows of this block: that wait is only needed before the first shared-memory
+                    // store of the epilogue, so it is taken after the TMEM loads and the arithmetic (off the critical path)
+                    const bool wait_nb = (q < 5) && (mb + 1 < MB);
                     tc_fence_after();
                     if (q4 == 0 && lane == 0) SK_TRACE(it, q, mb, 2);
                     const int row = mb * 128 + rib;
@@ -593,6 +631,9 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                     const uint32_t keep = ((t >= 0) && (t < p.T)) ? 0xffffffffu : 0u;
                     uint8_t* prow = sm + (row + RBK_PAD) * G::RB;
                     const uint32_t phase = swz_phase(row + RBK_PAD, G::RB);
+                    // whole block inside [0, T): no row has to be zeroed (uniform over the CTA; only the first / last tile of an item fails it)
+                    const bool interior = (tt0 + mb * 128 >= 0) && (tt0 + mb * 128 + 127 < p.T);
+                    const uint32_t srow = a_base + (uint32_t)(row + RBK_PAD) * G::RB;
                     if ((q & 1) == 0) {
                         // first conv of a pair: mid = lrelu(acc + b1) -> operand rows (two column groups per TMEM round trip)
 #pragma unroll
@@ -607,17 +648,24 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                                 if (gg == 1 && !two) break;
                                 const int c0 = cc + gg * CG;
                                 const uint32_t* rr = gg ? r1 : r0;
-                                float v[16];
+                                uint32_t hq[8];
 #pragma unroll
                                 for (int j4 = 0; j4 < CG; j4 += 4) {
                                     const float4 bb = *reinterpret_cast<const float4*>(bq_ + c0 + j4);
-                                    v[j4 + 0] = lrelu01(__uint_as_float(rr[j4 + 0]) + bb.x);
-                                    v[j4 + 1] = lrelu01(__uint_as_float(rr[j4 + 1]) + bb.y);
-                                    v[j4 + 2] = lrelu01(__uint_as_float(rr[j4 + 2]) + bb.z);
-                                    v[j4 + 3] = lrelu01(__uint_as_float(rr[j4 + 3]) + bb.w);
+                                    float v0 = __uint_as_float(rr[j4 + 0]), v1 = __uint_as_float(rr[j4 + 1]);
+                                    float v2 = __uint_as_float(rr[j4 + 2]), v3 = __uint_as_float(rr[j4 + 3]);
+                                    add2(v0, v1, bb.x, bb.y);
+                                    add2(v2, v3, bb.z, bb.w);
+                                    hq[j4 / 2] = lrelu_pack2(v0, v1);
+                                    hq[j4 / 2 + 1] = lrelu_pack2(v2, v3);
                                 }
-                                store_chunk8(prow, phase, c0 / 8, v, keep);
-                                store_chunk8(prow, phase, c0 / 8 + 1, v + 8, keep);
+                                if (!interior) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) hq[j] &= keep;
+                                }
+                                if (cc == 0 && gg == 0 && wait_nb) mbar_wait(bar_acc + 8 * (mb + 1), par);
+                                sts128(srow + ((((uint32_t)(c0 / 8)) ^ phase) << 4), hq[0], hq[1], hq[2], hq[3]);
+                                sts128(srow + ((((uint32_t)(c0 / 8 + 1)) ^ phase) << 4), hq[4], hq[5], hq[6], hq[7]);
                             }
                         }
                         tc_fence_before();
@@ -631,22 +679,28 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                             tmem_ld16(tlane + ACC0 + mb * C + cc, r);
                             tmem_ld16(tlane + mb * C + cc, xr);
                             tmem_ld_wait();
-                            float v[16];
+                            uint32_t hq[8];
 #pragma unroll
                             for (int j4 = 0; j4 < CG; j4 += 4) {
                                 const float4 bb = *reinterpret_cast<const float4*>(bq_ + cc + j4);
-                                v[j4 + 0] = fmaf(__uint_as_float(r[j4 + 0]), inv_q, bb.x) + __uint_as_float(xr[j4 + 0]);
-                                v[j4 + 1] = fmaf(__uint_as_float(r[j4 + 1]), inv_q, bb.y) + __uint_as_float(xr[j4 + 1]);
-                                v[j4 + 2] = fmaf(__uint_as_float(r[j4 + 2]), inv_q, bb.z) + __uint_as_float(xr[j4 + 2]);
-                                v[j4 + 3] = fmaf(__uint_as_float(r[j4 + 3]), inv_q, bb.w) + __uint_as_float(xr[j4 + 3]);
+                                float v0, v1, v2, v3;
+                                fma2(v0, v1, __uint_as_float(r[j4 + 0]), __uint_as_float(r[j4 + 1]), inv_q, inv_q, bb.x, bb.y);
+                                fma2(v2, v3, __uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3]), inv_q, inv_q, bb.z, bb.w);
+                                add2(v0, v1, __uint_as_float(xr[j4 + 0]), __uint_as_float(xr[j4 + 1]));
+                                add2(v2, v3, __uint_as_float(xr[j4 + 2]), __uint_as_float(xr[j4 + 3]));
+                                xr[j4 + 0] = __float_as_uint(v0); xr[j4 + 1] = __float_as_uint(v1);
+                                xr[j4 + 2] = __float_as_uint(v2); xr[j4 + 3] = __float_as_uint(v3);
+                                hq[j4 / 2] = lrelu_pack2(v0, v1);
+                                hq[j4 / 2 + 1] = lrelu_pack2(v2, v3);
                             }
-#pragma unroll
-                            for (int j = 0; j < CG; ++j) xr[j] = __float_as_uint(v[j]);
                             tmem_st16(tlane + mb * C + cc, xr);
+                            if (!interior) {
 #pragma unroll
-                            for (int j = 0; j < CG; ++j) v[j] = lrelu01(v[j]);
-                            store_chunk8(prow, phase, cc / 8, v, keep);
-                            store_chunk8(prow, phase, cc / 8 + 1, v + 8, keep);
+                                for (int j = 0; j < 8; ++j) hq[j] &= keep;
+                            }
+                            if (cc == 0 && wait_nb) mbar_wait(bar_acc + 8 * (mb + 1), par);
+                            sts128(srow + ((((uint32_t)(cc / 8)) ^ phase) << 4), hq[0], hq[1], hq[2], hq[3]);
+                            sts128(srow + ((((uint32_t)(cc / 8 + 1)) ^ phase) << 4), hq[4], hq[5], hq[6], hq[7]);
                         }
                         tmem_st_wait();
                         tc_fence_before();
@@ -748,13 +802,15 @@ int launch_resblock_t(const ResblockTC& a, cudaStream_t st) {
     const int TOUT = 128 * MB - 2 * halo;
     if (TOUT < 64) return SVB_ERR_UNSUPPORTED;
     dim3 grid((a.T + TOUT - 1) / TOUT, a.B);
-    p.stage_bytes = stage_bytes; p.nstage = nstage;
+    p.stage_bytes = stage_bytes; p.nstage = nstage; p.dual = 0;
     p.tiles_per_item = (int)grid.x; p.B = a.B;
     if (SKEW) {
         // persistent: one CTA per resident slot walks the (item, tile) list; SVB_RB_PERSIST=0 launches one CTA per tile
         static const int env_persist = rb_env_int("SVB_RB_PERSIST", 1);
         static const int env_pf = rb_env_int("SVB_RB_PF", 3);
+        static const int env_dual = rb_env_int("SVB_RB_DUAL", 1);
         p.pf_q = env_pf;
+        p.dual = env_dual;
         const int ntile = (int)grid.x * a.B;
         const int slots = sm_count() * MINB;
         grid = dim3(env_persist ? (ntile < slots ? ntile : slots) : ntile, 1);

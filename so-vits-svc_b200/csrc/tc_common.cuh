@@ -214,6 +214,31 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 __device__ __forceinline__ float lrelu01(float v) { return fmaxf(v, 0.1f * v); }   // LeakyReLU(0.1): max(v, 0.1 v)
 
+// ---- packed fp32 pairs (FADD2 / FMUL2 / FFMA2): element-wise IEEE round-to-nearest, bit-identical to the scalar
+// instructions, one issue slot for two values.  The fused-ResBlock epilogues are bound by instruction issue (~7 thread
+// instructions per accumulator element, tools/bench_rbskew.cu), so every halved instruction is time.
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {          // (a0, a1) += (b0, b1)
+    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+        : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {   // a*b + c
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\tfma.rn.f32x2 ra, ra, rb, rc;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+// LeakyReLU(0.1) of a pair, packed to fp16x2 (same arithmetic as pack_h2(lrelu01(a), lrelu01(b)))
+__device__ __forceinline__ uint32_t lrelu_pack2(float a, float b) {
+    float ma, mb;
+    mul2(ma, mb, a, b, 0.1f, 0.1f);
+    return pack_h2(fmaxf(a, ma), fmaxf(b, mb));
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // Write 8 fp16 values (one 16-byte chunk `chunk` of a swizzled operand row) given the row's base pointer
 // (operand base + row*row_bytes) and the row's swizzle phase ((row*row_bytes) >> 7) & mask.  `keep` is all-ones or 0.
 __device__ __forceinline__ void store_chunk8(uint8_t* row_ptr, uint32_t phase, int chunk, const float* v, uint32_t keep) {

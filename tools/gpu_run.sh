@@ -22,7 +22,8 @@ for step in "$@"; do
                env $e timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > "gpurun_out/bench_ab_$tag.json" 2> "gpurun_out/bench_ab_$tag.err"
                echo "ab [$e] rc=$?"; python tools/bench_brief.py "gpurun_out/bench_ab_$tag.json" | head -4
              done ;;
-    rbskew)  for cfg in "16 3" "16 7" "32 7" "64 7" "64 3"; do timeout 120 tools/bench_rbskew $cfg; done > gpurun_out/rbskew.log 2>&1; echo "rbskew rc=$?"; grep -E "per launch|period|conv" gpurun_out/rbskew.log | head -60 ;;
+    e2etrace) timeout 300 python tools/e2e_trace.py > gpurun_out/e2e_trace.log 2>&1; echo "e2etrace rc=$?"; cat gpurun_out/e2e_trace.log ;;
+    rbskew)  for cfg in "16 3" "16 7" "16 11" "32 3" "32 7" "64 7" "64 3"; do timeout 120 tools/bench_rbskew $cfg; done > gpurun_out/rbskew.log 2>&1; echo "rbskew rc=$?"; grep -E "per launch|period|conv" gpurun_out/rbskew.log | head -60 ;;
     snake)   timeout 600 python bench.py --vocoder nsf-snake-hifigan --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_snake.json 2> gpurun_out/bench_snake.err; echo "snake rc=$?"; cat gpurun_out/bench_snake.json ;;
     flow5)   timeout 300 python bench.py --workload flow5 --steps 20 --warmup 3 > gpurun_out/bench_flow5.json 2> gpurun_out/bench_flow5.err; echo "flow5 rc=$?"; cat gpurun_out/bench_flow5.json ;;
     refcuda) timeout 600 python bench.py --impl reference-cuda --steps 3 --warmup 2 > gpurun_out/bench_refcuda.json 2> gpurun_out/bench_refcuda.err; echo "refcuda rc=$?"; cat gpurun_out/bench_refcuda.json ;;
