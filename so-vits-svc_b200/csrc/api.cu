@@ -345,8 +345,12 @@ struct WsPlan {
 // single pair launch leaves the GPU half empty: wide stages (pair kernels, C >= 128) with at most ~3 waves of tiles.
 bool merge_branches(int C, int L, int B) {
     if (C < 128) return false;
+    // measured (config 2): merging stage 1 as well (12 waves of tiles), with the branches interleaved in launch order, takes the
+    // pair kernels from 3.44 to 3.22 ms per step - a k = 3 pair is memory-phase bound, a k = 11 pair MMA bound, side by side on
+    // an SM they fill each other's gaps
+    static const int max_waves = [] { const char* e = std::getenv("SVB_MERGE_WAVES"); return e ? std::atoi(e) : 64; }();
     const long long tiles = (long long)((L + 245) / 246) * B;
-    return tiles <= 3 * 148;
+    return tiles <= (long long)max_waves * 148;
 }
 
 WsPlan plan_ws(const svb_model_cfg& c, int B, int T, int gT) {
@@ -834,8 +838,27 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
                     pt[j].alpha = d == 2 ? 1.f / nk : 1.f; pt[j].beta = d == 2 ? 1.f : 0.f;
                     fl += 2.0 * 2.0 * S.Cout * (double)S.Cout * k * (double)Lout * B;
                 }
-                ProfScope ps(ctx, "pair_tc", st, fl, 3 * 3.0 * S.Cout * (double)Lout * B * sizeof(float));
-                trc = launch_pair_tc_multi(pt, 3, st);
+                if (d < 2) {
+                    ProfScope ps(ctx, "pair_tc", st, fl, 3 * 3.0 * S.Cout * (double)Lout * B * sizeof(float));
+                    trc = launch_pair_tc_multi(pt, 3, st);
+                } else {
+                    // The last pairs accumulate alpha*y into the stage output.  Three floating-point reductions in arrival order
+                    // would make the sum depend on the schedule ((a+b)+c vs (a+c)+b), so only TWO branches reduce into the zeroed
+                    // buffer (0 + a + b is exact in either order) and the third adds afterwards in a launch of its own: the
+                    // result is bit-reproducible from run to run and independent of the batch an item travels in.
+                    // The shortest and the longest kernel share the merged launch (memory-phase bound next to MMA bound), the middle
+                    // one follows alone.
+                    const double fl1 = 2.0 * 2.0 * S.Cout * (double)S.Cout * c.resblock_kernel_sizes[1] * (double)Lout * B;
+                    const PairTC outer[2] = {pt[0], pt[2]};
+                    {
+                        ProfScope ps(ctx, "pair_tc", st, fl - fl1, 2 * 3.0 * S.Cout * (double)Lout * B * sizeof(float));
+                        trc = launch_pair_tc_multi(outer, 2, st);
+                    }
+                    if (trc == 0) {
+                        ProfScope ps(ctx, "pair_tc", st, fl1, 3.0 * S.Cout * (double)Lout * B * sizeof(float));
+                        trc = launch_pair_tc_multi(pt + 1, 1, st);
+                    }
+                }
             }
             if (trc == 0) merged_done = true;
             else if (trc != SVB_ERR_UNSUPPORTED) return fail(ctx, trc, "branch-merged pair launch failed");

@@ -34,9 +34,12 @@ __device__ long long* g_rb_trace = nullptr;
 // block-skewed kernel (tools/bench_rbskew.cu): 256 slots per CTA, [q][mb][what] of the CTA's SECOND tile (steady state);
 // what = 0 issuer about to issue MMA(q, mb), 1 worker starts waiting for the accumulators, 2 sees them, 3 has handed the block on
 #define SK_TRACE(it, q, mb, w) do { if (g_rb_trace && (it) == 1) g_rb_trace[(size_t)blockIdx.x * 256 + (((q) * 8 + (mb)) * 4 + (w))] = clock64(); } while (0)
+// fine-grained epilogue trace of ONE block (conv 2, block 2, second tile): slots 208 + n
+#define SK_FINE(it, q, mb, n) do { if (g_rb_trace && (it) == 1 && (q) == 2 && (mb) == 2 && q4 == 0 && lane == 0) g_rb_trace[(size_t)blockIdx.x * 256 + 208 + (n)] = clock64(); } while (0)
 #else
 #define RB_TRACE(slot) do { } while (0)
 #define SK_TRACE(it, q, mb, w) do { } while (0)
+#define SK_FINE(it, q, mb, n) do { } while (0)
 #endif
 
 struct ResblockParams {
@@ -52,6 +55,7 @@ struct ResblockParams {
     int stage_bytes, nstage;         // block-skewed kernel: weight ring geometry (a stage holds one whole conv)
     int tiles_per_item, B;           // block-skewed kernel: persistent tile list (item-major)
     int pf_q;                        // conv index at which the next tile is prefetched into L2 (-1: off)
+    int park_ns;                     // block-skewed kernel: suspend-time hint of the barrier waits (0 = poll)
     int dual;                        // block-skewed kernel: two MMA issuers (warp 8: even row blocks, warp 9: odd ones + the weight ring)
 };
 __device__ unsigned long long g_rb_ticket[256];
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
 // Barriers: bar_a[b] completes once per round (round 0 = loader, round q+1 = epilogue of conv q), bar_acc[b] once per conv.
 // Every wait of round q only depends on arrivals of round q-1 of the other side, so the protocol cannot deadlock.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int C, int MB, int STAGE_KB, int MINB>
+template <int C, int MB, int STAGE_KB, int MINB, bool PAIR>
 __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const ResblockParams p) {
     using G = RBGeom<C, STAGE_KB>;
     constexpr int R1 = 128 * MB;
@@ -395,6 +399,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
     constexpr int ACC0 = MB * C;
     constexpr int NBG = MB / 2;                      // row blocks per worker group
     static_assert(MB >= 2 && MB <= 8 && MB % 2 == 0, "block-skewed ResBlock kernel: 2..8 row blocks");
+    static_assert(!PAIR || MB % 4 == 0, "paired epilogues take the blocks of a group two at a time");
     static_assert(C == 16 || C == 32 || C == 64, "block-skewed ResBlock kernel serves C <= 64");
 
     extern __shared__ uint8_t smem_raw[];
@@ -412,6 +417,8 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k = p.k;
     const int TOUT = R1 - 2 * p.halo;
+    const uint32_t park_ns = (uint32_t)p.park_ns;      // > 0: waiting threads are parked by the hardware instead of polling
+    auto WAIT = [park_ns](uint32_t bar, uint32_t parity) { if (park_ns) mbar_wait_park(bar, parity, park_ns); else mbar_wait(bar, parity); };
     // Persistent tile loop: CTA c owns the tiles c, c + gridDim.x, ... of the (item, tile) list.  The load of the next tile's
     // block b is issued by the thread that has just finished the last epilogue of block b, so the x read, the output
     // reduction and the first MMAs of the next tile overlap the tail of this one inside the CTA (before: load + final
@@ -457,7 +464,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
         for (int gq = 0; gq < nconv; ++gq) {
             const int q = gq % 6;
             const int s = gq % ns, use = gq / ns;
-            if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
+            if (use >= 1) WAIT(bar_empty + 8 * s, (use - 1) & 1);
             const uint32_t bytes = (uint32_t)k * G::SUB;
             if (elect_one()) {
                 mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
@@ -488,7 +495,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                 const uint32_t sl = (uint32_t)(L % ns);
                 if (L >= ns) {
                     const uint32_t bar = bar_empty + 8 * sl, par = (uint32_t)(L / ns - 1) & 1u;
-                    if (block) mbar_wait(bar, par);
+                    if (block) WAIT(bar, par);
                     else if (!mbar_try_wait(bar, par)) return;
                 }
                 mbar_arrive_expect_tx(bar_full + 8 * sl, wbytes);
@@ -499,21 +506,22 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
             int q = 0;
             for (int gq = 0; gq < nconv; ++gq, q = (q == 5 ? 0 : q + 1)) {
                 const uint32_t s = (uint32_t)(gq % ns), par = (uint32_t)q & 1u;
-                mbar_wait(bar_full + 8 * s, (uint32_t)(gq / ns) & 1u);
+                WAIT(bar_full + 8 * s, (uint32_t)(gq / ns) & 1u);
                 const int cd = (q & 1) ? 1 : p.dil[q >> 1];
-                const uint64_t a_step = (uint64_t)((uint32_t)(cd * G::RB) >> 4);
+                const uint32_t a_step = (uint32_t)(cd * G::RB) >> 4;
                 const uint64_t a_q = make_smem_desc(a_base + (uint32_t)(RBK_PAD - h * cd) * G::RB, G::RB, 0);
                 const uint64_t b_q = make_smem_desc(ring_base + s * (uint32_t)p.stage_bytes, G::RB, 0);
+                const uint32_t a_hi = (uint32_t)(a_q >> 32), b_hi = (uint32_t)(b_q >> 32);
 #pragma unroll 1
                 for (int mb = first; mb < MB; mb += step) {
                     if (feeds && next_load <= gq + ns - 1) try_refill(false);
                     if (step == 1) {
-                        if (mb == 0) { mbar_wait(bar_a, par); mbar_wait(bar_a + 8, par); }
-                        else if (mb + 1 < MB) mbar_wait(bar_a + 8 * (mb + 1), par);
+                        if (mb == 0) { WAIT(bar_a, par); WAIT(bar_a + 8, par); }
+                        else if (mb + 1 < MB) WAIT(bar_a + 8 * (mb + 1), par);
                     } else {
-                        if (mb == 1) mbar_wait(bar_a, par);                       // (block mb - 1 was covered by this thread's previous block otherwise)
-                        mbar_wait(bar_a + 8 * mb, par);
-                        if (mb + 1 < MB) mbar_wait(bar_a + 8 * (mb + 1), par);
+                        if (mb == 1) WAIT(bar_a, par);                       // (block mb - 1 was covered by this thread's previous block otherwise)
+                        WAIT(bar_a + 8 * mb, par);
+                        if (mb + 1 < MB) WAIT(bar_a + 8 * (mb + 1), par);
                     }
                     tc_fence_after();
                     SK_TRACE(gq / 6, q, mb, 0);
@@ -521,16 +529,18 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                     if (g_rb_trace && q == 0 && mb == 0 && gq / 6 < 8) g_rb_trace[(size_t)blockIdx.x * 256 + 200 + gq / 6] = clock64();   // tile starts
                     if (g_rb_trace && gq == 0 && mb == 0) { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); g_rb_trace[(size_t)blockIdx.x * 256 + 255] = smid; }
 #endif
-                    uint64_t ad = a_q + (uint64_t)(((uint32_t)(mb * 128) * G::RB) >> 4);
-                    uint64_t bd = b_q;
+                    // descriptors advance in their low words only (start address field; the tile and the ring stay far below its 14 bits)
+                    uint32_t ad = (uint32_t)a_q + (((uint32_t)(mb * 128) * G::RB) >> 4);
+                    uint32_t bd = (uint32_t)b_q;
                     uint32_t acc = 0u;
                     for (int tap = 0; tap < k; ++tap) {
 #pragma unroll
                         for (int ks = 0; ks < G::KSTEPS; ++ks)
-                            umma_f16(tmem_base + ACC0 + mb * C, ad + (uint64_t)((ks * 32) >> 4), bd + (uint64_t)((ks * 32) >> 4), idesc, (ks > 0) ? 1u : acc);
+                            umma_f16_split(tmem_base + ACC0 + mb * C, ad + (uint32_t)((ks * 32) >> 4), a_hi, bd + (uint32_t)((ks * 32) >> 4), b_hi, idesc,
+                                           (ks > 0) ? 1u : acc);
                         acc = 1u;
                         ad += a_step;
-                        bd += (uint64_t)(G::SUB >> 4);
+                        bd += (uint32_t)(G::SUB >> 4);
                     }
                     umma_commit(bar_acc + 8 * mb);
                 }
@@ -598,6 +608,131 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                 const uint32_t par = (uint32_t)q & 1u;
                 const float* __restrict__ bq_ = sbias + q * C;
                 const float inv_q = p.inv[q >> 1];
+                if (PAIR && q < 5) {
+                    // Two row blocks of the group per barrier round trip (mb0 and mb0 + 2).  A block epilogue is a chain of
+                    // long-latency steps (barrier polls ~200 clk each, tcgen05.ld ~150, the proxy fence ~100, the arrive ~100:
+                    // measured with the fine trace of tools/bench_rbskew.cu) around ~16 values of arithmetic per thread; with two
+                    // blocks per trip the chain is paid once for twice the data.
+#pragma unroll 1
+                    for (int mb0 = grp; mb0 < MB; mb0 += 4) {
+                        if (q == p.pf_q && has_next) {
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int tw = tt0n + (mb0 + 2 * u) * 128 + 32 * q4;
+#pragma unroll
+                                for (int c = lane; c < 2 * C; c += 32) {
+                                    const int tp = tw + ((c >= C) ? 31 : 0);
+                                    if (tp >= 0 && tp < p.T) prefetch_l2(xbn + (size_t)(c % C) * p.T + tp);
+                                }
+                            }
+                        }
+                        if (q4 == 0 && lane == 0) { SK_TRACE(it, q, mb0, 1); SK_TRACE(it, q, mb0 + 2, 1); }
+                        WAIT(bar_acc + 8 * mb0, par);
+                        WAIT(bar_acc + 8 * (mb0 + 2), par);
+                        tc_fence_after();
+                        if (q4 == 0 && lane == 0) { SK_TRACE(it, q, mb0, 2); SK_TRACE(it, q, mb0 + 2, 2); }
+                        uint32_t srow[2], keep[2];
+                        bool interior = true;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int mb = mb0 + 2 * u;
+                            const int row = mb * 128 + rib;
+                            const int t = tt0 + row;
+                            keep[u] = ((t >= 0) && (t < p.T)) ? 0xffffffffu : 0u;
+                            srow[u] = a_base + (uint32_t)(row + RBK_PAD) * G::RB;
+                            interior = interior && (tt0 + mb * 128 >= 0) && (tt0 + mb * 128 + 127 < p.T);
+                        }
+                        const uint32_t phase = swz_phase(rib + RBK_PAD, G::RB);      // 128 rows = a whole number of swizzle periods
+                        auto wait_neighbours = [&]() {
+                            // MMA(mb + 1, q) still reads operand rows of block mb: wait for it before the first store (the MMAs of
+                            // one issuer retire in order, so blocks mb0 - 1 .. mb0 + 3 are all done after these two polls)
+                            WAIT(bar_acc + 8 * (mb0 + 1), par);
+                            if (mb0 + 3 < MB) WAIT(bar_acc + 8 * (mb0 + 3), par);
+                        };
+                        if ((q & 1) == 0) {
+                            // mid = lrelu(acc + b1): 16 columns of both blocks per TMEM round trip
+#pragma unroll
+                            for (int cc = 0; cc < CH; cc += 16) {
+                                uint32_t r[2][16], hq[2][8];
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) tmem_ld16(tlane + ACC0 + (mb0 + 2 * u) * C + cc, r[u]);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                                    for (int j4 = 0; j4 < 16; j4 += 4) {
+                                        const float4 bb = *reinterpret_cast<const float4*>(bq_ + cc + j4);
+                                        float v0 = __uint_as_float(r[u][j4 + 0]), v1 = __uint_as_float(r[u][j4 + 1]);
+                                        float v2 = __uint_as_float(r[u][j4 + 2]), v3 = __uint_as_float(r[u][j4 + 3]);
+                                        add2(v0, v1, bb.x, bb.y);
+                                        add2(v2, v3, bb.z, bb.w);
+                                        hq[u][j4 / 2] = lrelu_pack2(v0, v1);
+                                        hq[u][j4 / 2 + 1] = lrelu_pack2(v2, v3);
+                                    }
+                                }
+                                if (!interior) {
+#pragma unroll
+                                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) hq[u][j] &= keep[u];
+                                }
+                                if (cc == 0) wait_neighbours();
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    sts128(srow[u] + ((((uint32_t)(cc / 8)) ^ phase) << 4), hq[u][0], hq[u][1], hq[u][2], hq[u][3]);
+                                    sts128(srow[u] + ((((uint32_t)(cc / 8 + 1)) ^ phase) << 4), hq[u][4], hq[u][5], hq[u][6], hq[u][7]);
+                                }
+                            }
+                        } else {
+                            // x <- x + acc/s + b2 (TMEM), operand rows <- lrelu(x): 8 columns of both blocks per round trip (the
+                            // residual doubles the registers per column)
+#pragma unroll
+                            for (int cc = 0; cc < CH; cc += 8) {
+                                uint32_t r[2][8], xr[2][8], hq[2][4];
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    tmem_ld8(tlane + ACC0 + (mb0 + 2 * u) * C + cc, r[u]);
+                                    tmem_ld8(tlane + (mb0 + 2 * u) * C + cc, xr[u]);
+                                }
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                                    for (int j4 = 0; j4 < 8; j4 += 4) {
+                                        const float4 bb = *reinterpret_cast<const float4*>(bq_ + cc + j4);
+                                        float v0, v1, v2, v3;
+                                        fma2(v0, v1, __uint_as_float(r[u][j4 + 0]), __uint_as_float(r[u][j4 + 1]), inv_q, inv_q, bb.x, bb.y);
+                                        fma2(v2, v3, __uint_as_float(r[u][j4 + 2]), __uint_as_float(r[u][j4 + 3]), inv_q, inv_q, bb.z, bb.w);
+                                        add2(v0, v1, __uint_as_float(xr[u][j4 + 0]), __uint_as_float(xr[u][j4 + 1]));
+                                        add2(v2, v3, __uint_as_float(xr[u][j4 + 2]), __uint_as_float(xr[u][j4 + 3]));
+                                        xr[u][j4 + 0] = __float_as_uint(v0); xr[u][j4 + 1] = __float_as_uint(v1);
+                                        xr[u][j4 + 2] = __float_as_uint(v2); xr[u][j4 + 3] = __float_as_uint(v3);
+                                        hq[u][j4 / 2] = lrelu_pack2(v0, v1);
+                                        hq[u][j4 / 2 + 1] = lrelu_pack2(v2, v3);
+                                    }
+                                    tmem_st8(tlane + (mb0 + 2 * u) * C + cc, xr[u]);
+                                }
+                                if (!interior) {
+#pragma unroll
+                                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) hq[u][j] &= keep[u];
+                                }
+                                if (cc == 0) wait_neighbours();
+#pragma unroll
+                                for (int u = 0; u < 2; ++u)
+                                    sts128(srow[u] + ((((uint32_t)(cc / 8)) ^ phase) << 4), hq[u][0], hq[u][1], hq[u][2], hq[u][3]);
+                            }
+                        }
+                        if (q & 1) tmem_st_wait();
+                        tc_fence_before();
+                        fence_proxy_async();
+                        mbar_arrive(bar_a + 8 * mb0);
+                        mbar_arrive(bar_a + 8 * (mb0 + 2));
+                        if (q4 == 0 && lane == 0) { SK_TRACE(it, q, mb0, 3); SK_TRACE(it, q, mb0 + 2, 3); }
+                    }
+                    continue;
+                }
 #pragma unroll 1
                 for (int mb = grp; mb < MB; mb += 2) {
                     float xn[C];
@@ -620,7 +755,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                         for (int c = 0; c < C; ++c) xn[c] = valid ? ldg_nc_v(xt + (size_t)c * p.T) : 0.f;
                     }
                     if (q4 == 0 && lane == 0) SK_TRACE(it, q, mb, 1);
-                    mbar_wait(bar_acc + 8 * mb, par);
+                    WAIT(bar_acc + 8 * mb, par);
                     // MMA(mb+1, q) still reads operand rows of this block: that wait is only needed before the first shared-memory
                     // store of the epilogue, so it is taken after the TMEM loads and the arithmetic (off the critical path)
                     const bool wait_nb = (q < 5) && (mb + 1 < MB);
@@ -640,9 +775,11 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                         for (int cc = 0; cc < CH; cc += 2 * CG) {
                             uint32_t r0[16], r1[16];
                             const bool two = (cc + CG) < CH;
+                            SK_FINE(it, q, mb, 0);
                             tmem_ld16(tlane + ACC0 + mb * C + cc, r0);
                             if (two) tmem_ld16(tlane + ACC0 + mb * C + cc + CG, r1);
                             tmem_ld_wait();
+                            SK_FINE(it, q, mb, 1);
 #pragma unroll
                             for (int gg = 0; gg < 2; ++gg) {
                                 if (gg == 1 && !two) break;
@@ -663,14 +800,19 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) hq[j] &= keep;
                                 }
-                                if (cc == 0 && gg == 0 && wait_nb) mbar_wait(bar_acc + 8 * (mb + 1), par);
+                                if (cc == 0 && gg == 0) SK_FINE(it, q, mb, 2);
+                                if (cc == 0 && gg == 0 && wait_nb) WAIT(bar_acc + 8 * (mb + 1), par);
+                                if (cc == 0 && gg == 0) SK_FINE(it, q, mb, 3);
                                 sts128(srow + ((((uint32_t)(c0 / 8)) ^ phase) << 4), hq[0], hq[1], hq[2], hq[3]);
                                 sts128(srow + ((((uint32_t)(c0 / 8 + 1)) ^ phase) << 4), hq[4], hq[5], hq[6], hq[7]);
                             }
                         }
+                        SK_FINE(it, q, mb, 4);
                         tc_fence_before();
                         fence_proxy_async();
+                        SK_FINE(it, q, mb, 5);
                         mbar_arrive(bar_a + 8 * mb);
+                        SK_FINE(it, q, mb, 6);
                     } else if (q < 5) {
                         // second conv of pair 0/1: x <- x + acc + b2 (TMEM), operand rows <- lrelu(x)
 #pragma unroll
@@ -698,7 +840,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) hq[j] &= keep;
                             }
-                            if (cc == 0 && wait_nb) mbar_wait(bar_acc + 8 * (mb + 1), par);
+                            if (cc == 0 && wait_nb) WAIT(bar_acc + 8 * (mb + 1), par);
                             sts128(srow + ((((uint32_t)(cc / 8)) ^ phase) << 4), hq[0], hq[1], hq[2], hq[3]);
                             sts128(srow + ((((uint32_t)(cc / 8 + 1)) ^ phase) << 4), hq[4], hq[5], hq[6], hq[7]);
                         }
@@ -739,7 +881,7 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                         }
                         if (has_next) {
                             // rows of this block are still read by the last MMAs of blocks mb-1 .. mb+1 of this tile
-                            if (mb + 1 < MB) mbar_wait(bar_acc + 8 * (mb + 1), par);
+                            if (mb + 1 < MB) WAIT(bar_acc + 8 * (mb + 1), par);
                             tc_fence_after();
                             put_block(mb, xn);
                         }
@@ -762,12 +904,12 @@ int rb_env_int(const char* name, int dflt) {
     return s ? std::atoi(s) : dflt;
 }
 
-template <int C, int MB, int STAGE_KB, int MINB, bool SKEW>
+template <int C, int MB, int STAGE_KB, int MINB, bool SKEW, bool PAIR = false>
 int launch_resblock_t(const ResblockTC& a, cudaStream_t st) {
     constexpr size_t smem = resblock_smem_bytes<C, MB, STAGE_KB>();
     static_assert((smem + 1024) * MINB <= 228 * 1024, "fused ResBlock kernel shared memory exceeds the SM budget");
     auto kernel = [] {
-        if constexpr (SKEW) return resblock_skew_kernel<C, MB, STAGE_KB, MINB>;
+        if constexpr (SKEW) return resblock_skew_kernel<C, MB, STAGE_KB, MINB, PAIR>;
         else return resblock_tc_kernel<C, MB, STAGE_KB, MINB>;
     }();
     // block-skewed kernel: a ring stage holds one whole conv (k taps); two stages when they fit next to the operand tile
@@ -802,15 +944,17 @@ int launch_resblock_t(const ResblockTC& a, cudaStream_t st) {
     const int TOUT = 128 * MB - 2 * halo;
     if (TOUT < 64) return SVB_ERR_UNSUPPORTED;
     dim3 grid((a.T + TOUT - 1) / TOUT, a.B);
-    p.stage_bytes = stage_bytes; p.nstage = nstage; p.dual = 0;
+    p.stage_bytes = stage_bytes; p.nstage = nstage; p.dual = 0; p.park_ns = 0;
     p.tiles_per_item = (int)grid.x; p.B = a.B;
     if (SKEW) {
         // persistent: one CTA per resident slot walks the (item, tile) list; SVB_RB_PERSIST=0 launches one CTA per tile
         static const int env_persist = rb_env_int("SVB_RB_PERSIST", 1);
         static const int env_pf = rb_env_int("SVB_RB_PF", 3);
         static const int env_dual = rb_env_int("SVB_RB_DUAL", 1);
+        static const int env_park = rb_env_int("SVB_RB_PARK", 0);      // measured: parking (300 / 2000 ns) 3.13 vs polling 3.07 ms per step
         p.pf_q = env_pf;
         p.dual = env_dual;
+        p.park_ns = env_park;
         const int ntile = (int)grid.x * a.B;
         const int slots = sm_count() * MINB;
         grid = dim3(env_persist ? (ntile < slots ? ntile : slots) : ntile, 1);
@@ -832,10 +976,16 @@ int launch_resblock_tc(const ResblockTC& a, cudaStream_t st) {
     if (variant < 0) variant = 2;     // measured: block-skewed hand-off 11.64 vs 11.95 ms/step
     if (variant == 2) {               // block-skewed hand-off (resblock_skew_kernel): two CTAs/SM for C <= 32, one for C = 64
         switch (a.C) {
-            case 16: return launch_resblock_t<16, 8, 8, 2, true>(a, st);
+            case 16: {
+                static const int env_pair = rb_env_int("SVB_RB_PAIR16", 1);     // two row blocks per epilogue round trip
+                if (env_pair) return launch_resblock_t<16, 8, 8, 2, true, true>(a, st);
+                return launch_resblock_t<16, 8, 8, 2, true>(a, st);
+            }
             case 32: {
                 static const int env_c32 = rb_env_int("SVB_RB_C32_ONE", 0);     // experiment: one CTA/SM with 1024-row tiles
+                static const int env_pair = rb_env_int("SVB_RB_PAIR32", 1);
                 if (env_c32) return launch_resblock_t<32, 8, 22, 1, true>(a, st);
+                if (env_pair) return launch_resblock_t<32, 4, 22, 2, true, true>(a, st);
                 return launch_resblock_t<32, 4, 22, 2, true>(a, st);
             }
             case 64: return launch_resblock_t<64, 4, 32, 1, true>(a, st);

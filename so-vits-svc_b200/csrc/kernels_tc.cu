@@ -58,13 +58,14 @@ struct PairParams {
     float alpha, beta, inv;
     __half* a16_out;     // optional second output: fp16 lrelu(out) in [B][T][C] (the next pair's TMA-loadable operand)
     int vec4;            // x / out 16-byte aligned and T % 4 == 0: the loader uses 128-bit loads along time
+    int prefetch;        // vec4 loader: L2 prefetch of the whole tile before the demand loads
     int red_out;         // loader pre-writes alpha*x (+ beta*old for beta == 1) into out, epilogue 2 only adds (RED): no x re-read
     uint32_t epoch; int dephase_clk;   // first-wave start skew (tc_common.cuh: dephase_first_wave)
 };
 // Up to three independent pairs (the three ResBlock branches of a stage at the same dilation index) in ONE launch:
 // blockIdx.z selects the branch.  A wide stage with few tiles (stage 0: 232 tiles of C = 256 on 148 SMs = 1.57 waves per
 // launch, i.e. 2 waves of time) is then scheduled as 696 CTAs of mixed length (k = 3 / 7 / 11) = 4.7 waves of the mean.
-struct PairParamsN { PairParams br[3]; };
+struct PairParamsN { PairParams br[3]; int nbr; };
 __device__ unsigned long long g_pair_ticket[256];
 uint32_t g_pair_epoch = 0;
 
@@ -84,8 +85,12 @@ constexpr size_t pair_smem_bytes() {
 
 template <int C, int MB, int STAGE_KB, int MINB, bool TMA_IN>
 __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const __grid_constant__ PairParamsN pn_, const __grid_constant__ CUtensorMap tmap) {
-    const PairParams& p = pn_.br[blockIdx.z];
-    if ((int)blockIdx.x * (128 * MB - (p.k - 1)) >= p.T) return;       // this branch has fewer tiles than the widest one
+    // branches interleaved along x (CTAs are dispatched x-fastest): neighbours in launch order - and therefore the CTAs that
+    // share an SM - belong to different branches, so a k = 3 pair (memory phases dominate) runs next to a k = 11 pair (MMA
+    // phases dominate) instead of the launch going through one homogeneous branch after the other
+    const int bz = (int)blockIdx.x % pn_.nbr, bx = (int)blockIdx.x / pn_.nbr;
+    const PairParams& p = pn_.br[bz];
+    if (bx * (128 * MB - (p.k - 1)) >= p.T) return;       // this branch has fewer tiles than the widest one
     using G = TCGeom<C, STAGE_KB>;
     constexpr int R1 = 128 * MB;
     constexpr int AROWS = TileRows<MB>::AROWS;
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const __grid_
     const int b = blockIdx.y;
     const int k = p.k, dil = p.dil;
     const int TOUT = R1 - (k - 1);
-    const int t0 = blockIdx.x * TOUT;
+    const int t0 = bx * TOUT;
     const int h2 = (k - 1) / 2, h1 = dil * (k - 1) / 2;
     const int tA0 = t0 - h2 - h1;          // time of A1 row 0
     const int tM0 = t0 - h2;               // time of mid (conv1 output / A2) row 0
@@ -242,6 +247,16 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const __grid_
             const int NGO = (NG + GPI - 1) / GPI;
             const int g_l = lane % GPI, ch_l = lane / GPI;
             const bool acc_old = p.beta != 0.f;
+            if (p.prefetch) {
+                // The item loop below is a chain of dependent round trips (8 loads -> convert -> store, ~5 per thread): pull the
+                // whole tile into L2 first, so that one DRAM latency is paid up front and the demand loads are L2 hits.
+                const int nline = (4 * NG + 31) / 32 + 1;                 // 128-byte lines per channel row (tAa is 16-byte aligned only)
+                for (int i = tid; i < C * nline; i += NWORK) {
+                    const int c = i / nline, l = i - c * nline;
+                    const int tp = tAa + 32 * l;
+                    if (tp >= 0 && tp < p.T) prefetch_l2(xb + (size_t)c * p.T + tp);
+                }
+            }
 #pragma unroll 1
             for (int item = warp; item < NGO * NCB; item += NWORK / 32) {
                 const int go = item % NGO, cb = item / NGO;
@@ -580,7 +595,9 @@ int launch_pair_t2(const PairTC* av, int nbr, cudaStream_t st) {
     {
         static const int env_vec4 = env_int("SVB_PAIR_VEC4", 1), env_red = env_int("SVB_PAIR_RED", 0)   /* measured: L2 reductions cost 0.7 ms/step, off */;
         const bool aligned = (a.T % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0);
+        static const int env_pf = env_int("SVB_PAIR_PF", 1);
         p.vec4 = (!TMA_IN && env_vec4 && aligned) ? 1 : 0;
+        p.prefetch = env_pf;
         p.red_out = (p.vec4 && env_red && !a.a16_out && a.x != a.out && (a.beta == 0.f || a.beta == 1.f)) ? 1 : 0;
         // tile period estimate (clk) for the first-wave de-phasing: two MMA phases at the shared-pipe rate + memory phases
         static const int env_dephase = env_int("SVB_PAIR_DEPHASE", -1);
@@ -592,7 +609,8 @@ int launch_pair_t2(const PairTC* av, int nbr, cudaStream_t st) {
     const int TOUT = 128 * MB - (a.k - 1);
     gx = std::max(gx, (a.T + TOUT - 1) / TOUT);
     }
-    dim3 grid(gx, a.B, nbr);
+    pn.nbr = nbr;
+    dim3 grid(gx * nbr, a.B, 1);
     pair_tc_kernel<C, MB, STAGE_KB, MINB, TMA_IN><<<grid, TC_THREADS, smem, st>>>(pn, tmap);
     launch_counter()++;
     return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;

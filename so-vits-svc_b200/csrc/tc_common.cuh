@@ -36,6 +36,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// try_wait with a suspend-time hint: the thread is parked by the hardware until the phase completes or `ns` elapse, instead of
+// coming back after the (short) default limit.  ncu on the fused ResBlock kernel: 13.7 % of ALL issued warp instructions were
+// the YIELD / TRYWAIT / BRA triples of polling warps, taking issue slots from the epilogue warps that bound the kernel.
+__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity, uint32_t ns = 2000) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(ns)
+            : "memory");
+    } while (!ok);
+}
 // Long waits (a role that idles for a whole phase of the others): poll with a back-off so the spinning warp does not eat the
 // issue slots of the warps doing the work (ncu on the SnakeAlias-loader conv: 11 % of all issued instructions were try_wait
 // / branch pairs of the idle MMA and producer warps).
@@ -139,6 +154,20 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Same MMA with the descriptors given as (low word, high word): only the low word (start address >> 4, LBO) changes from tap
+// to tap / K step to K step, so an issue loop can advance 32-bit values and keep the constant high words (SBO, version,
+// layout) out of the per-MMA arithmetic (the 64-bit form costs IADD3 + IMAD.X + two R2UR per descriptor and MMA).
+__device__ __forceinline__ void umma_f16_split(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // arrive on an mbarrier once all previously issued MMAs (of this thread) have completed

@@ -70,6 +70,18 @@ int main(int argc, char** argv) {
     for (int q = 0; q < 6; ++q)
         printf("  conv %d: issue->visible %.0f | worker wait %.0f | epilogue chain %.0f | issue-to-issue %.0f | issue - last dependency %.0f\n",
                q, exec[q] / n, idle[q] / n, epi[q] / n, gap[q] / n, react[q] / n);
+    {   // fine trace of (conv 2, block 2): averages over CTAs, relative to "accumulators visible"
+        double f[7] = {0}; int nf = 0;
+        for (size_t c = 0; c < max_ctas; ++c) {
+            const long long* t = &h[c * 256];
+            if (!t[0] || !t[208] || !t[214]) continue;
+            const long long v = t[(2 * 8 + 2) * 4 + 2];
+            for (int i = 0; i < 7; ++i) f[i] += (double)(t[208 + i] - v);
+            ++nf;
+        }
+        if (nf) printf("  fine (conv 2, block 2; clk after 'visible'): before LDTM %.0f | after wait::ld %.0f | math done %.0f | neighbour wait done %.0f | stores issued %.0f | after fence.proxy.async %.0f | after arrive %.0f\n",
+                       f[0] / nf, f[1] / nf, f[2] / nf, f[3] / nf, f[4] / nf, f[5] / nf, f[6] / nf);
+    }
     // one CTA in full, times relative to its tile start
     for (size_t c = 0; c < max_ctas; ++c) {
         const long long* t = &h[c * 256];

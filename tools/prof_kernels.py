@@ -21,13 +21,14 @@ xs = {}
 for i, u in enumerate(cfg.upsample_rates):
     L *= u
     xs[i] = (torch.randn((B, cfg.stage_channels[i], L), device=dev) * 1.3, L)
-for rep in range(3):
-    eng.debug_resblock(4, 2, xs[4][0], 1)      # C=16 k=11 fused, 2 CTAs/SM
-    eng.debug_resblock(3, 2, xs[3][0], 1)      # C=32 k=11
-    eng.debug_resblock(2, 2, xs[2][0], 0)      # C=64 k=11
-    eng.debug_pair(1, 2, 2, xs[1][0], 0)       # C=128 k=11 d=5, 1 CTA/SM
-    eng.debug_pair(1, 0, 0, xs[1][0], 0)       # C=128 k=3
-    eng.debug_pair(2, 2, 2, xs[2][0], 1)       # C=64 k=11, 2 CTAs/SM
-    eng.debug_pair(4, 0, 0, xs[4][0], 1)       # C=16 k=3
+# the SHIPPED variants: block-skewed fused ResBlock (variant 2), pair kernel tile variant 1 (two CTAs/SM where the tile allows)
+for rep in range(2):
+    eng.debug_resblock(4, 0, xs[4][0], 2)      # C=16 k=3   (epilogue-bound)
+    eng.debug_resblock(4, 2, xs[4][0], 2)      # C=16 k=11
+    eng.debug_resblock(3, 1, xs[3][0], 2)      # C=32 k=7
+    eng.debug_resblock(2, 1, xs[2][0], 2)      # C=64 k=7
+    eng.debug_pair(1, 1, 1, xs[1][0], 1)       # C=128 k=7 d=3
+    eng.debug_pair(1, 2, 2, xs[1][0], 1)       # C=128 k=11 d=5
+    eng.debug_pair(0, 1, 1, xs[0][0], 1)       # C=256 k=7 d=3
 torch.cuda.synchronize()
 print("done")
