@@ -750,9 +750,13 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                         // next tile, same block: the loads fly while this block's output is reduced into HBM
                         const int tn = tt0n + mb * 128 + rib;
                         const bool valid = (tn >= 0) && (tn < p.T);
-                        const float* __restrict__ xt = xbn + (valid ? tn : 0);
 #pragma unroll
-                        for (int c = 0; c < C; ++c) xn[c] = valid ? ldg_nc_v(xt + (size_t)c * p.T) : 0.f;
+                        for (int c = 0; c < C; ++c) xn[c] = 0.f;
+                        if (valid) {
+                            const float* __restrict__ xt = xbn + tn;          // 32-bit element offsets (C * T < 2^31): one IMAD.WIDE per load
+#pragma unroll
+                            for (int c = 0; c < C; ++c) xn[c] = ldg_nc_v(xt + c * p.T);
+                        }
                     }
                     if (q4 == 0 && lane == 0) SK_TRACE(it, q, mb, 1);
                     WAIT(bar_acc + 8 * mb, par);
@@ -860,21 +864,26 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const 
                             tmem_ld16(tlane + mb * C + cc, xr);
                             if (wr && ld_old) {
 #pragma unroll
-                                for (int j = 0; j < CG; ++j) oo[j] = ot[(size_t)(cc + j) * p.T];
+                                for (int j = 0; j < CG; ++j) oo[j] = ot[(cc + j) * p.T];
                             }
                             tmem_ld_wait();
                             if (wr) {
 #pragma unroll
                                 for (int j4 = 0; j4 < CG; j4 += 4) {
                                     const float4 bb = *reinterpret_cast<const float4*>(bq_ + cc + j4);
-                                    const float b4[4] = {bb.x, bb.y, bb.z, bb.w};
+                                    float y[4];
+                                    fma2(y[0], y[1], __uint_as_float(r[j4 + 0]), __uint_as_float(r[j4 + 1]), inv_q, inv_q, bb.x, bb.y);
+                                    fma2(y[2], y[3], __uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3]), inv_q, inv_q, bb.z, bb.w);
+                                    add2(y[0], y[1], __uint_as_float(xr[j4 + 0]), __uint_as_float(xr[j4 + 1]));
+                                    add2(y[2], y[3], __uint_as_float(xr[j4 + 2]), __uint_as_float(xr[j4 + 3]));
+                                    mul2(y[0], y[1], y[0], y[1], p.alpha, p.alpha);
+                                    mul2(y[2], y[3], y[2], y[3], p.alpha, p.alpha);
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) {
                                         const int j = j4 + e;
-                                        float y = p.alpha * (fmaf(__uint_as_float(r[j]), inv_q, b4[e]) + __uint_as_float(xr[j]));
-                                        if (ld_old) y = fmaf(p.beta, oo[j], y);
-                                        if (red_old) atomicAdd(ot + (size_t)(cc + j) * p.T, y);
-                                        else ot[(size_t)(cc + j) * p.T] = y;
+                                        if (ld_old) y[e] = fmaf(p.beta, oo[j], y[e]);
+                                        if (red_old) atomicAdd(ot + (cc + j) * p.T, y[e]);
+                                        else ot[(cc + j) * p.T] = y[e];
                                     }
                                 }
                             }
