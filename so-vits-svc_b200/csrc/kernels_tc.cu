@@ -58,7 +58,8 @@ struct PairParams {
     float alpha, beta, inv;
     __half* a16_out;     // optional second output: fp16 lrelu(out) in [B][T][C] (the next pair's TMA-loadable operand)
     int vec4;            // x / out 16-byte aligned and T % 4 == 0: the loader uses 128-bit loads along time
-    int prefetch;        // vec4 loader: L2 prefetch of the whole tile before the demand loads
+    int prefetch;        // vec4 loader: 1 = L2 prefetch of the whole tile before the demand loads, 2 = also of the slot's next tile
+    int prefetch_ahead;  // resident CTAs of the launch (distance, in launch order, to the tile that follows in this slot)
     int red_out;         // loader pre-writes alpha*x (+ beta*old for beta == 1) into out, epilogue 2 only adds (RED): no x re-read
     uint32_t epoch; int dephase_clk;   // first-wave start skew (tc_common.cuh: dephase_first_wave)
 };
@@ -338,6 +339,30 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const __grid_
             mbar_arrive(bar_a);
         }
         if (tid == 0) PAIR_TRACE(1);
+        if (!TMA_IN && p.vec4 && p.prefetch > 1) {
+            // The workers now idle until conv1's accumulators arrive: pull the tile of the CTA that will take this slot next
+            // into L2.  CTAs are dispatched in linear order (x fastest), `ahead` = resident slots of the launch, so the tile
+            // `ahead` positions further on is (about) the one that starts when this CTA retires; a wrong guess costs nothing
+            // but the prefetch.
+            const int lin = (int)blockIdx.x + (int)gridDim.x * (int)blockIdx.y + p.prefetch_ahead;
+            const int fy = lin / (int)gridDim.x, fx = lin - fy * (int)gridDim.x;
+            if (fy < (int)gridDim.y) {
+                const PairParams& pf_ = pn_.br[fx % pn_.nbr];
+                const int fbx = fx / pn_.nbr;
+                const int ft0 = fbx * (R1 - (pf_.k - 1));
+                if (ft0 < pf_.T) {
+                    const int fA0 = ft0 - (pf_.k - 1) / 2 - pf_.dil * (pf_.k - 1) / 2;
+                    const int frows = R1 + (pf_.k - 1) * pf_.dil;
+                    const int nline = (frows + 31) / 32 + 1;
+                    const float* __restrict__ fb = pf_.x + (size_t)fy * C * pf_.T;
+                    for (int i = tid; i < C * nline; i += NWORK) {
+                        const int c = i / nline, l = i - c * nline;
+                        const int tp = (fA0 & ~3) + 32 * l;
+                        if (tp >= 0 && tp < pf_.T) prefetch_l2(fb + (size_t)c * pf_.T + tp);
+                    }
+                }
+            }
+        }
 
         const int q = warp & 3, hsel = warp >> 2;
         const int rib = 32 * q + lane;                 // row inside a 128-row block == TMEM lane
@@ -595,9 +620,10 @@ int launch_pair_t2(const PairTC* av, int nbr, cudaStream_t st) {
     {
         static const int env_vec4 = env_int("SVB_PAIR_VEC4", 1), env_red = env_int("SVB_PAIR_RED", 0)   /* measured: L2 reductions cost 0.7 ms/step, off */;
         const bool aligned = (a.T % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0);
-        static const int env_pf = env_int("SVB_PAIR_PF", 1);
+        static const int env_pf = env_int("SVB_PAIR_PF", 2);
         p.vec4 = (!TMA_IN && env_vec4 && aligned) ? 1 : 0;
         p.prefetch = env_pf;
+        p.prefetch_ahead = sm_count() * MINB;
         p.red_out = (p.vec4 && env_red && !a.a16_out && a.x != a.out && (a.beta == 0.f || a.beta == 1.f)) ? 1 : 0;
         // tile period estimate (clk) for the first-wave de-phasing: two MMA phases at the shared-pipe rate + memory phases
         static const int env_dephase = env_int("SVB_PAIR_DEPHASE", -1);
