@@ -786,7 +786,7 @@ int run_generator(svb_ctx* ctx, const float* z, const float* g, int gT, const fl
             a.x = cur; a.x_ctot = S.Cin; a.cin_real = S.Cin; a.cinp = W.cinp; a.Tin = Lin; a.in_act = snake ? 0 : 1; a.in_slope = 0.1f;
             if (snake) { a.snake_ealpha = S.snake_in.ealpha; a.snake_invbeta = S.snake_in.inv_beta; a.snake_filt = ctx->snake_filt; }
             a.w = W.img; a.bias = W.bias; a.acc_scale = W.acc_scale; a.k = 2; a.pad_left = 1; a.n_rows = Lin + 1; a.N_total = W.N_total; a.NC = W.NC;
-            a.chunks_per_cta = pick_chunks_per_cta(Lin + 1, 128 * (snake ? convn_snake_mb(W.cinp) : convn_mb(W.cinp)), B, (W.N_total + W.NC - 1) / W.NC);
+            a.chunks_per_cta = pick_chunks_per_cta(Lin + 1, 128 * (snake ? convn_snake_mb(W.cinp) : convn_ups_mb(W.cinp)), B, (W.N_total + W.NC - 1) / W.NC);
             a.mode = 1; a.s = S.s; a.p = S.p; a.Ty = Lout; a.B = B;
             a.seg[0].y = X; a.seg[0].y_ctot = S.Cout;
             if (W.noise) { a.har = har; a.har_N = (int)N; a.noise_stride = W.noise_stride; a.noise_w0 = W.noise_w0; a.noise_wide = (W.noise == 2); }
@@ -1426,7 +1426,7 @@ int svb_load_weights(svb_ctx* ctx, const svb_tensor* tensors, int n_tensors, con
             const std::vector<float> nwv = w.v, nbv = b.v;
             const int s_ = S.s, Co = S.Cout, kk = S.k;
             const int ntot = Co * s_;
-            int nc = 256 / convn_mb(S.Cin);
+            int nc = 256 / (c.snake ? convn_mb(S.Cin) : convn_ups_mb(S.Cin));
             if (nc > ntot) nc = ntot;
             const int sp = S.noise_s, Kn = S.noise_K, pn_ = S.noise_p;
             const int nwin = (s_ - 1) * sp + Kn;                   // excitation window of one output row

@@ -140,6 +140,7 @@ struct ConvNTC {
 };
 int launch_convn_tc(const ConvNTC& a, cudaStream_t st);
 int convn_mb(int cinp);
+int convn_ups_mb(int cinp);
 int convn_snake_mb(int cinp);
 size_t convn_weight_image_bytes(int cinp, int N_total, int NC, int k, int noise);
 void convn_pack_weight_image(int cinp, int N_total, int NC, int k, const std::function<float(int, int, int)>& wcol,

@@ -991,9 +991,12 @@ int launch_resblock_tc(const ResblockTC& a, cudaStream_t st) {
                 return launch_resblock_t<16, 8, 8, 2, true>(a, st);
             }
             case 32: {
-                static const int env_c32 = rb_env_int("SVB_RB_C32_ONE", 0);     // experiment: one CTA/SM with 1024-row tiles
+                // 1024-row tiles, one CTA/SM: 1 = every kernel size, 2 = k = 11 only (the MMA-bound branch gains from the smaller
+                // halo share, 120 of 1024 rows instead of 120 of 512: resblock_tc 3.04 vs 3.07 ms/step; the epilogue-bound k = 3 / 7
+                // keep two CTAs per SM)
+                static const int env_c32 = rb_env_int("SVB_RB_C32_ONE", 2);
                 static const int env_pair = rb_env_int("SVB_RB_PAIR32", 1);
-                if (env_c32) return launch_resblock_t<32, 8, 22, 1, true>(a, st);
+                if (env_c32 == 1 || (env_c32 == 2 && a.k == 11)) return launch_resblock_t<32, 8, 22, 1, true, true>(a, st);
                 if (env_pair) return launch_resblock_t<32, 4, 22, 2, true, true>(a, st);
                 return launch_resblock_t<32, 4, 22, 2, true>(a, st);
             }

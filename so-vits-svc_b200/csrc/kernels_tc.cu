@@ -620,7 +620,8 @@ int launch_pair_t2(const PairTC* av, int nbr, cudaStream_t st) {
     {
         static const int env_vec4 = env_int("SVB_PAIR_VEC4", 1), env_red = env_int("SVB_PAIR_RED", 0)   /* measured: L2 reductions cost 0.7 ms/step, off */;
         const bool aligned = (a.T % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0);
-        static const int env_pf = env_int("SVB_PAIR_PF", 2);
+        static const int env_pf = env_int("SVB_PAIR_PF", 1);     // measured: 2 (also the slot's next tile) 3.50 vs 3.37 ms/step - 47 MB of
+                                                                 // prefetched lines per wave compete with the live tiles for L2
         p.vec4 = (!TMA_IN && env_vec4 && aligned) ? 1 : 0;
         p.prefetch = env_pf;
         p.prefetch_ahead = sm_count() * MINB;
