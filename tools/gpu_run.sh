@@ -31,6 +31,10 @@ for step in "$@"; do
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1; echo "launches rc=$?" ;;
     ncu_snake) timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:convn_tc_kernel<\\(int\\)128, \\(int\\)1, \\(int\\)2, \\(bool\\)1>" -s 6 -c 3 -f -o gpurun_out/prof_snake128 python bench.py --vocoder nsf-snake-hifigan --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_snake.log 2>&1; echo "ncu_snake rc=$?" ;;
     ncu_kern) timeout 900 ncu --set full --clock-control none --import-source on -k "regex:resblock_skew_kernel|pair_tc_kernel" -s 7 -c 7 -f -o gpurun_out/prof_kern python tools/prof_kernels.py > gpurun_out/ncu_kern.log 2>&1; echo "ncu_kern rc=$?" ;;
+    ncu_ups) for spec in "ups32:\(int\)32, \(int\)2, \(int\)2, \(bool\)0, \(int\)1:0" "ffn2:\(int\)384, \(int\)1, \(int\)1, \(bool\)0, \(int\)0:3" "ups128:\(int\)128, \(int\)2, \(int\)2, \(bool\)0, \(int\)1:0"; do
+               tag=${spec%%:*}; rest=${spec#*:}; pat=${rest%:*}; skip=${rest##*:}
+               timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:convn_tc_kernel<$pat" -s $skip -c 1 -f -o gpurun_out/prof_$tag python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_$tag.log 2>&1; echo "ncu_ups $tag rc=$?"
+             done ;;
     ncu_main) timeout 900 ncu --set full --clock-control none --import-source on -k "regex:flow_layer_kernel|resblock_skew_kernel" -c 13 -f -o gpurun_out/prof_main python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_main.log 2>&1; echo "ncu_main rc=$?" ;;
     ncu_prefix) timeout 900 ncu --set full --clock-control none --import-source on -k "regex:convn_tc_kernel|attn_rel_kernel" -s 60 -c 9 -f -o gpurun_out/prof_prefix python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_prefix.log 2>&1; echo "ncu_prefix rc=$?" ;;
     *) echo "unknown step $step" ;;
