@@ -394,18 +394,21 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const __grid_
                     if (g == 1 && !two) break;
                     const int cg0 = g ? c1 : c0;
                     const uint32_t* rr = g ? r1 : r0;
-                    float v[16];
+                    uint32_t hq[8];                     // packed fp32x2 arithmetic (bit-identical to the scalar form, half the issue slots)
 #pragma unroll
                     for (int j4 = 0; j4 < CG; j4 += 4) {
                         const float4 bq = *reinterpret_cast<const float4*>(sbias + cg0 + j4);
-                        v[j4 + 0] = lrelu01(__uint_as_float(rr[j4 + 0]) + bq.x);
-                        v[j4 + 1] = lrelu01(__uint_as_float(rr[j4 + 1]) + bq.y);
-                        v[j4 + 2] = lrelu01(__uint_as_float(rr[j4 + 2]) + bq.z);
-                        v[j4 + 3] = lrelu01(__uint_as_float(rr[j4 + 3]) + bq.w);
+                        float v0 = __uint_as_float(rr[j4 + 0]), v1 = __uint_as_float(rr[j4 + 1]);
+                        float v2 = __uint_as_float(rr[j4 + 2]), v3 = __uint_as_float(rr[j4 + 3]);
+                        add2(v0, v1, bq.x, bq.y);
+                        add2(v2, v3, bq.z, bq.w);
+                        hq[j4 / 2] = lrelu_pack2(v0, v1) & keep;
+                        hq[j4 / 2 + 1] = lrelu_pack2(v2, v3) & keep;
                     }
                     uint8_t* prow = sm + (cg0 / G::CPP) * APANEL + row * G::RB;
-                    store_chunk8(prow, phase, (cg0 % G::CPP) / 8, v, keep);
-                    if (CG == 16) store_chunk8(prow, phase, (cg0 % G::CPP) / 8 + 1, v + 8, keep);
+                    const uint32_t ch0 = (uint32_t)((cg0 % G::CPP) / 8);
+                    *reinterpret_cast<uint4*>(prow + ((ch0 ^ phase) << 4)) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+                    if (CG == 16) *reinterpret_cast<uint4*>(prow + (((ch0 + 1) ^ phase) << 4)) = make_uint4(hq[4], hq[5], hq[6], hq[7]);
                 }
             }
         }
@@ -452,17 +455,24 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) pair_tc_kernel(const __grid_
 #pragma unroll
                     for (int j4 = 0; j4 < CG; j4 += 4) {
                         const float4 bq = *reinterpret_cast<const float4*>(sbias + C + c0 + j4);
-                        const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+                        float y[4];
+                        fma2(y[0], y[1], __uint_as_float(r[j4 + 0]), __uint_as_float(r[j4 + 1]), p.inv, p.inv, bq.x, bq.y);
+                        fma2(y[2], y[3], __uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3]), p.inv, p.inv, bq.z, bq.w);
+                        add2(y[0], y[1], xr[j4 + 0], xr[j4 + 1]);
+                        add2(y[2], y[3], xr[j4 + 2], xr[j4 + 3]);
+                        mul2(y[0], y[1], y[0], y[1], p.alpha, p.alpha);
+                        mul2(y[2], y[3], y[2], y[3], p.alpha, p.alpha);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int j = j4 + e;
-                            const float y = p.alpha * (fmaf(__uint_as_float(r[j]), p.inv, bb[e]) + xr[j]);
-                            if (add_old) atomicAdd(ot + (size_t)(c0 + j) * p.T, y);
-                            else ot[(size_t)(c0 + j) * p.T] = y;
-                            xr[j] = lrelu01(y);
+                            if (add_old) atomicAdd(ot + (size_t)(c0 + j) * p.T, y[e]);
+                            else ot[(size_t)(c0 + j) * p.T] = y[e];
+                            xr[j] = y[e];
                         }
                     }
                     if (p.a16_out) {
+#pragma unroll
+                        for (int j = 0; j < CG; ++j) xr[j] = lrelu01(xr[j]);
                         uint4* dst = reinterpret_cast<uint4*>(p.a16_out + ((size_t)b * p.T + t) * C + c0);
                         dst[0] = make_uint4(pack_h2(xr[0], xr[1]), pack_h2(xr[2], xr[3]), pack_h2(xr[4], xr[5]), pack_h2(xr[6], xr[7]));
                         if (CG == 16) dst[1] = make_uint4(pack_h2(xr[8], xr[9]), pack_h2(xr[10], xr[11]), pack_h2(xr[12], xr[13]), pack_h2(xr[14], xr[15]));

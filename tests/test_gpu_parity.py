@@ -290,7 +290,7 @@ def test_own_prior_encoder_matches_oracle(cfg, sd):
 
 def test_full_size_properties(cfg, sd, eng):
     """BASELINE config 2 size (8 x 862 frames): batch independence (item i of a batch == item i alone, given its
-    own noise slice), finiteness, tc-vs-fp32 agreement, host-buffer entry point."""
+    own noise slice), run-to-run bit reproducibility, finiteness, tc-vs-fp32 agreement, host-buffer entry point."""
     B, T = 8, 862
     z_p, g, f0, noise = _case(cfg, sd, B, T)
     dv = lambda t: t.to(DEV)
@@ -303,6 +303,9 @@ def test_full_size_properties(cfg, sd, eng):
         one = eng.infer_tail(dv(z_p[i:i + 1]), dv(g[i:i + 1]), dv(f0[i:i + 1]), dv(noise["rand_ini"][i:i + 1]),
                              dv(noise["har_noise"][i:i + 1]))
         assert torch.equal(one[0], full[i]), precision
+        # run-to-run reproducibility: the branch-merged launches reduce into the stage output in an order-independent way
+        again = eng.infer_tail(dv(z_p), dv(g), dv(f0), dv(noise["rand_ini"]), dv(noise["har_noise"]))
+        assert torch.equal(again, full), precision
         outs[precision] = full
     eng.set_precision("fp32")
     err = float((outs["tc"] - outs["fp32"]).abs().max())
