@@ -393,6 +393,21 @@ __global__ void __launch_bounds__(CN_THREADS, MINB) convn_tc_kernel(const ConvNT
         } else {
             const bool view = VIEW && a.view_tstride != 0;
             const float* __restrict__ xb = view ? a.x + (size_t)b * a.view_bstride : a.x + ((size_t)b * a.x_ctot + xc0) * (size_t)a.Tin;
+            if (!view && kc == 0) {
+                // The loader below is a chain of 2-8 dependent global round trips (16-48 loads in flight per thread): request every
+                // line of the tile - all K chunks - from DRAM up front, so that the demand loads are L2 hits (a warp covers 32
+                // consecutive rows = one 128-byte line per channel; same idea as the pair kernel's tile prefetch)
+                const int ti0 = i0 - a.pad_left;
+                const int nl = (RA + 31) / 32 + 1;
+                for (int kk2 = 0; kk2 < nkc; ++kk2) {
+                    const float* __restrict__ xk = a.x + ((size_t)b * a.x_ctot + (kk2 ? a.k2_c0 : a.x_c0)) * (size_t)a.Tin;
+                    for (int idx = tid; idx < a.cin_real * nl; idx += CN_NWORK) {
+                        const int c = idx / nl, l = idx - c * nl;
+                        const int tp = min(max(ti0 + 32 * l, 0), a.Tin - 1);
+                        prefetch_l2(xk + (size_t)c * a.Tin + tp);
+                    }
+                }
+            }
             // one-block tiles (MB = 1) have ~130 rows for 256 loader threads: two threads share a row (half of the channels
             // each) and keep 48 loads in flight, so the tile costs 2-4 global round trips instead of 6-12 (the small GEMMs of
             // enc_p are a chain of such latencies: ~31 us per launch before, of which the loader was about a third)
