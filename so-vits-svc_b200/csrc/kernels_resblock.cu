@@ -388,7 +388,14 @@ __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_tc_kernel(const Re
 // The issuer therefore runs one to two blocks ahead of the epilogue warps and the tensor pipe works while accumulators
 // are being drained, inside ONE CTA - the overlap no longer depends on a second CTA being in a different phase.
 // Barriers: bar_a[b] completes once per round (round 0 = loader, round q+1 = epilogue of conv q), bar_acc[b] once per conv.
-// Every wait of round q only depends on arrivals of round q-1 of the other side, so the protocol cannot deadlock.
+// Every wait of round q only depends on arrivals of round q-1 of the other side, so the protocol cannot deadlock
+// (tests/test_skew_protocol.py models it with one or two issuers and single or paired epilogues).
+// Roles (320 threads): warps 0-3 / 4-7 = two epilogue groups owning the even / odd row blocks; warp 8 = MMA issuer; warp 9 =
+// weight ring and, in dual mode (the default), the second issuer: warp 8 issues the even blocks, warp 9 the odd ones, each
+// waiting for the previous round of blocks b-1, b, b+1 itself (the MMAs of one thread retire in order, which is what lets an
+// epilogue wait for acc[b] and acc[b+1] only).  PAIR: a group takes two of its blocks (b, b+2) per barrier round trip.
+// The kernel is persistent: CTA c walks the tiles c, c + gridDim.x, ...; the loads of the next tile's block b are issued by
+// the thread that finishes the last epilogue of block b.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int C, int MB, int STAGE_KB, int MINB, bool PAIR>
 __global__ void __launch_bounds__(RBK_THREADS, MINB) resblock_skew_kernel(const ResblockParams p) {
