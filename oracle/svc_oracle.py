@@ -296,15 +296,18 @@ def prologue(sd, c, f0, uv, sid, cfg, dtype, vol=None):
     g = sd["emb_g.weight"].to(dtype)[sid].transpose(1, 2)            # [B,gin,1]
     x = F.conv1d(c.to(dtype), sd["pre.weight"].to(dtype), sd["pre.bias"].to(dtype), padding=2) * x_mask
     x = x + sd["emb_uv.weight"].to(dtype)[uv.long()].transpose(1, 2)
-    if vol is not None:
-        raise NotImplementedError("vol_embedding is not part of the benchmark configs")
+    if vol is not None and "emb_vol.weight" in sd:
+        # models.py:513: vol = emb_vol(vol[:, :, None]).transpose(1, 2) with emb_vol = nn.Linear(1, hidden) (models.py:398-399)
+        v = F.linear(vol.to(dtype)[:, :, None], sd["emb_vol.weight"].to(dtype), sd["emb_vol.bias"].to(dtype))
+        x = x + v.transpose(1, 2)
     return x, x_mask, g
 
 
 @torch.no_grad()
-def infer(sd, cfg, c, f0, uv, sid, noise, noice_scale=0.35, dtype=torch.float32, taps: Optional[dict] = None):
-    """models.py:495-532 with predict_f0=False, vol=None.  ``noise`` = {"z_noise","rand_ini","har_noise"}."""
-    x, x_mask, g = prologue(sd, c, f0, uv, sid, cfg, dtype)
+def infer(sd, cfg, c, f0, uv, sid, noise, noice_scale=0.35, dtype=torch.float32, taps: Optional[dict] = None, vol=None):
+    """models.py:495-532 with predict_f0=False.  ``noise`` = {"z_noise","rand_ini","har_noise"}; ``vol`` [B,T] is used when the
+    checkpoint has a volume embedding (``emb_vol.*``), exactly like the reference ignores it otherwise."""
+    x, x_mask, g = prologue(sd, c, f0, uv, sid, cfg, dtype, vol=vol)
     z_p, m_p, logs_p = text_encoder(sd, x, x_mask, f0_to_coarse(f0), noise["z_noise"], noice_scale, cfg, dtype)
     z = flow_reverse(sd, z_p, x_mask, g, cfg, dtype)
     har = nsf_source(sd, f0, noise["rand_ini"], noise["har_noise"], cfg, dtype)

@@ -168,6 +168,20 @@ class SynthesizerTrn(_TailMixin, nn.Module):
         gm = gm.sum(dim=1)                              # [T,1,1,gin]
         return gm.transpose(0, -1).transpose(0, -2).squeeze(0)
 
+    def conditioning(self, c, g, vol=None):
+        """models.py:505-513: speaker conditioning g [B,gin,1] (or [1,gin,T] for a [T,S] speaker mix), the all-ones frame mask
+        and the volume embedding (0 when the checkpoint has none or no ``vol`` is given).  Plain torch indexing, any device."""
+        B, _, T = c.shape
+        if self.character_mix and len(g) > 1:           # [T,S] mix weights -> g [1,gin,T] (models.py:505-509)
+            g = self.mix_speakers(g)
+        else:
+            if g.dim() == 1:
+                g = g.unsqueeze(0)
+            g = self.emb_g(g).transpose(1, 2)
+        x_mask = torch.ones(B, 1, T, dtype=c.dtype, device=c.device)
+        v = self.emb_vol(vol[:, :, None]).transpose(1, 2) if (vol is not None and self.vol_embedding) else 0
+        return g, x_mask, v
+
     @torch.no_grad()
     def infer(self, c, f0, uv, g=None, noice_scale=0.35, seed=52468, predict_f0=False, vol=None):
         """models.py:495-532.  ``c`` [B,ssl,T], ``f0``/``uv`` [B,T], ``g`` [B,1] int64 (or [T,S] mix)."""
@@ -178,14 +192,7 @@ class SynthesizerTrn(_TailMixin, nn.Module):
         else:
             torch.manual_seed(seed)
         B, _, T = c.shape
-        if self.character_mix and len(g) > 1:           # [T,S] mix weights -> g [1,gin,T] (models.py:505-509)
-            g = self.mix_speakers(g)
-        else:
-            if g.dim() == 1:
-                g = g.unsqueeze(0)
-            g = self.emb_g(g).transpose(1, 2)
-        x_mask = torch.ones(B, 1, T, dtype=c.dtype, device=c.device)
-        v = self.emb_vol(vol[:, :, None]).transpose(1, 2) if (vol is not None and self.vol_embedding) else 0
+        g, x_mask, v = self.conditioning(c, g, vol)
         if self.use_automatic_f0_prediction and predict_f0:
             raise NotImplementedError("predict_f0 needs the reference f0_decoder: use patch_reference() (INTEGRATION.md)")
         eng = self._engine(c.device)

@@ -208,3 +208,43 @@ def test_fp16_operand_model_explains_the_tensor_core_tolerance(cfg, sd, monkeypa
     print(f"[parity] fp16-operand model of the tcgen05 path: L-inf vs fp32 oracle {err_model:.3e}, vs reference fixture {err_fixture:.3e}")
     assert 2e-4 < err_model < 2e-2          # same order as the measured 2.5-3.4e-3 of the CUDA path (profiles/r01/parity_final.txt)
     assert err_fixture < 2e-2
+
+
+def test_oracle_and_host_class_with_volume_embedding(cfg, sd):
+    """`vol_embedding=True` checkpoints (`emb_vol = nn.Linear(1, hidden)`, models.py:398-399,513): the oracle against the
+    reference's own run with per-frame volumes (tests/golden/make_golden_vol.py), and the stand-alone class's conditioning
+    (same state_dict keys, same volume term) against the oracle's prologue."""
+    gold = np.load(os.path.join(GOLD, "ref_infer_vol_b2_t22.npz"))
+    B, T = int(gold["B"]), int(gold["T"])
+    sdv = dict(sd)
+    sdv["emb_vol.weight"] = torch.from_numpy(gold["emb_vol_w"])
+    sdv["emb_vol.bias"] = torch.from_numpy(gold["emb_vol_b"])
+    c, f0, uv, sid, vol = (torch.from_numpy(gold[k]) for k in ("c", "f0", "uv", "sid", "vol"))
+    noise = synth.draw_noise(B, T, cfg, seed=int(gold["seed"]))
+    taps = {}
+    out, _ = O.infer(sdv, cfg, c, f0, uv, sid, noise, noice_scale=float(gold["noice_scale"]), taps=taps, vol=vol)
+    assert float((taps["z_p"] - torch.from_numpy(gold["z_p"])).abs().max()) < 1e-5
+    assert float((out - torch.from_numpy(gold["o"])).abs().max()) < 2e-5
+    # without the volumes the result must differ (the fixture's volumes move the waveform by 0.37)
+    out0, _ = O.infer(sdv, cfg, c, f0, uv, sid, noise, noice_scale=float(gold["noice_scale"]))
+    assert float((out0 - out).abs().max()) > 1e-2
+    # host class: emb_vol in the state_dict, the same volume term as the oracle
+    import json
+    import sovits_b200
+    from sovits_b200 import models
+    with open(sovits_b200.DEFAULT_CONFIG) as f:
+        kw = json.load(f)["model"]
+    kw["vol_embedding"] = True
+    net = models.SynthesizerTrn(1025, 20, **kw).eval()
+    assert {"emb_vol.weight", "emb_vol.bias"} <= set(net.state_dict().keys())
+    net.load_state_dict(sdv)
+    with torch.no_grad():
+        g_h, mask_h, v_h = net.conditioning(c, sid, vol)
+        x_h = net.pre(c) * mask_h + net.emb_uv(uv.long()).transpose(1, 2) + v_h
+    x_o, _, g_o = O.prologue(sdv, c, f0, uv, sid, cfg, torch.float32, vol=vol)
+    assert float((x_h - x_o).abs().max()) < 1e-5 and float((g_h - g_o).abs().max()) == 0.0
+    # a checkpoint without the embedding ignores `vol`, like the reference (models.py:513)
+    kw["vol_embedding"] = False
+    net0 = models.SynthesizerTrn(1025, 20, **kw).eval()
+    net0.load_state_dict(sd)
+    assert net0.conditioning(c, sid, vol)[2] == 0
